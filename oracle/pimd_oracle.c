@@ -1,0 +1,697 @@
+/* TEST INFRASTRUCTURE ONLY — see pimd_oracle.h. Plain C11, single thread, scalar loops.
+ * CPU restatement of the reference hot path; citations are /root/reference/<file>:<lines>. */
+#include "pimd_oracle.h"
+
+#include <float.h>
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORC_EPS 1.0e-7 /* include/common.h:45 */
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+
+/* ------------------------------------------------------------------ RANMAR (libs/random_mars.cpp) */
+struct orc_ranmars {
+    double u[98];
+    int i97, j97;
+    double c, cd, cm;
+    int have_spare;
+    double spare;
+};
+
+/* libs/random_mars.cpp:62-77 — lagged-Fibonacci subtract-with-borrow step plus the arithmetic sequence c */
+double orc_ranmars_uniform(orc_ranmars* r) {
+    double v = r->u[r->i97] - r->u[r->j97];
+    if (v < 0.0) v += 1.0;
+    r->u[r->i97] = v;
+    if (--r->i97 == 0) r->i97 = 97;
+    if (--r->j97 == 0) r->j97 = 97;
+    r->c -= r->cd;
+    if (r->c < 0.0) r->c += r->cm;
+    v -= r->c;
+    if (v < 0.0) v += 1.0;
+    return v;
+}
+
+/* libs/random_mars.cpp:10-56 — seed expansion into 97 24-bit fractions; one uniform is burnt at the end */
+orc_ranmars* orc_ranmars_new(int seed) {
+    if (seed <= 0 || seed > 900000000) return NULL;
+    orc_ranmars* r = (orc_ranmars*)calloc(1, sizeof *r);
+    int ij = (seed - 1) / 30082;
+    int kl = (seed - 1) - 30082 * ij;
+    int i = (ij / 177) % 177 + 2;
+    int j = ij % 177 + 2;
+    int k = (kl / 169) % 178 + 1;
+    int l = kl % 169;
+    for (int ii = 1; ii <= 97; ++ii) {
+        double s = 0.0, t = 0.5;
+        for (int jj = 1; jj <= 24; ++jj) {
+            int m = ((i * j) % 179) * k % 179;
+            i = j; j = k; k = m;
+            l = (53 * l + 1) % 169;
+            if ((l * m) % 64 >= 32) s += t;
+            t *= 0.5;
+        }
+        r->u[ii] = s;
+    }
+    r->c = 362436.0 / 16777216.0;
+    r->cd = 7654321.0 / 16777216.0;
+    r->cm = 16777213.0 / 16777216.0;
+    r->i97 = 97;
+    r->j97 = 33;
+    r->have_spare = 0;
+    (void)orc_ranmars_uniform(r);
+    return r;
+}
+
+/* libs/random_mars.cpp:83-103 — polar Box–Muller; the FIRST value returned is v2*fac, v1*fac is cached */
+double orc_ranmars_gaussian(orc_ranmars* r) {
+    if (r->have_spare) {
+        r->have_spare = 0;
+        return r->spare;
+    }
+    double v1, v2, rsq;
+    do {
+        v1 = 2.0 * orc_ranmars_uniform(r) - 1.0;
+        v2 = 2.0 * orc_ranmars_uniform(r) - 1.0;
+        rsq = v1 * v1 + v2 * v2;
+    } while (rsq >= 1.0 || rsq == 0.0);
+    double fac = sqrt(-2.0 * log(rsq) / rsq);
+    r->spare = v1 * fac;
+    r->have_spare = 1;
+    return v2 * fac;
+}
+
+void orc_ranmars_free(orc_ranmars* r) { free(r); }
+
+/* ------------------------------------------------------------------ state */
+struct orc_sim {
+    orc_config c;
+    int N, P, D;
+    double beta, thermo_beta, omega_p, k_spring; /* src/simulation.cpp:37-52 */
+    double rc;                                   /* effective cutoff, src/simulation.cpp:84-90 */
+    double *x, *p, *f, *f_spring, *f_phys;       /* [P][N][D] */
+    /* exchange tables (src/bosonic_exchange/quadratic_bosonic_exchange.cpp:8-16) */
+    double *E_kn, *V, *Vb, *prob, *tmp, *prim;
+    orc_ranmars** rng;                           /* one RANMAR per bead, seed+bead (src/simulation.cpp:58-59) */
+    double *nm_fwd, *nm_inv;                     /* [P][P] rows: fwd[k][j] = C_kj ; inv[j][k] as the reference stores them */
+    double *nm_ext;                              /* NormalModesPropagator::ext_forces (zero before the first step) */
+    double *scratch_x, *scratch_p;               /* [P][N][D] NM-space copies */
+};
+
+static size_t slab(const orc_sim* s) { return (size_t)s->N * s->D; }
+static size_t idx(const orc_sim* s, int b, int i, int a) { return ((size_t)b * s->N + i) * s->D + a; }
+
+/* src/common.cpp:41-43 */
+static double min_image(double dx, double L) { return dx - L * floor(dx / L + 0.5); }
+
+/* ------------------------------------------------------------------ pair / external potentials */
+/* Aziz HFDHE2 constants: src/potentials/aziz.cpp:6-13 */
+static const double AZ_RM = 5.60738, AZ_A = 0.5448504e6, AZ_EPS = 3.42016E-5, AZ_ALPHA = 13.353384,
+                    AZ_D = 1.241314, AZ_C6 = 1.3732412, AZ_C8 = 0.4253785, AZ_C10 = 0.1781;
+
+/* include/potentials/aziz.h:25-34 */
+static double aziz_F(double x) {
+    if (x >= AZ_D) return 1.0;
+    double q = AZ_D / x - 1.0;
+    return exp(-q * q);
+}
+static double aziz_dF(double x) {
+    if (x >= AZ_D) return 0.0;
+    double ix = 1.0 / x, q = AZ_D * ix - 1.0;
+    return 2.0 * AZ_D * ix * ix * q * exp(-q * q);
+}
+
+/* V(r): src/potentials/aziz.cpp:18-54 ; dV/dr: :56-106 (returned divided by r so grad = g * r_vec) */
+static double aziz_eval(double r, double* g_over_r) {
+    double xs = r / AZ_RM;
+    double rep = AZ_A * exp(-AZ_ALPHA * xs);
+    double t1 = -AZ_A * AZ_ALPHA * exp(-AZ_ALPHA * xs);
+    double v, dvdr;
+    if (xs > ORC_EPS && xs < 0.01) { /* hard-core branch: repulsion only */
+        v = AZ_EPS * rep;
+        dvdr = t1 * (AZ_EPS / AZ_RM);
+    } else {
+        double ix = 1.0 / xs, ix2 = ix * ix, ix6 = ix2 * ix2 * ix2, ix7 = ix6 * ix, ix8 = ix6 * ix2,
+               ix9 = ix8 * ix, ix10 = ix8 * ix2, ix11 = ix10 * ix;
+        /* V uses 1/(x*x) (aziz.cpp:44) while gradV uses (1/x)^2 (aziz.cpp:81-82); same to rounding */
+        double jx2 = 1.0 / (xs * xs), jx6 = jx2 * jx2 * jx2, jx8 = jx6 * jx2, jx10 = jx8 * jx2;
+        v = AZ_EPS * (rep - (AZ_C6 * jx6 + AZ_C8 * jx8 + AZ_C10 * jx10) * aziz_F(xs));
+        double t2 = (6.0 * AZ_C6 * ix7 + 8.0 * AZ_C8 * ix9 + 10.0 * AZ_C10 * ix11) * aziz_F(xs);
+        double t3 = -(AZ_C6 * ix6 + AZ_C8 * ix8 + AZ_C10 * ix10) * aziz_dF(xs);
+        dvdr = (AZ_EPS / AZ_RM) * (t1 + t2 + t3);
+    }
+    *g_over_r = dvdr / r;
+    return v;
+}
+
+double orc_pair_potential(int pot, double r, double par, double mass, double* g_over_r) {
+    double g = 0.0, v = 0.0;
+    switch (pot) {
+        case ORC_POT_AZIZ:
+            v = aziz_eval(r, &g);
+            break;
+        case ORC_POT_DIPOLE: /* src/potentials/dipole.cpp:5-45: V = s/r^3, grad = -3 s r_vec / r^5 */
+            v = par / (r * r * r);
+            g = -3.0 * par / (r * r * r * r * r);
+            break;
+        case ORC_POT_HARMONIC: { /* src/potentials/harmonic.cpp:3-23: k = m w^2, V = k r^2/2, grad = k r_vec */
+            double k = mass * par * par;
+            v = 0.5 * k * r * r;
+            g = k;
+            break;
+        }
+        default: /* include/potentials/potential.h:12-19 */
+            break;
+    }
+    if (g_over_r) *g_over_r = g;
+    return v;
+}
+
+static double int_param(const orc_sim* s) {
+    return s->c.int_pot == ORC_POT_DIPOLE ? s->c.int_strength : s->c.int_omega;
+}
+
+/* src/simulation.cpp:499-512 */
+static double separation(const orc_sim* s, const double* xb, int i, int j, double* d) {
+    double r2 = 0.0;
+    for (int a = 0; a < s->D; ++a) {
+        double dx = xb[(size_t)i * s->D + a] - xb[(size_t)j * s->D + a];
+        if (s->c.pbc) dx = min_image(dx, s->c.size);
+        d[a] = dx;
+        r2 += dx * dx;
+    }
+    return sqrt(r2);
+}
+
+/* src/simulation.cpp:428-455 — external force then the i<j pair loop with strict '<' cutoff */
+static void physical_forces(const orc_sim* s, const double* xb, double* out) {
+    const int N = s->N, D = s->D;
+    double kext = (s->c.ext_pot == ORC_POT_HARMONIC) ? s->c.mass * s->c.ext_omega * s->c.ext_omega : 0.0;
+    for (size_t q = 0; q < slab(s); ++q) out[q] = (-1.0) * (kext * xb[q]);
+    if (s->rc == 0.0) return;
+    double d[3];
+    for (int i = 0; i < N; ++i) {
+        for (int j = i + 1; j < N; ++j) {
+            double r = separation(s, xb, i, j, d);
+            if (r < s->rc || s->rc < 0.0) {
+                double g;
+                orc_pair_potential(s->c.int_pot, r, int_param(s), s->c.mass, &g);
+                for (int a = 0; a < D; ++a) {
+                    double f1 = (-1.0) * (g * d[a]);
+                    out[(size_t)i * D + a] += f1;
+                    out[(size_t)j * D + a] -= f1;
+                }
+            }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ springs */
+/* src/simulation.cpp:405-419 */
+static void ring_spring_forces(const orc_sim* s, int b, double* out) {
+    const int P = s->P;
+    const double* xc = s->x + (size_t)b * slab(s);
+    const double* xp = s->x + (size_t)((b - 1 + P) % P) * slab(s);
+    const double* xn = s->x + (size_t)((b + 1) % P) * slab(s);
+    for (size_t q = 0; q < slab(s); ++q) {
+        double dp = xp[q] - xc[q], dn = xn[q] - xc[q];
+        if (s->c.pbc) {
+            dp = min_image(dp, s->c.size);
+            dn = min_image(dn, s->c.size);
+        }
+        out[q] = s->k_spring * (dp + dn);
+    }
+}
+
+/* src/simulation.cpp:464-486 — spring energy of the link (b-1 -> b) */
+static double ring_spring_energy(const orc_sim* s, int b) {
+    const int P = s->P;
+    const double* xc = s->x + (size_t)b * slab(s);
+    const double* xp = s->x + (size_t)((b - 1 + P) % P) * slab(s);
+    double e = 0.0;
+    for (size_t q = 0; q < slab(s); ++q) {
+        double d = xp[q] - xc[q];
+        if (s->c.pbc) d = min_image(d, s->c.size);
+        e += d * d;
+    }
+    return e * (0.5 * s->k_spring);
+}
+
+/* ------------------------------------------------------------------ bosonic exchange (Feldman–Hirshberg) */
+/* src/bosonic_exchange/bosonic_exchange_base.cpp:30-64 — separation "second minus first" */
+static void bead_sep(const orc_sim* s, const double* x1, int l1, const double* x2, int l2, double* d) {
+    l1 %= s->N;
+    l2 %= s->N;
+    for (int a = 0; a < s->D; ++a) {
+        double dx = x2[(size_t)l2 * s->D + a] - x1[(size_t)l1 * s->D + a];
+        if (s->c.pbc) dx = min_image(dx, s->c.size);
+        d[a] = dx;
+    }
+}
+static double bead_sep2(const orc_sim* s, const double* x1, int l1, const double* x2, int l2) {
+    double d[3], r2 = 0.0;
+    bead_sep(s, x1, l1, x2, l2, d);
+    for (int a = 0; a < s->D; ++a) r2 += d[a] * d[a];
+    return r2;
+}
+
+/* quadratic_bosonic_exchange.cpp:63-71 — E_m^k lives at E_kn[m(m+1)/2 - k] */
+static double* Eat(const orc_sim* s, int m, int k) { return &s->E_kn[(size_t)m * (m + 1) / 2 - k]; }
+
+/* beta used by the exchange class = beta/P (bosonic_exchange_base.cpp:16-18) */
+static double exch_beta(const orc_sim* s) { return s->beta / s->P; }
+
+static void exchange_prepare(orc_sim* s) {
+    const int N = s->N;
+    const double k = s->k_spring, beta = exch_beta(s);
+    const double* first = s->x;                                 /* bead 1  (index 0)   */
+    const double* last = s->x + (size_t)(s->P - 1) * slab(s);   /* bead P  (index P-1) */
+
+    /* cycle energies, quadratic_bosonic_exchange.cpp:34-61 */
+    for (int v = 0; v < N; ++v) {
+        *Eat(s, v + 1, 1) = 0.5 * k * bead_sep2(s, first, v, last, v);
+        for (int u = v - 1; u >= 0; --u) {
+            double val = *Eat(s, v + 1, v - u) +
+                         0.5 * k * (+bead_sep2(s, last, u, first, u + 1) - bead_sep2(s, first, u + 1, last, v) +
+                                    bead_sep2(s, first, u, last, v));
+            *Eat(s, v + 1, v - u + 1) = val;
+        }
+    }
+    /* forward potentials, :73-99 */
+    s->V[0] = 0.0;
+    for (int m = 1; m <= N; ++m) {
+        double shift = DBL_MAX;
+        for (int kk = m; kk > 0; --kk) {
+            double val = *Eat(s, m, kk) + s->V[m - kk];
+            if (val < shift) shift = val;
+            s->tmp[kk - 1] = val;
+        }
+        double denom = 0.0;
+        for (int kk = m; kk > 0; --kk) denom += exp(-beta * (s->tmp[kk - 1] - shift));
+        s->V[m] = shift - (1.0 / beta) * log(denom / (double)m);
+    }
+    /* backward potentials, :101-128 */
+    s->Vb[N] = 0.0;
+    for (int l = N - 1; l > 0; --l) {
+        double shift = DBL_MAX;
+        for (int p = l; p < N; ++p) {
+            double val = *Eat(s, p + 1, p - l + 1) + s->Vb[p + 1];
+            if (val < shift) shift = val;
+            s->tmp[p] = val;
+        }
+        double denom = 0.0;
+        for (int p = l; p < N; ++p) denom += 1.0 / (p + 1) * exp(-beta * (s->tmp[p] - shift));
+        s->Vb[l] = shift - log(denom) / beta;
+    }
+    s->Vb[0] = s->V[N];
+    /* connection probabilities, :142-157 (entries with u > l+1 stay 0) */
+    memset(s->prob, 0, sizeof(double) * (size_t)N * N);
+    for (int l = 0; l < N - 1; ++l)
+        s->prob[(size_t)N * l + (l + 1)] = 1.0 - exp(-beta * (s->V[l + 1] + s->Vb[l + 1] - s->V[N]));
+    for (int u = 0; u < N; ++u)
+        for (int l = u; l < N; ++l)
+            s->prob[(size_t)N * l + u] =
+                1.0 / (l + 1) * exp(-beta * (s->V[u] + *Eat(s, l + 1, l - u + 1) + s->Vb[l + 1] - s->V[N]));
+}
+
+/* quadratic_bosonic_exchange.cpp:188-215 (bead index 0) */
+static void exchange_force_first(const orc_sim* s, double* out) {
+    const int N = s->N, D = s->D;
+    const double* x = s->x;
+    const double* xprev = s->x + (size_t)(s->P - 1) * slab(s);
+    const double* xnext = s->x + (size_t)(1 % s->P) * slab(s);
+    double d[3];
+    for (int l = 0; l < N; ++l) {
+        double acc[3] = {0, 0, 0};
+        for (int u = (l - 1 > 0 ? l - 1 : 0); u < N; ++u) {
+            bead_sep(s, x, l, xprev, u, d);
+            double pr = s->prob[(size_t)N * u + l];
+            for (int a = 0; a < D; ++a) acc[a] += pr * d[a];
+        }
+        bead_sep(s, x, l, xnext, l, d);
+        for (int a = 0; a < D; ++a) out[(size_t)l * D + a] = (acc[a] + d[a]) * s->k_spring;
+    }
+}
+
+/* quadratic_bosonic_exchange.cpp:159-186 (bead index P-1) */
+static void exchange_force_last(const orc_sim* s, double* out) {
+    const int N = s->N, D = s->D, P = s->P;
+    const double* x = s->x + (size_t)(P - 1) * slab(s);
+    const double* xnext = s->x;
+    const double* xprev = s->x + (size_t)((P - 2 + P) % P) * slab(s);
+    double d[3];
+    for (int l = 0; l < N; ++l) {
+        double acc[3] = {0, 0, 0};
+        for (int u = 0; u <= l + 1 && u < N; ++u) {
+            bead_sep(s, x, l, xnext, u, d);
+            double pr = s->prob[(size_t)N * l + u];
+            for (int a = 0; a < D; ++a) acc[a] += pr * d[a];
+        }
+        bead_sep(s, x, l, xprev, l, d);
+        for (int a = 0; a < D; ++a) out[(size_t)l * D + a] = (acc[a] + d[a]) * s->k_spring;
+    }
+}
+
+/* quadratic_bosonic_exchange.cpp:250-279 */
+static double exchange_prim_estimator(orc_sim* s) {
+    const int N = s->N;
+    const double beta = exch_beta(s);
+    s->prim[0] = 0.0;
+    for (int m = 1; m <= N; ++m) {
+        double shift = DBL_MAX;
+        for (int k = m; k > 0; --k) {
+            double val = *Eat(s, m, k) + s->V[m - k];
+            if (val < shift) shift = val;
+        }
+        double sig = 0.0;
+        for (int k = m; k > 0; --k) {
+            double e = *Eat(s, m, k);
+            sig += (s->prim[m - k] - e) * exp(-beta * (e + s->V[m - k] - shift));
+        }
+        s->prim[m] = sig / (m * exp(-beta * (s->V[m] - shift)));
+    }
+    return s->prim[N] / s->P; /* IPI convention */
+}
+
+/* ------------------------------------------------------------------ force assembly */
+static int bosonic_active(const orc_sim* s) { return s->c.bosonic && s->P > 1; } /* src/simulation.cpp:690 */
+
+/* src/simulation.cpp:353-374, 394-420 for all beads */
+void orc_update_forces(orc_sim* s) {
+    const int P = s->P;
+    if (bosonic_active(s)) exchange_prepare(s);
+    for (int b = 0; b < P; ++b) {
+        double* fs = s->f_spring + (size_t)b * slab(s);
+        double* fp = s->f_phys + (size_t)b * slab(s);
+        if (bosonic_active(s) && b == 0)
+            exchange_force_first(s, fs);
+        else if (bosonic_active(s) && b == P - 1)
+            exchange_force_last(s, fs);
+        else
+            ring_spring_forces(s, b, fs);
+        physical_forces(s, s->x + (size_t)b * slab(s), fp);
+        double* f = s->f + (size_t)b * slab(s);
+        for (size_t q = 0; q < slab(s); ++q) f[q] = fs[q] + fp[q];
+    }
+}
+
+/* ------------------------------------------------------------------ propagators */
+/* src/propagators/velocity_verlet.cpp:24-38 */
+static void moment_step(orc_sim* s, const double* force) {
+    size_t n = (size_t)s->P * slab(s);
+    for (size_t q = 0; q < n; ++q) s->p[q] += 0.5 * s->c.dt * force[q];
+}
+static void coords_step(orc_sim* s) {
+    size_t n = (size_t)s->P * slab(s);
+    for (size_t q = 0; q < n; ++q) s->x[q] += s->c.dt * s->p[q] / s->c.mass;
+}
+
+/* src/normal_modes.cpp:48-79 — row k of the real orthogonal Cartesian->NM matrix, and the row the
+ * reference stores for the inverse on rank j (column j of the same matrix) */
+static void build_nm(orc_sim* s) {
+    const int P = s->P;
+    for (int k = 0; k < P; ++k) {
+        double fund = 2.0 * M_PI / P * k;
+        double* row = s->nm_fwd + (size_t)k * P;
+        if (k == 0) {
+            for (int j = 0; j < P; ++j) row[j] = 1.0 / sqrt((double)P);
+        } else if (k < 0.5 * P) {
+            for (int j = 0; j < P; ++j) row[j] = sqrt(2.0 / P) * cos(fund * j);
+        } else if (k == 0.5 * P) {
+            for (int j = 0; j < P; ++j) row[j] = 1.0 / sqrt((double)P) * (j % 2 == 0 ? 1.0 : -1.0);
+        } else {
+            for (int j = 0; j < P; ++j) row[j] = -sqrt(2.0 / P) * sin(fund * j);
+        }
+        /* inverse row held by rank "k" (normal_modes.cpp:70-78); here index = this_bead */
+        double* inv = s->nm_inv + (size_t)k * P;
+        double pref = sqrt(2.0 / P);
+        memset(inv, 0, sizeof(double) * P);
+        inv[0] = 1.0 / sqrt((double)P);
+        for (int i = 1; i < 0.5 * P; ++i) inv[i] = pref * cos(fund * i);
+        if (P % 2 == 0) inv[P / 2] = 1.0 / sqrt((double)P) * (k % 2 == 0 ? 1.0 : -1.0);
+        for (int i = (int)ceil(0.5 * (P + 1)); i < P; ++i) inv[i] = -pref * sin(fund * i);
+    }
+}
+
+/* length-P dot products over the bead axis (src/normal_modes.cpp:99-129) */
+static void nm_apply(const orc_sim* s, const double* mat, const double* src, double* dst) {
+    const int P = s->P;
+    const size_t sl = slab(s);
+    for (int k = 0; k < P; ++k)
+        for (size_t q = 0; q < sl; ++q) {
+            double acc = 0;
+            for (int j = 0; j < P; ++j) acc += mat[(size_t)k * P + j] * src[(size_t)j * sl + q];
+            dst[(size_t)k * sl + q] = acc;
+        }
+}
+
+/* src/propagators/normal_modes_propagator.cpp:19-103 (distinguishable branch; Params rejects bosonic+NM,
+ * src/params.cpp:146-148) */
+static void nm_propagator_step(orc_sim* s) {
+    const int P = s->P;
+    const size_t sl = slab(s), n = (size_t)P * sl;
+    moment_step(s, s->nm_ext); /* half kick with the physical (external + pair) forces only */
+    nm_apply(s, s->nm_fwd, s->x, s->scratch_x);
+    nm_apply(s, s->nm_fwd, s->p, s->scratch_p);
+    for (int k = 0; k < P; ++k) {
+        double freq = 2 * s->omega_p * sin(k * M_PI / P);
+        double c = cos(freq * s->c.dt), sn = sin(freq * s->c.dt), mw = s->c.mass * freq;
+        for (size_t q = 0; q < sl; ++q) {
+            double xq = s->scratch_x[(size_t)k * sl + q], pq = s->scratch_p[(size_t)k * sl + q];
+            if (freq == 0) {
+                s->scratch_x[(size_t)k * sl + q] = xq + s->c.dt / s->c.mass * pq;
+                s->scratch_p[(size_t)k * sl + q] = pq;
+            } else {
+                s->scratch_x[(size_t)k * sl + q] = c * xq + sn / mw * pq;
+                s->scratch_p[(size_t)k * sl + q] = (-1) * mw * sn * xq + c * pq;
+            }
+        }
+    }
+    nm_apply(s, s->nm_inv, s->scratch_x, s->x);
+    nm_apply(s, s->nm_inv, s->scratch_p, s->p);
+    orc_update_forces(s);
+    memcpy(s->nm_ext, s->f_phys, sizeof(double) * n);
+    moment_step(s, s->nm_ext);
+}
+
+void orc_propagator_step(orc_sim* s) {
+    if (s->c.propagator == ORC_PROP_NORMAL_MODES) {
+        nm_propagator_step(s);
+        return;
+    }
+    /* src/propagators/velocity_verlet.cpp:7-22 */
+    moment_step(s, s->f);
+    coords_step(s);
+    orc_update_forces(s);
+    moment_step(s, s->f);
+}
+
+/* ------------------------------------------------------------------ thermostat */
+/* src/thermostats/thermostat.cpp:15-19, langevin.cpp:10-27, thermostat_coupling.cpp:29-47 */
+void orc_thermostat_step(orc_sim* s) {
+    if (s->c.thermostat != ORC_THERMO_LANGEVIN) return;
+    const int P = s->P, N = s->N, D = s->D;
+    const size_t sl = slab(s);
+    double c1 = exp(-0.5 * s->c.gamma * s->c.dt);
+    double c2 = sqrt((1 - c1 * c1) * s->c.mass / s->thermo_beta);
+    if (!s->c.nmthermostat) {
+        for (int b = 0; b < P; ++b)
+            for (int i = 0; i < N; ++i)
+                for (int a = 0; a < D; ++a) {
+                    double noise = orc_ranmars_gaussian(s->rng[b]);
+                    size_t q = idx(s, b, i, a);
+                    s->p[q] = c1 * s->p[q] + c2 * noise;
+                }
+        return;
+    }
+    nm_apply(s, s->nm_fwd, s->p, s->scratch_p);
+    for (int k = 0; k < P; ++k)
+        for (int i = 0; i < N; ++i)
+            for (int a = 0; a < D; ++a) {
+                double noise = orc_ranmars_gaussian(s->rng[k]);
+                size_t q = (size_t)k * sl + (size_t)i * D + a;
+                s->scratch_p[q] = c1 * s->scratch_p[q] + c2 * noise;
+            }
+    nm_apply(s, s->nm_inv, s->scratch_p, s->p);
+}
+
+/* src/simulation.cpp:581-603 — per-bead partial divided by N*P, then summed over beads in rank order */
+void orc_zero_momentum(orc_sim* s) {
+    const int P = s->P, N = s->N, D = s->D;
+    double cm[3] = {0, 0, 0};
+    for (int b = 0; b < P; ++b) {
+        double part[3] = {0, 0, 0};
+        for (int i = 0; i < N; ++i)
+            for (int a = 0; a < D; ++a) part[a] += s->p[idx(s, b, i, a)];
+        for (int a = 0; a < D; ++a) cm[a] += part[a] / (N * P);
+    }
+    for (int b = 0; b < P; ++b)
+        for (int i = 0; i < N; ++i)
+            for (int a = 0; a < D; ++a) s->p[idx(s, b, i, a)] -= cm[a];
+}
+
+/* src/simulation.cpp:246-259 */
+void orc_run_iteration(orc_sim* s) {
+    orc_thermostat_step(s);
+    if (s->c.fixcom) orc_zero_momentum(s);
+    orc_propagator_step(s);
+    orc_thermostat_step(s);
+    if (s->c.fixcom) orc_zero_momentum(s);
+}
+
+/* ------------------------------------------------------------------ observables */
+/* src/observables/energy.cpp:30-111, classical.cpp:32-78, bosonic.cpp:17-22; bead partials summed in
+ * bead order like ObservablesLogger::log (observable.cpp:92-116). Values stay in atomic units. */
+void orc_observables_calc(orc_sim* s, orc_observables* o) {
+    const int P = s->P, N = s->N, D = s->D;
+    const int bos = bosonic_active(s);
+    memset(o, 0, sizeof *o);
+    if (bos) exchange_prepare(s);
+    double kext = (s->c.ext_pot == ORC_POT_HARMONIC) ? s->c.mass * s->c.ext_omega * s->c.ext_omega : 0.0;
+    for (int b = 0; b < P; ++b) {
+        const double* xb = s->x + (size_t)b * slab(s);
+        /* kinetic (primitive estimator) */
+        double kin = 0.5 * D * N / s->beta;
+        if (b == 0 && bos)
+            kin += exchange_prim_estimator(s);
+        else
+            kin -= ring_spring_energy(s, b) / P;
+        o->kinetic += kin;
+        /* potential + "virial" */
+        double pot = 0, vir = 0, ipot = 0, epot = 0;
+        if (s->c.ext_pot != ORC_POT_FREE) {
+            double v = 0;
+            for (size_t q = 0; q < slab(s); ++q) v += xb[q] * xb[q];
+            epot = v * (0.5 * kext);
+            pot += epot;
+            for (size_t q = 0; q < slab(s); ++q) vir -= xb[q] * ((-1.0) * (kext * xb[q]));
+        }
+        if (s->rc != 0.0) {
+            double d[3];
+            for (int i = 0; i < N; ++i)
+                for (int j = i + 1; j < N; ++j) {
+                    double r = separation(s, xb, i, j, d);
+                    if (r < s->rc || s->rc < 0.0) {
+                        double g;
+                        double v = orc_pair_potential(s->c.int_pot, r, int_param(s), s->c.mass, &g);
+                        pot += v;
+                        ipot += v;
+                        for (int a = 0; a < D; ++a) vir -= xb[(size_t)i * D + a] * ((-1.0) * (g * d[a]));
+                    }
+                }
+        }
+        if (s->c.ext_pot != ORC_POT_FREE && s->c.int_pot != ORC_POT_FREE) {
+            o->ext_pot += epot / P;
+            o->int_pot += ipot / P;
+        }
+        if (s->c.ext_pot != ORC_POT_FREE || s->c.int_pot != ORC_POT_FREE) {
+            o->potential += pot / P;
+            o->virial += vir * (0.5 / P);
+        }
+        /* classical */
+        double ke = 0;
+        const double* pb = s->p + (size_t)b * slab(s);
+        for (size_t q = 0; q < slab(s); ++q) ke += pb[q] * pb[q];
+        ke *= 0.5 / s->c.mass;
+        o->cl_kinetic += ke;
+        double dof = (double)D * N * P;
+        o->temperature += 2.0 * ke / dof / P;
+        o->cl_spring += (b == 0 && bos) ? s->V[N] : ring_spring_energy(s, b);
+    }
+    if (bos) {
+        /* quadratic_bosonic_exchange.cpp:222-240 */
+        double beta = exch_beta(s), sum = 0;
+        for (int m = 1; m <= N; ++m) sum += *Eat(s, m, 1);
+        o->prob_dist = exp(-beta * (sum - s->V[N]) - lgamma(N + 1));
+        o->prob_all = exp(-beta * (*Eat(s, N, N) - s->V[N]));
+    }
+}
+
+/* ------------------------------------------------------------------ lifecycle */
+orc_sim* orc_create(const orc_config* cfg) {
+    orc_sim* s = (orc_sim*)calloc(1, sizeof *s);
+    s->c = *cfg;
+    s->N = cfg->natoms;
+    s->P = cfg->nbeads;
+    s->D = cfg->ndim;
+    s->beta = 1.0 / cfg->temperature;
+    s->thermo_beta = s->beta / s->P;
+    s->omega_p = s->P / s->beta;
+    s->k_spring = cfg->mass * s->omega_p * s->omega_p;
+    /* src/simulation.cpp:84-90 */
+    s->rc = (cfg->int_pot == ORC_POT_FREE) ? 0.0 : cfg->cutoff;
+    if (cfg->pbc) s->rc = fmin(s->rc, 0.5 * cfg->size);
+    size_t n = (size_t)s->P * s->N * s->D;
+    s->x = calloc(n, sizeof(double));
+    s->p = calloc(n, sizeof(double));
+    s->f = calloc(n, sizeof(double));
+    s->f_spring = calloc(n, sizeof(double));
+    s->f_phys = calloc(n, sizeof(double));
+    s->nm_ext = calloc(n, sizeof(double));
+    s->scratch_x = calloc(n, sizeof(double));
+    s->scratch_p = calloc(n, sizeof(double));
+    size_t N = s->N;
+    s->E_kn = calloc(N * (N + 1) / 2, sizeof(double));
+    s->V = calloc(N + 1, sizeof(double));
+    s->Vb = calloc(N + 1, sizeof(double));
+    s->prob = calloc(N * N, sizeof(double));
+    s->tmp = calloc(N, sizeof(double));
+    s->prim = calloc(N + 1, sizeof(double));
+    s->nm_fwd = calloc((size_t)s->P * s->P, sizeof(double));
+    s->nm_inv = calloc((size_t)s->P * s->P, sizeof(double));
+    build_nm(s);
+    s->rng = calloc(s->P, sizeof(orc_ranmars*));
+    for (int b = 0; b < s->P; ++b) s->rng[b] = orc_ranmars_new((int)(cfg->seed + (unsigned)b));
+    return s;
+}
+
+void orc_destroy(orc_sim* s) {
+    if (!s) return;
+    for (int b = 0; b < s->P; ++b) orc_ranmars_free(s->rng[b]);
+    free(s->rng);
+    free(s->x); free(s->p); free(s->f); free(s->f_spring); free(s->f_phys); free(s->nm_ext);
+    free(s->scratch_x); free(s->scratch_p);
+    free(s->E_kn); free(s->V); free(s->Vb); free(s->prob); free(s->tmp); free(s->prim);
+    free(s->nm_fwd); free(s->nm_inv);
+    free(s);
+}
+
+double orc_beta(const orc_sim* s) { return s->beta; }
+double orc_spring_constant(const orc_sim* s) { return s->k_spring; }
+double orc_cutoff_effective(const orc_sim* s) { return s->rc; }
+
+static double* pick(const orc_sim* s, char which) {
+    switch (which) {
+        case 'x': return s->x;
+        case 'p': return s->p;
+        case 'f': return s->f;
+        case 's': return s->f_spring;
+        case 'e': return s->f_phys;
+        default: return NULL;
+    }
+}
+void orc_set(orc_sim* s, char which, const double* src) {
+    double* d = pick(s, which);
+    if (d) memcpy(d, src, sizeof(double) * (size_t)s->P * slab(s));
+}
+void orc_get(const orc_sim* s, char which, double* dst) {
+    const double* d = pick(s, which);
+    if (d) memcpy(dst, d, sizeof(double) * (size_t)s->P * slab(s));
+}
+
+int orc_exchange_get(const orc_sim* s, char which, double* dst) {
+    size_t N = s->N, n = 0;
+    const double* src = NULL;
+    switch (which) {
+        case 'V': src = s->V; n = N + 1; break;
+        case 'B': src = s->Vb; n = N + 1; break;
+        case 'E': src = s->E_kn; n = N * (N + 1) / 2; break;
+        case 'P': src = s->prob; n = N * N; break;
+        default: return 0;
+    }
+    if (dst) memcpy(dst, src, n * sizeof(double));
+    return (int)n;
+}
