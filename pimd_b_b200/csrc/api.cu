@@ -1,0 +1,763 @@
+// C ABI of libpimdb200.so (include/pimdb200.h): lifecycle, state transfer, step sequencing, CUDA-graph capture,
+// deferred error reporting. No CPU fallback: every entry point needs a usable sm_100-class device.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "internal.cuh"
+
+namespace pimdb {
+int launch_pair_chunk(Sim* s, int bead_lo, int nb, bool with_obs);
+int launch_assemble_chunk(Sim* s, int bead_lo, int nb, bool with_pair);
+}  // namespace pimdb
+
+using namespace pimdb;
+
+static thread_local std::string g_create_error;
+
+#define API_TRY(expr)                      \
+    do {                                   \
+        int _rc = (expr);                  \
+        if (_rc != PIMDB_OK) return _rc;   \
+    } while (0)
+
+static int fail(Sim* s, int code, const std::string& msg) {
+    if (s) s->err = msg;
+    else g_create_error = msg;
+    return code;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// validation: the checks of the reference's Params (src/params.cpp:8-260) with the same messages
+static int validate(const pimdb_config* c, std::string& msg) {
+    char buf[256];
+    if (c->nbeads < 1) {
+        snprintf(buf, sizeof buf, "The specified number of beads (%d) is less than one!", c->nbeads);
+        msg = buf; return PIMDB_ERR_INVALID_ARGUMENT;
+    }
+    if (c->natoms < 1) {
+        snprintf(buf, sizeof buf, "The specified number of particles (%d) is smaller than one!", c->natoms);
+        msg = buf; return PIMDB_ERR_INVALID_ARGUMENT;
+    }
+    if (c->ndim < 1 || c->ndim > 3) { msg = "NDIM must be 1, 2 or 3"; return PIMDB_ERR_INVALID_ARGUMENT; }
+    if (c->propagator != PIMDB_PROP_CARTESIAN && c->propagator != PIMDB_PROP_NORMAL_MODES) {
+        msg = "The specified time propagator is not supported!"; return PIMDB_ERR_INVALID_ARGUMENT;
+    }
+    if (c->bosonic && c->propagator == PIMDB_PROP_NORMAL_MODES) {
+        msg = "Normal modes propogation is currently not available for bosons!"; return PIMDB_ERR_INVALID_ARGUMENT;
+    }
+    if (c->thermostat < PIMDB_THERMO_NONE || c->thermostat > PIMDB_THERMO_NOSE_HOOVER_NP_DIM) {
+        msg = "The specified thermostat is not supported!"; return PIMDB_ERR_INVALID_ARGUMENT;
+    }
+    if (c->thermostat >= PIMDB_THERMO_NOSE_HOOVER) {
+        msg = "Nose-Hoover thermostats are not part of this build of the B200 hot path (SURVEY.md 8f, rank 1)";
+        return PIMDB_ERR_INVALID_ARGUMENT;
+    }
+    if (c->nmthermostat && c->thermostat == PIMDB_THERMO_NONE) {
+        msg = "nmthermostat cannot be used in nve ensemble!"; return PIMDB_ERR_INVALID_ARGUMENT;
+    }
+    if (!(c->temperature > 0.0)) {
+        snprintf(buf, sizeof buf, "The specified temperature (%4.3f kelvin) is unphysical!", c->temperature);
+        msg = buf; return PIMDB_ERR_INVALID_ARGUMENT;
+    }
+    if (!(c->mass > 0.0)) {
+        snprintf(buf, sizeof buf, "The provided mass (%4.3f) is unphysical!", c->mass);
+        msg = buf; return PIMDB_ERR_INVALID_ARGUMENT;
+    }
+    if (!(c->size > 0.0)) {
+        snprintf(buf, sizeof buf, "The provided system size (%4.3f) is unphysical!", c->size);
+        msg = buf; return PIMDB_ERR_INVALID_ARGUMENT;
+    }
+    if (!(c->dt > 0.0)) { msg = "The time step must be positive"; return PIMDB_ERR_INVALID_ARGUMENT; }
+    switch (c->int_potential) {
+        case PIMDB_POT_FREE: case PIMDB_POT_AZIZ: case PIMDB_POT_HARMONIC: case PIMDB_POT_DIPOLE: break;
+        default: msg = "The specified interaction potential is not supported!"; return PIMDB_ERR_INVALID_ARGUMENT;
+    }
+    switch (c->ext_potential) {
+        case PIMDB_POT_FREE: case PIMDB_POT_HARMONIC: case PIMDB_POT_DOUBLE_WELL: case PIMDB_POT_COSINE: break;
+        default: msg = "The specified external potential is not supported!"; return PIMDB_ERR_INVALID_ARGUMENT;
+    }
+    if (c->bead_begin < 0 || c->bead_end > c->nbeads || c->bead_begin >= c->bead_end) {
+        msg = "bead range [bead_begin, bead_end) must be a non-empty sub-range of [0, nbeads)";
+        return PIMDB_ERR_INVALID_ARGUMENT;
+    }
+    const bool all_local = (c->bead_begin == 0 && c->bead_end == c->nbeads);
+    if (!all_local && (c->propagator == PIMDB_PROP_NORMAL_MODES || c->nmthermostat)) {
+        msg = "normal-mode propagator / thermostat need all beads on one handle in this build";
+        return PIMDB_ERR_INVALID_ARGUMENT;
+    }
+    if (c->natoms > 65535 * kTile) { msg = "natoms too large"; return PIMDB_ERR_INVALID_ARGUMENT; }
+    return PIMDB_OK;
+}
+
+// reference src/normal_modes.cpp:48-79 -- forward rows C[k][.] and the inverse rows each rank builds for itself
+static void build_nm_tables(const Sim* s, std::vector<double>& mats, std::vector<double>& tab) {
+    const int P = s->P;
+    const double pi = 3.14159265358979323846;  // std::numbers::pi
+    mats.assign((size_t)2 * P * P, 0.0);
+    tab.assign((size_t)3 * P, 0.0);
+    double* fwd = mats.data();
+    double* inv = mats.data() + (size_t)P * P;
+    for (int k = 0; k < P; ++k) {
+        const double fund = 2 * pi / P * k;
+        double* row = fwd + (size_t)k * P;
+        if (k == 0) {
+            for (int j = 0; j < P; ++j) row[j] = 1 / std::sqrt((double)P);
+        } else if (k < 0.5 * P) {
+            for (int j = 0; j < P; ++j) row[j] = std::sqrt(2.0 / P) * std::cos(fund * j);
+        } else if (k == 0.5 * P) {
+            for (int j = 0; j < P; ++j) row[j] = 1 / std::sqrt((double)P) * (j % 2 == 0 ? 1.0 : -1.0);
+        } else {
+            for (int j = 0; j < P; ++j) row[j] = -std::sqrt(2.0 / P) * std::sin(fund * j);
+        }
+        double* irow = inv + (size_t)k * P;   // held by the rank of bead k in the reference
+        const double pref = std::sqrt(2.0 / P);
+        irow[0] = 1 / std::sqrt((double)P);
+        for (int i = 1; i < 0.5 * P; ++i) irow[i] = pref * std::cos(fund * i);
+        if (P % 2 == 0) irow[P / 2] = 1 / std::sqrt((double)P) * (k % 2 == 0 ? 1.0 : -1.0);
+        for (int i = (int)std::ceil(0.5 * (P + 1)); i < P; ++i) irow[i] = -pref * std::sin(fund * i);
+        // free ring-polymer frequencies, src/propagators/normal_modes_propagator.cpp:13-16
+        const double freq = 2 * s->omega_p * std::sin(k * pi / P);
+        tab[k] = std::cos(freq * s->cfg.dt);
+        tab[P + k] = std::sin(freq * s->cfg.dt);
+        tab[2 * P + k] = s->cfg.mass * freq;
+    }
+}
+
+static void free_all(Sim* s) {
+    if (!s) return;
+    cudaSetDevice(s->device);
+    if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
+    if (s->graph) cudaGraphDestroy(s->graph);
+    for (auto& e : s->ev_pair) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    for (auto& e : s->ev_step) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    cudaFree(s->x); cudaFree(s->p); cudaFree(s->f); cudaFree(s->fs); cudaFree(s->fp);
+    cudaFree(s->stage_d); cudaFreeHost(s->stage_h);
+    cudaFree(s->tile_ij); cudaFree(s->pair_scratch);
+    cudaFree(s->exA); cudaFree(s->exV); cudaFree(s->exVb); cudaFree(s->exF); cudaFree(s->exPrim); cudaFree(s->exTab);
+    cudaFree(s->com_part); cudaFree(s->com); cudaFree(s->tickets); cudaFree(s->draw);
+    cudaFree(s->obs_d); cudaFreeHost(s->obs_h); cudaFree(s->obs_part);
+    cudaFreeHost(s->err_h);
+    cudaFree(s->nmC); cudaFree(s->nmFreq);
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
+    if (s->ev_join) cudaEventDestroy(s->ev_join);
+    if (s->stream_x) cudaStreamDestroy(s->stream_x);
+    if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+extern "C" int pimdb_abi_version(void) { return PIMDB_ABI_VERSION; }
+
+extern "C" const char* pimdb_last_error(const pimdb_sim* sim) {
+    if (!sim) return g_create_error.c_str();
+    return reinterpret_cast<const Sim*>(sim)->err.c_str();
+}
+
+#define CREATE_TRY(expr)                                                                         \
+    do {                                                                                         \
+        cudaError_t _e = (expr);                                                                 \
+        if (_e != cudaSuccess) {                                                                 \
+            g_create_error = std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " #expr; \
+            free_all(s);                                                                         \
+            return PIMDB_ERR_CUDA;                                                               \
+        }                                                                                        \
+    } while (0)
+
+extern "C" int pimdb_create(const pimdb_config* cfg, pimdb_sim** out) {
+    if (!out) return fail(nullptr, PIMDB_ERR_INVALID_ARGUMENT, "out is NULL");
+    *out = nullptr;
+    if (!cfg) return fail(nullptr, PIMDB_ERR_INVALID_ARGUMENT, "cfg is NULL");
+    std::string msg;
+    int rc = validate(cfg, msg);
+    if (rc != PIMDB_OK) return fail(nullptr, rc, msg);
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(nullptr, PIMDB_ERR_CUDA, "no CUDA device available (this library has no CPU fallback)");
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, PIMDB_ERR_CUDA, "invalid CUDA device ordinal");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess)
+        return fail(nullptr, PIMDB_ERR_CUDA, "cudaGetDeviceProperties failed");
+    if (prop.major != 10)
+        return fail(nullptr, PIMDB_ERR_CUDA, "libpimdb200 is built for sm_100a (B200) only; device is sm_" +
+                                                 std::to_string(prop.major) + std::to_string(prop.minor));
+
+    Sim* s = new (std::nothrow) Sim();
+    if (!s) return fail(nullptr, PIMDB_ERR_RUNTIME, "out of host memory");
+    s->cfg = *cfg;
+    s->device = cfg->device;
+    s->N = cfg->natoms; s->P = cfg->nbeads; s->D = cfg->ndim;
+    s->b0 = cfg->bead_begin; s->b1 = cfg->bead_end; s->Ploc = s->b1 - s->b0;
+    s->all_local = (s->b0 == 0 && s->b1 == s->P);
+    s->has_first = (s->b0 == 0);
+    s->has_last = (s->b1 == s->P);
+    s->bosonic = cfg->bosonic && s->P > 1;                       // src/simulation.cpp:690
+    s->S = (size_t)s->D * s->N;
+    // src/simulation.cpp:37-52 (i-PI convention)
+    s->beta = 1.0 / cfg->temperature;
+    s->thermo_beta = s->beta / s->P;
+    s->exch_beta = s->beta / s->P;                               // bosonic_exchange_base.cpp:16-18
+    s->omega_p = s->P / s->beta;
+    s->kspring = cfg->mass * s->omega_p * s->omega_p;
+    s->L = cfg->size;
+    // src/simulation.cpp:84-90
+    s->rc = (cfg->int_potential == PIMDB_POT_FREE) ? 0.0 : cfg->cutoff;
+    if (cfg->pbc) s->rc = std::fmin(s->rc, 0.5 * cfg->size);
+    s->pair_on = (s->rc != 0.0) && cfg->int_potential != PIMDB_POT_FREE;
+    s->kext = (cfg->ext_potential == PIMDB_POT_HARMONIC) ? cfg->mass * cfg->ext_omega * cfg->ext_omega : 0.0;
+    s->pair_par = (cfg->int_potential == PIMDB_POT_HARMONIC) ? cfg->mass * cfg->int_omega * cfg->int_omega
+                                                              : cfg->int_strength;
+    // src/thermostats/langevin.cpp:10-13
+    s->c1 = std::exp(-0.5 * cfg->gamma * cfg->dt);
+    s->c2 = std::sqrt((1 - s->c1 * s->c1) * cfg->mass / s->thermo_beta);
+    s->T = (s->N + kTile - 1) / kTile;
+    s->TP = s->T * (s->T + 1) / 2;
+
+    CREATE_TRY(cudaSetDevice(s->device));
+    int lo = 0, hi = 0;
+    CREATE_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CREATE_TRY(cudaStreamCreateWithPriority(&s->stream, cudaStreamNonBlocking, lo));
+    CREATE_TRY(cudaStreamCreateWithPriority(&s->stream_x, cudaStreamNonBlocking, hi));
+    CREATE_TRY(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+    CREATE_TRY(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
+
+    const size_t slab_bytes = s->S * sizeof(double);
+    const size_t own_bytes = slab_bytes * s->Ploc;
+    CREATE_TRY(cudaMalloc(&s->x, slab_bytes * (s->Ploc + 2)));
+    CREATE_TRY(cudaMalloc(&s->p, own_bytes));
+    CREATE_TRY(cudaMalloc(&s->f, own_bytes));
+    CREATE_TRY(cudaMalloc(&s->fs, own_bytes));
+    CREATE_TRY(cudaMalloc(&s->fp, own_bytes));
+    CREATE_TRY(cudaMalloc(&s->stage_d, own_bytes));
+    CREATE_TRY(cudaHostAlloc(&s->stage_h, own_bytes, cudaHostAllocDefault));
+    CREATE_TRY(cudaMemset(s->x, 0, slab_bytes * (s->Ploc + 2)));
+    CREATE_TRY(cudaMemset(s->p, 0, own_bytes));
+    CREATE_TRY(cudaMemset(s->f, 0, own_bytes));    // forces start at zero like the reference's (App. A-1)
+    CREATE_TRY(cudaMemset(s->fs, 0, own_bytes));
+    CREATE_TRY(cudaMemset(s->fp, 0, own_bytes));
+
+    if (s->pair_on) {
+        std::vector<ushort2> tiles;
+        tiles.reserve(s->TP);
+        for (int I = 0; I < s->T; ++I)
+            for (int J = I; J < s->T; ++J) tiles.push_back(make_ushort2((unsigned short)I, (unsigned short)J));
+        CREATE_TRY(cudaMalloc(&s->tile_ij, tiles.size() * sizeof(ushort2)));
+        CREATE_TRY(cudaMemcpy(s->tile_ij, tiles.data(), tiles.size() * sizeof(ushort2), cudaMemcpyHostToDevice));
+        const size_t per_bead = (size_t)s->T * s->T * s->D * kTile * sizeof(double);
+        size_t cap_mb = 4096;
+        if (const char* e = getenv("PIMDB_PAIR_SCRATCH_MB")) cap_mb = (size_t)std::max(1, atoi(e));
+        size_t chunk = (cap_mb << 20) / per_bead;
+        if (chunk < 1) chunk = 1;
+        if (chunk > (size_t)s->Ploc) chunk = s->Ploc;
+        s->bead_chunk = (int)chunk;
+        CREATE_TRY(cudaMalloc(&s->pair_scratch, per_bead * chunk));
+    }
+    if (s->bosonic) {
+        CREATE_TRY(cudaMalloc(&s->exA, sizeof(double) * 2 * s->N));
+        CREATE_TRY(cudaMalloc(&s->exV, sizeof(double) * (s->N + 1)));
+        CREATE_TRY(cudaMalloc(&s->exVb, sizeof(double) * (s->N + 1)));
+        CREATE_TRY(cudaMalloc(&s->exF, sizeof(double) * 2 * s->S));
+        CREATE_TRY(cudaMalloc(&s->exPrim, sizeof(double) * (s->N + 1)));
+        CREATE_TRY(cudaMemset(s->exV, 0, sizeof(double) * (s->N + 1)));
+        CREATE_TRY(cudaMemset(s->exVb, 0, sizeof(double) * (s->N + 1)));
+        CREATE_TRY(cudaMemset(s->exF, 0, sizeof(double) * 2 * s->S));
+    }
+    CREATE_TRY(cudaMalloc(&s->com_part, sizeof(double) * 4 * kMaxPartials));
+    CREATE_TRY(cudaMalloc(&s->com, sizeof(double) * 4));
+    CREATE_TRY(cudaMemset(s->com, 0, sizeof(double) * 4));
+    CREATE_TRY(cudaMalloc(&s->tickets, sizeof(unsigned int) * 4));
+    CREATE_TRY(cudaMemset(s->tickets, 0, sizeof(unsigned int) * 4));
+    CREATE_TRY(cudaMalloc(&s->draw, sizeof(unsigned long long)));
+    CREATE_TRY(cudaMemset(s->draw, 0, sizeof(unsigned long long)));
+    CREATE_TRY(cudaMalloc(&s->obs_d, sizeof(DevObs)));
+    CREATE_TRY(cudaMemset(s->obs_d, 0, sizeof(DevObs)));
+    CREATE_TRY(cudaHostAlloc(&s->obs_h, sizeof(DevObs), cudaHostAllocDefault));
+    CREATE_TRY(cudaMalloc(&s->obs_part, sizeof(double) * 8 * kMaxPartials));
+    CREATE_TRY(cudaHostAlloc(&s->err_h, sizeof(int), cudaHostAllocMapped));
+    *s->err_h = 0;
+    CREATE_TRY(cudaHostGetDevicePointer(&s->err_d, s->err_h, 0));
+    if (cfg->propagator == PIMDB_PROP_NORMAL_MODES || cfg->nmthermostat) {
+        std::vector<double> mats, tab;
+        build_nm_tables(s, mats, tab);
+        CREATE_TRY(cudaMalloc(&s->nmC, mats.size() * sizeof(double)));
+        CREATE_TRY(cudaMalloc(&s->nmFreq, tab.size() * sizeof(double)));
+        CREATE_TRY(cudaMemcpy(s->nmC, mats.data(), mats.size() * sizeof(double), cudaMemcpyHostToDevice));
+        CREATE_TRY(cudaMemcpy(s->nmFreq, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    CREATE_TRY(cudaDeviceSynchronize());
+    *out = reinterpret_cast<pimdb_sim*>(s);
+    return PIMDB_OK;
+}
+
+extern "C" void pimdb_destroy(pimdb_sim* sim) {
+    Sim* s = reinterpret_cast<Sim*>(sim);
+    if (!s) return;
+    cudaSetDevice(s->device);
+    cudaStreamSynchronize(s->stream);
+    cudaStreamSynchronize(s->stream_x);
+    free_all(s);
+}
+
+// ----------------------------------------------------------------------------------------------------
+static int check_deferred(Sim* s) {
+    if (*s->err_h != 0) {
+        const int e = *s->err_h;
+        *s->err_h = 0;
+        // same wording as the reference's std::overflow_error (quadratic_bosonic_exchange.cpp:92-97,119-124)
+        return fail(s, PIMDB_ERR_OVERFLOW,
+                    std::string("Invalid sig_denom / e_shift in bosonic exchange potential (non-finite ") +
+                        ((e & kErrOverflowFwd) ? "V" : "V_backwards") + ")");
+    }
+    return PIMDB_OK;
+}
+
+extern "C" int pimdb_synchronize(pimdb_sim* sim) {
+    Sim* s = reinterpret_cast<Sim*>(sim);
+    if (!s) return PIMDB_ERR_INVALID_ARGUMENT;
+    PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
+    PIMDB_CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+    return check_deferred(s);
+}
+
+static double* array_ptr(Sim* s, int which, bool& halo) {
+    halo = false;
+    switch (which) {
+        case PIMDB_X: halo = true; return s->x;
+        case PIMDB_P: return s->p;
+        case PIMDB_F: return s->f;
+        case PIMDB_F_SPRING: return s->fs;
+        case PIMDB_F_PHYS: return s->fp;
+        default: return nullptr;
+    }
+}
+
+extern "C" int pimdb_set_state(pimdb_sim* sim, int which, const double* host) {
+    Sim* s = reinterpret_cast<Sim*>(sim);
+    if (!s || !host) return PIMDB_ERR_INVALID_ARGUMENT;
+    bool halo;
+    double* dst = array_ptr(s, which, halo);
+    if (!dst) return fail(s, PIMDB_ERR_INVALID_ARGUMENT, "unknown state array");
+    PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
+    const size_t bytes = s->S * s->Ploc * sizeof(double);
+    // the caller's buffer may be pageable: stage through pinned memory so the copy is truly asynchronous-safe
+    PIMDB_CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+    memcpy(s->stage_h, host, bytes);
+    PIMDB_CUDA_TRY(s, cudaMemcpyAsync(s->stage_d, s->stage_h, bytes, cudaMemcpyHostToDevice, s->stream));
+    API_TRY(launch_aos_to_soa(s, dst, halo));
+    if (which == PIMDB_X && s->all_local) API_TRY(launch_fill_halos(s));
+    return PIMDB_OK;
+}
+
+extern "C" int pimdb_get_state(pimdb_sim* sim, int which, double* host) {
+    Sim* s = reinterpret_cast<Sim*>(sim);
+    if (!s || !host) return PIMDB_ERR_INVALID_ARGUMENT;
+    bool halo;
+    double* src = array_ptr(s, which, halo);
+    if (!src) return fail(s, PIMDB_ERR_INVALID_ARGUMENT, "unknown state array");
+    PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
+    const size_t bytes = s->S * s->Ploc * sizeof(double);
+    API_TRY(launch_soa_to_aos(s, src, halo));
+    PIMDB_CUDA_TRY(s, cudaMemcpyAsync(s->stage_h, s->stage_d, bytes, cudaMemcpyDeviceToHost, s->stream));
+    PIMDB_CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+    memcpy(host, s->stage_h, bytes);
+    return check_deferred(s);
+}
+
+// ----------------------------------------------------------------------------------------------------
+// force evaluation: exchange on the high-priority side stream, pair tiles + assembly on the main stream
+static int enqueue_forces(Sim* s) {
+    const bool ex = s->bosonic && (s->has_first || s->has_last);
+    if (ex) {
+        PIMDB_CUDA_TRY(s, cudaEventRecord(s->ev_fork, s->stream));
+        PIMDB_CUDA_TRY(s, cudaStreamWaitEvent(s->stream_x, s->ev_fork, 0));
+        API_TRY(launch_exchange(s, s->stream_x));
+        PIMDB_CUDA_TRY(s, cudaEventRecord(s->ev_join, s->stream_x));
+    }
+    bool joined = !ex;
+    if (s->pair_on) {
+        for (int lo = 0; lo < s->Ploc; lo += s->bead_chunk) {
+            const int nb = std::min(s->bead_chunk, s->Ploc - lo);
+            API_TRY(launch_pair_chunk(s, lo, nb, false));
+            if (!joined) {
+                PIMDB_CUDA_TRY(s, cudaStreamWaitEvent(s->stream, s->ev_join, 0));
+                joined = true;
+            }
+            API_TRY(launch_assemble_chunk(s, lo, nb, true));
+        }
+    } else {
+        if (!joined) PIMDB_CUDA_TRY(s, cudaStreamWaitEvent(s->stream, s->ev_join, 0));
+        API_TRY(launch_assemble_chunk(s, 0, s->Ploc, false));
+    }
+    return PIMDB_OK;
+}
+
+// Fuses consecutive element-wise stages into as few k_integrate launches as their fixed in-kernel order
+// (SUBCM -> O_PRE -> B -> O_POST -> A, SUM last) allows.
+struct Fuser {
+    Sim* s;
+    unsigned ops = 0;
+    int stage = -1;
+    int rc = PIMDB_OK;
+    explicit Fuser(Sim* sim) : s(sim) {}
+    void flush() {
+        if (ops && rc == PIMDB_OK) rc = launch_integrate(s, ops);
+        ops = 0;
+        stage = -1;
+    }
+    void put(unsigned op, int st) {
+        if (st <= stage) flush();
+        ops |= op;
+        stage = st;
+    }
+    void subcm() { put(OP_SUBCM, 0); }
+    void langevin() {
+        if (ops & (OP_O_PRE | OP_O_POST | OP_A | OP_SUM)) flush();
+        if (ops & (OP_B | OP_B_PHYS)) put(OP_O_POST, 3);
+        else put(OP_O_PRE, 1);
+    }
+    void kick(bool phys_only) {
+        if (ops & (OP_B | OP_B_PHYS)) flush();
+        put(phys_only ? OP_B_PHYS : OP_B, 2);
+    }
+    void drift() { put(OP_A | (s->all_local ? OP_HALO : 0u), 4); }
+    void sum() { put(OP_SUM, 5); }
+};
+
+static void thermostat_into(Sim* s, Fuser& fz) {
+    if (s->cfg.thermostat != PIMDB_THERMO_LANGEVIN) return;
+    if (s->cfg.nmthermostat) {
+        fz.flush();
+        if (fz.rc == PIMDB_OK) fz.rc = launch_nm_thermostat(s);
+    } else {
+        fz.langevin();
+    }
+}
+
+static void propagator_into(Sim* s, Fuser& fz) {
+    if (s->cfg.propagator == PIMDB_PROP_CARTESIAN) {
+        fz.kick(false);
+        fz.drift();
+        fz.flush();
+        if (!s->all_local) return;   // sharded: the host exchanges halos, then calls phase 2
+        if (fz.rc == PIMDB_OK) fz.rc = enqueue_forces(s);
+        fz.kick(false);
+    } else {
+        fz.flush();
+        if (fz.rc == PIMDB_OK) fz.rc = launch_nm_propagate(s);   // half kick (physical forces) + exact ring rotation
+        if (fz.rc == PIMDB_OK) fz.rc = launch_fill_halos(s);
+        if (fz.rc == PIMDB_OK) fz.rc = enqueue_forces(s);
+        fz.kick(true);
+    }
+}
+
+// body of Simulation::run, src/simulation.cpp:246-259
+static int enqueue_step(Sim* s) {
+    Fuser fz(s);
+    thermostat_into(s, fz);
+    if (s->cfg.fixcom) { fz.sum(); fz.subcm(); }
+    propagator_into(s, fz);
+    thermostat_into(s, fz);
+    if (s->cfg.fixcom) { fz.sum(); fz.subcm(); }
+    fz.flush();
+    return fz.rc;
+}
+
+static int require_all_local(Sim* s, const char* what) {
+    if (!s->all_local)
+        return fail(s, PIMDB_ERR_INVALID_ARGUMENT, std::string(what) + " needs all beads on this handle; use pimdb_step_phase with bead sharding");
+    return PIMDB_OK;
+}
+
+extern "C" int pimdb_update_neighbors(pimdb_sim* sim) {
+    Sim* s = reinterpret_cast<Sim*>(sim);
+    if (!s) return PIMDB_ERR_INVALID_ARGUMENT;
+    API_TRY(require_all_local(s, "pimdb_update_neighbors"));
+    PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
+    return launch_fill_halos(s);
+}
+
+extern "C" int pimdb_update_forces(pimdb_sim* sim) {
+    Sim* s = reinterpret_cast<Sim*>(sim);
+    if (!s) return PIMDB_ERR_INVALID_ARGUMENT;
+    PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
+    return enqueue_forces(s);
+}
+
+extern "C" int pimdb_moment_step(pimdb_sim* sim) {
+    Sim* s = reinterpret_cast<Sim*>(sim);
+    if (!s) return PIMDB_ERR_INVALID_ARGUMENT;
+    PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
+    return launch_integrate(s, OP_B);
+}
+
+extern "C" int pimdb_coords_step(pimdb_sim* sim) {
+    Sim* s = reinterpret_cast<Sim*>(sim);
+    if (!s) return PIMDB_ERR_INVALID_ARGUMENT;
+    PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
+    return launch_integrate(s, OP_A | (s->all_local ? OP_HALO : 0u));
+}
+
+extern "C" int pimdb_propagator_step(pimdb_sim* sim) {
+    Sim* s = reinterpret_cast<Sim*>(sim);
+    if (!s) return PIMDB_ERR_INVALID_ARGUMENT;
+    API_TRY(require_all_local(s, "pimdb_propagator_step"));
+    PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
+    Fuser fz(s);
+    propagator_into(s, fz);
+    fz.flush();
+    return fz.rc;
+}
+
+extern "C" int pimdb_thermostat_step(pimdb_sim* sim) {
+    Sim* s = reinterpret_cast<Sim*>(sim);
+    if (!s) return PIMDB_ERR_INVALID_ARGUMENT;
+    PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
+    Fuser fz(s);
+    thermostat_into(s, fz);
+    fz.flush();
+    return fz.rc;
+}
+
+extern "C" int pimdb_zero_momentum(pimdb_sim* sim) {
+    Sim* s = reinterpret_cast<Sim*>(sim);
+    if (!s) return PIMDB_ERR_INVALID_ARGUMENT;
+    API_TRY(require_all_local(s, "pimdb_zero_momentum"));
+    PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
+    Fuser fz(s);
+    fz.sum();
+    fz.subcm();
+    fz.flush();
+    return fz.rc;
+}
+
+extern "C" int pimdb_step(pimdb_sim* sim, int nsteps) {
+    Sim* s = reinterpret_cast<Sim*>(sim);
+    if (!s || nsteps < 0) return PIMDB_ERR_INVALID_ARGUMENT;
+    API_TRY(require_all_local(s, "pimdb_step"));
+    PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
+    if (s->timing) {   // eager path with CUDA events around every step and every pair-force launch
+        for (int i = 0; i < nsteps; ++i) {
+            cudaEvent_t e0, e1;
+            PIMDB_CUDA_TRY(s, cudaEventCreate(&e0));
+            PIMDB_CUDA_TRY(s, cudaEventCreate(&e1));
+            PIMDB_CUDA_TRY(s, cudaEventRecord(e0, s->stream));
+            API_TRY(enqueue_step(s));
+            PIMDB_CUDA_TRY(s, cudaEventRecord(e1, s->stream));
+            s->ev_step.emplace_back(e0, e1);
+        }
+        return PIMDB_OK;
+    }
+    if (!s->graph_exec) {
+        const unsigned long long before = s->launches;
+        PIMDB_CUDA_TRY(s, cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = enqueue_step(s);
+        cudaGraph_t g = nullptr;
+        cudaError_t ce = cudaStreamEndCapture(s->stream, &g);
+        if (rc != PIMDB_OK) { if (g) cudaGraphDestroy(g); return rc; }
+        PIMDB_CUDA_TRY(s, ce);
+        s->graph = g;
+        s->graph_kernels = s->launches - before;
+        s->launches = before;
+        PIMDB_CUDA_TRY(s, cudaGraphInstantiate(&s->graph_exec, s->graph, 0));
+    }
+    for (int i = 0; i < nsteps; ++i) {
+        PIMDB_CUDA_TRY(s, cudaGraphLaunch(s->graph_exec, s->stream));
+        s->launches += s->graph_kernels;
+    }
+    return PIMDB_OK;
+}
+
+// phases for bead sharding; the host runs the collectives in between (include/pimdb200.h)
+extern "C" int pimdb_step_phase(pimdb_sim* sim, int phase) {
+    Sim* s = reinterpret_cast<Sim*>(sim);
+    if (!s) return PIMDB_ERR_INVALID_ARGUMENT;
+    if (s->cfg.propagator != PIMDB_PROP_CARTESIAN || s->cfg.nmthermostat)
+        return fail(s, PIMDB_ERR_INVALID_ARGUMENT, "bead-sharded phases support the cartesian propagator / thermostat only");
+    PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
+    Fuser fz(s);
+    switch (phase) {
+        case 0:
+            thermostat_into(s, fz);
+            if (s->cfg.fixcom) fz.sum();
+            break;
+        case 1:
+            if (s->cfg.fixcom) fz.subcm();
+            fz.kick(false);
+            fz.put(OP_A, 4);   // no ring-wrap halo write: the host exchanges halos
+            break;
+        case 2:
+            fz.rc = enqueue_forces(s);
+            fz.kick(false);
+            thermostat_into(s, fz);
+            if (s->cfg.fixcom) fz.sum();
+            break;
+        case 3:
+            if (s->cfg.fixcom) fz.subcm();
+            break;
+        default:
+            return fail(s, PIMDB_ERR_INVALID_ARGUMENT, "phase must be 0..3");
+    }
+    fz.flush();
+    return fz.rc;
+}
+
+// ----------------------------------------------------------------------------------------------------
+extern "C" int pimdb_exchange_prepare(pimdb_sim* sim) {
+    Sim* s = reinterpret_cast<Sim*>(sim);
+    if (!s) return PIMDB_ERR_INVALID_ARGUMENT;
+    if (!s->bosonic) return fail(s, PIMDB_ERR_INVALID_ARGUMENT, "simulation is not bosonic");
+    if (!s->has_first && !s->has_last) return fail(s, PIMDB_ERR_INVALID_ARGUMENT, "this handle owns no exterior bead");
+    PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
+    return launch_exchange(s, s->stream);
+}
+
+extern "C" int pimdb_exchange_get(pimdb_sim* sim, int table, double* out, size_t n) {
+    Sim* s = reinterpret_cast<Sim*>(sim);
+    if (!s || !out) return PIMDB_ERR_INVALID_ARGUMENT;
+    if (!s->bosonic) return fail(s, PIMDB_ERR_INVALID_ARGUMENT, "simulation is not bosonic");
+    PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
+    const size_t N = s->N;
+    size_t need = 0;
+    const double* src = nullptr;
+    switch (table) {
+        case PIMDB_EXCH_V: need = N + 1; src = s->exV; break;
+        case PIMDB_EXCH_VB: need = N + 1; src = s->exVb; break;
+        case PIMDB_EXCH_E: need = N * (N + 1) / 2; break;
+        case PIMDB_EXCH_PROB: need = N * N; break;
+        default: return fail(s, PIMDB_ERR_INVALID_ARGUMENT, "unknown exchange table");
+    }
+    if (n < need) return fail(s, PIMDB_ERR_INVALID_ARGUMENT, "output buffer too small");
+    if (!src) {
+        if (s->exTabCap < need) {
+            cudaFree(s->exTab);
+            s->exTab = nullptr; s->exTabCap = 0;
+            PIMDB_CUDA_TRY(s, cudaMalloc(&s->exTab, need * sizeof(double)));
+            s->exTabCap = need;
+        }
+        API_TRY(launch_exchange_tables(s, table));
+        src = s->exTab;
+    }
+    PIMDB_CUDA_TRY(s, cudaMemcpyAsync(out, src, need * sizeof(double), cudaMemcpyDeviceToHost, s->stream));
+    PIMDB_CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+    return check_deferred(s);
+}
+
+// Observable::calculate for energy / classical / bosonic (src/observables/*.cpp), partials of the owned beads
+extern "C" int pimdb_observables_calc(pimdb_sim* sim, pimdb_observables* out) {
+    Sim* s = reinterpret_cast<Sim*>(sim);
+    if (!s || !out) return PIMDB_ERR_INVALID_ARGUMENT;
+    PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
+    PIMDB_CUDA_TRY(s, cudaMemsetAsync(s->obs_d, 0, sizeof(DevObs), s->stream));
+    API_TRY(launch_obs_elementwise(s));
+    if (s->pair_on) {
+        for (int lo = 0; lo < s->Ploc; lo += s->bead_chunk)
+            API_TRY(launch_pair_chunk(s, lo, std::min(s->bead_chunk, s->Ploc - lo), true));
+    }
+    if (s->bosonic && s->has_first) {
+        API_TRY(launch_exchange(s, s->stream));   // tables for the current positions
+        API_TRY(launch_exchange_estimators(s));
+    }
+    PIMDB_CUDA_TRY(s, cudaMemcpyAsync(s->obs_h, s->obs_d, sizeof(DevObs), cudaMemcpyDeviceToHost, s->stream));
+    PIMDB_CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+    API_TRY(check_deferred(s));
+    const DevObs& o = *s->obs_h;
+    const double P = s->P, N = s->N, D = s->D;
+    memset(out, 0, sizeof *out);
+    // energy.cpp:30-48: per bead NDIM*N/(2 beta); classical links subtract their spring energy / P;
+    // the bead-0 owner of a bosonic system adds primEstimator() = e[N]/P instead
+    out->kinetic = s->Ploc * (0.5 * D * N / s->beta) - o.spring_e[0] / P;
+    if (s->bosonic && s->has_first) out->kinetic += o.prim_est / P;
+    const bool ext_on = s->cfg.ext_potential != PIMDB_POT_FREE;
+    const bool int_on = s->cfg.int_potential != PIMDB_POT_FREE;
+    // energy.cpp:56-111
+    if (ext_on || int_on) {
+        out->potential = ((ext_on ? o.ext_v : 0.0) + o.pair_v) / P;
+        out->virial = ((ext_on ? o.ext_vir : 0.0) + o.pair_vir) * (0.5 / P);
+    }
+    if (ext_on && int_on) {
+        out->ext_pot = o.ext_v / P;
+        out->int_pot = o.pair_v / P;
+    }
+    // classical.cpp:32-78
+    out->cl_kinetic = o.p2 * (0.5 / s->cfg.mass);
+    out->temperature = 2.0 * out->cl_kinetic / (D * N * P) / P;
+    out->cl_spring = o.spring_e[0] + ((s->bosonic && s->has_first) ? o.v_n : 0.0);
+    // bosonic.cpp:17-22, quadratic_bosonic_exchange.cpp:222-240
+    if (s->bosonic && s->has_first) {
+        out->prob_dist = std::exp(-s->exch_beta * (o.e_diag_sum - o.v_n) - std::lgamma(N + 1.0));
+        out->prob_all = std::exp(-s->exch_beta * (o.e_full - o.v_n));
+    }
+    return PIMDB_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------
+extern "C" void* pimdb_get_stream(pimdb_sim* sim) {
+    Sim* s = reinterpret_cast<Sim*>(sim);
+    return s ? (void*)s->stream : nullptr;
+}
+
+extern "C" int pimdb_set_stream(pimdb_sim* sim, void* cuda_stream) {
+    Sim* s = reinterpret_cast<Sim*>(sim);
+    if (!s) return PIMDB_ERR_INVALID_ARGUMENT;
+    PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
+    PIMDB_CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+    if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+    s->stream = (cudaStream_t)cuda_stream;
+    s->own_stream = false;
+    return PIMDB_OK;
+}
+
+extern "C" void* pimdb_halo_ptr(pimdb_sim* sim, int which, size_t* count) {
+    Sim* s = reinterpret_cast<Sim*>(sim);
+    if (!s) return nullptr;
+    if (count) *count = s->S;
+    switch (which) {
+        case 0: return s->x + s->S;
+        case 1: return s->x + (size_t)s->Ploc * s->S;
+        case 2: return s->x;
+        case 3: return s->x + (size_t)(s->Ploc + 1) * s->S;
+        default: return nullptr;
+    }
+}
+
+extern "C" void* pimdb_com_ptr(pimdb_sim* sim) {
+    Sim* s = reinterpret_cast<Sim*>(sim);
+    return s ? (void*)s->com : nullptr;
+}
+
+extern "C" unsigned long long pimdb_launch_count(const pimdb_sim* sim) {
+    const Sim* s = reinterpret_cast<const Sim*>(sim);
+    return s ? s->launches : 0ull;
+}
+
+extern "C" int pimdb_timing_enable(pimdb_sim* sim, int on) {
+    Sim* s = reinterpret_cast<Sim*>(sim);
+    if (!s) return PIMDB_ERR_INVALID_ARGUMENT;
+    PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
+    PIMDB_CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+    for (auto& e : s->ev_pair) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    for (auto& e : s->ev_step) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    s->ev_pair.clear();
+    s->ev_step.clear();
+    s->timing = on != 0;
+    return PIMDB_OK;
+}
+
+// what = 0: pair-force kernel launches, 1: whole steps
+extern "C" int pimdb_timing_get(pimdb_sim* sim, int what, double* ms_avg, unsigned long long* count) {
+    Sim* s = reinterpret_cast<Sim*>(sim);
+    if (!s || !ms_avg || !count) return PIMDB_ERR_INVALID_ARGUMENT;
+    PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
+    PIMDB_CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+    auto& v = what == 0 ? s->ev_pair : s->ev_step;
+    double tot = 0.0;
+    for (auto& e : v) {
+        float ms = 0.f;
+        PIMDB_CUDA_TRY(s, cudaEventElapsedTime(&ms, e.first, e.second));
+        tot += ms;
+    }
+    *count = v.size();
+    *ms_avg = v.empty() ? 0.0 : tot / (double)v.size();
+    return PIMDB_OK;
+}

@@ -1,0 +1,121 @@
+// Internal declarations shared by the CUDA translation units of libpimdb200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "../../include/pimdb200.h"
+
+namespace pimdb {
+
+constexpr int kTile = 32;            // particles per pair-force tile (= warp width)
+constexpr int kMaxPartials = 1184;   // upper bound on blocks of reducing kernels (8 x 148 SMs)
+constexpr int kNumSM = 148;
+constexpr double kEps = 1.0e-7;      // reference include/common.h:45
+
+// Aziz HFDHE2 constants (reference src/potentials/aziz.cpp:6-13), atomic units.
+constexpr double kAzRm = 5.60738, kAzA = 0.5448504e6, kAzEps = 3.42016E-5, kAzAlpha = 13.353384,
+                 kAzD = 1.241314, kAzC6 = 1.3732412, kAzC8 = 0.4253785, kAzC10 = 0.1781;
+
+// device-side error flags (host-mapped)
+enum : int { kErrOverflowFwd = 1, kErrOverflowBwd = 2 };
+
+struct DevObs {  // partial sums produced on device; assembled into pimdb_observables on the host
+    double spring_e[1];      // sum over owned classical links of 0.5 k |x_b - x_{b-1}|^2 (exterior link excluded for bosons)
+    double ext_v;            // sum_b V_ext
+    double ext_vir;          // sum_b -x . F_ext
+    double pair_v;           // sum_b sum_{i<j} v
+    double pair_vir;         // sum_b sum_{i<j} -x_i . f_ij
+    double p2;               // sum p^2
+    double prim_est;         // e[N] of the primitive-estimator recursion (bead 0 owner only)
+    double v_n;              // V[N]
+    double e_diag_sum;       // sum_m E^{[m..m]}
+    double e_full;           // E^{[0..N-1]}
+    double pad[6];
+};
+
+struct Sim {
+    pimdb_config cfg{};
+    int N = 0, P = 0, D = 0, Ploc = 0, b0 = 0, b1 = 0;
+    int T = 0, TP = 0;                 // tiles per bead, upper-triangular tile pairs
+    bool all_local = false, has_first = false, has_last = false, bosonic = false;
+    bool pair_on = false;
+    size_t S = 0;                      // slab stride = D*N
+    double beta = 0, thermo_beta = 0, exch_beta = 0, omega_p = 0, kspring = 0, rc = 0, L = 0, kext = 0;
+    double c1 = 1, c2 = 0;             // Langevin friction / noise coefficients
+    double pair_par = 0;               // harmonic pair k or dipole strength
+
+    int device = 0;
+    cudaStream_t stream = nullptr, stream_x = nullptr;  // main stream, exchange side stream
+    bool own_stream = true;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+
+    // state (device). x has Ploc+2 slabs (halo, owned..., halo); the others Ploc slabs.
+    double *x = nullptr, *p = nullptr, *f = nullptr, *fs = nullptr, *fp = nullptr;
+    double *stage_d = nullptr;         // AoS staging [Ploc][N][D]
+    double *stage_h = nullptr;         // pinned host staging
+    // pair forces
+    ushort2* tile_ij = nullptr;        // TP entries (I,J), I<=J
+    double* pair_scratch = nullptr;    // [bead_chunk][T][T][D][32]
+    int bead_chunk = 0;
+    // exchange
+    double *exA = nullptr, *exV = nullptr, *exVb = nullptr, *exF = nullptr;  // A[N], V[N+1], Vb[N+1], F[2][D][N]
+    double *exPrim = nullptr;
+    double *exTab = nullptr; size_t exTabCap = 0;                          // on-demand E / prob tables
+    // reductions
+    double* com_part = nullptr;        // [kMaxPartials][4]
+    double* com = nullptr;             // [4] finalized sum of momenta over owned beads (allreduce target)
+    unsigned int* tickets = nullptr;   // last-block-done counters
+    unsigned long long* draw = nullptr;  // device counter of thermostat half-steps (noise draw index)
+    DevObs* obs_d = nullptr; DevObs* obs_h = nullptr;
+    double* obs_part = nullptr;        // [kMaxPartials][8]
+    int* err_h = nullptr; int* err_d = nullptr;  // mapped error flags
+    // normal modes
+    double *nmC = nullptr;             // [P][P] Cartesian->NM matrix rows (row k = mode k)
+    double *nmFreq = nullptr;          // [P] cos/sin tables: [3][P] = cos(w dt), sin(w dt), m*w
+    // graph
+    cudaGraph_t graph = nullptr; cudaGraphExec_t graph_exec = nullptr;
+    unsigned long long graph_kernels = 0;
+    bool p_shift_pending = false;      // fixcom: COM shift computed but not yet subtracted from p
+    unsigned long long launches = 0;
+    // timing
+    bool timing = false;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pair, ev_step;
+    std::string err;
+};
+
+// launch helpers --------------------------------------------------------------------------------------
+inline int grid_for(size_t items, int block, int max_blocks = 8 * kNumSM) {
+    size_t g = (items + block - 1) / block;
+    if (g < 1) g = 1;
+    if (g > (size_t)max_blocks) g = max_blocks;
+    return (int)g;
+}
+
+#define PIMDB_CUDA_TRY(sim, expr)                                                              \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess) {                                                                \
+            (sim)->err = std::string("CUDA error: ") + cudaGetErrorString(_e) + " at " #expr;   \
+            return PIMDB_ERR_CUDA;                                                              \
+        }                                                                                       \
+    } while (0)
+
+// kernels.cu entry points (host wrappers that enqueue on s->stream unless noted)
+int launch_pair_forces(Sim* s, bool with_obs);
+int launch_assemble(Sim* s);
+int launch_exchange(Sim* s, cudaStream_t st);          // prep + forward/backward + exterior forces
+int launch_exchange_tables(Sim* s, int table);
+int launch_exchange_estimators(Sim* s);
+int launch_fill_halos(Sim* s);
+enum : unsigned { OP_SUBCM = 1, OP_O_PRE = 2, OP_B = 4, OP_O_POST = 8, OP_A = 16, OP_SUM = 32, OP_HALO = 64, OP_B_PHYS = 128 };
+int launch_integrate(Sim* s, unsigned ops);
+int launch_nm_propagate(Sim* s);
+int launch_nm_thermostat(Sim* s);
+int launch_obs_elementwise(Sim* s);
+int launch_aos_to_soa(Sim* s, double* dst_soa, bool dst_has_halo);
+int launch_soa_to_aos(Sim* s, const double* src_soa, bool src_has_halo);
+
+}  // namespace pimdb

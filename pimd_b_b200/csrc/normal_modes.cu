@@ -1,0 +1,260 @@
+// Normal-mode transforms (K12): the NormalModesPropagator step and the normal-mode-coupled Langevin thermostat,
+// each fused into ONE kernel. FP64.
+//
+// Reference: src/normal_modes.cpp:48-129 (matrix rows, length-P dot products over the bead axis, window layout
+// [axis][atom][bead]), src/propagators/normal_modes_propagator.cpp:19-103 (half kick with the physical forces,
+// exact free-ring-polymer rotation per mode, back transform), src/thermostats/thermostat_coupling.cpp:29-47 and
+// src/thermostats/langevin.cpp:15-27 (O step on the normal-mode momenta).
+//
+// The reference gives every MPI rank one row of the matrix and synchronises four shared-memory windows with
+// barriers. Here a thread block stages a [P beads] x [TC columns] tile of x and p in shared memory (a "column"
+// is one (axis, particle) pair; the bead stride is D*N so tile rows are coalesced), applies the P x P matrix,
+// the per-mode update and the inverse matrix without leaving the SM, and writes the tile back: 1 read + 1 write
+// of x and p per transform pair instead of 4 window round trips. Sums run over j = 0..P-1 in the reference's order.
+#include "internal.cuh"
+#include "device_utils.cuh"
+
+namespace pimdb {
+
+struct NmArgs {
+    double *x, *p;             // x: first owned slab (halo already skipped); p: first slab
+    const double* fphys;       // physical forces for the half kick (propagator) or nullptr
+    const double* C;           // [P][P] forward rows: C[k][j]
+    const double* Cinv;        // [P][P] inverse rows as the reference stores them: Cinv[j][k]
+    const double* tab;         // [3][P]: cos(w_k dt), sin(w_k dt), m w_k
+    unsigned long long* draw; unsigned int* ticket;
+    int P, M, N, D, TC;
+    double hdt, dt_over_m, c1, c2;
+    unsigned long long seed;
+};
+
+// mode 0: propagator (x and p), mode 1: thermostat (p only)
+template <int MODE>
+__global__ void __launch_bounds__(256) k_nm_fused(NmArgs a) {
+    extern __shared__ double sm[];
+    const int P = a.P, TC = a.TC;
+    double* sx = sm;                    // [P][TC]
+    double* sp = sm + (size_t)P * TC;   // [P][TC]
+    __shared__ bool is_last;
+    const int tid = threadIdx.x;
+    const int tc = tid % TC, kg = tid / TC, KG = blockDim.x / TC;
+    const unsigned long long draw = (MODE == 1) ? *a.draw : 0ull;
+
+    for (int col0 = blockIdx.x * TC; col0 < a.M; col0 += gridDim.x * TC) {
+        const int col = col0 + tc;
+        const bool ok = col < a.M;
+        // 1. stage (propagator: with the half kick p += dt/2 f_phys, normal_modes_propagator.cpp:73-103)
+        for (int j = kg; j < P; j += KG) {
+            double pv = 0.0, xv = 0.0;
+            if (ok) {
+                pv = a.p[(size_t)j * a.M + col];
+                if (MODE == 0) {
+                    pv += a.hdt * a.fphys[(size_t)j * a.M + col];
+                    xv = a.x[(size_t)j * a.M + col];
+                }
+            }
+            sp[j * TC + tc] = pv;
+            if (MODE == 0) sx[j * TC + tc] = xv;
+        }
+        __syncthreads();
+        // 2. forward transform + per-mode update, results kept in registers until all reads are done
+        constexpr int KMAX = 32;        // P*TC/256 <= 32 by construction of TC
+        double rn_x[KMAX], rn_p[KMAX];
+        int cnt = 0;
+        for (int k = kg; k < P; k += KG, ++cnt) {
+            const double* crow = a.C + (size_t)k * P;
+            double xn = 0.0, pn = 0.0;
+            for (int j = 0; j < P; ++j) {
+                const double cj = __ldg(crow + j);
+                pn += cj * sp[j * TC + tc];
+                if (MODE == 0) xn += cj * sx[j * TC + tc];
+            }
+            if (MODE == 0) {
+                const double cs = a.tab[k], sn = a.tab[P + k], mw = a.tab[2 * P + k];
+                double xo, po;
+                if (mw == 0.0) {                 // freq == 0: free drift (normal_modes_propagator.cpp:33-35)
+                    xo = xn + a.dt_over_m * pn;
+                    po = pn;
+                } else {                         // exact harmonic rotation (:36-39)
+                    xo = cs * xn + sn / mw * pn;
+                    po = (-1.0) * mw * sn * xn + cs * pn;
+                }
+                rn_x[cnt] = xo;
+                rn_p[cnt] = po;
+            } else {
+                // Langevin O step on mode k: noise stream row = mode k * D + axis (DESIGN.md "RNG")
+                const int axis = ok ? col / a.N : 0, n = ok ? col % a.N : 0;
+                double z0, z1;
+                gaussian_pair((uint32_t)(n >> 1), (uint32_t)(k * a.D + axis), draw, a.seed, z0, z1);
+                rn_p[cnt] = a.c1 * pn + a.c2 * ((n & 1) ? z1 : z0);
+            }
+        }
+        __syncthreads();
+        cnt = 0;
+        for (int k = kg; k < P; k += KG, ++cnt) {
+            sp[k * TC + tc] = rn_p[cnt];
+            if (MODE == 0) sx[k * TC + tc] = rn_x[cnt];
+        }
+        __syncthreads();
+        // 3. inverse transform and store
+        for (int j = kg; j < P; j += KG) {
+            const double* irow = a.Cinv + (size_t)j * P;
+            double xc = 0.0, pc = 0.0;
+            for (int k = 0; k < P; ++k) {
+                const double ck = __ldg(irow + k);
+                pc += ck * sp[k * TC + tc];
+                if (MODE == 0) xc += ck * sx[k * TC + tc];
+            }
+            if (ok) {
+                a.p[(size_t)j * a.M + col] = pc;
+                if (MODE == 0) a.x[(size_t)j * a.M + col] = xc;
+            }
+        }
+        __syncthreads();
+    }
+    if (MODE == 1) {   // advance the noise draw counter once all blocks have read it
+        if (tid == 0) {
+            __threadfence();
+            unsigned int t = atomicAdd(a.ticket, 1u);
+            is_last = (t == gridDim.x - 1);
+        }
+        __syncthreads();
+        if (is_last && tid == 0) {
+            *a.ticket = 0u;
+            *a.draw = draw + 1ull;
+        }
+    }
+}
+
+static int launch_nm(Sim* s, int mode) {
+    NmArgs a;
+    a.x = s->x + s->S; a.p = s->p; a.fphys = s->fp;
+    a.C = s->nmC; a.Cinv = s->nmC + (size_t)s->P * s->P; a.tab = s->nmFreq;
+    a.draw = s->draw; a.ticket = s->tickets;
+    a.P = s->P; a.M = (int)s->S; a.N = s->N; a.D = s->D;
+    // tile width: P*TC/256 outputs per thread must stay <= 32 and the two tiles must fit in shared memory
+    int TC = 32;
+    while (TC > 1 && ((size_t)s->P * TC / 256 > 32 || (size_t)2 * s->P * TC * sizeof(double) > 200 * 1024)) TC >>= 1;
+    a.TC = TC;
+    a.hdt = 0.5 * s->cfg.dt; a.dt_over_m = s->cfg.dt / s->cfg.mass; a.c1 = s->c1; a.c2 = s->c2;
+    a.seed = s->cfg.seed;
+    const size_t smem = (size_t)2 * s->P * TC * sizeof(double);
+    const int grid = grid_for((a.M + TC - 1) / TC, 1, 4 * kNumSM);
+    if (mode == 0) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k_nm_fused<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_nm_fused<0><<<grid, 256, smem, s->stream>>>(a);
+    } else {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k_nm_fused<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_nm_fused<1><<<grid, 256, smem, s->stream>>>(a);
+    }
+    s->launches += 1;
+    PIMDB_CUDA_TRY(s, cudaGetLastError());
+    return PIMDB_OK;
+}
+
+int launch_nm_propagate(Sim* s) { return launch_nm(s, 0); }
+int launch_nm_thermostat(Sim* s) { return launch_nm(s, 1); }
+
+// ------------------------------------------------------------------------------------------------------
+// Element-wise estimator partials (K13): classical spring energy of the owned links, external potential and its
+// virial, sum p^2. Reference: Simulation::classicalSpringEnergy (src/simulation.cpp:464-486),
+// EnergyObservable::calculatePotential external part (src/observables/energy.cpp:62-74),
+// ClassicalObservable::calculateKineticEnergy (src/observables/classical.cpp:32-45).
+struct ObsArgs {
+    const double *x, *p;
+    double* part; unsigned int* ticket; DevObs* obs;
+    int N, D, Ploc, skip_link;   // skip_link: owned-bead index whose incoming link is the exterior (bosonic) one, or -1
+    size_t S;
+    double k, kext, L, invL, mass;
+    int pbc, ext_pot;
+    double ext_a, ext_b;
+};
+
+__global__ void __launch_bounds__(256) k_obs_elementwise(ObsArgs a) {
+    __shared__ double sm[4 * 32];
+    __shared__ bool is_last;
+    const long long total = (long long)a.Ploc * a.N;
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};   // spring d^2, ext V, ext virial, p^2
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int b = (int)(idx / a.N), n = (int)(idx % a.N);
+        const double* xc = a.x + (size_t)(b + 1) * a.S;
+        const double* xp = xc - a.S;
+        const double* pc = a.p + (size_t)b * a.S;
+        double r2 = 0.0, d2 = 0.0, pp = 0.0;
+        double xv[3] = {0.0, 0.0, 0.0};
+        for (int c = 0; c < a.D; ++c) {
+            const double xi = xc[(size_t)c * a.N + n];
+            xv[c] = xi;
+            double d = xp[(size_t)c * a.N + n] - xi;
+            if (a.pbc) d = min_image(d, a.L, a.invL);
+            d2 = fma(d, d, d2);
+            r2 = fma(xi, xi, r2);
+            const double pi = pc[(size_t)c * a.N + n];
+            pp = fma(pi, pi, pp);
+        }
+        if (b != a.skip_link) acc[0] += d2;
+        if (a.ext_pot == PIMDB_POT_HARMONIC) {
+            acc[1] += r2;                 // V = k/2 sum x^2 ; virial -x.F = k sum x^2 (scaled at the end)
+        } else if (a.ext_pot == PIMDB_POT_DOUBLE_WELL) {
+            // reference src/potentials/double_well.cpp:6-40: V = m lambda sum_c (x_c^2 - a^2)^2 ; grad = 4 m lambda (|x|^2 - a^2) x
+            double v = 0.0;
+            for (int c = 0; c < a.D; ++c) { double t = xv[c] * xv[c] - a.ext_b * a.ext_b; v += t * t; }
+            acc[1] += a.mass * a.ext_a * v;
+            acc[2] += 4.0 * a.mass * a.ext_a * (r2 - a.ext_b * a.ext_b) * r2;
+        } else if (a.ext_pot == PIMDB_POT_COSINE) {
+            // reference src/potentials/cosine.cpp:9-35
+            const double kk = 2.0 * M_PI / a.L;
+            for (int c = 0; c < a.D; ++c) {
+                acc[1] += a.ext_a * cos(kk * xv[c] + a.ext_b);
+                acc[2] += -xv[c] * (a.ext_a * kk * sin(kk * xv[c] + a.ext_b));
+            }
+        }
+        acc[3] += pp;
+    }
+    block_sum<4>(acc, sm);
+    if (threadIdx.x == 0) {
+        for (int c = 0; c < 4; ++c) a.part[blockIdx.x * 4 + c] = acc[c];
+        __threadfence();
+        unsigned int t = atomicAdd(a.ticket, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (is_last) {
+        __threadfence();
+        double tot[4] = {0.0, 0.0, 0.0, 0.0};
+        for (int blk = threadIdx.x; blk < (int)gridDim.x; blk += blockDim.x)
+            for (int c = 0; c < 4; ++c) tot[c] += __ldcg(&a.part[blk * 4 + c]);
+        block_sum<4>(tot, sm);
+        if (threadIdx.x == 0) {
+            a.obs->spring_e[0] = 0.5 * a.k * tot[0];
+            if (a.ext_pot == PIMDB_POT_HARMONIC) {
+                a.obs->ext_v = 0.5 * a.kext * tot[1];
+                a.obs->ext_vir = a.kext * tot[1];
+            } else {
+                a.obs->ext_v = tot[1];
+                a.obs->ext_vir = tot[2];
+            }
+            a.obs->p2 = tot[3];
+            *a.ticket = 0u;
+        }
+    }
+}
+
+int launch_obs_elementwise(Sim* s) {
+    ObsArgs a;
+    a.x = s->x; a.p = s->p; a.part = s->obs_part; a.ticket = s->tickets; a.obs = s->obs_d;
+    a.N = s->N; a.D = s->D; a.Ploc = s->Ploc;
+    a.skip_link = (s->bosonic && s->has_first) ? 0 : -1;
+    a.S = s->S; a.k = s->kspring; a.kext = s->kext; a.L = s->L; a.invL = 1.0 / s->L; a.mass = s->cfg.mass;
+    a.pbc = s->cfg.pbc; a.ext_pot = s->cfg.ext_potential;
+    if (s->cfg.ext_potential == PIMDB_POT_DOUBLE_WELL) { a.ext_a = s->cfg.ext_strength; a.ext_b = s->cfg.ext_location; }
+    else { a.ext_a = s->cfg.ext_amplitude; a.ext_b = s->cfg.ext_phase; }
+    const int grid = grid_for((size_t)s->Ploc * s->N, 256, kMaxPartials);
+    k_obs_elementwise<<<grid, 256, 0, s->stream>>>(a);
+    s->launches += 1;
+    PIMDB_CUDA_TRY(s, cudaGetLastError());
+    return PIMDB_OK;
+}
+
+}  // namespace pimdb
