@@ -97,11 +97,18 @@ __global__ void __launch_bounds__(256) k_pair_tiles(PairArgs a) {
         const int src = (lane + t) & 31;
         double d[D], xo[D];
         double r2 = 0.0;
+        // The reference always forms x_lower_index - x_higher_index before the minimum image
+        // (src/simulation.cpp:433-437, 503); mi(+L/2) = mi(-L/2) = -L/2, so the order matters for particles
+        // exactly half a box apart (perfect lattices). Only diagonal tiles can see the higher index first.
+        const bool swap = PBC && diag && (src < lane);
 #pragma unroll
         for (int c = 0; c < D; ++c) {
             xo[c] = __shfl_sync(kFullMask, xj[c], src);
             double dx = xi[c] - xo[c];
-            if (PBC) dx = min_image(dx, a.L, a.invL);
+            if (PBC) {
+                dx = min_image(swap ? -dx : dx, a.L, a.invL);
+                dx = swap ? -dx : dx;
+            }
             d[c] = dx;
             r2 = fma(dx, dx, r2);
         }
