@@ -206,6 +206,9 @@ unsigned long long pimdb_launch_count(const pimdb_sim* sim);
  * pimdb_timing_reset, measured with CUDA events on the handle's stream (bench.py's roofline). */
 int pimdb_timing_enable(pimdb_sim* sim, int on);
 int pimdb_timing_get(pimdb_sim* sim, int what, double* ms_avg, unsigned long long* count);
+/* Measured FP64 FMA throughput of the device (TFLOP/s, dependent-FMA micro-benchmark): the denominator of the
+ * pair-force roofline, which MEASURED_PEAKS.json does not provide. Not part of the reference surface. */
+int pimdb_bench_fp64_peak(int device, double* tflops);
 
 #ifdef __cplusplus
 }

@@ -77,6 +77,7 @@ SYMBOLS = {
     "pimdb_launch_count": (C.c_ulonglong, [_VP]),
     "pimdb_timing_enable": (C.c_int, [_VP, C.c_int]),
     "pimdb_timing_get": (C.c_int, [_VP, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]),
+    "pimdb_bench_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
 }
 
 _lib = None

@@ -761,3 +761,40 @@ extern "C" int pimdb_timing_get(pimdb_sim* sim, int what, double* ms_avg, unsign
     *ms_avg = v.empty() ? 0.0 : tot / (double)v.size();
     return PIMDB_OK;
 }
+
+// ----------------------------------------------------------------------------------------------------
+// FP64 FMA micro-benchmark: the denominator of the pair-force roofline (MEASURED_PEAKS.json has no FP64 figure).
+// 8 independent accumulators per thread, 4096 dependent rounds, 148 x 8 blocks of 256 threads.
+__global__ void __launch_bounds__(256) k_dfma_peak(double* out, int rounds, double a, double b) {
+    double r0 = threadIdx.x, r1 = r0 + 1, r2 = r0 + 2, r3 = r0 + 3, r4 = r0 + 4, r5 = r0 + 5, r6 = r0 + 6, r7 = r0 + 7;
+    for (int i = 0; i < rounds; ++i) {
+        r0 = fma(r0, a, b); r1 = fma(r1, a, b); r2 = fma(r2, a, b); r3 = fma(r3, a, b);
+        r4 = fma(r4, a, b); r5 = fma(r5, a, b); r6 = fma(r6, a, b); r7 = fma(r7, a, b);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((r0 + r1) + (r2 + r3)) + ((r4 + r5) + (r6 + r7));
+}
+
+extern "C" int pimdb_bench_fp64_peak(int device, double* tflops) {
+    if (!tflops) return PIMDB_ERR_INVALID_ARGUMENT;
+    if (cudaSetDevice(device) != cudaSuccess) return PIMDB_ERR_CUDA;
+    const int blocks = kNumSM * 8, threads = 256, rounds = 4096;
+    double* buf = nullptr;
+    if (cudaMalloc(&buf, sizeof(double) * blocks * threads) != cudaSuccess) return PIMDB_ERR_CUDA;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 6; ++rep) {
+        cudaEventRecord(e0);
+        k_dfma_peak<<<blocks, threads>>>(buf, rounds, 0.999999, 1e-9);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(buf); return PIMDB_ERR_CUDA; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 8.0 * rounds * (double)blocks * threads;
+        if (rep > 0) best = std::max(best, flops / (ms * 1e-3) * 1e-12);   // first launch = warm-up
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(buf);
+    *tflops = best;
+    return PIMDB_OK;
+}

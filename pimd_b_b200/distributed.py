@@ -1,0 +1,129 @@
+"""Bead sharding across the GPUs of one box: one process per GPU, torch.distributed for the plumbing.
+
+The reference runs one MPI rank per bead and moves, every step, one bead slice to each ring neighbour
+(MPI_Sendrecv, src/simulation.cpp:299-347), NDIM doubles for zeroMomentum (MPI_Allreduce, :595) and one double
+per observable column (src/observables/observable.cpp:105). Here rank r owns the contiguous bead range
+``bead_range(P, G, r)``; the same three exchanges become
+  * a ring halo exchange of the first / last owned bead slices (NCCL point-to-point over NVLink),
+  * an all-reduce of the ndim partial momentum sums (padded to 4 doubles),
+  * an all-reduce of the 10 observable partials on logging steps.
+Pair forces, springs of interior beads and the integrator never leave the GPU; the exchange recursion runs
+redundantly on the two ranks that own bead 1 and bead P (exactly what ranks 0 and P-1 do in the reference).
+
+``ShardedSimulation`` is written against a small *shard* protocol so that the collective choreography can be
+tested on CPU with the gloo backend (tests/test_sharding_gloo.py) and runs unchanged on NCCL:
+
+    shard.step_phase(k)            k = 0..3, see include/pimdb200.h
+    shard.send_first / send_last   tensors holding the first / last owned bead slice
+    shard.halo_before / halo_after tensors receiving the neighbours' slices
+    shard.com                      tensor (4,) of partial momentum sums
+    shard.observables_partial()    tensor (10,) float64
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+import torch.distributed as dist
+
+from ._cabi import OBS_FIELDS
+
+
+def bead_range(nbeads: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous, balanced bead ranges (the first ``nbeads % world`` ranks own one extra bead)."""
+    if world > nbeads:
+        raise ValueError(f"cannot shard {nbeads} beads over {world} ranks")
+    base, rem = divmod(nbeads, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+class _DevicePtrView:
+    """Zero-copy view of device memory owned by libpimdb200.so (``__cuda_array_interface__``)."""
+
+    def __init__(self, ptr: int, count: int):
+        self.__cuda_array_interface__ = {
+            "shape": (count,), "typestr": "<f8", "data": (ptr, False), "version": 3, "strides": None}
+
+
+class CudaShard:
+    """The product shard: a DeviceSim on this rank's GPU; its tensors alias the library's device buffers."""
+
+    def __init__(self, cfg, rank: int, world: int, device: int):
+        from .engine import DeviceSim
+        lo, hi = bead_range(cfg.nbeads, world, rank)
+        torch.cuda.set_device(device)
+        self.stream = torch.cuda.Stream(device=device)
+        self.sim = DeviceSim(cfg, lo, hi, device)
+        self.sim.set_stream(self.stream.cuda_stream)
+        dev = torch.device("cuda", device)
+
+        def view(which):
+            ptr, cnt = self.sim.halo_ptr(which)
+            return torch.as_tensor(_DevicePtrView(ptr, cnt), device=dev)
+
+        self.send_first, self.send_last = view(0), view(1)
+        self.halo_before, self.halo_after = view(2), view(3)
+        self.com = torch.as_tensor(_DevicePtrView(self.sim.com_ptr(), 4), device=dev)
+        self.device = dev
+
+    def step_phase(self, k: int):
+        self.sim.step_phase(k)
+
+    def observables_partial(self) -> torch.Tensor:
+        o = self.sim.observables()
+        return torch.tensor([o[n] for n in OBS_FIELDS], dtype=torch.float64, device=self.device)
+
+    def refresh_local_forces(self):
+        self.sim.update_forces()
+
+
+class ShardedSimulation:
+    """Runs Simulation::run's loop body (src/simulation.cpp:246-259) over bead shards."""
+
+    def __init__(self, cfg, shard, group=None):
+        self.cfg = cfg
+        self.shard = shard
+        self.group = group
+        self.rank = dist.get_rank(group)
+        self.world = dist.get_world_size(group)
+        self.prev = (self.rank - 1) % self.world
+        self.next = (self.rank + 1) % self.world
+
+    # Simulation::updateNeighboringCoordinates across ranks
+    def exchange_halos(self):
+        s = self.shard
+        if self.world == 1:
+            s.halo_before.copy_(s.send_last)
+            s.halo_after.copy_(s.send_first)
+            return
+        # Order matters when prev == next (two ranks): the k-th send to a peer pairs with its k-th receive.
+        ops = [
+            dist.P2POp(dist.isend, s.send_first, self.prev, self.group),
+            dist.P2POp(dist.isend, s.send_last, self.next, self.group),
+            dist.P2POp(dist.irecv, s.halo_after, self.next, self.group),
+            dist.P2POp(dist.irecv, s.halo_before, self.prev, self.group),
+        ]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+    def _allreduce_com(self):
+        if self.cfg.fixcom and self.world > 1:
+            dist.all_reduce(self.shard.com, op=dist.ReduceOp.SUM, group=self.group)
+
+    def step(self, nsteps: int = 1):
+        s = self.shard
+        for _ in range(nsteps):
+            s.step_phase(0)          # thermostat half step (+ local momentum sums)
+            self._allreduce_com()
+            s.step_phase(1)          # COM removal, B, A
+            self.exchange_halos()
+            s.step_phase(2)          # forces, B, thermostat half step (+ local momentum sums)
+            self._allreduce_com()
+            s.step_phase(3)          # COM removal
+
+    def observables(self) -> dict:
+        part = self.shard.observables_partial()
+        if self.world > 1:
+            dist.all_reduce(part, op=dist.ReduceOp.SUM, group=self.group)
+        return {n: float(v) for n, v in zip(OBS_FIELDS, part.tolist())}
