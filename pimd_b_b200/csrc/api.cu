@@ -10,6 +10,7 @@
 namespace pimdb {
 int launch_pair_chunk(Sim* s, int bead_lo, int nb, bool with_obs);
 int launch_assemble_chunk(Sim* s, int bead_lo, int nb, bool with_pair);
+int launch_exchange_part(Sim* s, cudaStream_t st, int part);
 }  // namespace pimdb
 
 using namespace pimdb;
@@ -135,7 +136,8 @@ static void free_all(Sim* s) {
     cudaFree(s->x); cudaFree(s->p); cudaFree(s->f); cudaFree(s->fs); cudaFree(s->fp);
     cudaFree(s->stage_d); cudaFreeHost(s->stage_h);
     cudaFree(s->tile_ij); cudaFree(s->pair_scratch);
-    cudaFree(s->exA); cudaFree(s->exV); cudaFree(s->exVb); cudaFree(s->exF); cudaFree(s->exPrim); cudaFree(s->exTab);
+    cudaFree(s->exA); cudaFree(s->exV); cudaFree(s->exVb); cudaFree(s->exF); cudaFree(s->exTab);
+    cudaFree(s->exCm); cudaFree(s->exCe); cudaFree(s->exWm); cudaFree(s->exWe);
     cudaFree(s->com_part); cudaFree(s->com); cudaFree(s->tickets); cudaFree(s->draw);
     cudaFree(s->obs_d); cudaFreeHost(s->obs_h); cudaFree(s->obs_part);
     cudaFreeHost(s->err_h);
@@ -254,11 +256,17 @@ extern "C" int pimdb_create(const pimdb_config* cfg, pimdb_sim** out) {
         CREATE_TRY(cudaMalloc(&s->pair_scratch, per_bead * chunk));
     }
     if (s->bosonic) {
-        CREATE_TRY(cudaMalloc(&s->exA, sizeof(double) * 2 * s->N));
+        const size_t NN = (size_t)s->N * s->N;
+        CREATE_TRY(cudaMalloc(&s->exA, sizeof(double) * s->N));
+        CREATE_TRY(cudaMalloc(&s->exCm, sizeof(double) * 2 * NN));
+        CREATE_TRY(cudaMalloc(&s->exCe, sizeof(int) * 2 * NN));
+        CREATE_TRY(cudaMalloc(&s->exWm, sizeof(double) * 2 * (s->N + 1)));
+        CREATE_TRY(cudaMalloc(&s->exWe, sizeof(int) * 2 * (s->N + 1)));
+        CREATE_TRY(cudaMemset(s->exWm, 0, sizeof(double) * 2 * (s->N + 1)));
+        CREATE_TRY(cudaMemset(s->exWe, 0, sizeof(int) * 2 * (s->N + 1)));
         CREATE_TRY(cudaMalloc(&s->exV, sizeof(double) * (s->N + 1)));
         CREATE_TRY(cudaMalloc(&s->exVb, sizeof(double) * (s->N + 1)));
         CREATE_TRY(cudaMalloc(&s->exF, sizeof(double) * 2 * s->S));
-        CREATE_TRY(cudaMalloc(&s->exPrim, sizeof(double) * (s->N + 1)));
         CREATE_TRY(cudaMemset(s->exV, 0, sizeof(double) * (s->N + 1)));
         CREATE_TRY(cudaMemset(s->exVb, 0, sizeof(double) * (s->N + 1)));
         CREATE_TRY(cudaMemset(s->exF, 0, sizeof(double) * 2 * s->S));
@@ -369,9 +377,13 @@ extern "C" int pimdb_get_state(pimdb_sim* sim, int which, double* host) {
 static int enqueue_forces(Sim* s) {
     const bool ex = s->bosonic && (s->has_first || s->has_last);
     if (ex) {
+        // Prefix sums + Boltzmann factors run on the main stream (wide, short). The two-block recurrence kernel is
+        // then launched on the high-priority side stream BEFORE the pair tiles, so its blocks are resident when
+        // the pair-force grid floods the SMs and the latency-bound chain overlaps the FP64-bound tiles.
+        API_TRY(launch_exchange_part(s, s->stream, 0));
         PIMDB_CUDA_TRY(s, cudaEventRecord(s->ev_fork, s->stream));
         PIMDB_CUDA_TRY(s, cudaStreamWaitEvent(s->stream_x, s->ev_fork, 0));
-        API_TRY(launch_exchange(s, s->stream_x));
+        API_TRY(launch_exchange_part(s, s->stream_x, 1));
         PIMDB_CUDA_TRY(s, cudaEventRecord(s->ev_join, s->stream_x));
     }
     bool joined = !ex;

@@ -6,31 +6,100 @@
 //   getDistinctProbability :222-229, getLongestProbability :238-240, primEstimator :250-279
 // and src/bosonic_exchange/bosonic_exchange_base.cpp:30-64 (minimum-image bead separations).
 //
-// Design (see DESIGN.md "exchange"):
-//   * E_kn is never materialised. With d2(u,v) = |r^P_v - r^1_u|^2 (minimum image) and the prefix sum
-//     A(w) = sum_{t<w} |r^1_{t+1} - r^P_t|^2, the reference's recurrence telescopes to
-//         E^{[u..v]} = k/2 [ A(v) - A(u) + d2(u,v) ],
-//     so every entry is 1 subtraction pattern + one distance, evaluated on the fly.
-//   * The N-step recursions run column-wise: as soon as V[j] is known every row m>j folds the term
-//     -beta (E^{[j..m-1]} + V[j]) into its own running (max, sum) pair ("online" log-sum-exp), so a step costs
-//     one barrier instead of two block reductions, and row j+1 is complete the moment column j has been applied.
-//     Forward and backward recursions are independent and run as two concurrent thread blocks.
-//   * Connection probabilities are evaluated on the fly inside the exterior-force kernel (one warp per particle
-//     and exterior bead); the N x N matrix is only built when a caller asks for it (pimdb_exchange_get).
+// Design (DESIGN.md "exchange"):
+//   1. Closed-form cycle energies. With d2(u,v) = |r^P_v - r^1_u|^2 (minimum image) and the prefix sum
+//      A(w) = sum_{t<w} |r^1_{t+1} - r^P_t|^2 the reference's recurrence telescopes to
+//          E^{[u..v]} = k/2 [ A(v) - A(u) + d2(u,v) ],      u <= v,
+//      so E_kn (N(N+1)/2 doubles) is never stored.
+//   2. All transcendental work is hoisted off the sequential chain. The Boltzmann factors
+//          c(u,v) = exp(-beta E^{[u..v]})
+//      depend on positions only; one fully parallel kernel evaluates them for all u <= v as *extended-range*
+//      numbers (mantissa in [1,2) + 32-bit binary exponent), because beta*E easily exceeds the range of exp().
+//   3. With W[m] = exp(-beta V[m]) and Wb[l] = exp(-beta Vb[l]) the two N-step recursions become linear
+//      triangular recurrences
+//          W[v+1] = 1/(v+1) sum_{j<=v} c(j,v) W[j],          Wb[l] = sum_{p>=l} c(l,p) Wb[p+1] / (p+1),
+//      evaluated column-wise in extended-range arithmetic: when W[j] is known every row v >= j adds its term.
+//      The dependency chain of a step is one multiply-add, one normalisation and one barrier -- no exp, no log,
+//      no block reduction. Mathematically this is the reference's shifted log-sum-exp with the shift carried
+//      exactly in the binary exponent, so it is robust for any positions the reference handles.
+//      V[m] = -(ln W[m])/beta is recovered in parallel afterwards. Forward and backward recursions are
+//      independent and run as two concurrent thread blocks; coefficient rows are prefetched with cp.async.
+//   4. Connection probabilities are products of known extended-range numbers,
+//          P(l->u) = W[u] c(u,l) Wb[l+1] / ((l+1) W[N]),
+//      evaluated on the fly in the exterior-force kernel (one warp per particle and exterior bead); the N x N
+//      matrix is only materialised when a caller asks for it (pimdb_exchange_get).
 #include "internal.cuh"
 #include "device_utils.cuh"
 
 namespace pimdb {
 
+// ---------------------------------------------------------------- extended-range positive numbers
+struct Ext {
+    double m;   // mantissa, in [1,2) when normalised (0 for an exact zero)
+    int e;      // value = m * 2^e
+};
+
+constexpr int kExtZeroExp = -(1 << 29);
+
+__device__ __forceinline__ double pow2i(int d) {   // 2^d for d in [-1022, 1023], 0 below
+    return d < -1022 ? 0.0 : __hiloint2double((1023 + d) << 20, 0);
+}
+
+__device__ __forceinline__ Ext ext_normalize(double m, int e) {
+    Ext r;
+    if (!(m > 0.0)) { r.m = m; r.e = kExtZeroExp; return r; }   // zero (or NaN, which then propagates)
+    const int hi = __double2hiint(m);
+    const int ex = ((hi >> 20) & 0x7ff) - 1023;
+    r.m = __hiloint2double((hi & 0x800fffff) | (1023 << 20), __double2loint(m));
+    r.e = e + ex;
+    return r;
+}
+
+// acc += a*b  (acc need not be normalised; its mantissa stays a moderate positive double)
+__device__ __forceinline__ void ext_fma(double& am, int& ae, double m1, int e1, double m2, int e2) {
+    const double tm = m1 * m2;
+    const int te = e1 + e2;
+    const int emax = max(ae, te);
+    am = fma(am, pow2i(max(ae - emax, -1100)), tm * pow2i(max(te - emax, -1100)));
+    ae = emax;
+}
+
+__device__ __forceinline__ double ext_to_double(double m, int e) {
+    if (e < -1070) return 0.0;
+    if (e < -1000) return (m * pow2i(e + 200)) * pow2i(-200);
+    return m * pow2i(min(e, 1023));
+}
+
+// exp(-y) for y >= 0 of any magnitude, as an extended-range number. The reduction t = -y*log2(e) = n + r keeps r
+// exact to ~2^-100 |y| by splitting log2(e) and using FMAs, so the relative error is that of exp2() itself.
+__device__ __forceinline__ Ext ext_exp_neg(double y) {
+    const double L2E_HI = 1.4426950408889634;          // log2(e) rounded to double
+    const double L2E_LO = 2.0355273740931033e-17;      // log2(e) - L2E_HI
+    double t = -y * L2E_HI;
+    double n = rint(t);
+    n = fmax(n, -1.0e9);
+    double r = fma(-y, L2E_HI, -n);                    // exact product, one rounding
+    r = fma(-y, L2E_LO, r);
+    Ext o;
+    o.m = exp2(r);                                     // in [2^-0.5, 2^0.5]
+    o.e = (int)n;
+    return ext_normalize(o.m, o.e);
+}
+
+// ---------------------------------------------------------------- arguments
 struct ExArgs {
     const double *x1, *xP;     // bead 1 and bead P slices, [D][N]
     const double *x2, *xPm1;   // bead 2 (next of first) and bead P-1 (previous of last)
-    double *A, *V, *Vb, *F;    // A[N], V[N+1], Vb[N+1], F[2][D][N]
-    double* prim;              // e[N+1] scratch of the primitive-estimator recursion
+    double* A;                 // A[N] prefix sums
+    double *Cfm, *Cbm;         // coefficient mantissas: Cf[j][v] = c(j,v) (v>=j), Cb[p][l] = c(l,p) (l<=p); N x N each
+    int *Cfe, *Cbe;            // ... and binary exponents
+    double *Wm, *Wbm;          // W[0..N], Wb[0..N] mantissas
+    int *We, *Wbe;             // ... exponents
+    double *V, *Vb, *F;        // V[N+1], Vb[N+1], F[2][D][N]
     DevObs* obs;
     int* err;
     int N, D, pbc, do_first, do_last;
-    double k, beta, L, invL;
+    double k, beta, h, L, invL;   // h = beta*k/2
 };
 
 template <int D>
@@ -51,22 +120,19 @@ __device__ __forceinline__ double cycle_energy(const ExArgs& a, int u, int v) {
     return 0.5 * a.k * (a.A[v] - a.A[u] + dist2<D>(a, a.x1, u, a.xP, v));
 }
 
-// ---------------------------------------------------------------- prefix sums A(w), by one whole block
-// Called at the top of both recursion blocks (each fills its own copy of A, so the two blocks never wait for
-// each other): N distances + a block scan, a few microseconds.
+// ---------------------------------------------------------------- 1. prefix sums A(w), one block
 template <int D>
-__device__ __forceinline__ void prefix_block(const ExArgs& a, double* A) {
+__global__ void __launch_bounds__(1024) k_exch_prefix(ExArgs a) {
     __shared__ double warp_tot[32];
     __shared__ double carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid < 32) warp_tot[tid] = 0.0;
     if (tid == 0) carry = 0.0;
     __syncthreads();
-    // A[w] = sum_{t<w} link[t], link[t] = d2(P_t, 1_{t+1}); processed in chunks of blockDim, inclusive scan per chunk
+    // A[w] = sum_{t<w} link[t], link[t] = d2(P_t, 1_{t+1}); chunks of blockDim, inclusive scan per chunk
     for (int base = 0; base < a.N; base += blockDim.x) {
         const int w = base + tid;                      // produces A[w+1]
-        double link = (w < a.N - 1) ? dist2<D>(a, a.xP, w, a.x1, w + 1) : 0.0;
-        double v = link;
+        double v = (w < a.N - 1) ? dist2<D>(a, a.xP, w, a.x1, w + 1) : 0.0;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             double t = __shfl_up_sync(kFullMask, v, o);
@@ -84,94 +150,197 @@ __device__ __forceinline__ void prefix_block(const ExArgs& a, double* A) {
             warp_tot[lane] = t;
         }
         __syncthreads();
-        double incl = carry + (warp > 0 ? warp_tot[warp - 1] : 0.0) + v;
-        if (w + 1 < a.N) A[w + 1] = incl;
+        const double incl = carry + (warp > 0 ? warp_tot[warp - 1] : 0.0) + v;
+        if (w + 1 < a.N) a.A[w + 1] = incl;
         __syncthreads();
         if (tid == blockDim.x - 1) carry = incl;
         __syncthreads();
     }
-    if (tid == 0) A[0] = 0.0;
-    __syncthreads();
+    if (tid == 0) a.A[0] = 0.0;
 }
 
-// ---------------------------------------------------------------- forward / backward recursions
-// online log-sum-exp accumulator
-struct Lse {
-    double mx, s;
-    __device__ __forceinline__ void init() { mx = -INFINITY; s = 0.0; }
-    __device__ __forceinline__ void add(double t) {
-        if (t > mx) { s = s * exp(mx - t) + 1.0; mx = t; }
-        else s += exp(t - mx);
+// ---------------------------------------------------------------- 2. Boltzmann factors, fully parallel
+// element (r,s) of the N x N index square:  s >= r -> Cf[r][s] = c(r,s);  s <= r -> Cb[r][s] = c(s,r)
+template <int D>
+__global__ void __launch_bounds__(256) k_exch_coeff(ExArgs a) {
+    const int N = a.N;
+    const long long tot = (long long)N * N;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (long long)gridDim.x * blockDim.x) {
+        const int r = (int)(i / N), s = (int)(i % N);
+        const int u = min(r, s), v = max(r, s);
+        const double y = a.h * (a.A[v] - a.A[u] + dist2<D>(a, a.x1, u, a.xP, v));
+        const Ext c = ext_exp_neg(fmax(y, 0.0));
+        if (s >= r) { a.Cfm[i] = c.m; a.Cfe[i] = c.e; }
+        if (s <= r) { a.Cbm[i] = c.m; a.Cbe[i] = c.e; }
     }
-};
+}
 
-// block 0: V[1..N]  (V[0] = 0);  block 1: Vb[N-1..1]  (Vb[N] = 0)
-template <int D, int R>
-__global__ void __launch_bounds__(1024) k_exch_recursion(ExArgs a) {
-    extern __shared__ double sv[];   // V or Vb values, N+1 doubles
+// ---------------------------------------------------------------- 3. the two recurrences
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int K>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(K)); }
+
+// One thread block evaluates one recurrence: FWD: W[1..N] from W[0] = 1;  !FWD: Wb[N-1..1] from Wb[N] = 1.
+// Thread t owns rows t, t+nt, ... (R of them). Step s applies the newly known value (W[s] or Wb[N-s]) to every
+// row that still needs it, then the thread whose row became complete publishes it and everybody meets at a barrier.
+// The loop is issue-bound (16 warps x instructions per step), so everything is specialised at compile time and
+// addresses advance by pointer increments.
+// ST > 0: coefficient rows are staged through an ST-deep cp.async ring in shared memory (each thread copies and
+//         later reads only its own elements, so cp.async.wait_group is the only synchronisation they need);
+// ST == 0: large N, coefficients are read straight from global memory (R independent loads per thread and step).
+// smem: sWm[N+2] | sInv[N+2] (reciprocals 1/i, so no division sits on the chain) | stage mantissas [ST][R][nt]
+//       | sWe[N+2] | stage exponents [ST][R][nt]
+template <bool FWD, int R, int ST>
+__device__ __forceinline__ void recur_body(const ExArgs& a, double* smem_d) {
+    static_assert(ST == 0 || (ST & (ST - 1)) == 0, "ring depth must be a power of two");
     const int tid = threadIdx.x, nt = blockDim.x, N = a.N;
-    const double beta = a.beta;
-    Lse acc[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) acc[r].init();
-    a.A += (size_t)blockIdx.x * N;   // private copy of the prefix sums (copy 0 is the one later kernels read)
-    prefix_block<D>(a, a.A);
+    double* sWm = smem_d;
+    double* sInv = sWm + (N + 2);
+    double* stm = sInv + (N + 2);
+    int* sWe = (int*)(stm + (size_t)ST * R * nt);
+    int* ste = sWe + (N + 2);
+    const int nsteps = FWD ? N : N - 1;     // forward: coefficient row j = s; backward: row p = N-1-s
+    const int dstep = FWD ? N : -N;         // coefficient offset advance per step
 
-    if (blockIdx.x == 0) {
-        // thread owns rows v = tid + r*nt  (V index m = v+1)
-        if (tid == 0) sv[0] = 0.0;
-        __syncthreads();
-        for (int j = 0; j < N; ++j) {
-            const double vj = sv[j];
+    // row-validity of my R rows at coefficient row `row`: forward col in [row, N); backward col in [1, row]
+    auto need = [&](int col, int row) { return FWD ? (col >= row && col < N) : (col >= 1 && col <= row); };
+
+    const double* gm = (FWD ? a.Cfm : a.Cbm) + (FWD ? 0 : (long long)(N - 1) * N) + tid;   // prefetch cursor
+    const int* ge = (FWD ? a.Cfe : a.Cbe) + (FWD ? 0 : (long long)(N - 1) * N) + tid;
+    int s_issue = 0;
+    auto issue = [&]() {
+        if (ST > 0) {
+            if (s_issue < nsteps) {
+                const int row = FWD ? s_issue : (N - 1 - s_issue);
+                const int slot = s_issue & (ST > 0 ? ST - 1 : 0);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    if (need(tid + r * nt, row)) {
+                        cp_async8(&stm[(slot * R + r) * nt + tid], gm + r * nt);
+                        cp_async4(&ste[(slot * R + r) * nt + tid], ge + r * nt);
+                    }
+                }
+            }
+            cp_async_commit();
+            ++s_issue;
+            gm += dstep;
+            ge += dstep;
+        }
+    };
+
+    double am[R];
+    int ae[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) { am[r] = 0.0; ae[r] = kExtZeroExp; }
+    if (tid == 0) {
+        sWm[FWD ? 0 : N] = 1.0;
+        sWe[FWD ? 0 : N] = 0;
+    }
+    for (int i = tid; i <= N; i += nt) sInv[i] = i > 0 ? 1.0 / (double)i : 0.0;
+#pragma unroll
+    for (int s = 0; s < ST - 1; ++s) issue();
+    __syncthreads();
+
+    // owner (thread, register slot) of the row that completes in the current step, tracked incrementally
+    int own_t = FWD ? 0 : (N - 1) % nt;
+    int own_r = FWD ? 0 : (N - 1) / nt;
+    const double* lm = (FWD ? a.Cfm : a.Cbm) + (FWD ? 0 : (long long)(N - 1) * N) + tid;   // direct-load cursor (ST == 0)
+    const int* le = (FWD ? a.Cfe : a.Cbe) + (FWD ? 0 : (long long)(N - 1) * N) + tid;
+    const int warp = tid >> 5;
+
+    for (int s = 0; s < nsteps; ++s) {
+        const int row = FWD ? s : (N - 1 - s);
+        // With one row per thread a warp has nothing left to do once all its rows are complete (forward: rows < s,
+        // backward: rows > p): it leaves the loop and the per-step barrier shrinks with it.
+        int bar_count = nt;
+        if (R == 1) {
+            if (FWD) {
+                if (32 * warp + 31 < s) break;
+                bar_count = nt - 32 * (s >> 5);
+            } else {
+                if (32 * warp > row) break;
+                bar_count = 32 * ((row >> 5) + 1);
+            }
+        }
+        double cm[R];
+        int ce[R];
+        if (ST > 0) {
+            cp_async_wait<(ST > 1 ? ST - 2 : 0)>();    // this thread's copies for step s have landed
+            const int slot = s & (ST > 0 ? ST - 1 : 0);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const int v = tid + r * nt;
-                if (v >= j && v < N) acc[r].add(-beta * (cycle_energy<D>(a, j, v) + vj));
+                cm[r] = stm[(slot * R + r) * nt + tid];
+                ce[r] = ste[(slot * R + r) * nt + tid];
             }
-            // row v == j is now complete
-            const int owner = j % nt, rr = j / nt;
-            if (tid == owner) {
-                double mx = 0.0, s = 1.0;
-#pragma unroll
-                for (int r = 0; r < R; ++r) if (r == rr) { mx = acc[r].mx; s = acc[r].s; }
-                double val = -(mx + log(s / (double)(j + 1))) / beta;
-                if (!isfinite(val)) atomicOr(a.err, kErrOverflowFwd);
-                sv[j + 1] = val;
-                a.V[j + 1] = val;
-            }
-            __syncthreads();
-        }
-        if (tid == 0) a.V[0] = 0.0;
-    } else {
-        // thread owns rows l = tid + r*nt, l in [1, N-1]; column q = p+1 from N down to 2
-        if (tid == 0) sv[N] = 0.0;
-        __syncthreads();
-        for (int q = N; q >= 2; --q) {
-            const int p = q - 1;
-            const double vq = sv[q];
-            const double lq = log((double)q);
+        } else {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const int l = tid + r * nt;
-                if (l >= 1 && l <= p) acc[r].add(-beta * (cycle_energy<D>(a, l, p) + vq) - lq);
+                const bool nd = need(tid + r * nt, row);
+                cm[r] = nd ? __ldg(lm + r * nt) : 0.0;
+                ce[r] = nd ? __ldg(le + r * nt) : 0;
             }
-            const int owner = p % nt, rr = p / nt;   // row l == p complete
-            if (tid == owner) {
-                double mx = 0.0, s = 1.0;
-#pragma unroll
-                for (int r = 0; r < R; ++r) if (r == rr) { mx = acc[r].mx; s = acc[r].s; }
-                double val = -(mx + log(s)) / beta;
-                if (!isfinite(val)) atomicOr(a.err, kErrOverflowBwd);
-                sv[p] = val;
-                a.Vb[p] = val;
-            }
-            __syncthreads();
+            lm += dstep;
+            le += dstep;
         }
-        if (tid == 0) a.Vb[N] = 0.0;
+        const int src = FWD ? s : (N - s);         // index of the known value: W[j] or Wb[p+1]
+        double wm = sWm[src];
+        const int we = sWe[src];
+        if (!FWD) wm *= sInv[row + 1];             // the 1/(p+1) weight of the backward sum
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+            if (need(tid + r * nt, row)) ext_fma(am[r], ae[r], cm[r], ce[r], wm, we);
+        // the row that just became complete: forward row v == j (-> W[j+1]); backward row l == p (-> Wb[p])
+        if (tid == own_t && (FWD || row >= 1)) {
+            double fm = am[0];
+            int fe = ae[0];
+#pragma unroll
+            for (int r = 1; r < R; ++r) if (r == own_r) { fm = am[r]; fe = ae[r]; }
+            if (FWD) fm *= sInv[row + 1];
+            const Ext w = ext_normalize(fm, fe);
+            sWm[FWD ? row + 1 : row] = w.m;
+            sWe[FWD ? row + 1 : row] = w.e;
+        }
+        if (FWD) { if (++own_t == nt) { own_t = 0; ++own_r; } }
+        else { if (--own_t < 0) { own_t = nt - 1; --own_r; } }
+        if (ST > 1) issue();
+        asm volatile("bar.sync 1, %0;" ::"r"(bar_count) : "memory");
+        if (ST == 1) issue();
+    }
+    if (ST > 0) cp_async_wait<0>();
+    __syncthreads();
+
+    // V = -(ln W)/beta in parallel; publish W for the force kernel
+    const double LN2 = 0.6931471805599453;
+    double* Wm_g = FWD ? a.Wm : a.Wbm;
+    int* We_g = FWD ? a.We : a.Wbe;
+    double* V_g = FWD ? a.V : a.Vb;
+    for (int i = (FWD ? 0 : 1) + tid; i <= N; i += nt) {
+        const double m = sWm[i];
+        const int e = sWe[i];
+        Wm_g[i] = m;
+        We_g[i] = e;
+        const double val = -(log(m) + (double)e * LN2) / a.beta;
+        if (!isfinite(val)) atomicOr(a.err, FWD ? kErrOverflowFwd : kErrOverflowBwd);
+        V_g[i] = (i == (FWD ? 0 : N)) ? 0.0 : val;
     }
 }
 
-// ---------------------------------------------------------------- exterior spring forces (K7 + K8)
+template <int R, int ST>
+__global__ void __launch_bounds__(1024) k_exch_recur(ExArgs a) {
+    extern __shared__ double smem_d[];
+    if (blockIdx.x == 0) recur_body<true, R, ST>(a, smem_d);
+    else recur_body<false, R, ST>(a, smem_d);
+}
+
+// ---------------------------------------------------------------- 4. exterior spring forces (K7 + K8)
 // one warp per (exterior bead, particle l)
 template <int D>
 __global__ void __launch_bounds__(256) k_exch_forces(ExArgs a) {
@@ -181,18 +350,24 @@ __global__ void __launch_bounds__(256) k_exch_forces(ExArgs a) {
     if (w >= 2 * N) return;
     const int which = w / N, l = w % N;   // 0: first bead, 1: last bead
     if ((which == 0 && !a.do_first) || (which == 1 && !a.do_last)) return;
-    const double beta = a.beta, VN = a.V[N];
+    const double iWN = 1.0 / a.Wm[N];
+    const int eWN = a.We[N];
     double acc[D];
 #pragma unroll
     for (int c = 0; c < D; ++c) acc[c] = 0.0;
 
     if (which == 0) {
         // f_l = k [ sum_{u=max(0,l-1)}^{N-1} P(u->l) mi(r^P_u - r^1_l) + mi(r^2_l - r^1_l) ]
-        const double Vl = a.V[l];
+        const double wl = a.Wm[l] * iWN;
+        const int el = a.We[l] - eWN;
         for (int u = max(0, l - 1) + lane; u < N; u += 32) {
             double pr;
-            if (u == l - 1) pr = 1.0 - exp(-beta * (Vl + a.Vb[l] - VN));
-            else pr = exp(-beta * (Vl + cycle_energy<D>(a, l, u) + a.Vb[u + 1] - VN)) / (double)(u + 1);
+            if (u == l - 1) {
+                pr = 1.0 - ext_to_double(wl * a.Wbm[l], el + a.Wbe[l]);
+            } else {
+                const size_t ci = (size_t)l * N + u;
+                pr = ext_to_double(wl * a.Cfm[ci] * a.Wbm[u + 1] * (1.0 / (double)(u + 1)), el + a.Cfe[ci] + a.Wbe[u + 1]);
+            }
 #pragma unroll
             for (int c = 0; c < D; ++c) {
                 double dx = a.xP[(size_t)c * N + u] - a.x1[(size_t)c * N + l];
@@ -212,12 +387,18 @@ __global__ void __launch_bounds__(256) k_exch_forces(ExArgs a) {
         }
     } else {
         // f_l = k [ sum_{u=0}^{min(l+1,N-1)} P(l->u) mi(r^1_u - r^P_l) + mi(r^{P-1}_l - r^P_l) ]
-        const double Vbl1 = a.Vb[l + 1];
+        const double wb = a.Wbm[l + 1] * iWN;
+        const int eb = a.Wbe[l + 1] - eWN;
+        const double il1 = 1.0 / (double)(l + 1);
         const int uend = min(l + 1, N - 1);
         for (int u = lane; u <= uend; u += 32) {
             double pr;
-            if (u == l + 1) pr = 1.0 - exp(-beta * (a.V[l + 1] + Vbl1 - VN));
-            else pr = exp(-beta * (a.V[u] + cycle_energy<D>(a, u, l) + Vbl1 - VN)) / (double)(l + 1);
+            if (u == l + 1) {
+                pr = 1.0 - ext_to_double(wb * a.Wm[l + 1], eb + a.We[l + 1]);
+            } else {
+                const size_t ci = (size_t)l * N + u;
+                pr = ext_to_double(wb * a.Cbm[ci] * a.Wm[u] * il1, eb + a.Cbe[ci] + a.We[u]);
+            }
 #pragma unroll
             for (int c = 0; c < D; ++c) {
                 double dx = a.x1[(size_t)c * N + u] - a.xP[(size_t)c * N + l];
@@ -236,36 +417,38 @@ __global__ void __launch_bounds__(256) k_exch_forces(ExArgs a) {
             }
         }
     }
-    if (w == 0 && lane == 0) a.Vb[0] = VN;   // V_backwards[0] = V[N] (quadratic_bosonic_exchange.cpp:127)
+    if (w == 0 && lane == 0) a.Vb[0] = a.V[N];   // V_backwards[0] = V[N] (quadratic_bosonic_exchange.cpp:127)
 }
 
 // ---------------------------------------------------------------- estimators (bead-0 owner only), one block
-// e[m] = sum_{j<m} w(m,j) (e[j] - E^{[j..m-1]}),  w(m,j) = exp(-beta (E^{[j..m-1]} + V[j] - V[m])) / m
-// Column-wise like the recursions; the dependency chain per step is one FMA (no exp/log on it).
+// e[m] = sum_{j<m} w(m,j) (e[j] - E^{[j..m-1]}),  w(m,j) = c(j,m-1) W[j] / (m W[m])   (primEstimator :250-279)
+// Column-wise; the weights are extended-range products (no exp), the chain per step is one FMA + one barrier.
 template <int D, int R>
 __global__ void __launch_bounds__(1024) k_exch_estimators(ExArgs a) {
     extern __shared__ double se[];   // e[0..N]
     __shared__ double red[32];
     const int tid = threadIdx.x, nt = blockDim.x, N = a.N;
-    const double beta = a.beta;
-    double acc[R], vm[R];
+    double acc[R], iwm[R];
+    int iwe[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         acc[r] = 0.0;
         const int v = tid + r * nt;
-        vm[r] = v < N ? a.V[v + 1] : 0.0;
+        iwm[r] = v < N ? 1.0 / (a.Wm[v + 1] * (double)(v + 1)) : 0.0;
+        iwe[r] = v < N ? -a.We[v + 1] : 0;
     }
     if (tid == 0) se[0] = 0.0;
     __syncthreads();
     for (int j = 0; j < N; ++j) {
-        const double ej = se[j], vj = a.V[j];
+        const double ej = se[j], wjm = a.Wm[j];
+        const int wje = a.We[j];
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             const int v = tid + r * nt;
             if (v >= j && v < N) {
-                double e = cycle_energy<D>(a, j, v);
-                double wgt = exp(-beta * (e + vj - vm[r])) / (double)(v + 1);
-                acc[r] = fma(wgt, ej - e, acc[r]);
+                const size_t ci = (size_t)j * N + v;
+                const double wgt = ext_to_double(a.Cfm[ci] * wjm * iwm[r], a.Cfe[ci] + wje + iwe[r]);
+                acc[r] = fma(wgt, ej - cycle_energy<D>(a, j, v), acc[r]);
             }
         }
         const int owner = j % nt, rr = j / nt;
@@ -304,16 +487,18 @@ __global__ void k_exch_table_E(ExArgs a, double* out) {
     }
 }
 
-template <int D>
 __global__ void k_exch_table_prob(ExArgs a, double* out) {
     const int N = a.N;
     const long long tot = (long long)N * N;
-    const double beta = a.beta, VN = a.V[N];
+    const double iWN = 1.0 / a.Wm[N];
+    const int eWN = a.We[N];
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (long long)gridDim.x * blockDim.x) {
         const int l = (int)(i / N), u = (int)(i % N);
         double pr = 0.0;
-        if (u == l + 1) pr = 1.0 - exp(-beta * (a.V[l + 1] + a.Vb[l + 1] - VN));
-        else if (u <= l) pr = exp(-beta * (a.V[u] + cycle_energy<D>(a, u, l) + a.Vb[l + 1] - VN)) / (double)(l + 1);
+        if (u == l + 1) pr = 1.0 - ext_to_double(a.Wm[l + 1] * a.Wbm[l + 1] * iWN, a.We[l + 1] + a.Wbe[l + 1] - eWN);
+        else if (u <= l)
+            pr = ext_to_double(a.Wm[u] * a.Cbm[i] * a.Wbm[l + 1] * iWN / (double)(l + 1),
+                               a.We[u] + a.Cbe[i] + a.Wbe[l + 1] - eWN);
         out[i] = pr;
     }
 }
@@ -332,17 +517,19 @@ static ExArgs make_args(Sim* s) {
         a.xP = s->x + (size_t)s->Ploc * S;
         a.x2 = nullptr;
     }
-    if (s->has_last) {
-        if (!s->has_first) a.xP = s->x + (size_t)s->Ploc * S;
-        a.xPm1 = s->x + (size_t)(s->Ploc - 1) * S;                     // previous of last (owned or leading halo)
-    } else {
-        a.xPm1 = nullptr;
-    }
-    a.A = s->exA; a.V = s->exV; a.Vb = s->exVb; a.F = s->exF; a.prim = s->exPrim;
+    a.xPm1 = s->has_last ? s->x + (size_t)(s->Ploc - 1) * S : nullptr; // previous of last (owned or leading halo)
+    const size_t NN = (size_t)s->N * s->N;
+    a.A = s->exA;
+    a.Cfm = s->exCm; a.Cbm = s->exCm + NN;
+    a.Cfe = s->exCe; a.Cbe = s->exCe + NN;
+    a.Wm = s->exWm; a.Wbm = s->exWm + (s->N + 1);
+    a.We = s->exWe; a.Wbe = s->exWe + (s->N + 1);
+    a.V = s->exV; a.Vb = s->exVb; a.F = s->exF;
     a.obs = s->obs_d; a.err = s->err_d;
     a.N = s->N; a.D = s->D; a.pbc = s->cfg.pbc;
     a.do_first = s->has_first; a.do_last = s->has_last;
-    a.k = s->kspring; a.beta = s->exch_beta; a.L = s->L; a.invL = 1.0 / s->L;
+    a.k = s->kspring; a.beta = s->exch_beta; a.h = 0.5 * s->exch_beta * s->kspring;
+    a.L = s->L; a.invL = 1.0 / s->L;
     return a;
 }
 
@@ -355,43 +542,65 @@ static int rows_per_thread(int N, int& nt) {
     return R;
 }
 
-template <int D>
-static int run_recursion(Sim* s, const ExArgs& a, cudaStream_t st) {
-    int nt;
-    const int R = rows_per_thread(s->N, nt);
-    const size_t smem = (size_t)(s->N + 1) * sizeof(double);
-#define PIMDB_REC(RR)                                                                                          \
-    case RR:                                                                                                   \
-        if (smem > 48 * 1024)                                                                                  \
-            cudaFuncSetAttribute(k_exch_recursion<D, RR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        k_exch_recursion<D, RR><<<2, nt, smem, st>>>(a);                                                       \
-        break;
-    switch (R) {
-        PIMDB_REC(1) PIMDB_REC(2) PIMDB_REC(4) PIMDB_REC(8) PIMDB_REC(16) PIMDB_REC(32)
-        default:
-            s->err = "natoms too large for the single-block exchange recursion (max 32768)";
-            return PIMDB_ERR_INVALID_ARGUMENT;
+template <int R, int ST>
+static int launch_recur(Sim* s, const ExArgs& a, cudaStream_t st, int nt) {
+    const size_t smem = ((size_t)(s->N + 2) + (size_t)ST * R * nt) * (sizeof(double) + sizeof(int)) + (size_t)(s->N + 2) * sizeof(double);
+    if (smem > 220 * 1024) {
+        s->err = "natoms too large for the single-block exchange recursion of this build";
+        return PIMDB_ERR_INVALID_ARGUMENT;
     }
-#undef PIMDB_REC
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(k_exch_recur<R, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    k_exch_recur<R, ST><<<2, nt, smem, st>>>(a);
     return PIMDB_OK;
 }
 
+static int run_recursion(Sim* s, const ExArgs& a, cudaStream_t st) {
+    int nt;
+    const int R = rows_per_thread(s->N, nt);
+    switch (R) {
+        case 1: return launch_recur<1, 8>(s, a, st, nt);    // N <= 1024
+        case 2: return launch_recur<2, 4>(s, a, st, nt);    // N <= 2048
+        case 4: return launch_recur<4, 0>(s, a, st, nt);    // N <= 4096: direct global loads
+        case 8: return launch_recur<8, 0>(s, a, st, nt);    // N <= 8192
+        case 16: return launch_recur<16, 0>(s, a, st, nt);  // N <= 16384
+        default:
+            s->err = "natoms too large for the single-block exchange recursion (max 16384)";
+            return PIMDB_ERR_INVALID_ARGUMENT;
+    }
+}
+
+// part 0: prefix sums + Boltzmann factors (fully parallel, a few microseconds);
+// part 1: the two recurrences (2 thread blocks, latency-bound) + the exterior forces.
+// They are separate so the caller can start part 1 on a side stream *before* it floods the GPU with pair tiles.
 template <int D>
-static int exchange_impl(Sim* s, cudaStream_t st) {
+static int exchange_impl(Sim* s, cudaStream_t st, int part) {
     ExArgs a = make_args(s);
-    int rc = run_recursion<D>(s, a, st);
-    if (rc != PIMDB_OK) return rc;
-    const int grid = (2 * s->N * 32 + 255) / 256;
-    k_exch_forces<D><<<grid, 256, 0, st>>>(a);
-    s->launches += 2;
+    if (part == 0) {
+        k_exch_prefix<D><<<1, 1024, 0, st>>>(a);
+        k_exch_coeff<D><<<grid_for((size_t)s->N * s->N, 256, 16 * kNumSM), 256, 0, st>>>(a);
+        s->launches += 2;
+    } else {
+        int rc = run_recursion(s, a, st);
+        if (rc != PIMDB_OK) return rc;
+        const int grid = (2 * s->N * 32 + 255) / 256;
+        k_exch_forces<D><<<grid, 256, 0, st>>>(a);
+        s->launches += 2;
+    }
     PIMDB_CUDA_TRY(s, cudaGetLastError());
     return PIMDB_OK;
 }
 
+int launch_exchange_part(Sim* s, cudaStream_t st, int part) {
+    if (s->D == 1) return exchange_impl<1>(s, st, part);
+    if (s->D == 2) return exchange_impl<2>(s, st, part);
+    return exchange_impl<3>(s, st, part);
+}
+
 int launch_exchange(Sim* s, cudaStream_t st) {
-    if (s->D == 1) return exchange_impl<1>(s, st);
-    if (s->D == 2) return exchange_impl<2>(s, st);
-    return exchange_impl<3>(s, st);
+    int rc = launch_exchange_part(s, st, 0);
+    if (rc != PIMDB_OK) return rc;
+    return launch_exchange_part(s, st, 1);
 }
 
 template <int D>
@@ -407,9 +616,9 @@ static int estimators_impl(Sim* s) {
         k_exch_estimators<D, RR><<<1, nt, smem, s->stream>>>(a);                                                \
         break;
     switch (R) {
-        PIMDB_EST(1) PIMDB_EST(2) PIMDB_EST(4) PIMDB_EST(8) PIMDB_EST(16) PIMDB_EST(32)
+        PIMDB_EST(1) PIMDB_EST(2) PIMDB_EST(4) PIMDB_EST(8) PIMDB_EST(16)
         default:
-            s->err = "natoms too large for the exchange estimator kernel (max 32768)";
+            s->err = "natoms too large for the exchange estimator kernel (max 16384)";
             return PIMDB_ERR_INVALID_ARGUMENT;
     }
 #undef PIMDB_EST
@@ -429,7 +638,7 @@ static int tables_impl(Sim* s, int table) {
     ExArgs a = make_args(s);
     const size_t n = table == PIMDB_EXCH_E ? (size_t)s->N * (s->N + 1) / 2 : (size_t)s->N * s->N;
     if (table == PIMDB_EXCH_E) k_exch_table_E<D><<<grid_for(n, 256), 256, 0, s->stream>>>(a, s->exTab);
-    else k_exch_table_prob<D><<<grid_for(n, 256), 256, 0, s->stream>>>(a, s->exTab);
+    else k_exch_table_prob<<<grid_for(n, 256), 256, 0, s->stream>>>(a, s->exTab);
     s->launches += 1;
     PIMDB_CUDA_TRY(s, cudaGetLastError());
     return PIMDB_OK;
