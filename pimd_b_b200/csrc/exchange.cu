@@ -169,7 +169,7 @@ __global__ void __launch_bounds__(256) k_exch_coeff(ExArgs a) {
         const int r = (int)(i / N), s = (int)(i % N);
         const int u = min(r, s), v = max(r, s);
         const double y = a.h * (a.A[v] - a.A[u] + dist2<D>(a, a.x1, u, a.xP, v));
-        const Ext c = ext_exp_neg(fmax(y, 0.0));
+        const Ext c = ext_exp_neg(y < 0.0 ? 0.0 : y);   // (a NaN position stays NaN and is reported, like the reference)
         if (s >= r) { a.Cfm[i] = c.m; a.Cfe[i] = c.e; }
         if (s <= r) { a.Cbm[i] = c.m; a.Cbe[i] = c.e; }
     }

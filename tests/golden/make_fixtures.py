@@ -1,0 +1,127 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures under tests/golden/ (run in the build container, where /root/reference and
+oracle/_ref exist; the fixtures are committed, this script documents how they were made).
+
+    python tests/golden/make_fixtures.py
+
+1. refcases.npz   -- frames of the reference's OWN golden regression cases (/root/reference/tests/cases/<case>):
+                     positions (angstrom), velocities (angstrom/ps), forces (eV/angstrom) of frames 1, 50 and the
+                     last one for every bead, the first rows of simulation.out, and the case's INI text. A frame's
+                     positions and forces are a stand-alone force known-answer test.
+2. refprobe.npz   -- raw-double outputs of the UNMODIFIED reference (oracle/_ref/ref_probe_ndim*, built by
+                     oracle/Makefile) for the paths no reference test covers: Aziz / dipole / harmonic-pair forces,
+                     minimum image, cutoff, NDIM = 2, fixcom, exchange tables, observables, and short Langevin /
+                     NVE / normal-mode trajectories (these pin the RANMAR stream and the loop order bit for bit).
+"""
+from __future__ import annotations
+
+import sys
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[2]
+sys.path.insert(0, str(ROOT))
+
+from pimd_b_b200 import io as pio  # noqa: E402
+from pimd_b_b200.config import SimConfig  # noqa: E402
+from tests.helpers import (ANGSTROM, DALTON, FEMTOSECOND, KELVIN, MEV, lattice_positions, maxwell_momenta,  # noqa: E402
+                           run_ref_probe)
+
+REF_CASES = Path("/root/reference/tests/cases")
+OUT = Path(__file__).resolve().parent
+
+CASES = ["bosonic_quadratic_harmonic_dynamics", "dist_harmonic_dynamics",
+         "bosonic_quadratic_harmonic_nmthermostat_dynamics", "dist_harmonic_nm_propagation_dynamics",
+         "bosonic_quadratic_harmonic", "dist_harmonic"]
+
+
+def make_refcases():
+    out = {}
+    for case in CASES:
+        d = REF_CASES / case
+        ini = next(d.glob("*.ini")).read_text()
+        out[f"{case}/ini"] = np.array(ini)
+        so = pio.read_simulation_out(str(d / "simulation.out"))
+        out[f"{case}/simout_columns"] = np.array(list(so.keys()))
+        out[f"{case}/simout_head"] = np.stack([v[:6] for v in so.values()], axis=1)
+        if not (d / "position_0.xyz").exists():
+            continue
+        nb = len(list(d.glob("position_*.xyz")))
+        xs, vs, fs = [], [], []
+        for b in range(nb):
+            xf = pio.read_dump_frames(str(d / f"position_{b}.xyz"), 3)
+            vf = pio.read_dump_frames(str(d / f"velocity_{b}.dat"), 3)
+            ff = pio.read_dump_frames(str(d / f"force_{b}.dat"), 3)
+            sel = [1, min(50, len(xf) - 2), len(xf) - 1]
+            xs.append([xf[i] for i in sel])
+            vs.append([vf[i] for i in sel])
+            fs.append([ff[i] for i in sel])
+        # -> [frame][bead][atom][3]
+        out[f"{case}/x"] = np.transpose(np.asarray(xs), (1, 0, 2, 3))
+        out[f"{case}/v"] = np.transpose(np.asarray(vs), (1, 0, 2, 3))
+        out[f"{case}/f"] = np.transpose(np.asarray(fs), (1, 0, 2, 3))
+    np.savez_compressed(OUT / "refcases.npz", **out)
+    print("wrote refcases.npz", sum(v.nbytes for v in out.values()) // 1024, "KiB raw")
+
+
+def probe_configs():
+    """name -> (SimConfig, x, p) for the reference paths that have no golden case."""
+    rng = np.random.default_rng(20261017)
+    items = {}
+    N, P = 27, 6
+    L = (N / 0.02186) ** (1 / 3) * ANGSTROM
+    he = dict(nbeads=P, natoms=N, ndim=3, bosonic=True, fixcom=True, pbc=True, temperature=2 * KELVIN,
+              mass=4.0026 * DALTON, size=L, interaction="aziz", cutoff=-1 * ANGSTROM, external="free",
+              thermostat="langevin", seed=12345, dt=FEMTOSECOND, obs_classical="kelvin", obs_bosonic="true")
+    c = SimConfig(**he)
+    x, p = lattice_positions(c, rng, 0.15 * ANGSTROM), maxwell_momenta(c, rng)
+    items["aziz_pbc_bosonic"] = (c, x, p)
+    items["aziz_pbc_bosonic_cutoff"] = (SimConfig(**{**he, "cutoff": 5 * ANGSTROM}), x, p)
+    items["aziz_pbc_dist_nve"] = (SimConfig(**{**he, "bosonic": False, "thermostat": "none"}), x, p)
+    c = SimConfig(**{**he, "natoms": 8, "nbeads": 4, "size": (8 / 0.02186) ** (1 / 3) * ANGSTROM})
+    items["aziz_pbc_exact_lattice"] = (c, lattice_positions(c, rng, 0.0), maxwell_momenta(c, rng))
+    c = SimConfig(nbeads=8, natoms=12, ndim=2, bosonic=False, fixcom=False, pbc=False, temperature=5 * KELVIN,
+                  mass=1.0, size=200.0, interaction="dipole", int_strength=1.0, external="harmonic",
+                  ext_omega=3 * MEV, thermostat="langevin", propagator="normal_modes", nmthermostat=True,
+                  seed=777, dt=FEMTOSECOND, obs_classical="kelvin")
+    items["dipole_2d_nm"] = (c, rng.uniform(-100, 100, size=(8, 12, 2)), maxwell_momenta(c, rng))
+    c = SimConfig(nbeads=4, natoms=10, ndim=3, bosonic=True, fixcom=True, pbc=False, temperature=5.802 * KELVIN,
+                  mass=1.0, size=300.0, interaction="harmonic", int_omega=1 * MEV, external="harmonic",
+                  ext_omega=3 * MEV, thermostat="langevin", nmthermostat=True, seed=5, dt=FEMTOSECOND,
+                  obs_classical="kelvin", obs_bosonic="true")
+    items["harmonic_pair_bosonic_nmthermo"] = (c, rng.uniform(-30, 30, size=(4, 10, 3)), maxwell_momenta(c, rng))
+    c = SimConfig(nbeads=5, natoms=7, ndim=1, bosonic=True, fixcom=False, pbc=True, temperature=3 * KELVIN,
+                  mass=2.0, size=50.0, interaction="harmonic", int_omega=2 * MEV, cutoff=20.0, external="free",
+                  thermostat="none", seed=9, dt=FEMTOSECOND, obs_classical="kelvin", obs_bosonic="true")
+    items["harmonic_pair_1d_pbc_cutoff"] = (c, rng.uniform(-25, 25, size=(5, 7, 1)), maxwell_momenta(c, rng))
+    return items
+
+
+def make_refprobe():
+    out = {}
+    for name, (cfg, x, p) in probe_configs().items():
+        out[f"{name}/cfg"] = np.array(repr(cfg.as_dict()))
+        out[f"{name}/x"] = x
+        out[f"{name}/p"] = p
+        r = run_ref_probe(cfg, x, p, "forces")
+        for k in ("f", "f_spring", "f_phys"):
+            out[f"{name}/{k}"] = r[k]
+        out[f"{name}/obs_names"] = np.array(list(r["obs"].keys()))
+        out[f"{name}/obs_values"] = np.array(list(r["obs"].values()))
+        if cfg.bosonic:
+            for k in ("exch_V", "exch_Vb", "exch_E", "exch_prob"):
+                out[f"{name}/{k}"] = r[k]
+            out[f"{name}/exch_scalar_names"] = np.array(list(r["exch_scalars"].keys()))
+            out[f"{name}/exch_scalar_values"] = np.array(list(r["exch_scalars"].values()))
+        K = 12
+        t = run_ref_probe(cfg, x, p, "traj", k=K, every=K)
+        for k in ("x", "p", "f"):
+            out[f"{name}/traj{K}_{k}"] = t[f"{k}_{K}"]
+    np.savez_compressed(OUT / "refprobe.npz", **out)
+    print("wrote refprobe.npz", sum(v.nbytes for v in out.values()) // 1024, "KiB raw")
+
+
+if __name__ == "__main__":
+    make_refcases()
+    make_refprobe()
