@@ -257,7 +257,7 @@ extern "C" int pimdb_create(const pimdb_config* cfg, pimdb_sim** out) {
     }
     if (s->bosonic) {
         const size_t NN = (size_t)s->N * s->N;
-        CREATE_TRY(cudaMalloc(&s->exA, sizeof(double) * s->N));
+        CREATE_TRY(cudaMalloc(&s->exA, sizeof(double) * (2 * s->N + 2)));   // A[N] | Inv[N+1]
         CREATE_TRY(cudaMalloc(&s->exCm, sizeof(double) * 2 * NN));
         CREATE_TRY(cudaMalloc(&s->exCe, sizeof(int) * 2 * NN));
         CREATE_TRY(cudaMalloc(&s->exWm, sizeof(double) * 2 * (s->N + 1)));

@@ -91,6 +91,7 @@ struct ExArgs {
     const double *x1, *xP;     // bead 1 and bead P slices, [D][N]
     const double *x2, *xPm1;   // bead 2 (next of first) and bead P-1 (previous of last)
     double* A;                 // A[N] prefix sums
+    double* Inv;               // Inv[i] = 1/i, i = 0..N (Inv[0] = 0): no FP64 division in the O(N^2) loops
     double *Cfm, *Cbm;         // coefficient mantissas: Cf[j][v] = c(j,v) (v>=j), Cb[p][l] = c(l,p) (l<=p); N x N each
     int *Cfe, *Cbe;            // ... and binary exponents
     double *Wm, *Wbm;          // W[0..N], Wb[0..N] mantissas
@@ -157,6 +158,7 @@ __global__ void __launch_bounds__(1024) k_exch_prefix(ExArgs a) {
         __syncthreads();
     }
     if (tid == 0) a.A[0] = 0.0;
+    for (int i = tid; i <= a.N; i += blockDim.x) a.Inv[i] = i > 0 ? 1.0 / (double)i : 0.0;
 }
 
 // ---------------------------------------------------------------- 2. Boltzmann factors, fully parallel
@@ -340,6 +342,166 @@ __global__ void __launch_bounds__(1024) k_exch_recur(ExArgs a) {
     else recur_body<false, R, ST>(a, smem_d);
 }
 
+// ---------------------------------------------------------------- 3b. warp-decoupled recurrence (N <= 1024)
+// Same arithmetic as recur_body<., 1, .>, different synchronisation. The barrier version forces all warps through
+// every step in lock-step, so a step costs the serial latency of a whole warp's instruction stream (~480 cycles
+// measured). Here only ONE warp is on the dependency chain at any time:
+//   * "value #s" in step order is W[s] (forward) or Wb[N-s] (backward); step s turns it into value #s+1, owned by
+//     the thread of row r(s) = s (forward) / N-1-s (backward). 32 consecutive steps are owned by one warp.
+//   * inside its 32 owner steps a warp hands the new value from lane to lane with shuffles (no shared-memory round
+//     trip, no barrier: ~100 cycles per step, DFMA latency 8.3 and shuffle ~25 cycles measured, profiles/microbench.cu);
+//   * every value is also published to shared memory as ONE 16-byte entry {mantissa, exponent, tag = s+1}; data and
+//     flag travel in the same 128-bit store, so no fence sits on the chain. Every other warp consumes published
+//     values at its own pace -- four columns per poll, so it is faster than the owner and never holds it up -- and
+//     takes over as owner when its rows come up (one ~160-cycle shared-memory hand-off per 32 steps).
+//   Dependencies are acyclic (a warp only ever waits for values owned by earlier warps), so there is no deadlock.
+// smem: entries int4[N+2] | sInv[N+2] | ring mantissas [ST][nt] | ring exponents [ST][nt]
+__device__ __forceinline__ int4 lds_volatile_v4(const int4* p) {
+    int4 r;
+    unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("ld.volatile.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
+    return r;
+}
+__device__ __forceinline__ void sts_volatile_v4(int4* p, int4 v) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("st.volatile.shared.v4.s32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
+template <bool FWD, int ST>
+__device__ __forceinline__ void recur_decoupled(const ExArgs& a, double* smem_d) {
+    static_assert(ST >= 8 && (ST & (ST - 1)) == 0, "ring depth must be a power of two >= 8");
+    constexpr int NB = 4;                            // columns a consumer applies per poll
+    const int tid = threadIdx.x, nt = blockDim.x, N = a.N, lane = tid & 31, warp = tid >> 5;
+    int4* sW = (int4*)smem_d;                        // {m.lo, m.hi, e, tag}
+    double* sInv = (double*)(sW + (N + 2));
+    double* stm = sInv + (N + 2);
+    int* ste = (int*)(stm + (size_t)ST * nt);
+    const int nsteps = FWD ? N : N - 1;
+    const int dstep = FWD ? N : -N;
+    const int v = tid;                                              // my row
+    const bool row_ok = FWD ? (v < N) : (v >= 1 && v < N);
+    // steps in which my warp owns the completing row
+    const int own_lo = FWD ? 32 * warp : max(0, N - 1 - (32 * warp + 31));
+    const int own_hi = min(nsteps - 1, FWD ? 32 * warp + 31 : N - 1 - 32 * warp);
+
+    auto need = [&](int s) {   // does my row take part in step s ?
+        const int r = FWD ? s : (N - 1 - s);
+        return row_ok && (FWD ? (v >= r) : (v <= r));
+    };
+    auto idx_of = [&](int s) { return FWD ? s : N - s; };           // where value #s lives
+    const double* gm = (FWD ? a.Cfm : a.Cbm) + (FWD ? 0 : (long long)(N - 1) * N) + tid;
+    const int* ge = (FWD ? a.Cfe : a.Cbe) + (FWD ? 0 : (long long)(N - 1) * N) + tid;
+    int s_issue = 0;
+    auto issue = [&]() {
+        if (s_issue < nsteps && need(s_issue)) {
+            const int slot = s_issue & (ST - 1);
+            cp_async8(&stm[slot * nt + tid], gm);
+            cp_async4(&ste[slot * nt + tid], ge);
+        }
+        cp_async_commit();
+        ++s_issue;
+        gm += dstep;
+        ge += dstep;
+    };
+    auto wait_value = [&](int s) {                                  // spin until value #s is published
+        int4 w;
+        do { w = lds_volatile_v4(&sW[idx_of(s)]); } while (w.w != s + 1);
+        return w;
+    };
+
+    for (int i = tid; i <= N + 1; i += nt) sW[i] = make_int4(0, 0, 0, 0);
+    for (int i = tid; i <= N; i += nt) sInv[i] = i > 0 ? 1.0 / (double)i : 0.0;
+#pragma unroll
+    for (int s = 0; s < ST - 1; ++s) issue();
+    __syncthreads();
+    if (tid == 0) sts_volatile_v4(&sW[idx_of(0)], make_int4(__double2loint(1.0), __double2hiint(1.0), 0, 1));
+
+    double am = 0.0;
+    int ae = kExtZeroExp;
+    int s = 0;
+    // ---- consumer phase: columns owned by earlier warps; every row of my warp takes part in all of them
+    while (s < own_lo) {
+        if (own_lo - s >= NB) {
+            wait_value(s + NB - 1);                                 // values are published in order
+            cp_async_wait<ST - 1 - NB>();
+            double cm[NB], wm[NB];
+            int ce[NB], we[NB];
+#pragma unroll
+            for (int k = 0; k < NB; ++k) {
+                const int4 w = sW[idx_of(s + k)];
+                wm[k] = __hiloint2double(w.y, w.x);
+                we[k] = w.z;
+                if (!FWD) wm[k] *= sInv[N - (s + k)];
+                const int slot = (s + k) & (ST - 1);
+                cm[k] = stm[slot * nt + tid];
+                ce[k] = ste[slot * nt + tid];
+            }
+            if (row_ok) {
+#pragma unroll
+                for (int k = 0; k < NB; ++k) ext_fma(am, ae, cm[k], ce[k], wm[k], we[k]);
+            }
+#pragma unroll
+            for (int k = 0; k < NB; ++k) issue();
+            s += NB;
+        } else {
+            const int4 w = wait_value(s);
+            cp_async_wait<ST - 1 - NB>();
+            double wm = __hiloint2double(w.y, w.x);
+            if (!FWD) wm *= sInv[N - s];
+            const int slot = s & (ST - 1);
+            if (row_ok) ext_fma(am, ae, stm[slot * nt + tid], ste[slot * nt + tid], wm, w.z);
+            issue();
+            ++s;
+        }
+    }
+    // ---- owner phase: the completing rows are my warp's; the chain runs lane to lane through shuffles
+    if (s <= own_hi) {
+        const int4 w0 = wait_value(s);
+        double wm = __hiloint2double(w0.y, w0.x);
+        int we = w0.z;
+        for (; s <= own_hi; ++s) {
+            cp_async_wait<ST - 1 - NB>();
+            const int slot = s & (ST - 1);
+            const double cm = stm[slot * nt + tid];
+            const int ce = ste[slot * nt + tid];
+            const double um = FWD ? wm : wm * sInv[N - s];          // backward: the 1/(p+1) weight, p+1 = N-s
+            if (need(s)) ext_fma(am, ae, cm, ce, um, we);
+            const int lane_o = (FWD ? s : (N - 1 - s)) & 31;
+            const Ext fin = ext_normalize(FWD ? am * sInv[s + 1] : am, ae);
+            wm = __shfl_sync(kFullMask, fin.m, lane_o);
+            we = __shfl_sync(kFullMask, fin.e, lane_o);
+            if (lane == lane_o)
+                sts_volatile_v4(&sW[idx_of(s + 1)], make_int4(__double2loint(fin.m), __double2hiint(fin.m), fin.e, s + 2));
+            issue();
+        }
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+
+    // V = -(ln W)/beta in parallel; publish W for the force kernel
+    const double LN2 = 0.6931471805599453;
+    double* Wm_g = FWD ? a.Wm : a.Wbm;
+    int* We_g = FWD ? a.We : a.Wbe;
+    double* V_g = FWD ? a.V : a.Vb;
+    for (int i = (FWD ? 0 : 1) + tid; i <= N; i += nt) {
+        const int4 w = sW[i];
+        const double m = __hiloint2double(w.y, w.x);
+        const int e = w.z;
+        Wm_g[i] = m;
+        We_g[i] = e;
+        const double val = -(log(m) + (double)e * LN2) / a.beta;
+        if (!isfinite(val)) atomicOr(a.err, FWD ? kErrOverflowFwd : kErrOverflowBwd);
+        V_g[i] = (i == (FWD ? 0 : N)) ? 0.0 : val;
+    }
+}
+
+template <int ST>
+__global__ void __launch_bounds__(1024) k_exch_recur_dec(ExArgs a) {
+    extern __shared__ double smem_d[];
+    if (blockIdx.x == 0) recur_decoupled<true, ST>(a, smem_d);
+    else recur_decoupled<false, ST>(a, smem_d);
+}
+
 // ---------------------------------------------------------------- 4. exterior spring forces (K7 + K8)
 // one warp per (exterior bead, particle l)
 template <int D>
@@ -366,7 +528,7 @@ __global__ void __launch_bounds__(256) k_exch_forces(ExArgs a) {
                 pr = 1.0 - ext_to_double(wl * a.Wbm[l], el + a.Wbe[l]);
             } else {
                 const size_t ci = (size_t)l * N + u;
-                pr = ext_to_double(wl * a.Cfm[ci] * a.Wbm[u + 1] * (1.0 / (double)(u + 1)), el + a.Cfe[ci] + a.Wbe[u + 1]);
+                pr = ext_to_double(wl * a.Cfm[ci] * a.Wbm[u + 1] * a.Inv[u + 1], el + a.Cfe[ci] + a.Wbe[u + 1]);
             }
 #pragma unroll
             for (int c = 0; c < D; ++c) {
@@ -389,7 +551,7 @@ __global__ void __launch_bounds__(256) k_exch_forces(ExArgs a) {
         // f_l = k [ sum_{u=0}^{min(l+1,N-1)} P(l->u) mi(r^1_u - r^P_l) + mi(r^{P-1}_l - r^P_l) ]
         const double wb = a.Wbm[l + 1] * iWN;
         const int eb = a.Wbe[l + 1] - eWN;
-        const double il1 = 1.0 / (double)(l + 1);
+        const double il1 = a.Inv[l + 1];
         const int uend = min(l + 1, N - 1);
         for (int u = lane; u <= uend; u += 32) {
             double pr;
@@ -434,7 +596,7 @@ __global__ void __launch_bounds__(1024) k_exch_estimators(ExArgs a) {
     for (int r = 0; r < R; ++r) {
         acc[r] = 0.0;
         const int v = tid + r * nt;
-        iwm[r] = v < N ? 1.0 / (a.Wm[v + 1] * (double)(v + 1)) : 0.0;
+        iwm[r] = v < N ? a.Inv[v + 1] / a.Wm[v + 1] : 0.0;
         iwe[r] = v < N ? -a.We[v + 1] : 0;
     }
     if (tid == 0) se[0] = 0.0;
@@ -520,6 +682,7 @@ static ExArgs make_args(Sim* s) {
     a.xPm1 = s->has_last ? s->x + (size_t)(s->Ploc - 1) * S : nullptr; // previous of last (owned or leading halo)
     const size_t NN = (size_t)s->N * s->N;
     a.A = s->exA;
+    a.Inv = s->exA + s->N;
     a.Cfm = s->exCm; a.Cbm = s->exCm + NN;
     a.Cfe = s->exCe; a.Cbe = s->exCe + NN;
     a.Wm = s->exWm; a.Wbm = s->exWm + (s->N + 1);
@@ -558,8 +721,17 @@ static int launch_recur(Sim* s, const ExArgs& a, cudaStream_t st, int nt) {
 static int run_recursion(Sim* s, const ExArgs& a, cudaStream_t st) {
     int nt;
     const int R = rows_per_thread(s->N, nt);
+    if (R == 1 && !getenv("PIMDB_EXCH_BARRIER")) {           // N <= 1024: warp-decoupled kernel
+        constexpr int ST = 16;
+        const size_t smem = (size_t)(s->N + 2) * (sizeof(int4) + sizeof(double)) +
+                            (size_t)ST * nt * (sizeof(double) + sizeof(int)) + 16;
+        if (smem > 48 * 1024)
+            cudaFuncSetAttribute(k_exch_recur_dec<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_exch_recur_dec<ST><<<2, nt, smem, st>>>(a);
+        return PIMDB_OK;
+    }
     switch (R) {
-        case 1: return launch_recur<1, 8>(s, a, st, nt);    // N <= 1024
+        case 1: return launch_recur<1, 8>(s, a, st, nt);    // N <= 1024 (barrier variant, PIMDB_EXCH_BARRIER=1)
         case 2: return launch_recur<2, 4>(s, a, st, nt);    // N <= 2048
         case 4: return launch_recur<4, 0>(s, a, st, nt);    // N <= 4096: direct global loads
         case 8: return launch_recur<8, 0>(s, a, st, nt);    // N <= 8192
