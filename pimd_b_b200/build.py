@@ -73,6 +73,26 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     return LIB
 
 
+HOST_DIR = PKG / "host"
+HOST_BIN = PKG / "pimdb_gpu"
+
+
+def build_host(force: bool = False) -> Path:
+    """pimdb_gpu: the C++20 host mirror of the reference's plugin surface + entry point, linked against the C ABI."""
+    srcs = [HOST_DIR / "pimdb_host.cpp", HOST_DIR / "pimdb_gpu.cpp"]
+    deps = srcs + [HOST_DIR / "pimdb_host.hpp", PKG.parent / "include" / "pimdb200.h", LIB]
+    if force or _stale(HOST_BIN, deps):
+        cxx = os.environ.get("CXX") or shutil.which("g++") or "g++"
+        cuda_lib = str(Path(nvcc_path()).resolve().parent.parent / "lib64")
+        cmd = [cxx, "-std=c++20", "-O2", "-o", str(HOST_BIN), *map(str, srcs), f"-L{PKG}", "-lpimdb200",
+               "-Wl,-rpath,$ORIGIN", f"-L{cuda_lib}", f"-Wl,-rpath,{cuda_lib}", "-lcudart"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("host build failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+    return HOST_BIN
+
+
 if __name__ == "__main__":
     p = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
     print(p)
+    print(build_host(force="--force" in sys.argv))

@@ -18,6 +18,61 @@ __device__ __forceinline__ double min_image(double dx, double L, double invL) {
     return dx - L * fl;
 }
 
+// Vector form for the hot pair loop: D multiplications + roundings and ONE rarely taken branch.
+// rint(dx/L) equals floor(dx/L + 0.5) except at exact ties (|dx| an odd multiple of L/2); ties -- and anything within
+// 1e-9 of one -- take the out-of-line exact path that evaluates the reference's expression literally.
+template <int D>
+__device__ __noinline__ void min_image_exact(double (&d)[D], double L) {
+#pragma unroll
+    for (int c = 0; c < D; ++c) d[c] -= L * floor(d[c] / L + 0.5);
+}
+template <int D>
+__device__ __forceinline__ void min_image_vec(double (&d)[D], double L, double invL) {
+    double n[D];
+    bool tie = false;
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        const double q = d[c] * invL;
+        n[c] = rint(q);
+        tie |= fabs(q - n[c]) > 0.5 - 1e-9;
+    }
+    if (tie) {
+        min_image_exact<D>(d, L);
+    } else {
+#pragma unroll
+        for (int c = 0; c < D; ++c) d[c] = fma(-L, n[c], d[c]);
+    }
+}
+
+// exp(t) for t <= 0 in the hot loops: no range branches, constants from the constant bank.
+// t is clamped at -700 (e^-700 ~ 1e-304 is far below anything it is added to); n = rint(t log2 e),
+// r = t - n ln2 (two FMAs, |r| <= 0.3466), degree-12 Taylor polynomial (remainder 1.7e-16), scaling by 2^n through
+// the exponent field (n >= -1010 keeps the result normal).
+static __constant__ double c_exp_poly[13] = {
+    1.0, 1.0, 0.5, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320, 1.0 / 362880, 1.0 / 3628800,
+    1.0 / 39916800, 1.0 / 479001600};
+__device__ __forceinline__ double exp_neg_fast(double t) {
+    t = fmax(t, -700.0);
+    const double n = rint(t * 1.4426950408889634);
+    double r = fma(n, -6.93147180369123816490e-01, t);       // ln2 high part (fdlibm split)
+    r = fma(n, -1.90821492927058770002e-10, r);              // ln2 low part
+    double p = c_exp_poly[12];
+#pragma unroll
+    for (int k = 11; k >= 0; --k) p = fma(p, r, c_exp_poly[k]);
+    const int ni = __double2int_rn(n);
+    return __hiloint2double(__double2hiint(p) + (ni << 20), __double2loint(p));
+}
+
+// 1/sqrt(x) for x comfortably inside the float range: single-precision seed + two Newton steps in double
+// (22 -> 44 -> 88 bits), no special-case branch.
+__device__ __forceinline__ double rsqrt_fast(double x) {
+    double y = (double)rsqrtf((float)x);
+    const double hx = 0.5 * x;
+    y = y * fma(-hx * y, y, 1.5);
+    y = y * fma(-hx * y, y, 1.5);
+    return y;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);

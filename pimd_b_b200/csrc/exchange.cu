@@ -503,13 +503,35 @@ __global__ void __launch_bounds__(1024) k_exch_recur_dec(ExArgs a) {
 }
 
 // ---------------------------------------------------------------- 4. exterior spring forces (K7 + K8)
-// one warp per (exterior bead, particle l)
+// one block of kFT threads per (exterior bead, particle l): the u-sum is latency-bound (a handful of dependent
+// global loads per term), so it is spread over 4 warps and the partials are combined in a fixed order
+constexpr int kFT = 128;
 template <int D>
-__global__ void __launch_bounds__(256) k_exch_forces(ExArgs a) {
-    const int lane = threadIdx.x & 31;
-    const int w = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+__device__ __forceinline__ void block_reduce_store(double (&acc)[D], double* sred) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int c = 0; c < D; ++c) acc[c] = warp_sum(acc[c]);
+    if (lane == 0) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) sred[warp * D + c] = acc[c];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            double t = 0.0;
+            for (int k = 0; k < kFT / 32; ++k) t += sred[k * D + c];
+            acc[c] = t;
+        }
+    }
+}
+
+template <int D>
+__global__ void __launch_bounds__(kFT) k_exch_forces(ExArgs a) {
+    __shared__ double sred[(kFT / 32) * D];
+    const int lane = threadIdx.x;          // position in the u-stride of this block
+    const int w = blockIdx.x;
     const int N = a.N;
-    if (w >= 2 * N) return;
     const int which = w / N, l = w % N;   // 0: first bead, 1: last bead
     if ((which == 0 && !a.do_first) || (which == 1 && !a.do_last)) return;
     const double iWN = 1.0 / a.Wm[N];
@@ -522,7 +544,8 @@ __global__ void __launch_bounds__(256) k_exch_forces(ExArgs a) {
         // f_l = k [ sum_{u=max(0,l-1)}^{N-1} P(u->l) mi(r^P_u - r^1_l) + mi(r^2_l - r^1_l) ]
         const double wl = a.Wm[l] * iWN;
         const int el = a.We[l] - eWN;
-        for (int u = max(0, l - 1) + lane; u < N; u += 32) {
+#pragma unroll 2
+        for (int u = max(0, l - 1) + lane; u < N; u += kFT) {
             double pr;
             if (u == l - 1) {
                 pr = 1.0 - ext_to_double(wl * a.Wbm[l], el + a.Wbe[l]);
@@ -537,8 +560,7 @@ __global__ void __launch_bounds__(256) k_exch_forces(ExArgs a) {
                 acc[c] = fma(pr, dx, acc[c]);
             }
         }
-#pragma unroll
-        for (int c = 0; c < D; ++c) acc[c] = warp_sum(acc[c]);
+        block_reduce_store<D>(acc, sred);
         if (lane == 0) {
 #pragma unroll
             for (int c = 0; c < D; ++c) {
@@ -553,7 +575,8 @@ __global__ void __launch_bounds__(256) k_exch_forces(ExArgs a) {
         const int eb = a.Wbe[l + 1] - eWN;
         const double il1 = a.Inv[l + 1];
         const int uend = min(l + 1, N - 1);
-        for (int u = lane; u <= uend; u += 32) {
+#pragma unroll 2
+        for (int u = lane; u <= uend; u += kFT) {
             double pr;
             if (u == l + 1) {
                 pr = 1.0 - ext_to_double(wb * a.Wm[l + 1], eb + a.We[l + 1]);
@@ -568,8 +591,7 @@ __global__ void __launch_bounds__(256) k_exch_forces(ExArgs a) {
                 acc[c] = fma(pr, dx, acc[c]);
             }
         }
-#pragma unroll
-        for (int c = 0; c < D; ++c) acc[c] = warp_sum(acc[c]);
+        block_reduce_store<D>(acc, sred);
         if (lane == 0) {
 #pragma unroll
             for (int c = 0; c < D; ++c) {
@@ -755,8 +777,7 @@ static int exchange_impl(Sim* s, cudaStream_t st, int part) {
     } else {
         int rc = run_recursion(s, a, st);
         if (rc != PIMDB_OK) return rc;
-        const int grid = (2 * s->N * 32 + 255) / 256;
-        k_exch_forces<D><<<grid, 256, 0, st>>>(a);
+        k_exch_forces<D><<<2 * s->N, kFT, 0, st>>>(a);
         s->launches += 2;
     }
     PIMDB_CUDA_TRY(s, cudaGetLastError());

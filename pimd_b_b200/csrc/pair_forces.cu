@@ -35,16 +35,16 @@ __device__ __forceinline__ double pair_eval(double r2, double par, double& v) {
         if (WANT_V) v = 0.5 * par * r2;
         return par;
     } else if (POT == PIMDB_POT_DIPOLE) {       // reference src/potentials/dipole.cpp:5-45 (par = strength)
-        double ir = rsqrt(r2);
+        double ir = rsqrt_fast(r2);
         double ir2 = ir * ir;
         double ir3 = ir2 * ir;
         if (WANT_V) v = par * ir3;
         return -3.0 * par * ir3 * ir2;
     } else {                                    // Aziz HFDHE2, reference src/potentials/aziz.cpp:18-106
-        double ir = rsqrt(r2);
+        double ir = rsqrt_fast(r2);
         double r = r2 * ir;
         double xs = r * (1.0 / kAzRm);
-        double e1 = exp(-kAzAlpha * xs);
+        double e1 = exp_neg_fast(-kAzAlpha * xs);
         double t1 = -kAzA * kAzAlpha * e1;
         double dvdr;
         if (xs > kEps && xs < 0.01) {           // hard-core branch: repulsion only (aziz.cpp:39-42, 78-79)
@@ -56,7 +56,7 @@ __device__ __forceinline__ double pair_eval(double r2, double par, double& v) {
             double fdamp = 1.0, dfdamp = 0.0;
             if (xs < kAzD) {                    // include/potentials/aziz.h:25-34
                 double q = kAzD * ix - 1.0;
-                fdamp = exp(-q * q);
+                fdamp = exp_neg_fast(-q * q);
                 dfdamp = 2.0 * kAzD * ix2 * q * fdamp;
             }
             double disp = kAzC6 * ix6 + kAzC8 * ix8 + kAzC10 * ix10;
@@ -104,13 +104,14 @@ __global__ void __launch_bounds__(256) k_pair_tiles(PairArgs a) {
 #pragma unroll
         for (int c = 0; c < D; ++c) {
             xo[c] = __shfl_sync(kFullMask, xj[c], src);
-            double dx = xi[c] - xo[c];
-            if (PBC) {
-                dx = min_image(swap ? -dx : dx, a.L, a.invL);
-                dx = swap ? -dx : dx;
-            }
-            d[c] = dx;
-            r2 = fma(dx, dx, r2);
+            const double dx = xi[c] - xo[c];
+            d[c] = swap ? -dx : dx;
+        }
+        if (PBC) min_image_vec<D>(d, a.L, a.invL);
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            d[c] = swap ? -d[c] : d[c];
+            r2 = fma(d[c], d[c], r2);
         }
         bool active = vi && (jbase + src < a.N) && !(diag && t == 16 && lane >= 16);
         if (CUT) active = active && (sqrt(r2) < a.rc);   // strict '<' (src/simulation.cpp:444)

@@ -1,0 +1,45 @@
+// pimdb_gpu: the reference's `pimdb` entry point (src/pimdb.cpp:31-68) on top of the B200 hot path.
+//   pimdb_gpu [-in config.ini] [--dim D] [--device K] [--bosonic_alg]
+// Same INI schema, same output/ files (simulation.out, position_b.xyz, velocity_b.dat, force_b.dat, report.txt),
+// same error reporting ("[X] <kind>: <message>", exit code 0 like the reference). NDIM is a run-time flag here
+// (compile-time in the reference, CMakeLists.txt:44-48).
+#include <cstring>
+#include <iostream>
+#include <string>
+
+#include "pimdb_host.hpp"
+
+int main(int argc, char** argv) {
+    std::string config = "config.ini";
+    int ndim = 3, device = 0;
+    bool info = false;
+    try {
+        for (int i = 1; i < argc; ++i) {
+            if (!std::strcmp(argv[i], "--dim")) {
+                if (i + 1 < argc && std::isdigit((unsigned char)argv[i + 1][0])) ndim = std::atoi(argv[++i]);
+                else { std::cout << "Program runs 1-, 2- and 3-dimensional systems (select with --dim D)\n"; info = true; }
+            } else if (!std::strcmp(argv[i], "--bosonic_alg")) {
+                std::cout << "Program was compiled with quadratic bosonic algorithm.\n";
+                info = true;
+            } else if (!std::strcmp(argv[i], "--device")) {
+                if (i + 1 < argc) device = std::atoi(argv[++i]);
+            } else if (!std::strcmp(argv[i], "-in")) {
+                if (i + 1 < argc) config = argv[++i];
+                else throw std::invalid_argument("-in option requires a filename argument");
+            }
+        }
+        if (!info) {
+            std::cout << "[*] Initializing the simulation parameters\n";
+            pimdb_host::Params params(config, ndim);
+            pimdb_host::Simulation sim(params, device);
+            sim.run();
+        }
+    } catch (const std::invalid_argument& ex) {
+        std::cout << "[X] Invalid argument error: " << ex.what() << '\n';
+    } catch (const std::overflow_error& ex) {
+        std::cout << "[X] Overflow error: " << ex.what() << '\n';
+    } catch (const std::exception& ex) {
+        std::cout << "[X] Error: " << ex.what() << '\n';
+    }
+    return 0;
+}

@@ -122,6 +122,136 @@ def make_refprobe():
     print("wrote refprobe.npz", sum(v.nbytes for v in out.values()) // 1024, "KiB raw")
 
 
+E2E_INIS = {
+    # the reference's own initial conditions (mt19937(seed+bead): uniform positions, Maxwell-Boltzmann momenta) and
+    # no noise -> the whole run is deterministic and comparable file by file
+    "nve_trap_bosonic": """[simulation]
+dt = 1.0 femtosecond
+steps = 200
+sfreq = 50
+threshold = 0.0
+nbeads = 4
+fixcom = true
+bosonic = true
+seed = 90846
+pbc = false
+initial_position = random
+initial_velocity = random
+thermostat = none
+[system]
+temperature = 5.802 kelvin
+natoms = 8
+size = 300.0 atomic_unit
+mass = 1.0 atomic_unit
+[interaction_potential]
+name = free
+[external_potential]
+name = harmonic
+omega = 3.0 millielectronvolt
+[output]
+positions = angstrom
+velocities = angstrom/ps
+forces = ev/ang
+[observables]
+energy = kelvin
+classical = kelvin
+bosonic = true
+""",
+    "nve_aziz_grid_pbc": """[simulation]
+dt = 0.5 femtosecond
+steps = 120
+sfreq = 40
+threshold = 0.0
+nbeads = 4
+fixcom = false
+bosonic = true
+seed = 4242
+pbc = true
+initial_position = grid
+initial_velocity = random
+thermostat = none
+[system]
+temperature = 2.0 kelvin
+natoms = 27
+size = 10.73 angstrom
+mass = 4.0026 dalton
+[interaction_potential]
+name = aziz
+cutoff = 5.0 angstrom
+[external_potential]
+name = free
+[output]
+positions = angstrom
+velocities = off
+forces = ev/ang
+[observables]
+energy = kelvin
+classical = kelvin
+bosonic = true
+""",
+    "nve_dipole_nm_propagator": """[simulation]
+dt = 1.0 femtosecond
+steps = 150
+sfreq = 50
+threshold = 0.0
+nbeads = 6
+fixcom = true
+bosonic = false
+seed = 777
+pbc = false
+initial_position = random
+initial_velocity = random
+propagator = normal_modes
+thermostat = none
+[system]
+temperature = 5.0 kelvin
+natoms = 10
+size = 200.0 atomic_unit
+mass = 1.0 atomic_unit
+[interaction_potential]
+name = dipole
+strength = 1.0
+[external_potential]
+name = harmonic
+omega = 3.0 millielectronvolt
+[output]
+positions = angstrom
+velocities = angstrom/ps
+forces = off
+[observables]
+energy = kelvin
+classical = kelvin
+""",
+}
+
+
+def make_e2e():
+    """Run the UNMODIFIED reference program (oracle/_ref/pimdb_ndim3) end to end and keep its output files."""
+    import os, shutil, subprocess, tempfile
+    out = {}
+    for name, ini in E2E_INIS.items():
+        ndim = 2 if "dipole" in name else 3
+        tmp = Path(tempfile.mkdtemp(prefix="e2e_"))
+        (tmp / "config.ini").write_text(ini)
+        nb = int([l for l in ini.splitlines() if l.startswith("nbeads")][0].split("=")[1])
+        subprocess.run([str(ROOT / "oracle" / "_ref" / f"pimdb_ndim{ndim}"), "-in", "config.ini"], cwd=tmp, check=True,
+                       env=dict(os.environ, PIMDB_NP=str(nb)), stdout=subprocess.DEVNULL)
+        out[f"{name}/ini"] = np.array(ini)
+        out[f"{name}/ndim"] = np.array(ndim)
+        so = pio.read_simulation_out(str(tmp / "output" / "simulation.out"))
+        out[f"{name}/simout_columns"] = np.array(list(so.keys()))
+        out[f"{name}/simout"] = np.stack(list(so.values()), axis=1)
+        out[f"{name}/simout_text"] = np.array((tmp / "output" / "simulation.out").read_text())
+        for kind, pat in (("x", "position_{}.xyz"), ("v", "velocity_{}.dat"), ("f", "force_{}.dat")):
+            if (tmp / "output" / pat.format(0)).exists():
+                out[f"{name}/{kind}"] = np.asarray(
+                    [pio.read_dump_frames(str(tmp / "output" / pat.format(b)), ndim) for b in range(nb)])
+        shutil.rmtree(tmp, ignore_errors=True)
+    np.savez_compressed(OUT / "refe2e.npz", **out)
+    print("wrote refe2e.npz", sum(v.nbytes for v in out.values()) // 1024, "KiB raw")
+
+
 if __name__ == "__main__":
     make_refcases()
     make_refprobe()
+    make_e2e()

@@ -1,0 +1,64 @@
+"""Black-box acceptance of the C++ host mirror (pimd_b_b200/pimdb_gpu): same INI in, same output files out.
+
+tests/golden/refe2e.npz holds complete runs of the UNMODIFIED reference program (oracle/_ref/pimdb_ndim*, made by
+tests/golden/make_fixtures.py:make_e2e) for deterministic configurations: the reference's own initial conditions
+(std::mt19937(seed+bead) uniform positions / grid, Maxwell-Boltzmann momenta) and thermostat = none. pimdb_gpu
+restates those initial conditions on the host, runs the steps on the GPU and must reproduce simulation.out and the
+per-bead dumps. Comparison rule = the reference's own regression test (tests/main.py:77-86: np.allclose, rtol 1e-5)
+and, stricter, 1e-7 on the observables / 1e-8 on the dumped state.
+"""
+import subprocess
+
+import numpy as np
+import pytest
+
+from pimd_b_b200 import io as pio
+from tests.helpers import GOLDEN_DIR, ROOT
+
+pytestmark = pytest.mark.gpu
+E2E = np.load(GOLDEN_DIR / "refe2e.npz")
+CASES = sorted({k.split("/")[0] for k in E2E.files})
+BIN = ROOT / "pimd_b_b200" / "pimdb_gpu"
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_pimdb_gpu_reproduces_reference_run(gpu_required, case, tmp_path):
+    if not BIN.exists():
+        from pimd_b_b200 import build
+        build.build_host()
+    ndim = int(E2E[f"{case}/ndim"])
+    (tmp_path / "config.ini").write_text(str(E2E[f"{case}/ini"]))
+    r = subprocess.run([str(BIN), "-in", "config.ini", "--dim", str(ndim)], cwd=tmp_path, capture_output=True,
+                       text=True, timeout=300)
+    assert "[X]" not in r.stdout, r.stdout
+    assert "finished running successfully" in r.stdout, r.stdout + r.stderr
+    got = pio.read_simulation_out(str(tmp_path / "output" / "simulation.out"))
+    cols = [str(c) for c in E2E[f"{case}/simout_columns"]]
+    assert list(got.keys()) == cols                      # same header, same column order
+    ref = E2E[f"{case}/simout"]
+    for i, c in enumerate(cols):
+        assert np.allclose(got[c], ref[:, i], rtol=1e-5), c          # the reference's own acceptance rule
+        scale = np.max(np.abs(ref[:, i])) + 1e-300
+        assert np.max(np.abs(got[c] - ref[:, i])) <= 2e-7 * max(scale, 1.0), (c, got[c], ref[:, i])
+    nb = E2E[f"{case}/x"].shape[0]
+    for kind, pat in (("x", "position_{}.xyz"), ("v", "velocity_{}.dat"), ("f", "force_{}.dat")):
+        key = f"{case}/{kind}"
+        if key not in E2E.files:
+            continue
+        for b in range(nb):
+            frames = np.asarray(pio.read_dump_frames(str(tmp_path / "output" / pat.format(b)), ndim))
+            refb = E2E[key][b]
+            assert frames.shape == refb.shape
+            assert np.max(np.abs(frames - refb)) <= 1e-8 * np.max(np.abs(E2E[key])), (kind, b)
+    # the header line is byte-identical to the reference's
+    assert (tmp_path / "output" / "simulation.out").read_text().splitlines()[0] == \
+        str(E2E[f"{case}/simout_text"]).splitlines()[0]
+    assert (tmp_path / "output" / "report.txt").exists()
+
+
+def test_pimdb_gpu_reports_config_errors_like_the_reference(gpu_required, tmp_path):
+    (tmp_path / "config.ini").write_text("[simulation]\nnbeads = 4\nbosonic = true\npropagator = normal_modes\n"
+                                         "thermostat = langevin\n")
+    r = subprocess.run([str(BIN), "-in", "config.ini"], cwd=tmp_path, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0       # the reference prints the error and returns 0 (src/pimdb.cpp:57-67)
+    assert "[X] Invalid argument error: Normal modes propogation is currently not available for bosons!" in r.stdout
