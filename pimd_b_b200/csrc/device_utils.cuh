@@ -21,23 +21,25 @@ __device__ __forceinline__ double min_image(double dx, double L, double invL) {
 // Vector form for the hot pair loop: D multiplications + roundings and ONE rarely taken branch.
 // rint(dx/L) equals floor(dx/L + 0.5) except at exact ties (|dx| an odd multiple of L/2); ties -- and anything within
 // 1e-9 of one -- take the out-of-line exact path that evaluates the reference's expression literally.
-template <int D>
-__device__ __noinline__ void min_image_exact(double (&d)[D], double L) {
-#pragma unroll
-    for (int c = 0; c < D; ++c) d[c] -= L * floor(d[c] / L + 0.5);
+// `negate`: the reference would have formed the separation with the opposite sign (x_lower - x_higher on a diagonal
+// tile); that only matters at a tie, where mi(+L/2) = mi(-L/2) = -L/2, so it is handled in the exact path only.
+static __device__ __noinline__ double min_image_exact(double d, double L, bool negate) {
+    if (negate) d = -d;
+    d -= L * floor(d / L + 0.5);
+    return negate ? -d : d;
 }
 template <int D>
-__device__ __forceinline__ void min_image_vec(double (&d)[D], double L, double invL) {
-    double n[D];
-    bool tie = false;
+__device__ __forceinline__ void min_image_vec(double (&d)[D], double L, double invL, bool negate = false) {
+    double n[D], worst = 0.0;
 #pragma unroll
     for (int c = 0; c < D; ++c) {
         const double q = d[c] * invL;
         n[c] = rint(q);
-        tie |= fabs(q - n[c]) > 0.5 - 1e-9;
+        worst = fmax(worst, fabs(q - n[c]));
     }
-    if (tie) {
-        min_image_exact<D>(d, L);
+    if (worst > 0.5 - 1e-9) {
+#pragma unroll
+        for (int c = 0; c < D; ++c) d[c] = min_image_exact(d[c], L, negate);
     } else {
 #pragma unroll
         for (int c = 0; c < D; ++c) d[c] = fma(-L, n[c], d[c]);
@@ -56,9 +58,15 @@ __device__ __forceinline__ double exp_neg_fast(double t) {
     const double n = rint(t * 1.4426950408889634);
     double r = fma(n, -6.93147180369123816490e-01, t);       // ln2 high part (fdlibm split)
     r = fma(n, -1.90821492927058770002e-10, r);              // ln2 low part
-    double p = c_exp_poly[12];
-#pragma unroll
-    for (int k = 11; k >= 0; --k) p = fma(p, r, c_exp_poly[k]);
+    // Estrin evaluation: the pair loop is bound by dependent-instruction latency (8.3 cycles per DFMA), so the
+    // 12-deep Horner chain is folded into a depth-5 tree (same coefficients, 4 more multiplications)
+    const double* c = c_exp_poly;
+    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
+    const double a01 = fma(c[1], r, c[0]), a23 = fma(c[3], r, c[2]), a45 = fma(c[5], r, c[4]), a67 = fma(c[7], r, c[6]);
+    const double a89 = fma(c[9], r, c[8]), aab = fma(c[11], r, c[10]);
+    const double b0 = fma(a23, r2, a01), b1 = fma(a67, r2, a45), b2 = fma(aab, r2, a89);
+    const double lo = fma(b1, r4, b0), hi = fma(c[12], r4, b2);
+    const double p = fma(hi, r8, lo);
     const int ni = __double2int_rn(n);
     return __hiloint2double(__double2hiint(p) + (ni << 20), __double2loint(p));
 }

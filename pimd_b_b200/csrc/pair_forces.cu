@@ -18,6 +18,9 @@
 
 namespace pimdb {
 
+#ifndef PIMDB_PAIR_MINBLOCKS
+#define PIMDB_PAIR_MINBLOCKS 3
+#endif
 struct PairArgs {
     const double* x;      // first bead of this launch, slab stride S
     double* scratch;      // [nb][T][T][D][32]
@@ -69,7 +72,7 @@ __device__ __forceinline__ double pair_eval(double r2, double par, double& v) {
 }
 
 template <int D, int POT, bool PBC, bool CUT, bool OBS>
-__global__ void __launch_bounds__(256) k_pair_tiles(PairArgs a) {
+__global__ void __launch_bounds__(256, PIMDB_PAIR_MINBLOCKS) k_pair_tiles(PairArgs a) {
     const int lane = threadIdx.x & 31;
     const long long item = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (item >= (long long)a.nb * a.TP) return;  // whole warp exits together
@@ -104,15 +107,11 @@ __global__ void __launch_bounds__(256) k_pair_tiles(PairArgs a) {
 #pragma unroll
         for (int c = 0; c < D; ++c) {
             xo[c] = __shfl_sync(kFullMask, xj[c], src);
-            const double dx = xi[c] - xo[c];
-            d[c] = swap ? -dx : dx;
+            d[c] = xi[c] - xo[c];
         }
-        if (PBC) min_image_vec<D>(d, a.L, a.invL);
+        if (PBC) min_image_vec<D>(d, a.L, a.invL, swap);
 #pragma unroll
-        for (int c = 0; c < D; ++c) {
-            d[c] = swap ? -d[c] : d[c];
-            r2 = fma(d[c], d[c], r2);
-        }
+        for (int c = 0; c < D; ++c) r2 = fma(d[c], d[c], r2);
         bool active = vi && (jbase + src < a.N) && !(diag && t == 16 && lane >= 16);
         if (CUT) active = active && (sqrt(r2) < a.rc);   // strict '<' (src/simulation.cpp:444)
         if (!active) r2 = 1.0;                            // keep the arithmetic finite on masked lanes
