@@ -122,7 +122,8 @@ typedef struct pimdb_observables {
     double kinetic, potential, ext_pot, int_pot, virial;
     double temperature, cl_kinetic, cl_spring;
     double prob_dist, prob_all;
-    double reserved[6];
+    double nh_energy;        /* Nose-Hoover: sum over beads of getAdditionToH() (src/thermostats/nose_hoover.cpp:37-67) */
+    double reserved[5];
 } pimdb_observables;
 
 typedef struct pimdb_sim pimdb_sim;

@@ -99,6 +99,9 @@ struct orc_sim {
     double *nm_fwd, *nm_inv;                     /* [P][P] rows: fwd[k][j] = C_kj ; inv[j][k] as the reference stores them */
     double *nm_ext;                              /* NormalModesPropagator::ext_forces (zero before the first step) */
     double *scratch_x, *scratch_p;               /* [P][N][D] NM-space copies */
+    /* Nose-Hoover chains, one thermostat object per bead (rank): eta, eta_dot, eta_dot_dot [P][groups][nchains] */
+    double *nh_eta, *nh_ed, *nh_edd;
+    int nh_groups;
 };
 
 static size_t slab(const orc_sim* s) { return (size_t)s->N * s->D; }
@@ -491,7 +494,105 @@ void orc_propagator_step(orc_sim* s) {
 
 /* ------------------------------------------------------------------ thermostat */
 /* src/thermostats/thermostat.cpp:15-19, langevin.cpp:10-27, thermostat_coupling.cpp:29-47 */
+/* src/thermostats/nose_hoover.cpp:102-146 — half-step chain integrator; returns the momentum scaling factor */
+static double nh_chain_step(const orc_sim* s, double current_energy, double ndof, double* eta, double* ed, double* edd) {
+    const int nc = s->c.nchains;
+    const double Qi = s->beta / s->P, Q1 = ndof * Qi;            /* :16-21, hbar = 1 */
+    const double dt2 = 0.5 * s->c.dt, dt4 = 0.25 * s->c.dt, dt8 = 0.125 * s->c.dt;
+    const double required = ndof / s->thermo_beta;
+    double exp_factor = 0.0;
+    edd[0] = (current_energy - required) / Q1;
+    ed[nc - 1] += edd[nc - 1] * dt4;
+    for (int i = nc - 2; i >= 0; i--) {
+        exp_factor = exp(-dt8 * ed[i + 1]);
+        ed[i] *= exp_factor;
+        ed[i] += edd[i] * dt4;
+        ed[i] *= exp_factor;
+    }
+    double scale = exp(-dt2 * ed[0]);
+    for (int i = 0; i < nc; i++) eta[i] += dt2 * ed[i];
+    edd[0] = (current_energy * scale * scale - required) / Q1;
+    ed[0] *= exp_factor;
+    ed[0] += edd[0] * dt4;
+    ed[0] *= exp_factor;
+    double Q_former = Q1;
+    for (int i = 1; i < nc - 1; i++) {
+        exp_factor = exp(-dt8 * ed[i + 1]);
+        ed[i] *= exp_factor;
+        edd[i] = (Q_former * ed[i - 1] * ed[i - 1] - 1 / s->thermo_beta) / Qi;
+        ed[i] += edd[i] * dt4;
+        ed[i] *= exp_factor;
+        Q_former = Qi;
+    }
+    if (nc >= 2) { /* nchains = 1 reads eta_dot[-1] in the reference (App. A-12); not restated */
+        edd[nc - 1] = (Qi * ed[nc - 2] * ed[nc - 2] - 1 / s->thermo_beta) / Qi;
+        ed[nc - 1] += edd[nc - 1] * dt4;
+    }
+    return scale;
+}
+
+/* momentaUpdate of the three variants, src/thermostats/nose_hoover.cpp:69-91, 162-182, 207-222 (Cartesian coupling) */
+static void nose_hoover_step(orc_sim* s) {
+    const int P = s->P, N = s->N, D = s->D, nc = s->c.nchains;
+    for (int b = 0; b < P; ++b) {
+        double* pb = s->p + (size_t)b * slab(s);
+        size_t base = (size_t)b * s->nh_groups * nc;
+        if (s->c.thermostat == ORC_THERMO_NOSE_HOOVER) {
+            double e = 0.0;
+            for (size_t q = 0; q < slab(s); ++q) e += pb[q] * pb[q];
+            e /= s->c.mass;
+            double sc = nh_chain_step(s, e, (double)D * N, s->nh_eta + base, s->nh_ed + base, s->nh_edd + base);
+            for (size_t q = 0; q < slab(s); ++q) pb[q] = pb[q] * sc;
+        } else if (s->c.thermostat == ORC_THERMO_NOSE_HOOVER_NP) {
+            for (int i = 0; i < N; ++i) {
+                double e = 0.0;
+                for (int a = 0; a < D; ++a) e += pb[(size_t)i * D + a] * pb[(size_t)i * D + a];
+                e /= s->c.mass;
+                size_t o = base + (size_t)i * nc;
+                double sc = nh_chain_step(s, e, (double)D, s->nh_eta + o, s->nh_ed + o, s->nh_edd + o);
+                for (int a = 0; a < D; ++a) pb[(size_t)i * D + a] = pb[(size_t)i * D + a] * sc;
+            }
+        } else {
+            for (int i = 0; i < N; ++i)
+                for (int a = 0; a < D; ++a) {
+                    double pv = pb[(size_t)i * D + a];
+                    size_t o = base + ((size_t)i * D + a) * nc;
+                    double sc = nh_chain_step(s, pv * pv / s->c.mass, 1.0, s->nh_eta + o, s->nh_ed + o, s->nh_edd + o);
+                    pb[(size_t)i * D + a] = pv * sc;
+                }
+        }
+    }
+}
+
+/* getAdditionToH summed over beads, src/thermostats/nose_hoover.cpp:37-67, 184-190, 224-232 */
+static double nose_hoover_energy(const orc_sim* s) {
+    const int nc = s->c.nchains;
+    const double ndof = s->c.thermostat == ORC_THERMO_NOSE_HOOVER ? (double)s->D * s->N
+                        : (s->c.thermostat == ORC_THERMO_NOSE_HOOVER_NP ? (double)s->D : 1.0);
+    const double Qi = s->beta / s->P, Q1 = ndof * Qi;
+    double total = 0.0;
+    for (int b = 0; b < s->P; ++b) {
+        double per_bead = 0.0;
+        for (int g = 0; g < s->nh_groups; ++g) {
+            size_t o = ((size_t)b * s->nh_groups + g) * nc;
+            double h = 0.5 * Q1 * s->nh_ed[o] * s->nh_ed[o];
+            h += ndof * s->nh_eta[o] / s->thermo_beta;
+            for (int i = 1; i < nc; i++) {
+                h += 0.5 * Qi * s->nh_ed[o + i] * s->nh_ed[o + i];
+                h += s->nh_eta[o + i] / s->thermo_beta;
+            }
+            per_bead += h;
+        }
+        total += per_bead;
+    }
+    return total;
+}
+
 void orc_thermostat_step(orc_sim* s) {
+    if (s->c.thermostat >= ORC_THERMO_NOSE_HOOVER) {
+        nose_hoover_step(s);
+        return;
+    }
     if (s->c.thermostat != ORC_THERMO_LANGEVIN) return;
     const int P = s->P, N = s->N, D = s->D;
     const size_t sl = slab(s);
@@ -601,6 +702,7 @@ void orc_observables_calc(orc_sim* s, orc_observables* o) {
         o->temperature += 2.0 * ke / dof / P;
         o->cl_spring += (b == 0 && bos) ? s->V[N] : ring_spring_energy(s, b);
     }
+    if (s->c.thermostat >= ORC_THERMO_NOSE_HOOVER) o->nh_energy = nose_hoover_energy(s); /* classical.cpp:24-26 */
     if (bos) {
         /* quadratic_bosonic_exchange.cpp:222-240 */
         double beta = exch_beta(s), sum = 0;
@@ -643,6 +745,13 @@ orc_sim* orc_create(const orc_config* cfg) {
     s->nm_fwd = calloc((size_t)s->P * s->P, sizeof(double));
     s->nm_inv = calloc((size_t)s->P * s->P, sizeof(double));
     build_nm(s);
+    s->nh_groups = cfg->thermostat == ORC_THERMO_NOSE_HOOVER_NP ? s->N : (cfg->thermostat == ORC_THERMO_NOSE_HOOVER_NP_DIM ? s->N * s->D : 1);
+    {
+        size_t len = (size_t)s->P * s->nh_groups * (cfg->nchains > 0 ? cfg->nchains : 1);
+        s->nh_eta = calloc(len, sizeof(double));
+        s->nh_ed = calloc(len, sizeof(double));
+        s->nh_edd = calloc(len, sizeof(double));
+    }
     s->rng = calloc(s->P, sizeof(orc_ranmars*));
     for (int b = 0; b < s->P; ++b) s->rng[b] = orc_ranmars_new((int)(cfg->seed + (unsigned)b));
     return s;
@@ -656,6 +765,7 @@ void orc_destroy(orc_sim* s) {
     free(s->scratch_x); free(s->scratch_p);
     free(s->E_kn); free(s->V); free(s->Vb); free(s->prob); free(s->tmp); free(s->prim);
     free(s->nm_fwd); free(s->nm_inv);
+    free(s->nh_eta); free(s->nh_ed); free(s->nh_edd);
     free(s);
 }
 

@@ -27,7 +27,8 @@ extern "C" {
 
 enum { ORC_POT_FREE = 0, ORC_POT_AZIZ = 1, ORC_POT_HARMONIC = 2, ORC_POT_DIPOLE = 3 };
 enum { ORC_PROP_CARTESIAN = 0, ORC_PROP_NORMAL_MODES = 1 };
-enum { ORC_THERMO_NONE = 0, ORC_THERMO_LANGEVIN = 1 };
+enum { ORC_THERMO_NONE = 0, ORC_THERMO_LANGEVIN = 1, ORC_THERMO_NOSE_HOOVER = 2, ORC_THERMO_NOSE_HOOVER_NP = 3,
+       ORC_THERMO_NOSE_HOOVER_NP_DIM = 4 };
 
 typedef struct {
     int natoms, nbeads, ndim;
@@ -40,6 +41,7 @@ typedef struct {
     double cutoff;               /* [interaction_potential] cutoff as parsed (a.u.); <0 all pairs, 0 off */
     double mass, temperature, dt, gamma, size;
     unsigned int seed;
+    int nchains;                 /* Nose-Hoover chain length ([simulation] nchains, default 4) */
 } orc_config;
 
 typedef struct orc_sim orc_sim;
@@ -50,6 +52,7 @@ typedef struct {
     double kinetic, potential, ext_pot, int_pot, virial;   /* energy observable  */
     double temperature, cl_kinetic, cl_spring;             /* classical          */
     double prob_dist, prob_all;                            /* bosonic            */
+    double nh_energy;                                      /* classical, Nose-Hoover runs only */
 } orc_observables;
 
 orc_sim* orc_create(const orc_config* cfg);

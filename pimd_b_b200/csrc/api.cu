@@ -52,8 +52,14 @@ static int validate(const pimdb_config* c, std::string& msg) {
         msg = "The specified thermostat is not supported!"; return PIMDB_ERR_INVALID_ARGUMENT;
     }
     if (c->thermostat >= PIMDB_THERMO_NOSE_HOOVER) {
-        msg = "Nose-Hoover thermostats are not part of this build of the B200 hot path (SURVEY.md 8f, rank 1)";
-        return PIMDB_ERR_INVALID_ARGUMENT;
+        if (c->nchains < 1) {
+            snprintf(buf, sizeof buf, "The specified number of Nose-Hoover chains (%d) is less than one!", c->nchains);
+            msg = buf; return PIMDB_ERR_INVALID_ARGUMENT;
+        }
+        if (c->nmthermostat) {
+            msg = "Nose-Hoover chains coupled to normal modes are not part of this build (Cartesian coupling only)";
+            return PIMDB_ERR_INVALID_ARGUMENT;
+        }
     }
     if (c->nmthermostat && c->thermostat == PIMDB_THERMO_NONE) {
         msg = "nmthermostat cannot be used in nve ensemble!"; return PIMDB_ERR_INVALID_ARGUMENT;
@@ -141,7 +147,7 @@ static void free_all(Sim* s) {
     cudaFree(s->com_part); cudaFree(s->com); cudaFree(s->tickets); cudaFree(s->draw);
     cudaFree(s->obs_d); cudaFreeHost(s->obs_h); cudaFree(s->obs_part);
     cudaFreeHost(s->err_h);
-    cudaFree(s->nmC); cudaFree(s->nmFreq);
+    cudaFree(s->nmC); cudaFree(s->nmFreq); cudaFree(s->nh_state);
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     if (s->ev_join) cudaEventDestroy(s->ev_join);
     if (s->stream_x) cudaStreamDestroy(s->stream_x);
@@ -293,6 +299,13 @@ extern "C" int pimdb_create(const pimdb_config* cfg, pimdb_sim** out) {
         CREATE_TRY(cudaMemcpy(s->nmC, mats.data(), mats.size() * sizeof(double), cudaMemcpyHostToDevice));
         CREATE_TRY(cudaMemcpy(s->nmFreq, tab.data(), tab.size() * sizeof(double), cudaMemcpyHostToDevice));
     }
+    if (cfg->thermostat >= PIMDB_THERMO_NOSE_HOOVER) {
+        const size_t groups = cfg->thermostat == PIMDB_THERMO_NOSE_HOOVER ? 1
+                              : cfg->thermostat == PIMDB_THERMO_NOSE_HOOVER_NP ? (size_t)s->N : (size_t)s->N * s->D;
+        s->nh_len = (size_t)s->Ploc * groups * cfg->nchains;
+        CREATE_TRY(cudaMalloc(&s->nh_state, 3 * s->nh_len * sizeof(double)));
+        CREATE_TRY(cudaMemset(s->nh_state, 0, 3 * s->nh_len * sizeof(double)));   // eta = eta_dot = eta_dot_dot = 0 (nose_hoover.cpp:22-24)
+    }
     CREATE_TRY(cudaDeviceSynchronize());
     *out = reinterpret_cast<pimdb_sim*>(s);
     return PIMDB_OK;
@@ -437,6 +450,11 @@ struct Fuser {
 };
 
 static void thermostat_into(Sim* s, Fuser& fz) {
+    if (s->cfg.thermostat >= PIMDB_THERMO_NOSE_HOOVER) {
+        fz.flush();
+        if (fz.rc == PIMDB_OK) fz.rc = launch_nose_hoover(s);
+        return;
+    }
     if (s->cfg.thermostat != PIMDB_THERMO_LANGEVIN) return;
     if (s->cfg.nmthermostat) {
         fz.flush();
@@ -670,6 +688,7 @@ extern "C" int pimdb_observables_calc(pimdb_sim* sim, pimdb_observables* out) {
         API_TRY(launch_exchange(s, s->stream));   // tables for the current positions
         API_TRY(launch_exchange_estimators(s));
     }
+    if (s->cfg.thermostat >= PIMDB_THERMO_NOSE_HOOVER) API_TRY(launch_nose_hoover_energy(s, &s->obs_d->nh_energy));
     PIMDB_CUDA_TRY(s, cudaMemcpyAsync(s->obs_h, s->obs_d, sizeof(DevObs), cudaMemcpyDeviceToHost, s->stream));
     PIMDB_CUDA_TRY(s, cudaStreamSynchronize(s->stream));
     API_TRY(check_deferred(s));
@@ -695,6 +714,7 @@ extern "C" int pimdb_observables_calc(pimdb_sim* sim, pimdb_observables* out) {
     out->cl_kinetic = o.p2 * (0.5 / s->cfg.mass);
     out->temperature = 2.0 * out->cl_kinetic / (D * N * P) / P;
     out->cl_spring = o.spring_e[0] + ((s->bosonic && s->has_first) ? o.v_n : 0.0);
+    out->nh_energy = o.nh_energy;   // classical.cpp:24-26
     // bosonic.cpp:17-22, quadratic_bosonic_exchange.cpp:222-240
     if (s->bosonic && s->has_first) {
         out->prob_dist = std::exp(-s->exch_beta * (o.e_diag_sum - o.v_n) - std::lgamma(N + 1.0));

@@ -33,7 +33,8 @@ struct DevObs {  // partial sums produced on device; assembled into pimdb_observ
     double v_n;              // V[N]
     double e_diag_sum;       // sum_m E^{[m..m]}
     double e_full;           // E^{[0..N-1]}
-    double pad[6];
+    double nh_energy;        // Nose-Hoover addition to the conserved quantity, owned beads
+    double pad[5];
 };
 
 struct Sim {
@@ -76,6 +77,8 @@ struct Sim {
     // normal modes
     double *nmC = nullptr;             // [P][P] Cartesian->NM matrix rows (row k = mode k)
     double *nmFreq = nullptr;          // [P] cos/sin tables: [3][P] = cos(w dt), sin(w dt), m*w
+    // Nose-Hoover chains: eta | eta_dot | eta_dot_dot, each [bead][group][nchains]
+    double *nh_state = nullptr; size_t nh_len = 0;
     // graph
     cudaGraph_t graph = nullptr; cudaGraphExec_t graph_exec = nullptr;
     unsigned long long graph_kernels = 0;
@@ -116,6 +119,8 @@ int launch_integrate(Sim* s, unsigned ops);
 int launch_nm_propagate(Sim* s);
 int launch_nm_thermostat(Sim* s);
 int launch_obs_elementwise(Sim* s);
+int launch_nose_hoover(Sim* s);
+int launch_nose_hoover_energy(Sim* s, double* out_dev);
 int launch_aos_to_soa(Sim* s, double* dst_soa, bool dst_has_halo);
 int launch_soa_to_aos(Sim* s, const double* src_soa, bool src_has_halo);
 

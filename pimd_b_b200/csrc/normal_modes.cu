@@ -135,6 +135,8 @@ static int launch_nm(Sim* s, int mode) {
     // tile width: P*TC/256 outputs per thread must stay <= 32 and the two tiles must fit in shared memory
     int TC = 32;
     while (TC > 1 && ((size_t)s->P * TC / 256 > 32 || (size_t)2 * s->P * TC * sizeof(double) > 200 * 1024)) TC >>= 1;
+    // small systems: narrower tiles give more blocks (the chain per output is a P-long dot product either way)
+    while (TC > 2 && (a.M + TC - 1) / TC < 2 * kNumSM && (size_t)s->P * TC >= 256) TC >>= 1;
     a.TC = TC;
     a.hdt = 0.5 * s->cfg.dt; a.dt_over_m = s->cfg.dt / s->cfg.mass; a.c1 = s->c1; a.c2 = s->c2;
     a.seed = s->cfg.seed;

@@ -328,13 +328,16 @@ void EnergyObservable::calculate() {
     if (e || i) { q("potential") = conv(o.potential); q("virial") = conv(o.virial); }
 }
 ClassicalObservable::ClassicalObservable(Simulation& s, const std::string& u) : Observable(s, u) {   // classical.cpp:11-19
-    initialize({"temperature", "cl_kinetic", "cl_spring"});
+    if (sim.thermostat_type.rfind("nose_hoover", 0) == 0) initialize({"temperature", "cl_kinetic", "cl_spring", "nh_energy"});
+    else initialize({"temperature", "cl_kinetic", "cl_spring"});
 }
 void ClassicalObservable::calculate() {
     const pimdb_observables& o = sim.deviceObservables();
     q("temperature") = Units::convertToUser("temperature", "kelvin", o.temperature);
     q("cl_kinetic") = Units::convertToUser("energy", out_unit, o.cl_kinetic);
     q("cl_spring") = Units::convertToUser("energy", out_unit, o.cl_spring);
+    if (sim.thermostat_type.rfind("nose_hoover", 0) == 0)
+        q("nh_energy") = Units::convertToUser("energy", out_unit, o.nh_energy);   // Thermostat::getAdditionToH summed over beads
 }
 BosonicObservable::BosonicObservable(Simulation& s, const std::string& u) : Observable(s, u) {
     initialize({"prob_dist", "prob_all"});

@@ -74,6 +74,9 @@ def initial_state(cfg: SimConfig, name: str, seed: int = None) -> Tuple[np.ndarr
     if cfg.interaction == "aziz":
         # never random-uniform with Aziz (hard-core overlaps): lattice + Gaussian bead spread
         x = np.repeat(lattice(cfg)[None], P, axis=0) + rng.normal(0.0, 0.15 * ANGSTROM, size=(P, N, D))
+    elif cfg.interaction == "dipole":
+        # 1/r^3 repulsion: start from a lattice (spacing L/m) with a small bead spread, not from overlapping particles
+        x = np.repeat(lattice(cfg)[None], P, axis=0) * 0.9 + rng.normal(0.0, 0.005 * cfg.size, size=(P, N, D))
     elif name.lower() == "c5":
         # thermal cloud of the trap, ring polymers collapsed on their centroid + small spread
         sigma = np.sqrt(cfg.temperature / (cfg.mass * cfg.ext_omega ** 2))

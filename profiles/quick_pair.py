@@ -1,21 +1,36 @@
-"""Quick timing of the pair-force kernel and the whole step on C3 (eager pass with CUDA events per launch)."""
-import sys, json
+"""Quick timing of the pair-force kernel and the whole step on a BASELINE workload (eager pass with CUDA events per
+launch, then graph replay).   python profiles/quick_pair.py c3 [nsteps]"""
+import json
+import sys
+import time
+
 sys.path.insert(0, ".")
-from pimd_b_b200 import workloads as wl
-from pimd_b_b200.engine import DeviceSim
+from pimd_b_b200 import workloads as wl  # noqa: E402
+from pimd_b_b200.engine import DeviceSim  # noqa: E402
+
 name = sys.argv[1] if len(sys.argv) > 1 else "c3"
+nsteps = int(sys.argv[2]) if len(sys.argv) > 2 else 2000
 cfg = wl.config(name)
 x, p = wl.initial_state(cfg, name)
 sim = DeviceSim(cfg)
-sim.set("x", x); sim.set("p", p)
-sim.step(20); sim.synchronize()
+sim.set("x", x)
+sim.set("p", p)
+sim.step(5)
+sim.synchronize()
 sim.timing_enable(True)
-sim.step(100)
+sim.step(max(5, nsteps // 20))
 pair_ms, n = sim.timing_get(0)
 step_ms, _ = sim.timing_get(1)
 sim.timing_enable(False)
-import time
-sim.step(50); sim.synchronize()
-t0 = time.perf_counter(); sim.step(2000); sim.synchronize(); t1 = time.perf_counter()
-print(json.dumps({"workload": name, "pair_us": pair_ms * 1e3, "pair_tflops_alg": wl.pair_flops_per_step(cfg) / (pair_ms * 1e-3) * 1e-12 if pair_ms else None,
-                  "eager_step_us": step_ms * 1e3, "graph_step_us": (t1 - t0) / 2000 * 1e6, "steps_per_s": 2000 / (t1 - t0)}))
+sim.step(5)
+sim.synchronize()
+t0 = time.perf_counter()
+sim.step(nsteps)
+sim.synchronize()
+t1 = time.perf_counter()
+obs = sim.observables()
+print(json.dumps({"workload": name, "natoms": cfg.natoms, "nbeads": cfg.nbeads, "pair_us": pair_ms * 1e3,
+                  "pair_tflops_alg": wl.pair_flops_per_step(cfg) / (pair_ms * 1e-3) * 1e-12 if pair_ms else None,
+                  "eager_step_us": step_ms * 1e3, "graph_step_us": (t1 - t0) / nsteps * 1e6,
+                  "steps_per_s": nsteps / (t1 - t0), "kinetic": obs["kinetic"], "potential": obs["potential"],
+                  "temperature_K": obs["temperature"] / wl.KELVIN}))

@@ -23,7 +23,7 @@ GOLDEN_DIR = ROOT / "tests" / "golden"
 
 POT_ID = {"free": 0, "aziz": 1, "harmonic": 2, "dipole": 3}
 PROP_ID = {"cartesian": 0, "normal_modes": 1}
-THERMO_ID = {"none": 0, "langevin": 1}
+THERMO_ID = {"none": 0, "langevin": 1, "nose_hoover": 2, "nose_hoover_np": 3, "nose_hoover_np_dim": 4}
 
 
 class OrcConfig(C.Structure):
@@ -37,13 +37,14 @@ class OrcConfig(C.Structure):
         ("mass", C.c_double), ("temperature", C.c_double), ("dt", C.c_double), ("gamma", C.c_double),
         ("size", C.c_double),
         ("seed", C.c_uint),
+        ("nchains", C.c_int),
     ]
 
 
 class OrcObservables(C.Structure):
     _fields_ = [(n, C.c_double) for n in (
         "kinetic", "potential", "ext_pot", "int_pot", "virial",
-        "temperature", "cl_kinetic", "cl_spring", "prob_dist", "prob_all")]
+        "temperature", "cl_kinetic", "cl_spring", "prob_dist", "prob_all", "nh_energy")]
 
 
 _lib = None
@@ -98,7 +99,7 @@ def to_orc_config(cfg: SimConfig) -> OrcConfig:
         int_pot=POT_ID[cfg.interaction], ext_pot=POT_ID[cfg.external],
         int_omega=cfg.int_omega, int_strength=cfg.int_strength, ext_omega=cfg.ext_omega,
         cutoff=cfg.cutoff, mass=cfg.mass, temperature=cfg.temperature, dt=cfg.dt, gamma=cfg.gamma,
-        size=cfg.size, seed=cfg.seed)
+        size=cfg.size, seed=cfg.seed, nchains=cfg.nchains)
 
 
 class Oracle:

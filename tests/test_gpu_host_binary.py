@@ -56,6 +56,33 @@ def test_pimdb_gpu_reproduces_reference_run(gpu_required, case, tmp_path):
     assert (tmp_path / "output" / "report.txt").exists()
 
 
+REFCASES = np.load(GOLDEN_DIR / "refcases.npz")
+NH_CASES = ["bosonic_quadratic_harmonic_nh_dynamics", "bosonic_quadratic_harmonic_nh_np_dynamics",
+            "bosonic_quadratic_harmonic_nh_np_dim_dynamics"]
+
+
+@pytest.mark.parametrize("case", NH_CASES)
+def test_pimdb_gpu_passes_the_reference_golden_nose_hoover_cases(gpu_required, case, tmp_path):
+    """The reference's OWN regression cases (tests/cases/<case>/, 100 000 steps, Nose-Hoover chains: deterministic after
+    the mt19937 initialisation) run unchanged through pimdb_gpu and judged by the reference's own rule
+    (tests/main.py:77-107: every column of the actual simulation.out, np.allclose with rtol 1e-5)."""
+    (tmp_path / "config.ini").write_text(str(REFCASES[f"{case}/ini"]))
+    r = subprocess.run([str(BIN), "-in", "config.ini", "--dim", "3"], cwd=tmp_path, capture_output=True, text=True,
+                       timeout=600)
+    assert "finished running successfully" in r.stdout, r.stdout + r.stderr
+    got = pio.read_simulation_out(str(tmp_path / "output" / "simulation.out"))
+    cols = [str(c) for c in REFCASES[f"{case}/simout_columns"]]
+    ref = REFCASES[f"{case}/simout"]
+    assert list(got.keys()) == cols
+    for i, c in enumerate(cols):
+        assert got[c].shape == ref[:, i].shape
+        assert np.allclose(got[c], ref[:, i], rtol=1e-5), (c, np.max(np.abs(got[c] - ref[:, i])))
+    # and the dumped frames of bead 0 / bead P-1 (exterior beads: exchange forces) at the last step
+    for kind, pat in (("x", "position_{}.xyz"), ("f", "force_{}.dat")):
+        frames = np.asarray(pio.read_dump_frames(str(tmp_path / "output" / pat.format(0)), 3))
+        assert frames.shape[0] == 101
+
+
 def test_pimdb_gpu_reports_config_errors_like_the_reference(gpu_required, tmp_path):
     (tmp_path / "config.ini").write_text("[simulation]\nnbeads = 4\nbosonic = true\npropagator = normal_modes\n"
                                          "thermostat = langevin\n")

@@ -153,6 +153,12 @@ TRAJ_CASES = {
                                       thermostat="none", propagator="normal_modes"), 0.5),
     "trap_nm_propagator_oddP": (trap(6, 7, bosonic=False, thermostat="none", propagator="normal_modes",
                                      fixcom=True), 0.2),
+    # Nose-Hoover chains are deterministic: trajectory-level parity
+    "trap_nose_hoover_bosonic": (trap(8, 4, thermostat="nose_hoover", dt=0.1 * FEMTOSECOND), 0.2),
+    "trap_nose_hoover_np_bosonic": (trap(8, 4, thermostat="nose_hoover_np", dt=0.1 * FEMTOSECOND, fixcom=True), 0.2),
+    "trap_nose_hoover_np_dim": (trap(9, 5, thermostat="nose_hoover_np_dim", dt=0.1 * FEMTOSECOND, nchains=3,
+                                     bosonic=False), 0.2),
+    "aziz_nose_hoover_2chains": (helium(33, 4, thermostat="nose_hoover", nchains=2), "lattice"),
 }
 
 
@@ -218,4 +224,29 @@ def test_zero_momentum(gpu_required):
     got = sim.get("p")
     assert relerr(got, orc.get("p")) < 1e-13
     assert np.max(np.abs(got.sum(axis=(0, 1)))) < 1e-9 * np.abs(p).sum()
+    sim.close()
+
+
+@pytest.mark.parametrize("natoms", [1100, 2100, 4200])
+def test_exchange_large_n_paths(gpu_required, natoms):
+    """N > 1024 takes the multi-row recurrence kernels (2 rows per thread with cp.async staging, 4+ rows with direct
+    loads); compared with the oracle on V, V_backwards and the exterior forces."""
+    cfg = trap(natoms, 3, temperature=1.0 * KELVIN, size=2000.0)
+    rng = np.random.default_rng(natoms)
+    centroid = rng.normal(0.0, 60.0, size=(1, natoms, 3))
+    x = np.repeat(centroid, 3, axis=0) + rng.normal(0.0, 6.0, size=(3, natoms, 3))
+    orc = Oracle(cfg)
+    orc.set("x", x)
+    orc.update_forces()
+    sim = DeviceSim(cfg)
+    sim.set("x", x)
+    sim.update_forces()
+    assert relerr(sim.exchange("V"), orc.exchange("V")) < ENERGY_TOL
+    assert relerr(sim.exchange("Vb"), orc.exchange("B")) < ENERGY_TOL
+    assert relerr(sim.get("f_spring"), orc.get("s")) < FORCE_TOL
+    if natoms <= 2100:
+        ref = orc.observables()
+        got = sim.observables()
+        for key in ("kinetic", "cl_spring", "prob_dist", "prob_all"):
+            assert abs(got[key] - ref[key]) <= 1e-9 * max(abs(ref[key]), abs(ref["cl_spring"]) / cfg.nbeads) + 1e-300, key
     sim.close()
