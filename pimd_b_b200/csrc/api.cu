@@ -143,7 +143,7 @@ static void free_all(Sim* s) {
     cudaFree(s->stage_d); cudaFreeHost(s->stage_h);
     cudaFree(s->tile_ij); cudaFree(s->pair_scratch);
     cudaFree(s->exA); cudaFree(s->exV); cudaFree(s->exVb); cudaFree(s->exF); cudaFree(s->exTab);
-    cudaFree(s->exCm); cudaFree(s->exCe); cudaFree(s->exWm); cudaFree(s->exWe);
+    cudaFree(s->exC); cudaFree(s->exWm); cudaFree(s->exWe);
     cudaFree(s->com_part); cudaFree(s->com); cudaFree(s->tickets); cudaFree(s->draw);
     cudaFree(s->obs_d); cudaFreeHost(s->obs_h); cudaFree(s->obs_part);
     cudaFreeHost(s->err_h);
@@ -264,8 +264,7 @@ extern "C" int pimdb_create(const pimdb_config* cfg, pimdb_sim** out) {
     if (s->bosonic) {
         const size_t NN = (size_t)s->N * s->N;
         CREATE_TRY(cudaMalloc(&s->exA, sizeof(double) * (2 * s->N + 2)));   // A[N] | Inv[N+1]
-        CREATE_TRY(cudaMalloc(&s->exCm, sizeof(double) * 2 * NN));
-        CREATE_TRY(cudaMalloc(&s->exCe, sizeof(int) * 2 * NN));
+        CREATE_TRY(cudaMalloc(&s->exC, sizeof(int4) * 2 * NN));
         CREATE_TRY(cudaMalloc(&s->exWm, sizeof(double) * 2 * (s->N + 1)));
         CREATE_TRY(cudaMalloc(&s->exWe, sizeof(int) * 2 * (s->N + 1)));
         CREATE_TRY(cudaMemset(s->exWm, 0, sizeof(double) * 2 * (s->N + 1)));
@@ -828,5 +827,36 @@ extern "C" int pimdb_bench_fp64_peak(int device, double* tflops) {
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     cudaFree(buf);
     *tflops = best;
+    return PIMDB_OK;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// Profiling aid (not part of the reference surface, not declared in pimdb200.h): average warm duration in
+// microseconds of the two halves of the exchange chain, measured with CUDA events on the handle's stream.
+//   out[0] = prefix sums + Boltzmann factors, out[1] = recurrences + exterior forces
+extern "C" int pimdb_debug_exchange_timing(pimdb_sim* sim, int reps, double* out) {
+    Sim* s = reinterpret_cast<Sim*>(sim);
+    if (!s || !out || !s->bosonic) return PIMDB_ERR_INVALID_ARGUMENT;
+    PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
+    cudaEvent_t e[3];
+    for (auto& ev : e) cudaEventCreate(&ev);
+    double acc[2] = {0.0, 0.0};
+    for (int r = 0; r < reps + 2; ++r) {
+        cudaEventRecord(e[0], s->stream);
+        API_TRY(launch_exchange_part(s, s->stream, 0));
+        cudaEventRecord(e[1], s->stream);
+        API_TRY(launch_exchange_part(s, s->stream, 1));
+        cudaEventRecord(e[2], s->stream);
+        PIMDB_CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+        if (r >= 2) {
+            float a = 0.f, b = 0.f;
+            cudaEventElapsedTime(&a, e[0], e[1]);
+            cudaEventElapsedTime(&b, e[1], e[2]);
+            acc[0] += a; acc[1] += b;
+        }
+    }
+    for (auto& ev : e) cudaEventDestroy(ev);
+    out[0] = acc[0] / reps * 1e3;
+    out[1] = acc[1] / reps * 1e3;
     return PIMDB_OK;
 }

@@ -86,14 +86,17 @@ __device__ __forceinline__ Ext ext_exp_neg(double y) {
     return ext_normalize(o.m, o.e);
 }
 
+__device__ __forceinline__ int4 ext_pack(double m, int e) { return make_int4(__double2loint(m), __double2hiint(m), e, 0); }
+__device__ __forceinline__ double ext_m(const int4& c) { return __hiloint2double(c.y, c.x); }
+
 // ---------------------------------------------------------------- arguments
 struct ExArgs {
     const double *x1, *xP;     // bead 1 and bead P slices, [D][N]
     const double *x2, *xPm1;   // bead 2 (next of first) and bead P-1 (previous of last)
     double* A;                 // A[N] prefix sums
     double* Inv;               // Inv[i] = 1/i, i = 0..N (Inv[0] = 0): no FP64 division in the O(N^2) loops
-    double *Cfm, *Cbm;         // coefficient mantissas: Cf[j][v] = c(j,v) (v>=j), Cb[p][l] = c(l,p) (l<=p); N x N each
-    int *Cfe, *Cbe;            // ... and binary exponents
+    int4 *Cf, *Cb;             // Boltzmann factors, packed {mantissa lo, hi, binary exponent, 0}, N x N each:
+                               //   Cf[j][v] = c(j,v) (v >= j);  Cb[p][l] = c(l,p) / (p+1) (l <= p, backward weight folded in)
     double *Wm, *Wbm;          // W[0..N], Wb[0..N] mantissas
     int *We, *Wbe;             // ... exponents
     double *V, *Vb, *F;        // V[N+1], Vb[N+1], F[2][D][N]
@@ -172,8 +175,11 @@ __global__ void __launch_bounds__(256) k_exch_coeff(ExArgs a) {
         const int u = min(r, s), v = max(r, s);
         const double y = a.h * (a.A[v] - a.A[u] + dist2<D>(a, a.x1, u, a.xP, v));
         const Ext c = ext_exp_neg(y < 0.0 ? 0.0 : y);   // (a NaN position stays NaN and is reported, like the reference)
-        if (s >= r) { a.Cfm[i] = c.m; a.Cfe[i] = c.e; }
-        if (s <= r) { a.Cbm[i] = c.m; a.Cbe[i] = c.e; }
+        if (s >= r) a.Cf[i] = ext_pack(c.m, c.e);
+        if (s <= r) {   // backward table: the 1/(p+1) weight of the sum (p = r) is folded in here, off the chain
+            const Ext cb = ext_normalize(c.m * a.Inv[r + 1], c.e);
+            a.Cb[i] = ext_pack(cb.m, cb.e);
+        }
     }
 }
 
@@ -185,6 +191,10 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
 __device__ __forceinline__ void cp_async4(void* smem, const void* gmem) {
     unsigned s = (unsigned)__cvta_generic_to_shared(smem);
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 template <int K>
@@ -198,25 +208,22 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // ST > 0: coefficient rows are staged through an ST-deep cp.async ring in shared memory (each thread copies and
 //         later reads only its own elements, so cp.async.wait_group is the only synchronisation they need);
 // ST == 0: large N, coefficients are read straight from global memory (R independent loads per thread and step).
-// smem: sWm[N+2] | sInv[N+2] (reciprocals 1/i, so no division sits on the chain) | stage mantissas [ST][R][nt]
-//       | sWe[N+2] | stage exponents [ST][R][nt]
+// smem: ring int4[ST][R][nt] | sWm[N+2] | sInv[N+2] (reciprocals 1/i, so no division sits on the chain) | sWe[N+2]
 template <bool FWD, int R, int ST>
 __device__ __forceinline__ void recur_body(const ExArgs& a, double* smem_d) {
     static_assert(ST == 0 || (ST & (ST - 1)) == 0, "ring depth must be a power of two");
     const int tid = threadIdx.x, nt = blockDim.x, N = a.N;
-    double* sWm = smem_d;
+    int4* ring = (int4*)smem_d;
+    double* sWm = (double*)(ring + (size_t)ST * R * nt);
     double* sInv = sWm + (N + 2);
-    double* stm = sInv + (N + 2);
-    int* sWe = (int*)(stm + (size_t)ST * R * nt);
-    int* ste = sWe + (N + 2);
+    int* sWe = (int*)(sInv + (N + 2));
     const int nsteps = FWD ? N : N - 1;     // forward: coefficient row j = s; backward: row p = N-1-s
     const int dstep = FWD ? N : -N;         // coefficient offset advance per step
 
     // row-validity of my R rows at coefficient row `row`: forward col in [row, N); backward col in [1, row]
     auto need = [&](int col, int row) { return FWD ? (col >= row && col < N) : (col >= 1 && col <= row); };
 
-    const double* gm = (FWD ? a.Cfm : a.Cbm) + (FWD ? 0 : (long long)(N - 1) * N) + tid;   // prefetch cursor
-    const int* ge = (FWD ? a.Cfe : a.Cbe) + (FWD ? 0 : (long long)(N - 1) * N) + tid;
+    const int4* gc = (FWD ? a.Cf : a.Cb) + (FWD ? 0 : (long long)(N - 1) * N) + tid;   // prefetch cursor
     int s_issue = 0;
     auto issue = [&]() {
         if (ST > 0) {
@@ -224,17 +231,12 @@ __device__ __forceinline__ void recur_body(const ExArgs& a, double* smem_d) {
                 const int row = FWD ? s_issue : (N - 1 - s_issue);
                 const int slot = s_issue & (ST > 0 ? ST - 1 : 0);
 #pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    if (need(tid + r * nt, row)) {
-                        cp_async8(&stm[(slot * R + r) * nt + tid], gm + r * nt);
-                        cp_async4(&ste[(slot * R + r) * nt + tid], ge + r * nt);
-                    }
-                }
+                for (int r = 0; r < R; ++r)
+                    if (need(tid + r * nt, row)) cp_async16(&ring[(slot * R + r) * nt + tid], gc + r * nt);
             }
             cp_async_commit();
             ++s_issue;
-            gm += dstep;
-            ge += dstep;
+            gc += dstep;
         }
     };
 
@@ -254,8 +256,7 @@ __device__ __forceinline__ void recur_body(const ExArgs& a, double* smem_d) {
     // owner (thread, register slot) of the row that completes in the current step, tracked incrementally
     int own_t = FWD ? 0 : (N - 1) % nt;
     int own_r = FWD ? 0 : (N - 1) / nt;
-    const double* lm = (FWD ? a.Cfm : a.Cbm) + (FWD ? 0 : (long long)(N - 1) * N) + tid;   // direct-load cursor (ST == 0)
-    const int* le = (FWD ? a.Cfe : a.Cbe) + (FWD ? 0 : (long long)(N - 1) * N) + tid;
+    const int4* lc = (FWD ? a.Cf : a.Cb) + (FWD ? 0 : (long long)(N - 1) * N) + tid;   // direct-load cursor (ST == 0)
     const int warp = tid >> 5;
 
     for (int s = 0; s < nsteps; ++s) {
@@ -279,23 +280,23 @@ __device__ __forceinline__ void recur_body(const ExArgs& a, double* smem_d) {
             const int slot = s & (ST > 0 ? ST - 1 : 0);
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                cm[r] = stm[(slot * R + r) * nt + tid];
-                ce[r] = ste[(slot * R + r) * nt + tid];
+                const int4 c = ring[(slot * R + r) * nt + tid];
+                cm[r] = ext_m(c);
+                ce[r] = c.z;
             }
         } else {
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const bool nd = need(tid + r * nt, row);
-                cm[r] = nd ? __ldg(lm + r * nt) : 0.0;
-                ce[r] = nd ? __ldg(le + r * nt) : 0;
+                const int4 c = nd ? __ldg(lc + r * nt) : make_int4(0, 0, 0, 0);
+                cm[r] = ext_m(c);
+                ce[r] = c.z;
             }
-            lm += dstep;
-            le += dstep;
+            lc += dstep;
         }
         const int src = FWD ? s : (N - s);         // index of the known value: W[j] or Wb[p+1]
-        double wm = sWm[src];
+        const double wm = sWm[src];                 // (the backward 1/(p+1) weight is already inside Cb)
         const int we = sWe[src];
-        if (!FWD) wm *= sInv[row + 1];             // the 1/(p+1) weight of the backward sum
 #pragma unroll
         for (int r = 0; r < R; ++r)
             if (need(tid + r * nt, row)) ext_fma(am[r], ae[r], cm[r], ce[r], wm, we);
@@ -337,7 +338,7 @@ __device__ __forceinline__ void recur_body(const ExArgs& a, double* smem_d) {
 
 template <int R, int ST>
 __global__ void __launch_bounds__(1024) k_exch_recur(ExArgs a) {
-    extern __shared__ double smem_d[];
+    extern __shared__ __align__(16) double smem_d[];
     if (blockIdx.x == 0) recur_body<true, R, ST>(a, smem_d);
     else recur_body<false, R, ST>(a, smem_d);
 }
@@ -355,7 +356,7 @@ __global__ void __launch_bounds__(1024) k_exch_recur(ExArgs a) {
 //     values at its own pace -- four columns per poll, so it is faster than the owner and never holds it up -- and
 //     takes over as owner when its rows come up (one ~160-cycle shared-memory hand-off per 32 steps).
 //   Dependencies are acyclic (a warp only ever waits for values owned by earlier warps), so there is no deadlock.
-// smem: entries int4[N+2] | sInv[N+2] | ring mantissas [ST][nt] | ring exponents [ST][nt]
+// smem: entries int4[N+2] | coefficient ring int4[ST][nt] | sInv[N+2]
 __device__ __forceinline__ int4 lds_volatile_v4(const int4* p) {
     int4 r;
     unsigned a = (unsigned)__cvta_generic_to_shared(p);
@@ -373,9 +374,8 @@ __device__ __forceinline__ void recur_decoupled(const ExArgs& a, double* smem_d)
     constexpr int NB = 4;                            // columns a consumer applies per poll
     const int tid = threadIdx.x, nt = blockDim.x, N = a.N, lane = tid & 31, warp = tid >> 5;
     int4* sW = (int4*)smem_d;                        // {m.lo, m.hi, e, tag}
-    double* sInv = (double*)(sW + (N + 2));
-    double* stm = sInv + (N + 2);
-    int* ste = (int*)(stm + (size_t)ST * nt);
+    int4* ring = sW + (N + 2);
+    double* sInv = (double*)(ring + (size_t)ST * nt);
     const int nsteps = FWD ? N : N - 1;
     const int dstep = FWD ? N : -N;
     const int v = tid;                                              // my row
@@ -389,19 +389,13 @@ __device__ __forceinline__ void recur_decoupled(const ExArgs& a, double* smem_d)
         return row_ok && (FWD ? (v >= r) : (v <= r));
     };
     auto idx_of = [&](int s) { return FWD ? s : N - s; };           // where value #s lives
-    const double* gm = (FWD ? a.Cfm : a.Cbm) + (FWD ? 0 : (long long)(N - 1) * N) + tid;
-    const int* ge = (FWD ? a.Cfe : a.Cbe) + (FWD ? 0 : (long long)(N - 1) * N) + tid;
+    const int4* gc = (FWD ? a.Cf : a.Cb) + (FWD ? 0 : (long long)(N - 1) * N) + tid;
     int s_issue = 0;
     auto issue = [&]() {
-        if (s_issue < nsteps && need(s_issue)) {
-            const int slot = s_issue & (ST - 1);
-            cp_async8(&stm[slot * nt + tid], gm);
-            cp_async4(&ste[slot * nt + tid], ge);
-        }
+        if (s_issue < nsteps && need(s_issue)) cp_async16(&ring[(s_issue & (ST - 1)) * nt + tid], gc);
         cp_async_commit();
         ++s_issue;
-        gm += dstep;
-        ge += dstep;
+        gc += dstep;
     };
     auto wait_value = [&](int s) {                                  // spin until value #s is published
         int4 w;
@@ -431,10 +425,9 @@ __device__ __forceinline__ void recur_decoupled(const ExArgs& a, double* smem_d)
                 const int4 w = sW[idx_of(s + k)];
                 wm[k] = __hiloint2double(w.y, w.x);
                 we[k] = w.z;
-                if (!FWD) wm[k] *= sInv[N - (s + k)];
-                const int slot = (s + k) & (ST - 1);
-                cm[k] = stm[slot * nt + tid];
-                ce[k] = ste[slot * nt + tid];
+                const int4 c = ring[((s + k) & (ST - 1)) * nt + tid];
+                cm[k] = ext_m(c);
+                ce[k] = c.z;
             }
             if (row_ok) {
 #pragma unroll
@@ -446,10 +439,8 @@ __device__ __forceinline__ void recur_decoupled(const ExArgs& a, double* smem_d)
         } else {
             const int4 w = wait_value(s);
             cp_async_wait<ST - 1 - NB>();
-            double wm = __hiloint2double(w.y, w.x);
-            if (!FWD) wm *= sInv[N - s];
-            const int slot = s & (ST - 1);
-            if (row_ok) ext_fma(am, ae, stm[slot * nt + tid], ste[slot * nt + tid], wm, w.z);
+            const int4 c = ring[(s & (ST - 1)) * nt + tid];
+            if (row_ok) ext_fma(am, ae, ext_m(c), c.z, __hiloint2double(w.y, w.x), w.z);
             issue();
             ++s;
         }
@@ -461,11 +452,8 @@ __device__ __forceinline__ void recur_decoupled(const ExArgs& a, double* smem_d)
         int we = w0.z;
         for (; s <= own_hi; ++s) {
             cp_async_wait<ST - 1 - NB>();
-            const int slot = s & (ST - 1);
-            const double cm = stm[slot * nt + tid];
-            const int ce = ste[slot * nt + tid];
-            const double um = FWD ? wm : wm * sInv[N - s];          // backward: the 1/(p+1) weight, p+1 = N-s
-            if (need(s)) ext_fma(am, ae, cm, ce, um, we);
+            const int4 c = ring[(s & (ST - 1)) * nt + tid];
+            if (need(s)) ext_fma(am, ae, ext_m(c), c.z, wm, we);
             const int lane_o = (FWD ? s : (N - 1 - s)) & 31;
             const Ext fin = ext_normalize(FWD ? am * sInv[s + 1] : am, ae);
             wm = __shfl_sync(kFullMask, fin.m, lane_o);
@@ -497,7 +485,7 @@ __device__ __forceinline__ void recur_decoupled(const ExArgs& a, double* smem_d)
 
 template <int ST>
 __global__ void __launch_bounds__(1024) k_exch_recur_dec(ExArgs a) {
-    extern __shared__ double smem_d[];
+    extern __shared__ __align__(16) double smem_d[];
     if (blockIdx.x == 0) recur_decoupled<true, ST>(a, smem_d);
     else recur_decoupled<false, ST>(a, smem_d);
 }
@@ -551,7 +539,8 @@ __global__ void __launch_bounds__(kFT) k_exch_forces(ExArgs a) {
                 pr = 1.0 - ext_to_double(wl * a.Wbm[l], el + a.Wbe[l]);
             } else {
                 const size_t ci = (size_t)l * N + u;
-                pr = ext_to_double(wl * a.Cfm[ci] * a.Wbm[u + 1] * a.Inv[u + 1], el + a.Cfe[ci] + a.Wbe[u + 1]);
+                const int4 c = __ldg(&a.Cf[ci]);
+                pr = ext_to_double(wl * ext_m(c) * a.Wbm[u + 1] * a.Inv[u + 1], el + c.z + a.Wbe[u + 1]);
             }
 #pragma unroll
             for (int c = 0; c < D; ++c) {
@@ -573,7 +562,6 @@ __global__ void __launch_bounds__(kFT) k_exch_forces(ExArgs a) {
         // f_l = k [ sum_{u=0}^{min(l+1,N-1)} P(l->u) mi(r^1_u - r^P_l) + mi(r^{P-1}_l - r^P_l) ]
         const double wb = a.Wbm[l + 1] * iWN;
         const int eb = a.Wbe[l + 1] - eWN;
-        const double il1 = a.Inv[l + 1];
         const int uend = min(l + 1, N - 1);
 #pragma unroll 2
         for (int u = lane; u <= uend; u += kFT) {
@@ -582,7 +570,8 @@ __global__ void __launch_bounds__(kFT) k_exch_forces(ExArgs a) {
                 pr = 1.0 - ext_to_double(wb * a.Wm[l + 1], eb + a.We[l + 1]);
             } else {
                 const size_t ci = (size_t)l * N + u;
-                pr = ext_to_double(wb * a.Cbm[ci] * a.Wm[u] * il1, eb + a.Cbe[ci] + a.We[u]);
+                const int4 c = __ldg(&a.Cb[ci]);                       // = c(u,l) / (l+1)
+                pr = ext_to_double(wb * ext_m(c) * a.Wm[u], eb + c.z + a.We[u]);
             }
 #pragma unroll
             for (int c = 0; c < D; ++c) {
@@ -631,7 +620,8 @@ __global__ void __launch_bounds__(1024) k_exch_estimators(ExArgs a) {
             const int v = tid + r * nt;
             if (v >= j && v < N) {
                 const size_t ci = (size_t)j * N + v;
-                const double wgt = ext_to_double(a.Cfm[ci] * wjm * iwm[r], a.Cfe[ci] + wje + iwe[r]);
+                const int4 c = __ldg(&a.Cf[ci]);
+                const double wgt = ext_to_double(ext_m(c) * wjm * iwm[r], c.z + wje + iwe[r]);
                 acc[r] = fma(wgt, ej - cycle_energy<D>(a, j, v), acc[r]);
             }
         }
@@ -681,8 +671,7 @@ __global__ void k_exch_table_prob(ExArgs a, double* out) {
         double pr = 0.0;
         if (u == l + 1) pr = 1.0 - ext_to_double(a.Wm[l + 1] * a.Wbm[l + 1] * iWN, a.We[l + 1] + a.Wbe[l + 1] - eWN);
         else if (u <= l)
-            pr = ext_to_double(a.Wm[u] * a.Cbm[i] * a.Wbm[l + 1] * iWN / (double)(l + 1),
-                               a.We[u] + a.Cbe[i] + a.Wbe[l + 1] - eWN);
+            pr = ext_to_double(a.Wm[u] * ext_m(a.Cb[i]) * a.Wbm[l + 1] * iWN, a.We[u] + a.Cb[i].z + a.Wbe[l + 1] - eWN);
         out[i] = pr;
     }
 }
@@ -705,8 +694,7 @@ static ExArgs make_args(Sim* s) {
     const size_t NN = (size_t)s->N * s->N;
     a.A = s->exA;
     a.Inv = s->exA + s->N;
-    a.Cfm = s->exCm; a.Cbm = s->exCm + NN;
-    a.Cfe = s->exCe; a.Cbe = s->exCe + NN;
+    a.Cf = s->exC; a.Cb = s->exC + NN;
     a.Wm = s->exWm; a.Wbm = s->exWm + (s->N + 1);
     a.We = s->exWe; a.Wbe = s->exWe + (s->N + 1);
     a.V = s->exV; a.Vb = s->exVb; a.F = s->exF;
@@ -729,7 +717,7 @@ static int rows_per_thread(int N, int& nt) {
 
 template <int R, int ST>
 static int launch_recur(Sim* s, const ExArgs& a, cudaStream_t st, int nt) {
-    const size_t smem = ((size_t)(s->N + 2) + (size_t)ST * R * nt) * (sizeof(double) + sizeof(int)) + (size_t)(s->N + 2) * sizeof(double);
+    const size_t smem = (size_t)ST * R * nt * sizeof(int4) + (size_t)(s->N + 2) * (2 * sizeof(double) + sizeof(int)) + 16;
     if (smem > 220 * 1024) {
         s->err = "natoms too large for the single-block exchange recursion of this build";
         return PIMDB_ERR_INVALID_ARGUMENT;
@@ -744,12 +732,17 @@ static int run_recursion(Sim* s, const ExArgs& a, cudaStream_t st) {
     int nt;
     const int R = rows_per_thread(s->N, nt);
     if (R == 1 && !getenv("PIMDB_EXCH_BARRIER")) {           // N <= 1024: warp-decoupled kernel
-        constexpr int ST = 16;
-        const size_t smem = (size_t)(s->N + 2) * (sizeof(int4) + sizeof(double)) +
-                            (size_t)ST * nt * (sizeof(double) + sizeof(int)) + 16;
-        if (smem > 48 * 1024)
-            cudaFuncSetAttribute(k_exch_recur_dec<ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k_exch_recur_dec<ST><<<2, nt, smem, st>>>(a);
+        // coefficient ring: 16 rows in flight up to 512 rows per block, 8 beyond (shared-memory budget)
+        const int ST = nt <= 512 ? 16 : 8;
+        const size_t smem = (size_t)(s->N + 2) * (sizeof(int4) + sizeof(double)) + (size_t)ST * nt * sizeof(int4) + 16;
+        if (ST == 16) {
+            if (smem > 48 * 1024)
+                cudaFuncSetAttribute(k_exch_recur_dec<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k_exch_recur_dec<16><<<2, nt, smem, st>>>(a);
+        } else {
+            cudaFuncSetAttribute(k_exch_recur_dec<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k_exch_recur_dec<8><<<2, nt, smem, st>>>(a);
+        }
         return PIMDB_OK;
     }
     switch (R) {

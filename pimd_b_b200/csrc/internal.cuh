@@ -63,8 +63,8 @@ struct Sim {
     int bead_chunk = 0;
     // exchange
     double *exA = nullptr, *exV = nullptr, *exVb = nullptr, *exF = nullptr;  // A[N], V[N+1], Vb[N+1], F[2][D][N]
-    double *exCm = nullptr, *exWm = nullptr;                               // Boltzmann factors [2][N][N], W/Wb [2][N+1] (mantissas)
-    int *exCe = nullptr, *exWe = nullptr;                                  // ... binary exponents
+    int4 *exC = nullptr;                                                   // Boltzmann factors [2][N][N], packed extended-range numbers
+    double *exWm = nullptr; int *exWe = nullptr;                           // W/Wb [2][N+1]: mantissas, binary exponents
     double *exTab = nullptr; size_t exTabCap = 0;                          // on-demand E / prob tables
     // reductions
     double* com_part = nullptr;        // [kMaxPartials][4]

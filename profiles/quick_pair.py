@@ -28,6 +28,23 @@ t0 = time.perf_counter()
 sim.step(nsteps)
 sim.synchronize()
 t1 = time.perf_counter()
+exch_us = None
+if cfg.bosonic:   # the exchange chain alone (prefix + factors + recurrences + exterior forces), warm caches
+    sim.exchange_prepare()
+    sim.synchronize()
+    t2 = time.perf_counter()
+    for _ in range(200):
+        sim.exchange_prepare()
+    sim.synchronize()
+    exch_us = (time.perf_counter() - t2) / 200 * 1e6
+parts = None
+if cfg.bosonic:
+    import ctypes as C
+    arr = (C.c_double * 2)()
+    sim.lib.pimdb_debug_exchange_timing.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_double)]
+    sim.lib.pimdb_debug_exchange_timing(sim.h, 100, arr)
+    parts = {"prefix_plus_factors_us": arr[0], "recurrences_plus_forces_us": arr[1]}
+print(json.dumps({"exchange_chain_us": exch_us, "parts": parts}))
 obs = sim.observables()
 print(json.dumps({"workload": name, "natoms": cfg.natoms, "nbeads": cfg.nbeads, "pair_us": pair_ms * 1e3,
                   "pair_tflops_alg": wl.pair_flops_per_step(cfg) / (pair_ms * 1e-3) * 1e-12 if pair_ms else None,
