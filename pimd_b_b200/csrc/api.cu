@@ -858,5 +858,17 @@ extern "C" int pimdb_debug_exchange_timing(pimdb_sim* sim, int reps, double* out
     for (auto& ev : e) cudaEventDestroy(ev);
     out[0] = acc[0] / reps * 1e3;
     out[1] = acc[1] / reps * 1e3;
+    if (getenv("PIMDB_EXCH_DEBUG")) {   // per-warp clock64 stamps of one more run: out[2 + 3*(dir*32 + warp) + {0,1,2}]
+        if (!s->dbg_buf) cudaMalloc(&s->dbg_buf, sizeof(long long) * 64 * 3);
+        cudaMemset(s->dbg_buf, 0, sizeof(long long) * 64 * 3);
+        API_TRY(launch_exchange_part(s, s->stream, 0));
+        API_TRY(launch_exchange_part(s, s->stream, 1));
+        PIMDB_CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+        long long h[64 * 3];
+        cudaMemcpy(h, s->dbg_buf, sizeof h, cudaMemcpyDeviceToHost);
+        for (int i = 0; i < 64 * 3; ++i) out[2 + i] = (double)h[i];
+        cudaFree(s->dbg_buf);
+        s->dbg_buf = nullptr;
+    }
     return PIMDB_OK;
 }

@@ -102,6 +102,7 @@ struct ExArgs {
     double *V, *Vb, *F;        // V[N+1], Vb[N+1], F[2][D][N]
     DevObs* obs;
     int* err;
+    long long* dbg;            // optional profiling buffer (clock64 stamps per warp), nullptr in production
     int N, D, pbc, do_first, do_last;
     double k, beta, h, L, invL;   // h = beta*k/2
 };
@@ -356,7 +357,7 @@ __global__ void __launch_bounds__(1024) k_exch_recur(ExArgs a) {
 //     values at its own pace -- four columns per poll, so it is faster than the owner and never holds it up -- and
 //     takes over as owner when its rows come up (one ~160-cycle shared-memory hand-off per 32 steps).
 //   Dependencies are acyclic (a warp only ever waits for values owned by earlier warps), so there is no deadlock.
-// smem: entries int4[N+2] | coefficient ring int4[ST][nt] | sInv[N+2]
+// smem: entries int4[N+2] | coefficient ring int4[ST][nt] | sInv[N+2] | (FAST) kapS[32][nt]
 __device__ __forceinline__ int4 lds_volatile_v4(const int4* p) {
     int4 r;
     unsigned a = (unsigned)__cvta_generic_to_shared(p);
@@ -368,7 +369,7 @@ __device__ __forceinline__ void sts_volatile_v4(int4* p, int4 v) {
     asm volatile("st.volatile.shared.v4.s32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-template <bool FWD, int ST>
+template <bool FWD, int ST, bool FAST>
 __device__ __forceinline__ void recur_decoupled(const ExArgs& a, double* smem_d) {
     static_assert(ST >= 8 && (ST & (ST - 1)) == 0, "ring depth must be a power of two >= 8");
     constexpr int NB = 4;                            // columns a consumer applies per poll
@@ -391,8 +392,9 @@ __device__ __forceinline__ void recur_decoupled(const ExArgs& a, double* smem_d)
     auto idx_of = [&](int s) { return FWD ? s : N - s; };           // where value #s lives
     const int4* gc = (FWD ? a.Cf : a.Cb) + (FWD ? 0 : (long long)(N - 1) * N) + tid;
     int s_issue = 0;
-    auto issue = [&]() {
-        if (s_issue < nsteps && need(s_issue)) cp_async16(&ring[(s_issue & (ST - 1)) * nt + tid], gc);
+    auto issue = [&]() {   // (the fast owner phase keeps its coefficients in registers: no ring traffic for those steps)
+        if (s_issue < nsteps && need(s_issue) && !(FAST && s_issue >= own_lo))
+            cp_async16(&ring[(s_issue & (ST - 1)) * nt + tid], gc);
         cp_async_commit();
         ++s_issue;
         gc += dstep;
@@ -402,7 +404,27 @@ __device__ __forceinline__ void recur_decoupled(const ExArgs& a, double* smem_d)
         do { w = lds_volatile_v4(&sW[idx_of(s)]); } while (w.w != s + 1);
         return w;
     };
+    // (Backing far consumers off with __nanosleep between polls was measured and does not help: the owner's step
+    // time is not set by the pollers.)
 
+    // FAST: the (up to) 32 Boltzmann factors this row needs during its warp's owner phase, as plain doubles in shared
+    // memory, kapS[k][thread] (a factor below 2^-1022 becomes 0, which the fast path's validity window makes
+    // harmless). Loaded in independent batches of 8 so the global-load latency is paid four times, not 32.
+    double* kapS = sInv + (N + 2);
+    if (FAST) {
+        const int4* Cg0 = FWD ? a.Cf : a.Cb;
+        for (int k0 = 0; k0 < 32; k0 += 8) {
+            int4 raw[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int st = own_lo + k0 + k;
+                raw[k] = (st <= own_hi && need(st)) ? __ldg(&Cg0[(long long)(FWD ? st : (N - 1 - st)) * N + v])
+                                                    : make_int4(0, 0, kExtZeroExp, 0);
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) kapS[(k0 + k) * nt + tid] = ext_to_double(ext_m(raw[k]), raw[k].z);
+        }
+    }
     for (int i = tid; i <= N + 1; i += nt) sW[i] = make_int4(0, 0, 0, 0);
     for (int i = tid; i <= N; i += nt) sInv[i] = i > 0 ? 1.0 / (double)i : 0.0;
 #pragma unroll
@@ -413,6 +435,7 @@ __device__ __forceinline__ void recur_decoupled(const ExArgs& a, double* smem_d)
     double am = 0.0;
     int ae = kExtZeroExp;
     int s = 0;
+    const long long t_begin = a.dbg ? clock64() : 0;
     // ---- consumer phase: columns owned by earlier warps; every row of my warp takes part in all of them
     while (s < own_lo) {
         if (own_lo - s >= NB) {
@@ -445,23 +468,96 @@ __device__ __forceinline__ void recur_decoupled(const ExArgs& a, double* smem_d)
             ++s;
         }
     }
+    const long long t_own0 = a.dbg ? clock64() : 0;
     // ---- owner phase: the completing rows are my warp's; the chain runs lane to lane through shuffles
     if (s <= own_hi) {
-        const int4 w0 = wait_value(s);
-        double wm = __hiloint2double(w0.y, w0.x);
-        int we = w0.z;
-        for (; s <= own_hi; ++s) {
-            cp_async_wait<ST - 1 - NB>();
-            const int4 c = ring[(s & (ST - 1)) * nt + tid];
-            if (need(s)) ext_fma(am, ae, ext_m(c), c.z, wm, we);
-            const int lane_o = (FWD ? s : (N - 1 - s)) & 31;
-            const Ext fin = ext_normalize(FWD ? am * sInv[s + 1] : am, ae);
-            wm = __shfl_sync(kFullMask, fin.m, lane_o);
-            we = __shfl_sync(kFullMask, fin.e, lane_o);
-            if (lane == lane_o)
-                sts_volatile_v4(&sW[idx_of(s + 1)], make_int4(__double2loint(fin.m), __double2hiint(fin.m), fin.e, s + 2));
-            issue();
+        auto row_of = [&](int st) { return FWD ? st : (N - 1 - st); };
+        int s_resume = s;                 // first step whose result is NOT yet published
+        bool exact = !FAST;
+        if (FAST) {
+            // Block-scaled fast path. Inside one 32-step owner phase every W is written as omega * 2^E with a common
+            // binary exponent E and a plain double omega, so a step is ONE fma + ONE multiply + ONE shuffle (no
+            // exponent alignment, no normalisation on the chain). It is exact as long as every omega of the phase
+            // stays within 2^+-400 of the phase's first value and no accumulator starts above 2^600 on that scale:
+            // whatever a plain double then flushes to zero is < 2^-622 and negligible against the result. The moment
+            // a value leaves that window the phase is redone from the untouched extended-range accumulators
+            // (below); nothing out of range has been published by then. The loop is deliberately NOT unrolled: it
+            // runs once per warp, and straight-line code executed once is bound by instruction fetch.
+            const int4 w0 = wait_value(s);
+            const int E = w0.z;
+            double om = __hiloint2double(w0.y, w0.x);
+            const int d = ae - E;
+            double A = (am == 0.0) ? 0.0 : ext_to_double(am, min(d, 600));
+            exact = __any_sync(kFullMask, (am != 0.0) && (d > 600));
+            if (!exact) {
+                // Measured on B200 (profiles/microbench2.cu): fma + mul + shuffle = 46 cycles per step; shared-memory
+                // operands loaded inside the step add 65, a compare-and-branch range check 55, a divergent publish 91.
+                // Hence: operands are prefetched one step ahead, the range check is an integer test on the exponent
+                // bits folded into a predicate (no branch; once it fails nothing more is published and the phase
+                // is redone below), and the published entry is computed by all lanes with only the store predicated.
+                const double* kp = kapS + tid;
+                double kcur = *kp;
+                double icur = FWD ? sInv[s + 1] : 1.0;
+                bool okall = true;
+#pragma unroll 1
+                for (int st = s; st <= own_hi; ++st) {
+                    kp += nt;
+                    const bool more = st < own_hi;
+                    const double knext = more ? *kp : 0.0;
+                    const double inext = (FWD && more) ? sInv[st + 2] : 1.0;
+                    if (need(st)) A = fma(kcur, om, A);
+                    const int lane_o = row_of(st) & 31;
+                    const double nxt = __shfl_sync(kFullMask, FWD ? A * icur : A, lane_o);
+                    om = nxt;
+                    const int hi = __double2hiint(nxt);
+                    const unsigned ex = (unsigned)(hi >> 20) & 0xfffu;          // sign + biased exponent
+                    okall = okall && (ex - 623u < 800u);                          // positive, within 2^+-400, not NaN/inf/0
+                    const int4 entry = make_int4(__double2loint(nxt), (hi & 0x000fffff) | 0x3ff00000, E + (int)ex - 1023, st + 2);
+                    if (okall && lane == lane_o) sts_volatile_v4(&sW[idx_of(st + 1)], entry);
+                    s_resume = okall ? st + 1 : s_resume;
+                    kcur = knext;
+                    icur = inext;
+                }
+                exact = !okall;
+            }
         }
+        if (exact) {
+            // Extended-range path. As the fallback of the fast path it restarts the phase from the pre-phase
+            // accumulators, re-applies the already published columns without publishing them again (coefficients
+            // straight from global memory: rare), and continues from the first unpublished step.
+            const int4* Cg = FWD ? a.Cf : a.Cb;
+            const int4 w0 = wait_value(s);
+            double wm = __hiloint2double(w0.y, w0.x);
+            int we = w0.z;
+#pragma unroll 1
+            for (; s <= own_hi; ++s) {
+                if (FAST && s > own_lo && s <= s_resume) {
+                    const int4 w = wait_value(s);
+                    wm = __hiloint2double(w.y, w.x);
+                    we = w.z;
+                }
+                if (!FAST) cp_async_wait<ST - 1 - NB>();
+                if (need(s)) {
+                    const int4 c = FAST ? __ldg(&Cg[(long long)row_of(s) * N + v]) : ring[(s & (ST - 1)) * nt + tid];
+                    ext_fma(am, ae, ext_m(c), c.z, wm, we);
+                }
+                if (!FAST || s >= s_resume) {
+                    const int lane_o = row_of(s) & 31;
+                    const Ext fin = ext_normalize(FWD ? am * sInv[s + 1] : am, ae);
+                    wm = __shfl_sync(kFullMask, fin.m, lane_o);
+                    we = __shfl_sync(kFullMask, fin.e, lane_o);
+                    if (lane == lane_o)
+                        sts_volatile_v4(&sW[idx_of(s + 1)], make_int4(__double2loint(fin.m), __double2hiint(fin.m), fin.e, s + 2));
+                }
+                if (!FAST) issue();
+            }
+        }
+    }
+    if (a.dbg && lane == 0) {
+        long long* o = a.dbg + ((FWD ? 0 : 32) + warp) * 3;
+        o[0] = t_own0 - t_begin;            // cycles spent as a consumer (incl. waiting)
+        o[1] = clock64() - t_own0;          // cycles spent as the owner
+        o[2] = t_begin;
     }
     cp_async_wait<0>();
     __syncthreads();
@@ -483,11 +579,11 @@ __device__ __forceinline__ void recur_decoupled(const ExArgs& a, double* smem_d)
     }
 }
 
-template <int ST>
+template <int ST, bool FAST>
 __global__ void __launch_bounds__(1024) k_exch_recur_dec(ExArgs a) {
     extern __shared__ __align__(16) double smem_d[];
-    if (blockIdx.x == 0) recur_decoupled<true, ST>(a, smem_d);
-    else recur_decoupled<false, ST>(a, smem_d);
+    if (blockIdx.x == 0) recur_decoupled<true, ST, FAST>(a, smem_d);
+    else recur_decoupled<false, ST, FAST>(a, smem_d);
 }
 
 // ---------------------------------------------------------------- 4. exterior spring forces (K7 + K8)
@@ -698,7 +794,7 @@ static ExArgs make_args(Sim* s) {
     a.Wm = s->exWm; a.Wbm = s->exWm + (s->N + 1);
     a.We = s->exWe; a.Wbe = s->exWe + (s->N + 1);
     a.V = s->exV; a.Vb = s->exVb; a.F = s->exF;
-    a.obs = s->obs_d; a.err = s->err_d;
+    a.obs = s->obs_d; a.err = s->err_d; a.dbg = s->dbg_buf;
     a.N = s->N; a.D = s->D; a.pbc = s->cfg.pbc;
     a.do_first = s->has_first; a.do_last = s->has_last;
     a.k = s->kspring; a.beta = s->exch_beta; a.h = 0.5 * s->exch_beta * s->kspring;
@@ -735,13 +831,20 @@ static int run_recursion(Sim* s, const ExArgs& a, cudaStream_t st) {
         // coefficient ring: 16 rows in flight up to 512 rows per block, 8 beyond (shared-memory budget)
         const int ST = nt <= 512 ? 16 : 8;
         const size_t smem = (size_t)(s->N + 2) * (sizeof(int4) + sizeof(double)) + (size_t)ST * nt * sizeof(int4) + 16;
-        if (ST == 16) {
+        if (nt <= 512 && !getenv("PIMDB_EXCH_NOFAST")) {
+            // block-scaled fast owner phase: + a [32][nt] tile of plain-double factors, ring depth 8
+            const size_t smem_fast = (size_t)(s->N + 2) * (sizeof(int4) + sizeof(double)) + (size_t)8 * nt * sizeof(int4) +
+                                     (size_t)32 * nt * sizeof(double) + 16;
+            if (smem_fast > 48 * 1024)
+                cudaFuncSetAttribute(k_exch_recur_dec<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast);
+            k_exch_recur_dec<8, true><<<2, nt, smem_fast, st>>>(a);
+        } else if (ST == 16) {
             if (smem > 48 * 1024)
-                cudaFuncSetAttribute(k_exch_recur_dec<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            k_exch_recur_dec<16><<<2, nt, smem, st>>>(a);
+                cudaFuncSetAttribute(k_exch_recur_dec<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k_exch_recur_dec<16, false><<<2, nt, smem, st>>>(a);
         } else {
-            cudaFuncSetAttribute(k_exch_recur_dec<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            k_exch_recur_dec<8><<<2, nt, smem, st>>>(a);
+            cudaFuncSetAttribute(k_exch_recur_dec<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k_exch_recur_dec<8, false><<<2, nt, smem, st>>>(a);
         }
         return PIMDB_OK;
     }
