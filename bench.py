@@ -209,11 +209,25 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    graph_note = "CUDA graph replay (pimdb_step)"
+    launches_per_step = None
     with torch.cuda.stream(stream):
         # ---- warm-up (W >= 3 untimed steps; also captures the CUDA graph)
         stepper(W)
         observe()
         barrier()
+        if world > 1:
+            l_a = launch_count()
+            stepper(1)
+            launches_per_step = launch_count() - l_a      # kernels of one sharded step (NCCL kernels not counted)
+            ok = driver.enable_graph()
+            flags = torch.tensor([1.0 if ok else 0.0], device=dev)
+            dist.all_reduce(flags, op=dist.ReduceOp.MIN)
+            if flags.item() < 0.5:
+                driver._graph = None
+            graph_note = ("torch CUDA graph of the sharded step incl. NCCL halo + all-reduce" if flags.item() > 0.5
+                          else "eager phases + NCCL (graph capture unavailable: %s)" % getattr(driver, "_graph_error", "?"))
+            barrier()
 
         # ---- timed region: exactly K steps, L2 flushed between steps, CUDA events on the launching stream
         clocks = ClockSampler(local_rank) if rank == 0 else None
@@ -232,6 +246,8 @@ def main():
         barrier()
         wall1 = time.perf_counter()
         gpu_launches = launch_count() - l0
+        if launches_per_step is not None and getattr(driver, "_graph", None) is not None:
+            gpu_launches = launches_per_step * K + (launch_count() - l0)   # graph replays do not pass through the library's counter
         total_ms = sum(a.elapsed_time(b) for a, b in ev)
         clk = clocks.stop() if clocks else None
         if world > 1:
@@ -300,8 +316,16 @@ def main():
                 sim.timing_enable(False)
                 flops = workloads.pair_flops_per_step(cfg) / max(1, (npair // 50))
                 ach = flops / (pair_ms * 1e-3) * 1e-12
+                traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture
+                try:
+                    prof = json.loads((ROOT / "profiles" / "r01_ncu_summary.json").read_text())
+                    if args.workload == "c3":
+                        traffic = prof["kernels"]["k_pair_tiles"]["dram_traffic_bytes"]
+                except Exception:
+                    pass
                 roofline = {"kernel": "k_pair_tiles", "bound": "fp64", "achieved": ach, "peak": fp64_peak,
-                            "unit": "TFLOP/s", "frac": ach / fp64_peak if fp64_peak else None, "traffic": None,
+                            "unit": "TFLOP/s", "frac": ach / fp64_peak if fp64_peak else None, "traffic": traffic,
+                            "traffic_source": "profiles/r01_ncu_summary.json (ncu --set full, bytes per launch)",
                             "peak_source": "DFMA micro-benchmark in this run (MEASURED_PEAKS.json has no FP64 figure)",
                             "flops_per_launch": flops, "ms_per_launch": pair_ms, "launches_timed": npair,
                             "share_of_step": pair_ms * (npair / 50) / step_ms if step_ms else None,
@@ -330,7 +354,8 @@ def main():
             "config": {"workload": workloads.DESCRIPTION[args.workload], "natoms": cfg.natoms, "nbeads": cfg.nbeads,
                        "ndim": cfg.ndim, "parallelism": f"bead-sharded x{world}" if world > 1 else "single GPU",
                        "l2": "flushed between timed steps (256 MiB write)" if flush is not None else "not flushed",
-                       "estimators_every": args.sfreq, "timing": "CUDA events per step on the launching stream, max over ranks"},
+                       "estimators_every": args.sfreq, "timing": "CUDA events per step on the launching stream, max over ranks",
+                       "launch": graph_note},
             "ms_per_step_back_to_back": b2b_ms, "steps_per_s_back_to_back": 1e3 / b2b_ms,
             "wall_s_timed_region": wall1 - wall0,
             "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clk,

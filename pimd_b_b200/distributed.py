@@ -111,7 +111,37 @@ class ShardedSimulation:
         if self.cfg.fixcom and self.world > 1:
             dist.all_reduce(self.shard.com, op=dist.ReduceOp.SUM, group=self.group)
 
+    # ---- CUDA-graph replay of one sharded step (kernels of all four phases + the NCCL halo / all-reduce calls) ----
+    def enable_graph(self) -> bool:
+        """Capture one step into a torch CUDA graph (NCCL collectives are capturable); returns False and stays on
+        the eager path if capture is not possible in this environment. Call from inside the shard's stream context."""
+        if getattr(self, "_graph", None) is not None:
+            return True
+        if not torch.cuda.is_available() or not hasattr(self.shard, "stream"):
+            return False
+        try:
+            self._step_eager(2)                       # warm-up: NCCL communicators, lazy allocations
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=self.shard.stream, capture_error_mode="thread_local"):
+                self._step_eager(1)
+            self._graph = g
+            return True
+        except Exception as exc:   # pragma: no cover - depends on the NCCL / driver combination
+            self._graph = None
+            self._graph_error = repr(exc)
+            torch.cuda.synchronize()
+            return False
+
     def step(self, nsteps: int = 1):
+        g = getattr(self, "_graph", None)
+        if g is not None:
+            for _ in range(nsteps):
+                g.replay()
+            return
+        self._step_eager(nsteps)
+
+    def _step_eager(self, nsteps: int = 1):
         s = self.shard
         for _ in range(nsteps):
             s.step_phase(0)          # thermostat half step (+ local momentum sums)

@@ -62,6 +62,11 @@ FORCE_CASES = {
     "harmonic_pair_cutoff_1d": (trap(37, 5, D=1, bosonic=False, interaction="harmonic", int_omega=1 * MEV,
                                      cutoff=40.0), 0.3),
     "free_trap_bosonic_golden_like": (trap(8, 8), 1.0),
+    # stiff springs + uncorrelated bead positions: beta*E ~ 1e3-1e4 per link, W drops by e^-thousands per step, so
+    # every 32-step owner phase of the recurrence leaves its 2^+-400 window and takes the exact fallback path
+    "stiff_random_bosonic_fallback_N80": (trap(80, 4, mass=4.0026 * DALTON, temperature=2 * KELVIN, size=40.0), 1.0),
+    "stiff_random_bosonic_fallback_N200_pbc": (trap(200, 3, mass=4.0026 * DALTON, temperature=2 * KELVIN, size=60.0,
+                                                    pbc=True, external="free"), 1.0),
     "free_trap_bosonic_N16_P32": (trap(16, 32), 1.0),
     "free_trap_bosonic_P2": (trap(12, 2), 0.2),
     "free_trap_bosonic_N1": (trap(1, 4), 0.2),
@@ -95,7 +100,8 @@ def test_forces_match_oracle(gpu_required, name):
 
 
 @pytest.mark.parametrize("name", ["aziz_pbc_bosonic", "free_trap_bosonic_golden_like", "free_trap_bosonic_N16_P32",
-                                  "free_free_bosonic_pbc", "dipole_2d_trap_bosonic", "free_trap_bosonic_P2"])
+                                  "free_free_bosonic_pbc", "dipole_2d_trap_bosonic", "free_trap_bosonic_P2",
+                                  "stiff_random_bosonic_fallback_N80", "stiff_random_bosonic_fallback_N200_pbc"])
 def test_exchange_tables_match_oracle(gpu_required, name):
     cfg, kind = FORCE_CASES[name]
     x, p = make_inputs(cfg, 11, kind)
