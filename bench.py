@@ -220,7 +220,10 @@ def main():
             l_a = launch_count()
             stepper(1)
             launches_per_step = launch_count() - l_a      # kernels of one sharded step (NCCL kernels not counted)
-            ok = driver.enable_graph()
+            # Capturing the NCCL point-to-point calls hung on this pool's boxes (round 1): opt-in only.
+            ok = driver.enable_graph() if os.environ.get("PIMDB_SHARD_GRAPH") == "1" else False
+            if not ok and not hasattr(driver, "_graph_error"):
+                driver._graph_error = "disabled (set PIMDB_SHARD_GRAPH=1 to try)"
             flags = torch.tensor([1.0 if ok else 0.0], device=dev)
             dist.all_reduce(flags, op=dist.ReduceOp.MIN)
             if flags.item() < 0.5:
