@@ -16,6 +16,7 @@ int launch_exchange_part(Sim* s, cudaStream_t st, int part);
 using namespace pimdb;
 
 static thread_local std::string g_create_error;
+static int settle_momenta(Sim* s);
 
 #define API_TRY(expr)                      \
     do {                                   \
@@ -359,6 +360,7 @@ extern "C" int pimdb_set_state(pimdb_sim* sim, int which, const double* host) {
     double* dst = array_ptr(s, which, halo);
     if (!dst) return fail(s, PIMDB_ERR_INVALID_ARGUMENT, "unknown state array");
     PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
+    if (which == PIMDB_P) s->p_shift_pending = false;   // the caller replaces the momenta: nothing left to settle
     const size_t bytes = s->S * s->Ploc * sizeof(double);
     // the caller's buffer may be pageable: stage through pinned memory so the copy is truly asynchronous-safe
     PIMDB_CUDA_TRY(s, cudaStreamSynchronize(s->stream));
@@ -376,6 +378,7 @@ extern "C" int pimdb_get_state(pimdb_sim* sim, int which, double* host) {
     double* src = array_ptr(s, which, halo);
     if (!src) return fail(s, PIMDB_ERR_INVALID_ARGUMENT, "unknown state array");
     PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
+    if (which == PIMDB_P) API_TRY(settle_momenta(s));
     const size_t bytes = s->S * s->Ploc * sizeof(double);
     API_TRY(launch_soa_to_aos(s, src, halo));
     PIMDB_CUDA_TRY(s, cudaMemcpyAsync(s->stage_h, s->stage_d, bytes, cudaMemcpyDeviceToHost, s->stream));
@@ -480,16 +483,40 @@ static void propagator_into(Sim* s, Fuser& fz) {
     }
 }
 
+// A centre-of-mass shift whose sums are known (com[]) but which has not been subtracted from p yet. pimdb_step leaves
+// the second zeroMomentum of an iteration in this state so that the subtraction rides in the first kernel of the next
+// iteration instead of costing a launch; every other entry point settles it first, so callers never see it.
+static int settle_momenta(Sim* s) {
+    if (!s->p_shift_pending) return PIMDB_OK;
+    s->p_shift_pending = false;
+    return launch_integrate(s, OP_SUBCM);
+}
+
 // body of Simulation::run, src/simulation.cpp:246-259
-static int enqueue_step(Sim* s) {
+static int enqueue_step(Sim* s, bool defer_last_com) {
     Fuser fz(s);
+    if (s->p_shift_pending) { fz.subcm(); s->p_shift_pending = false; }
     thermostat_into(s, fz);
     if (s->cfg.fixcom) { fz.sum(); fz.subcm(); }
     propagator_into(s, fz);
     thermostat_into(s, fz);
-    if (s->cfg.fixcom) { fz.sum(); fz.subcm(); }
+    if (s->cfg.fixcom) {
+        fz.sum();
+        if (defer_last_com) s->p_shift_pending = true;
+        else fz.subcm();
+    }
     fz.flush();
     return fz.rc;
+}
+
+// pimdb_step replays one captured iteration, so every iteration must start in the same state: with fixcom that is
+// "a shift is pending". A pending shift of zero is a no-op (p - 0.0 == p bit for bit).
+static int make_entry_state_uniform(Sim* s) {
+    if (s->cfg.fixcom && !s->p_shift_pending) {
+        PIMDB_CUDA_TRY(s, cudaMemsetAsync(s->com, 0, sizeof(double) * 4, s->stream));
+        s->p_shift_pending = true;
+    }
+    return PIMDB_OK;
 }
 
 static int require_all_local(Sim* s, const char* what) {
@@ -517,6 +544,7 @@ extern "C" int pimdb_moment_step(pimdb_sim* sim) {
     Sim* s = reinterpret_cast<Sim*>(sim);
     if (!s) return PIMDB_ERR_INVALID_ARGUMENT;
     PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
+    API_TRY(settle_momenta(s));
     return launch_integrate(s, OP_B);
 }
 
@@ -524,6 +552,7 @@ extern "C" int pimdb_coords_step(pimdb_sim* sim) {
     Sim* s = reinterpret_cast<Sim*>(sim);
     if (!s) return PIMDB_ERR_INVALID_ARGUMENT;
     PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
+    API_TRY(settle_momenta(s));
     return launch_integrate(s, OP_A | (s->all_local ? OP_HALO : 0u));
 }
 
@@ -532,6 +561,7 @@ extern "C" int pimdb_propagator_step(pimdb_sim* sim) {
     if (!s) return PIMDB_ERR_INVALID_ARGUMENT;
     API_TRY(require_all_local(s, "pimdb_propagator_step"));
     PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
+    API_TRY(settle_momenta(s));
     Fuser fz(s);
     propagator_into(s, fz);
     fz.flush();
@@ -542,6 +572,7 @@ extern "C" int pimdb_thermostat_step(pimdb_sim* sim) {
     Sim* s = reinterpret_cast<Sim*>(sim);
     if (!s) return PIMDB_ERR_INVALID_ARGUMENT;
     PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
+    API_TRY(settle_momenta(s));
     Fuser fz(s);
     thermostat_into(s, fz);
     fz.flush();
@@ -553,6 +584,7 @@ extern "C" int pimdb_zero_momentum(pimdb_sim* sim) {
     if (!s) return PIMDB_ERR_INVALID_ARGUMENT;
     API_TRY(require_all_local(s, "pimdb_zero_momentum"));
     PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
+    API_TRY(settle_momenta(s));
     Fuser fz(s);
     fz.sum();
     fz.subcm();
@@ -571,16 +603,17 @@ extern "C" int pimdb_step(pimdb_sim* sim, int nsteps) {
             PIMDB_CUDA_TRY(s, cudaEventCreate(&e0));
             PIMDB_CUDA_TRY(s, cudaEventCreate(&e1));
             PIMDB_CUDA_TRY(s, cudaEventRecord(e0, s->stream));
-            API_TRY(enqueue_step(s));
+            API_TRY(enqueue_step(s, true));
             PIMDB_CUDA_TRY(s, cudaEventRecord(e1, s->stream));
             s->ev_step.emplace_back(e0, e1);
         }
         return PIMDB_OK;
     }
+    if (nsteps > 0) API_TRY(make_entry_state_uniform(s));
     if (!s->graph_exec) {
         const unsigned long long before = s->launches;
         PIMDB_CUDA_TRY(s, cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
-        int rc = enqueue_step(s);
+        int rc = enqueue_step(s, true);
         cudaGraph_t g = nullptr;
         cudaError_t ce = cudaStreamEndCapture(s->stream, &g);
         if (rc != PIMDB_OK) { if (g) cudaGraphDestroy(g); return rc; }
@@ -604,6 +637,7 @@ extern "C" int pimdb_step_phase(pimdb_sim* sim, int phase) {
     if (s->cfg.propagator != PIMDB_PROP_CARTESIAN || s->cfg.nmthermostat)
         return fail(s, PIMDB_ERR_INVALID_ARGUMENT, "bead-sharded phases support the cartesian propagator / thermostat only");
     PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
+    API_TRY(settle_momenta(s));
     Fuser fz(s);
     switch (phase) {
         case 0:
@@ -677,6 +711,7 @@ extern "C" int pimdb_observables_calc(pimdb_sim* sim, pimdb_observables* out) {
     Sim* s = reinterpret_cast<Sim*>(sim);
     if (!s || !out) return PIMDB_ERR_INVALID_ARGUMENT;
     PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
+    API_TRY(settle_momenta(s));
     PIMDB_CUDA_TRY(s, cudaMemsetAsync(s->obs_d, 0, sizeof(DevObs), s->stream));
     API_TRY(launch_obs_elementwise(s));
     if (s->pair_on) {

@@ -372,8 +372,10 @@ __device__ __forceinline__ void sts_volatile_v4(int4* p, int4 v) {
 template <bool FWD, int ST, bool FAST>
 __device__ __forceinline__ void recur_decoupled(const ExArgs& a, double* smem_d) {
     static_assert(ST >= 8 && (ST & (ST - 1)) == 0, "ring depth must be a power of two >= 8");
-    constexpr int NB = 4;                            // columns a consumer applies per poll
-    const int tid = threadIdx.x, nt = blockDim.x, N = a.N, lane = tid & 31, warp = tid >> 5;
+    constexpr int NB = 4;                            // columns a consumer applies per poll (2 was measured: slower hand-offs)
+    int tid;   // read %tid.x once into a register (the compiler otherwise re-reads the special register inside the chain loop)
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+    const int nt = blockDim.x, N = a.N, lane = tid & 31, warp = tid >> 5;
     int4* sW = (int4*)smem_d;                        // {m.lo, m.hi, e, tag}
     int4* ring = sW + (N + 2);
     double* sInv = (double*)(ring + (size_t)ST * nt);
@@ -385,10 +387,10 @@ __device__ __forceinline__ void recur_decoupled(const ExArgs& a, double* smem_d)
     const int own_lo = FWD ? 32 * warp : max(0, N - 1 - (32 * warp + 31));
     const int own_hi = min(nsteps - 1, FWD ? 32 * warp + 31 : N - 1 - 32 * warp);
 
-    auto need = [&](int s) {   // does my row take part in step s ?
-        const int r = FWD ? s : (N - 1 - s);
-        return row_ok && (FWD ? (v >= r) : (v <= r));
-    };
+    // does my row take part in step s ?  forward: v >= s; backward: v <= N-1-s  -- both are "s <= last_need", one
+    // integer compare against a per-thread constant (nothing is re-derived from %tid inside the chain loops)
+    const int last_need = row_ok ? (FWD ? v : N - 1 - v) : -1;
+    auto need = [&](int s) { return s <= last_need; };
     auto idx_of = [&](int s) { return FWD ? s : N - s; };           // where value #s lives
     const int4* gc = (FWD ? a.Cf : a.Cb) + (FWD ? 0 : (long long)(N - 1) * N) + tid;
     int s_issue = 0;
