@@ -8,9 +8,11 @@ std::runtime_error / CUDA failures -> RuntimeError.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
-LIB_PATH = Path(__file__).resolve().parent / "libpimdb200.so"
+# PIMDB200_LIB points at an alternative build of the same ABI (kernel experiments); the default is the in-tree library
+LIB_PATH = Path(os.environ.get("PIMDB200_LIB") or Path(__file__).resolve().parent / "libpimdb200.so")
 
 PIMDB_OK, ERR_INVALID_ARGUMENT, ERR_OVERFLOW, ERR_RUNTIME, ERR_CUDA = range(5)
 

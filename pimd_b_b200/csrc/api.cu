@@ -196,6 +196,7 @@ extern "C" int pimdb_create(const pimdb_config* cfg, pimdb_sim** out) {
     if (!s) return fail(nullptr, PIMDB_ERR_RUNTIME, "out of host memory");
     s->cfg = *cfg;
     s->device = cfg->device;
+    s->sm_count = prop.multiProcessorCount;
     s->N = cfg->natoms; s->P = cfg->nbeads; s->D = cfg->ndim;
     s->b0 = cfg->bead_begin; s->b1 = cfg->bead_end; s->Ploc = s->b1 - s->b0;
     s->all_local = (s->b0 == 0 && s->b1 == s->P);

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cstdint>
+#include <cstring>
 
 namespace pimdb {
 
@@ -18,9 +19,10 @@ __device__ __forceinline__ double min_image(double dx, double L, double invL) {
     return dx - L * fl;
 }
 
-// Vector form for the hot pair loop: D multiplications + roundings and ONE rarely taken branch.
-// rint(dx/L) equals floor(dx/L + 0.5) except at exact ties (|dx| an odd multiple of L/2); ties -- and anything within
-// 1e-9 of one -- take the out-of-line exact path that evaluates the reference's expression literally.
+// Vector form for the hot pair loop: per axis one multiplication, one rounding and one FMA, plus ONE rarely taken
+// branch decided by integer compares. rint(dx/L) equals floor(dx/L + 0.5) except at exact ties (|dx| an odd multiple
+// of L/2); a result within 2^-19 (relative) of +-L/2 -- tested on the high words, `thr_hi` = high word of
+// (L/2)(1 - 2^-19) -- takes the out-of-line exact path that evaluates the reference's expression literally.
 // `negate`: the reference would have formed the separation with the opposite sign (x_lower - x_higher on a diagonal
 // tile); that only matters at a tie, where mi(+L/2) = mi(-L/2) = -L/2, so it is handled in the exact path only.
 static __device__ __noinline__ double min_image_exact(double d, double L, bool negate) {
@@ -28,57 +30,93 @@ static __device__ __noinline__ double min_image_exact(double d, double L, bool n
     d -= L * floor(d / L + 0.5);
     return negate ? -d : d;
 }
+inline int min_image_tie_threshold(double L) {
+    const double thr = 0.5 * L * (1.0 - 1.0 / 524288.0);
+    unsigned long long u;
+    memcpy(&u, &thr, 8);
+    return (int)(u >> 32);
+}
 template <int D>
-__device__ __forceinline__ void min_image_vec(double (&d)[D], double L, double invL, bool negate = false) {
-    double n[D], worst = 0.0;
+__device__ __forceinline__ void min_image_vec(double (&d)[D], double L, double invL, int thr_hi, bool negate = false) {
+    double w[D];
+    int worst = 0;
 #pragma unroll
     for (int c = 0; c < D; ++c) {
-        const double q = d[c] * invL;
-        n[c] = rint(q);
-        worst = fmax(worst, fabs(q - n[c]));
+        w[c] = fma(-L, rint(d[c] * invL), d[c]);
+        worst = max(worst, __double2hiint(w[c]) & 0x7fffffff);
     }
-    if (worst > 0.5 - 1e-9) {
+    if (worst >= thr_hi) {
 #pragma unroll
         for (int c = 0; c < D; ++c) d[c] = min_image_exact(d[c], L, negate);
     } else {
 #pragma unroll
-        for (int c = 0; c < D; ++c) d[c] = fma(-L, n[c], d[c]);
+        for (int c = 0; c < D; ++c) d[c] = w[c];
     }
 }
 
-// exp(t) for t <= 0 in the hot loops: no range branches, constants from the constant bank.
-// t is clamped at -700 (e^-700 ~ 1e-304 is far below anything it is added to); n = rint(t log2 e),
-// r = t - n ln2 (two FMAs, |r| <= 0.3466), degree-12 Taylor polynomial (remainder 1.7e-16), scaling by 2^n through
-// the exponent field (n >= -1010 keeps the result normal).
-static __constant__ double c_exp_poly[13] = {
-    1.0, 1.0, 0.5, 1.0 / 6, 1.0 / 24, 1.0 / 120, 1.0 / 720, 1.0 / 5040, 1.0 / 40320, 1.0 / 362880, 1.0 / 3628800,
-    1.0 / 39916800, 1.0 / 479001600};
-__device__ __forceinline__ double exp_neg_fast(double t) {
-    t = fmax(t, -700.0);
-    const double n = rint(t * 1.4426950408889634);
-    double r = fma(n, -6.93147180369123816490e-01, t);       // ln2 high part (fdlibm split)
-    r = fma(n, -1.90821492927058770002e-10, r);              // ln2 low part
-    // Estrin evaluation: the pair loop is bound by dependent-instruction latency (8.3 cycles per DFMA), so the
-    // 12-deep Horner chain is folded into a depth-5 tree (same coefficients, 4 more multiplications)
-    const double* c = c_exp_poly;
-    const double r2 = r * r, r4 = r2 * r2, r8 = r4 * r4;
-    const double a01 = fma(c[1], r, c[0]), a23 = fma(c[3], r, c[2]), a45 = fma(c[5], r, c[4]), a67 = fma(c[7], r, c[6]);
-    const double a89 = fma(c[9], r, c[8]), aab = fma(c[11], r, c[10]);
-    const double b0 = fma(a23, r2, a01), b1 = fma(a67, r2, a45), b2 = fma(aab, r2, a89);
-    const double lo = fma(b1, r4, b0), hi = fma(c[12], r4, b2);
-    const double p = fma(hi, r8, lo);
-    const int ni = __double2int_rn(n);
-    return __hiloint2double(__double2hiint(p) + (ni << 20), __double2loint(p));
+// exp() for non-positive arguments in the hot loops, no FP64 compares and no conversions, evaluated in base 2:
+// n = round(t log2 e) by the 1.5*2^52 shift (the integer n is the low word of the shifted sum), f = t log2 e - n
+// (|f| <= 1/2, FMAs against a two-part log2 e), 2^f by the degree-12 Taylor polynomial in f ln2 (remainder 1.7e-16)
+// in even/odd Horner form, scaling by 2^n through the exponent field. Results below 2^-1020 return 0 (decided by an
+// integer compare on the shifted sum, so -inf and huge arguments are safe; a NaN propagates).
+// The constants whose low word is not zero travel as kernel parameters (ExpConsts inside the argument struct): the
+// compiler then keeps them in uniform registers for the whole loop instead of re-materialising each one with two
+// moves per use (that was a third of the pair loop's instructions).
+struct ExpConsts {
+    double l2e_hi, l2e_lo;
+    double p[13];          // p[k] = ln2^k / k!   (p[0] = 1)
+};
+inline ExpConsts make_exp_consts() {
+    ExpConsts k;
+    k.l2e_hi = 1.4426950408889634;          // log2(e) rounded to double
+    k.l2e_lo = 2.0355273740931033e-17;      // log2(e) - l2e_hi
+    long double ln2 = 0.693147180559945309417232121458176568L, t = 1.0L;
+    for (int i = 0; i <= 12; ++i) {
+        k.p[i] = (double)t;
+        t = t * ln2 / (long double)(i + 1);
+    }
+    return k;
+}
+constexpr double kExpShift = 6755399441055744.0;   // 1.5 * 2^52
+// 2^f * 2^n from the shifted sum s = n + kExpShift and the reduced argument f
+__device__ __forceinline__ double exp2_finish(double s, double f, const ExpConsts& k) {
+    const double f2 = f * f;
+    double pe = fma(k.p[12], f2, k.p[10]), po = fma(k.p[11], f2, k.p[9]);
+    pe = fma(pe, f2, k.p[8]); po = fma(po, f2, k.p[7]);
+    pe = fma(pe, f2, k.p[6]); po = fma(po, f2, k.p[5]);
+    pe = fma(pe, f2, k.p[4]); po = fma(po, f2, k.p[3]);
+    pe = fma(pe, f2, k.p[2]); po = fma(po, f2, k.p[1]);
+    pe = fma(pe, f2, 1.0);
+    const double p = fma(po, f, pe);
+    // s >= kExpShift - 1020  <=>  n >= -1020 (positive doubles order like their bit patterns; -inf is negative)
+    const bool under = __double_as_longlong(s) < 0x4337FFFFFFFFFC04LL;
+    const int ni = __double2loint(s);
+    return __hiloint2double(under ? 0 : __double2hiint(p) + (ni << 20), under ? 0 : __double2loint(p));
+}
+// exp(t), t <= 0
+__device__ __forceinline__ double exp_neg_fast(double t, const ExpConsts& k) {
+    const double s = fma(t, k.l2e_hi, kExpShift);
+    const double n = s - kExpShift;
+    double f = fma(t, k.l2e_hi, -n);
+    f = fma(t, k.l2e_lo, f);
+    return exp2_finish(s, f, k);
+}
+// exp(K2 x / log2 e) = 2^(K2 x) for K2 x <= 0 with the product formed inside the FMAs: two operations fewer on the
+// pair loop. K2 = (rate) * log2(e) is rounded once, so the argument carries a relative error of 1.1e-16 -- the same
+// size as the rounding of the reference's own product -alpha * x before it calls exp().
+__device__ __forceinline__ double exp2_lin_fast(double x, double K2, const ExpConsts& k) {
+    const double s = fma(x, K2, kExpShift);
+    const double n = s - kExpShift;
+    return exp2_finish(s, fma(x, K2, -n), k);
 }
 
-// 1/sqrt(x) for x comfortably inside the float range: single-precision seed + two Newton steps in double
-// (22 -> 44 -> 88 bits), no special-case branch.
+// 1/sqrt(x): the hardware's double-precision seed (MUFU.RSQ64H, ~2^-22) + one third-order step
+// y (1 + e/2 + 3e^2/8), e = 1 - x y^2 (remainder ~ e^3/3 ~ 2^-67), no conversions and no special-case branch.
 __device__ __forceinline__ double rsqrt_fast(double x) {
-    double y = (double)rsqrtf((float)x);
-    const double hx = 0.5 * x;
-    y = y * fma(-hx * y, y, 1.5);
-    y = y * fma(-hx * y, y, 1.5);
-    return y;
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double e = fma(-x * y, y, 1.0);
+    return fma(y * e, fma(0.375, e, 0.5), y);
 }
 
 __device__ __forceinline__ double warp_sum(double v) {

@@ -357,7 +357,7 @@ __global__ void __launch_bounds__(1024) k_exch_recur(ExArgs a) {
 //     values at its own pace -- four columns per poll, so it is faster than the owner and never holds it up -- and
 //     takes over as owner when its rows come up (one ~160-cycle shared-memory hand-off per 32 steps).
 //   Dependencies are acyclic (a warp only ever waits for values owned by earlier warps), so there is no deadlock.
-// smem: entries int4[N+2] | coefficient ring int4[ST][nt] | sInv[N+2] | (FAST) kapS[32][nt]
+// smem: entries int4[N+2] | coefficient ring int4[ST][nt] | sInv[N+2] | (FAST) kapS[33][nt]
 __device__ __forceinline__ int4 lds_volatile_v4(const int4* p) {
     int4 r;
     unsigned a = (unsigned)__cvta_generic_to_shared(p);
@@ -426,6 +426,7 @@ __device__ __forceinline__ void recur_decoupled(const ExArgs& a, double* smem_d)
 #pragma unroll
             for (int k = 0; k < 8; ++k) kapS[(k0 + k) * nt + tid] = ext_to_double(ext_m(raw[k]), raw[k].z);
         }
+        kapS[32 * nt + tid] = 0.0;            // row 32: the operand prefetched during the phase's last step
     }
     for (int i = tid; i <= N + 1; i += nt) sW[i] = make_int4(0, 0, 0, 0);
     for (int i = tid; i <= N; i += nt) sInv[i] = i > 0 ? 1.0 / (double)i : 0.0;
@@ -485,40 +486,55 @@ __device__ __forceinline__ void recur_decoupled(const ExArgs& a, double* smem_d)
             // a value leaves that window the phase is redone from the untouched extended-range accumulators
             // (below); nothing out of range has been published by then. The loop is deliberately NOT unrolled: it
             // runs once per warp, and straight-line code executed once is bound by instruction fetch.
+            // A published entry of such a phase is {omega (plain double), E, tag}: no normalisation work in the
+            // loop; entries are therefore NOT normalised in general (consumers treat them as mantissa * 2^E with a
+            // mantissa anywhere in 2^+-400), and each phase renormalises its first value so E does not drift.
             const int4 w0 = wait_value(s);
-            const int E = w0.z;
-            double om = __hiloint2double(w0.y, w0.x);
+            const Ext n0 = ext_normalize(__hiloint2double(w0.y, w0.x), w0.z);
+            const int E = n0.e;
+            double om = n0.m;
             const int d = ae - E;
             double A = (am == 0.0) ? 0.0 : ext_to_double(am, min(d, 600));
-            exact = __any_sync(kFullMask, (am != 0.0) && (d > 600));
+            exact = __any_sync(kFullMask, (am != 0.0) && (d > 600)) || !(om > 0.0);
             if (!exact) {
                 // Measured on B200 (profiles/microbench2.cu): fma + mul + shuffle = 46 cycles per step; shared-memory
                 // operands loaded inside the step add 65, a compare-and-branch range check 55, a divergent publish 91.
-                // Hence: operands are prefetched one step ahead, the range check is an integer test on the exponent
-                // bits folded into a predicate (no branch; once it fails nothing more is published and the phase
-                // is redone below), and the published entry is computed by all lanes with only the store predicated.
+                // Hence: the factor is prefetched one step ahead, the 1/(v+1) weight is a per-lane constant (only the
+                // completing lane's product is used), the range check is an integer test on the exponent bits folded
+                // into a predicate (no branch; once it fails nothing more is published and the phase is redone
+                // below). The loop is software-pipelined by one step: iteration st issues the chain's fma and
+                // multiply first and only then checks and publishes the value the PREVIOUS iteration produced (every
+                // lane holds it after the broadcast shuffle), so the integer work and the store sit in the shadow of
+                // the FP64 latency. Every instruction here also costs one issue slot per co-resident consumer warp
+                // (in-order issue, 4 warps per scheduler), so the body is kept to ~20 instructions.
                 const double* kp = kapS + tid;
                 double kcur = *kp;
-                double icur = FWD ? sInv[s + 1] : 1.0;
+                const double myw = FWD ? sInv[min(v + 1, N)] : 1.0;
                 bool okall = true;
+                int lane_o = (FWD ? s : N - 1 - s) & 31;
+                int4* wp = &sW[idx_of(s)];
 #pragma unroll 1
                 for (int st = s; st <= own_hi; ++st) {
                     kp += nt;
-                    const bool more = st < own_hi;
-                    const double knext = more ? *kp : 0.0;
-                    const double inext = (FWD && more) ? sInv[st + 2] : 1.0;
-                    if (need(st)) A = fma(kcur, om, A);
-                    const int lane_o = row_of(st) & 31;
-                    const double nxt = __shfl_sync(kFullMask, FWD ? A * icur : A, lane_o);
-                    om = nxt;
-                    const int hi = __double2hiint(nxt);
-                    const unsigned ex = (unsigned)(hi >> 20) & 0xfffu;          // sign + biased exponent
-                    okall = okall && (ex - 623u < 800u);                          // positive, within 2^+-400, not NaN/inf/0
-                    const int4 entry = make_int4(__double2loint(nxt), (hi & 0x000fffff) | 0x3ff00000, E + (int)ex - 1023, st + 2);
-                    if (okall && lane == lane_o) sts_volatile_v4(&sW[idx_of(st + 1)], entry);
-                    s_resume = okall ? st + 1 : s_resume;
+                    const double knext = *kp;
+                    A = fma(kcur, om, A);                                     // kapS is 0 where a row takes no part
+                    const double t = FWD ? A * myw : A;
+                    {   // value #st (st == s: re-stores the hand-off value, renormalised -- same number, same tag)
+                        const unsigned hi = (unsigned)__double2hiint(om);
+                        okall = okall && (hi - (623u << 20) < (800u << 20));   // positive, within 2^+-400, not NaN/inf/0
+                        if (okall && lane == 0) sts_volatile_v4(wp, make_int4(__double2loint(om), (int)hi, E, st + 1));
+                        s_resume = okall ? st : s_resume;
+                    }
+                    om = __shfl_sync(kFullMask, t, lane_o);
+                    lane_o = (lane_o + (FWD ? 1 : -1)) & 31;
+                    wp += FWD ? 1 : -1;
                     kcur = knext;
-                    icur = inext;
+                }
+                {   // the phase's last value, #(own_hi + 1)
+                    const unsigned hi = (unsigned)__double2hiint(om);
+                    okall = okall && (hi - (623u << 20) < (800u << 20));
+                    if (okall && lane == 0) sts_volatile_v4(wp, make_int4(__double2loint(om), (int)hi, E, own_hi + 2));
+                    s_resume = okall ? own_hi + 1 : s_resume;
                 }
                 exact = !okall;
             }
@@ -571,8 +587,9 @@ __device__ __forceinline__ void recur_decoupled(const ExArgs& a, double* smem_d)
     double* V_g = FWD ? a.V : a.Vb;
     for (int i = (FWD ? 0 : 1) + tid; i <= N; i += nt) {
         const int4 w = sW[i];
-        const double m = __hiloint2double(w.y, w.x);
-        const int e = w.z;
+        const Ext wn = ext_normalize(__hiloint2double(w.y, w.x), w.z);   // fast-path entries are not normalised
+        const double m = wn.m;
+        const int e = wn.e;
         Wm_g[i] = m;
         We_g[i] = e;
         const double val = -(log(m) + (double)e * LN2) / a.beta;
@@ -836,7 +853,7 @@ static int run_recursion(Sim* s, const ExArgs& a, cudaStream_t st) {
         if (nt <= 512 && !getenv("PIMDB_EXCH_NOFAST")) {
             // block-scaled fast owner phase: + a [32][nt] tile of plain-double factors, ring depth 8
             const size_t smem_fast = (size_t)(s->N + 2) * (sizeof(int4) + sizeof(double)) + (size_t)8 * nt * sizeof(int4) +
-                                     (size_t)32 * nt * sizeof(double) + 16;
+                                     (size_t)33 * nt * sizeof(double) + 16;
             if (smem_fast > 48 * 1024)
                 cudaFuncSetAttribute(k_exch_recur_dec<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast);
             k_exch_recur_dec<8, true><<<2, nt, smem_fast, st>>>(a);

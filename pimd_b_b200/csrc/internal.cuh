@@ -49,6 +49,7 @@ struct Sim {
     double pair_par = 0;               // harmonic pair k or dipole strength
 
     int device = 0;
+    int sm_count = 148;
     cudaStream_t stream = nullptr, stream_x = nullptr;  // main stream, exchange side stream
     bool own_stream = true;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
