@@ -144,7 +144,7 @@ static void free_all(Sim* s) {
     cudaFree(s->stage_d); cudaFreeHost(s->stage_h);
     cudaFree(s->tile_ij); cudaFree(s->pair_scratch);
     cudaFree(s->exA); cudaFree(s->exV); cudaFree(s->exVb); cudaFree(s->exF); cudaFree(s->exTab);
-    cudaFree(s->exC); cudaFree(s->exWm); cudaFree(s->exWe);
+    cudaFree(s->exC); cudaFree(s->exK); cudaFree(s->exB); cudaFree(s->exWm); cudaFree(s->exWe);
     cudaFree(s->com_part); cudaFree(s->com); cudaFree(s->tickets); cudaFree(s->draw);
     cudaFree(s->obs_d); cudaFreeHost(s->obs_h); cudaFree(s->obs_part);
     cudaFreeHost(s->err_h);
@@ -267,6 +267,11 @@ extern "C" int pimdb_create(const pimdb_config* cfg, pimdb_sim** out) {
         const size_t NN = (size_t)s->N * s->N;
         CREATE_TRY(cudaMalloc(&s->exA, sizeof(double) * (2 * s->N + 2)));   // A[N] | Inv[N+1]
         CREATE_TRY(cudaMalloc(&s->exC, sizeof(int4) * 2 * NN));
+        if (s->N <= 512) {   // the fast recurrence's block-scaled copy (exchange.cu: k_exch_coeff_tiles)
+            CREATE_TRY(cudaMalloc(&s->exK, sizeof(double) * 2 * (NN + 512)));
+            CREATE_TRY(cudaMemset(s->exK, 0, sizeof(double) * 2 * (NN + 512)));
+            CREATE_TRY(cudaMalloc(&s->exB, sizeof(int) * 2 * (size_t)((s->N + 31) / 32) * s->N));
+        }
         CREATE_TRY(cudaMalloc(&s->exWm, sizeof(double) * 2 * (s->N + 1)));
         CREATE_TRY(cudaMalloc(&s->exWe, sizeof(int) * 2 * (s->N + 1)));
         CREATE_TRY(cudaMemset(s->exWm, 0, sizeof(double) * 2 * (s->N + 1)));

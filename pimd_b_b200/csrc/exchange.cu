@@ -97,6 +97,9 @@ struct ExArgs {
     double* Inv;               // Inv[i] = 1/i, i = 0..N (Inv[0] = 0): no FP64 division in the O(N^2) loops
     int4 *Cf, *Cb;             // Boltzmann factors, packed {mantissa lo, hi, binary exponent, 0}, N x N each:
                                //   Cf[j][v] = c(j,v) (v >= j);  Cb[p][l] = c(l,p) / (p+1) (l <= p, backward weight folded in)
+    double *Kf, *Kb;           // the same factors block-scaled for the fast recurrence (N <= 512), or nullptr:
+                               //   K[r][v] = C[r][v] * 2^-B[r/32][v] as a plain double (0 outside the triangle)
+    int *Bf, *Bb;              //   B[rb][v] = largest binary exponent of C[32rb .. 32rb+31][v]
     double *Wm, *Wbm;          // W[0..N], Wb[0..N] mantissas
     int *We, *Wbe;             // ... exponents
     double *V, *Vb, *F;        // V[N+1], Vb[N+1], F[2][D][N]
@@ -180,6 +183,68 @@ __global__ void __launch_bounds__(256) k_exch_coeff(ExArgs a) {
         if (s <= r) {   // backward table: the 1/(p+1) weight of the sum (p = r) is folded in here, off the chain
             const Ext cb = ext_normalize(c.m * a.Inv[r + 1], c.e);
             a.Cb[i] = ext_pack(cb.m, cb.e);
+        }
+    }
+}
+
+// Tile version for N <= 512: one block per 32 x 32 tile of the index square also emits the block-scaled copy the
+// fast recurrence consumes -- per (32-row block rb, column v) the largest binary exponent B and the factors as plain
+// doubles relative to 2^B. A factor more than 2^1022 below its block's largest becomes 0; it multiplies values that
+// the fast recurrence keeps within 2^+-400 of each other, so it could not have contributed.
+template <int D>
+__global__ void __launch_bounds__(256) k_exch_coeff_tiles(ExArgs a) {
+    __shared__ int s_ef[8][32], s_eb[8][32];
+    const int N = a.N, nb = (N + 31) >> 5;
+    const int rb = blockIdx.x / nb, sb = blockIdx.x % nb;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int sc = sb * 32 + tx;                       // column (the recurrence's row index v or l)
+    double mf[4], mb[4];
+    int ef[4], eb[4];
+    int maxf = kExtZeroExp, maxb = kExtZeroExp;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r = rb * 32 + ty + 8 * k;
+        mf[k] = 0.0; mb[k] = 0.0; ef[k] = kExtZeroExp; eb[k] = kExtZeroExp;
+        if (r < N && sc < N) {
+            const int u = min(r, sc), v = max(r, sc);
+            const double y = a.h * (a.A[v] - a.A[u] + dist2<D>(a, a.x1, u, a.xP, v));
+            const Ext c = ext_exp_neg(y < 0.0 ? 0.0 : y);   // (a NaN position stays NaN and is reported, like the reference)
+            const long long i = (long long)r * N + sc;
+            if (sc >= r) {
+                a.Cf[i] = ext_pack(c.m, c.e);
+                mf[k] = c.m; ef[k] = c.e;
+            }
+            if (sc <= r) {   // backward table: the 1/(p+1) weight of the sum (p = r) is folded in here, off the chain
+                const Ext cb = ext_normalize(c.m * a.Inv[r + 1], c.e);
+                a.Cb[i] = ext_pack(cb.m, cb.e);
+                mb[k] = cb.m; eb[k] = cb.e;
+            }
+        }
+        maxf = max(maxf, ef[k]);
+        maxb = max(maxb, eb[k]);
+    }
+    s_ef[ty][tx] = maxf;
+    s_eb[ty][tx] = maxb;
+    __syncthreads();
+#pragma unroll
+    for (int w = 0; w < 8; ++w) {
+        maxf = max(maxf, s_ef[w][tx]);
+        maxb = max(maxb, s_eb[w][tx]);
+    }
+    if (sc < N) {
+        if (ty == 0) {
+            a.Bf[rb * N + sc] = maxf;
+            a.Bb[rb * N + sc] = maxb;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int r = rb * 32 + ty + 8 * k;
+            if (r < N) {
+                const long long i = (long long)r * N + sc;
+                // (NaN mantissas propagate; an exact zero has exponent kExtZeroExp and scales to 0)
+                a.Kf[i] = mf[k] * pow2i(max(ef[k] - maxf, -1100));
+                a.Kb[i] = mb[k] * pow2i(max(eb[k] - maxb, -1100));
+            }
         }
     }
 }
@@ -357,7 +422,7 @@ __global__ void __launch_bounds__(1024) k_exch_recur(ExArgs a) {
 //     values at its own pace -- four columns per poll, so it is faster than the owner and never holds it up -- and
 //     takes over as owner when its rows come up (one ~160-cycle shared-memory hand-off per 32 steps).
 //   Dependencies are acyclic (a warp only ever waits for values owned by earlier warps), so there is no deadlock.
-// smem: entries int4[N+2] | coefficient ring int4[ST][nt] | sInv[N+2] | (FAST) kapS[33][nt]
+// smem: entries int4[N+2] | coefficient ring int4[ST][nt] | sInv[N+2]
 __device__ __forceinline__ int4 lds_volatile_v4(const int4* p) {
     int4 r;
     unsigned a = (unsigned)__cvta_generic_to_shared(p);
@@ -369,7 +434,7 @@ __device__ __forceinline__ void sts_volatile_v4(int4* p, int4 v) {
     asm volatile("st.volatile.shared.v4.s32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
-template <bool FWD, int ST, bool FAST>
+template <bool FWD, int ST>
 __device__ __forceinline__ void recur_decoupled(const ExArgs& a, double* smem_d) {
     static_assert(ST >= 8 && (ST & (ST - 1)) == 0, "ring depth must be a power of two >= 8");
     constexpr int NB = 4;                            // columns a consumer applies per poll (2 was measured: slower hand-offs)
@@ -394,8 +459,8 @@ __device__ __forceinline__ void recur_decoupled(const ExArgs& a, double* smem_d)
     auto idx_of = [&](int s) { return FWD ? s : N - s; };           // where value #s lives
     const int4* gc = (FWD ? a.Cf : a.Cb) + (FWD ? 0 : (long long)(N - 1) * N) + tid;
     int s_issue = 0;
-    auto issue = [&]() {   // (the fast owner phase keeps its coefficients in registers: no ring traffic for those steps)
-        if (s_issue < nsteps && need(s_issue) && !(FAST && s_issue >= own_lo))
+    auto issue = [&]() {
+        if (s_issue < nsteps && need(s_issue))
             cp_async16(&ring[(s_issue & (ST - 1)) * nt + tid], gc);
         cp_async_commit();
         ++s_issue;
@@ -409,25 +474,6 @@ __device__ __forceinline__ void recur_decoupled(const ExArgs& a, double* smem_d)
     // (Backing far consumers off with __nanosleep between polls was measured and does not help: the owner's step
     // time is not set by the pollers.)
 
-    // FAST: the (up to) 32 Boltzmann factors this row needs during its warp's owner phase, as plain doubles in shared
-    // memory, kapS[k][thread] (a factor below 2^-1022 becomes 0, which the fast path's validity window makes
-    // harmless). Loaded in independent batches of 8 so the global-load latency is paid four times, not 32.
-    double* kapS = sInv + (N + 2);
-    if (FAST) {
-        const int4* Cg0 = FWD ? a.Cf : a.Cb;
-        for (int k0 = 0; k0 < 32; k0 += 8) {
-            int4 raw[8];
-#pragma unroll
-            for (int k = 0; k < 8; ++k) {
-                const int st = own_lo + k0 + k;
-                raw[k] = (st <= own_hi && need(st)) ? __ldg(&Cg0[(long long)(FWD ? st : (N - 1 - st)) * N + v])
-                                                    : make_int4(0, 0, kExtZeroExp, 0);
-            }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) kapS[(k0 + k) * nt + tid] = ext_to_double(ext_m(raw[k]), raw[k].z);
-        }
-        kapS[32 * nt + tid] = 0.0;            // row 32: the operand prefetched during the phase's last step
-    }
     for (int i = tid; i <= N + 1; i += nt) sW[i] = make_int4(0, 0, 0, 0);
     for (int i = tid; i <= N; i += nt) sInv[i] = i > 0 ? 1.0 / (double)i : 0.0;
 #pragma unroll
@@ -475,100 +521,23 @@ __device__ __forceinline__ void recur_decoupled(const ExArgs& a, double* smem_d)
     // ---- owner phase: the completing rows are my warp's; the chain runs lane to lane through shuffles
     if (s <= own_hi) {
         auto row_of = [&](int st) { return FWD ? st : (N - 1 - st); };
-        int s_resume = s;                 // first step whose result is NOT yet published
-        bool exact = !FAST;
-        if (FAST) {
-            // Block-scaled fast path. Inside one 32-step owner phase every W is written as omega * 2^E with a common
-            // binary exponent E and a plain double omega, so a step is ONE fma + ONE multiply + ONE shuffle (no
-            // exponent alignment, no normalisation on the chain). It is exact as long as every omega of the phase
-            // stays within 2^+-400 of the phase's first value and no accumulator starts above 2^600 on that scale:
-            // whatever a plain double then flushes to zero is < 2^-622 and negligible against the result. The moment
-            // a value leaves that window the phase is redone from the untouched extended-range accumulators
-            // (below); nothing out of range has been published by then. The loop is deliberately NOT unrolled: it
-            // runs once per warp, and straight-line code executed once is bound by instruction fetch.
-            // A published entry of such a phase is {omega (plain double), E, tag}: no normalisation work in the
-            // loop; entries are therefore NOT normalised in general (consumers treat them as mantissa * 2^E with a
-            // mantissa anywhere in 2^+-400), and each phase renormalises its first value so E does not drift.
-            const int4 w0 = wait_value(s);
-            const Ext n0 = ext_normalize(__hiloint2double(w0.y, w0.x), w0.z);
-            const int E = n0.e;
-            double om = n0.m;
-            const int d = ae - E;
-            double A = (am == 0.0) ? 0.0 : ext_to_double(am, min(d, 600));
-            exact = __any_sync(kFullMask, (am != 0.0) && (d > 600)) || !(om > 0.0);
-            if (!exact) {
-                // Measured on B200 (profiles/microbench2.cu): fma + mul + shuffle = 46 cycles per step; shared-memory
-                // operands loaded inside the step add 65, a compare-and-branch range check 55, a divergent publish 91.
-                // Hence: the factor is prefetched one step ahead, the 1/(v+1) weight is a per-lane constant (only the
-                // completing lane's product is used), the range check is an integer test on the exponent bits folded
-                // into a predicate (no branch; once it fails nothing more is published and the phase is redone
-                // below). The loop is software-pipelined by one step: iteration st issues the chain's fma and
-                // multiply first and only then checks and publishes the value the PREVIOUS iteration produced (every
-                // lane holds it after the broadcast shuffle), so the integer work and the store sit in the shadow of
-                // the FP64 latency. Every instruction here also costs one issue slot per co-resident consumer warp
-                // (in-order issue, 4 warps per scheduler), so the body is kept to ~20 instructions.
-                const double* kp = kapS + tid;
-                double kcur = *kp;
-                const double myw = FWD ? sInv[min(v + 1, N)] : 1.0;
-                bool okall = true;
-                int lane_o = (FWD ? s : N - 1 - s) & 31;
-                int4* wp = &sW[idx_of(s)];
+        const int4 w0 = wait_value(s);
+        double wm = __hiloint2double(w0.y, w0.x);
+        int we = w0.z;
 #pragma unroll 1
-                for (int st = s; st <= own_hi; ++st) {
-                    kp += nt;
-                    const double knext = *kp;
-                    A = fma(kcur, om, A);                                     // kapS is 0 where a row takes no part
-                    const double t = FWD ? A * myw : A;
-                    {   // value #st (st == s: re-stores the hand-off value, renormalised -- same number, same tag)
-                        const unsigned hi = (unsigned)__double2hiint(om);
-                        okall = okall && (hi - (623u << 20) < (800u << 20));   // positive, within 2^+-400, not NaN/inf/0
-                        if (okall && lane == 0) sts_volatile_v4(wp, make_int4(__double2loint(om), (int)hi, E, st + 1));
-                        s_resume = okall ? st : s_resume;
-                    }
-                    om = __shfl_sync(kFullMask, t, lane_o);
-                    lane_o = (lane_o + (FWD ? 1 : -1)) & 31;
-                    wp += FWD ? 1 : -1;
-                    kcur = knext;
-                }
-                {   // the phase's last value, #(own_hi + 1)
-                    const unsigned hi = (unsigned)__double2hiint(om);
-                    okall = okall && (hi - (623u << 20) < (800u << 20));
-                    if (okall && lane == 0) sts_volatile_v4(wp, make_int4(__double2loint(om), (int)hi, E, own_hi + 2));
-                    s_resume = okall ? own_hi + 1 : s_resume;
-                }
-                exact = !okall;
+        for (; s <= own_hi; ++s) {
+            cp_async_wait<ST - 1 - NB>();
+            if (need(s)) {
+                const int4 c = ring[(s & (ST - 1)) * nt + tid];
+                ext_fma(am, ae, ext_m(c), c.z, wm, we);
             }
-        }
-        if (exact) {
-            // Extended-range path. As the fallback of the fast path it restarts the phase from the pre-phase
-            // accumulators, re-applies the already published columns without publishing them again (coefficients
-            // straight from global memory: rare), and continues from the first unpublished step.
-            const int4* Cg = FWD ? a.Cf : a.Cb;
-            const int4 w0 = wait_value(s);
-            double wm = __hiloint2double(w0.y, w0.x);
-            int we = w0.z;
-#pragma unroll 1
-            for (; s <= own_hi; ++s) {
-                if (FAST && s > own_lo && s <= s_resume) {
-                    const int4 w = wait_value(s);
-                    wm = __hiloint2double(w.y, w.x);
-                    we = w.z;
-                }
-                if (!FAST) cp_async_wait<ST - 1 - NB>();
-                if (need(s)) {
-                    const int4 c = FAST ? __ldg(&Cg[(long long)row_of(s) * N + v]) : ring[(s & (ST - 1)) * nt + tid];
-                    ext_fma(am, ae, ext_m(c), c.z, wm, we);
-                }
-                if (!FAST || s >= s_resume) {
-                    const int lane_o = row_of(s) & 31;
-                    const Ext fin = ext_normalize(FWD ? am * sInv[s + 1] : am, ae);
-                    wm = __shfl_sync(kFullMask, fin.m, lane_o);
-                    we = __shfl_sync(kFullMask, fin.e, lane_o);
-                    if (lane == lane_o)
-                        sts_volatile_v4(&sW[idx_of(s + 1)], make_int4(__double2loint(fin.m), __double2hiint(fin.m), fin.e, s + 2));
-                }
-                if (!FAST) issue();
-            }
+            const int lane_o = row_of(s) & 31;
+            const Ext fin = ext_normalize(FWD ? am * sInv[s + 1] : am, ae);
+            wm = __shfl_sync(kFullMask, fin.m, lane_o);
+            we = __shfl_sync(kFullMask, fin.e, lane_o);
+            if (lane == lane_o)
+                sts_volatile_v4(&sW[idx_of(s + 1)], make_int4(__double2loint(fin.m), __double2hiint(fin.m), fin.e, s + 2));
+            issue();
         }
     }
     if (a.dbg && lane == 0) {
@@ -598,11 +567,289 @@ __device__ __forceinline__ void recur_decoupled(const ExArgs& a, double* smem_d)
     }
 }
 
-template <int ST, bool FAST>
+// (am, ae) += acc * 2^e for a plain non-negative double acc; out of line: it runs once per 32 columns
+static __device__ __noinline__ void ext_fold(double& am, int& ae, double acc, int e) {
+    if (acc > 0.0 || acc != acc) {
+        const Ext t = ext_normalize(acc, e);
+        const int emax = max(ae, t.e);
+        am = fma(am, pow2i(max(ae - emax, -1100)), t.m * pow2i(max(t.e - emax, -1100)));
+        ae = emax;
+    }
+}
+
+// ---------------------------------------------------------------- 3c. fast warp-decoupled recurrence (N <= 512)
+// Same protocol as recur_decoupled (tagged 16-byte entries, one owner warp on the chain, everybody else consuming),
+// with both sides of the work made cheap enough that the chain itself is what is left:
+//   * consumers read the BLOCK-SCALED factors K (plain doubles, k_exch_coeff_tiles) through an 8-byte cp.async ring and
+//     accumulate a 32-column phase as a plain dot product, acc += K * omega -- one FP64 instruction per column instead
+//     of an extended-range multiply-add (~25 instructions). Published entries of a fast phase share one binary exponent
+//     E, so the partial sum is folded into the extended-range accumulator once per phase (and whenever an entry's
+//     exponent differs, which is what entries of the exact fallback path do -- then every column is folded
+//     separately, still correct). This matters twice: a consumer shares its scheduler with the owner (in-order issue,
+//     4 warps each), and the NEXT owner cannot start before it has applied every earlier column.
+//   * the owner phase is the block-scaled loop described below (operands prefetched, publish software-pipelined).
+// smem: entries int4[N+2] | factor ring double[48][512] | sInv[N+2]
+template <bool FWD>
+__device__ __forceinline__ void recur_fast(const ExArgs& a, double* smem_d) {
+    constexpr int ST = 48;                           // ring depth: 12 groups of 4 columns per thread
+    constexpr int AHEAD = 11;                        // groups in flight ahead of the consumer (global latency ~1000+ cycles
+                                                     // against ~100 cycles per column: 12 columns ahead was measured too few)
+    constexpr int RS = 512;                          // row stride of the ring: a compile-time constant, so every
+                                                     // shared-memory address in the loops is base + immediate
+    int tid;   // read %tid.x once into a register (the compiler otherwise re-reads the special register inside the chain loop)
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+    const int nt = blockDim.x, N = a.N, lane = tid & 31, warp = tid >> 5;
+    int4* sW = (int4*)smem_d;                        // {omega.lo, omega.hi, e, tag}
+    double* ring = (double*)(sW + (N + 2));
+    double* sInv = ring + (size_t)ST * RS;
+    const int nsteps = FWD ? N : N - 1;
+    const int dstep = FWD ? N : -N;
+    const int v = tid;                                              // my row
+    const bool row_ok = FWD ? (v < N) : (v >= 1 && v < N);
+    // steps in which my warp owns the completing row; they use the factor rows r = 32 warp .. 32 warp + 31
+    const int own_lo = FWD ? 32 * warp : max(0, N - 1 - (32 * warp + 31));
+    const int own_hi = min(nsteps - 1, FWD ? 32 * warp + 31 : N - 1 - 32 * warp);
+    const int last_need = row_ok ? (FWD ? v : N - 1 - v) : -1;
+    auto need = [&](int s) { return s <= last_need; };
+    auto idx_of = [&](int s) { return FWD ? s : N - s; };           // where value #s lives
+    auto row_of = [&](int st) { return FWD ? st : (N - 1 - st); };  // factor row used by step st
+    const double* Kg = FWD ? a.Kf : a.Kb;
+    const int* Bg = FWD ? a.Bf : a.Bb;
+    // Factor ring, private per thread: column s of my row lives in slot (s + off) % 48, with `off` chosen per warp so
+    // that the 32 columns of the warp's OWN phase sit in slots 0..34 without wrapping -- the owner loop then walks a
+    // plain pointer. Columns travel in aligned groups of four (one cp.async group each), AHEAD groups ahead of the
+    // consumer; the copies run on through the own phase (s <= own_hi), whose factors are read from the same ring.
+    // A group may reach up to three columns past own_hi (or past the table: the allocation is padded) -- never read.
+    const int off = (ST * 1024 - (own_lo & ~3)) % ST;
+    double* const ring_me = ring + tid;
+    auto slot_ptr = [&](int s) { return ring_me + ((s + off) % ST) * RS; };
+    const double* gk = Kg + (FWD ? 0 : (long long)(N - 1) * N) + tid;
+    int s_issue = 0;
+    double* ip = slot_ptr(0);                                       // slot of column s_issue
+    auto issue4 = [&]() {
+        if (s_issue <= own_hi && row_ok) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) cp_async8(ip + k * RS, gk + (long long)k * dstep);
+        }
+        cp_async_commit();
+        s_issue += 4;
+        gk += 4 * (long long)dstep;
+        ip += 4 * RS;
+        if (ip >= ring_me + ST * RS) ip -= ST * RS;
+    };
+    auto wait_value = [&](int s) {                                  // spin until value #s is published
+        int4 w;
+        do { w = lds_volatile_v4(&sW[idx_of(s)]); } while (w.w != s + 1);
+        return w;
+    };
+
+    if (!row_ok) {                             // rows outside the recurrence never copy: their ring slots stay 0
+#pragma unroll 4
+        for (int k = 0; k < ST; ++k) ring_me[k * RS] = 0.0;
+    }
+    for (int i = tid; i <= N + 1; i += nt) sW[i] = make_int4(0, 0, 0, 0);
+    for (int i = tid; i <= N; i += nt) sInv[i] = i > 0 ? 1.0 / (double)i : 0.0;
+#pragma unroll 1
+    for (int g = 0; g < AHEAD; ++g) issue4();
+    // my own block's scale: the owner phase works on factors K (relative to 2^Bown) and folds 2^Bown into the weight
+    const int Bown = row_ok ? Bg[warp * N + v] : kExtZeroExp;
+    __syncthreads();
+    if (tid == 0) sts_volatile_v4(&sW[idx_of(0)], make_int4(__double2loint(1.0), __double2hiint(1.0), 0, 1));
+
+    double am = 0.0;                                 // extended-range accumulator of my row (normalised)
+    int ae = kExtZeroExp;
+    double acc = 0.0;                                // plain partial sum of the current run of columns, scale 2^(Bq + Eph)
+    int Eph = 0, Bq = 0;
+    auto fold = [&]() {                              // am * 2^ae += acc * 2^(Bq + Eph)
+        ext_fold(am, ae, acc, Bq + Eph);
+        acc = 0.0;
+    };
+    auto apply = [&](const int4& w, double kk) {     // one column the careful way (warp-uniform branch: w is broadcast)
+        if (w.z != Eph) { fold(); Eph = w.z; }
+        acc = fma(kk, __hiloint2double(w.y, w.x), acc);
+    };
+    int s = 0;
+    double* rp = slot_ptr(0);                        // slot of column s
+    auto advance = [&](int n) {
+        rp += n * RS;
+        if (rp >= ring_me + ST * RS) rp -= ST * RS;
+    };
+    const long long t_begin = a.dbg ? clock64() : 0;
+    // ---- consumer phases: columns owned by earlier warps, one 32-row factor block q at a time
+    // invariant: issued groups = floor(s / 4) + AHEAD, so "all but the AHEAD-1 newest groups" covers the group of column s
+    int Bnext = (own_lo > 0 && row_ok) ? Bg[(row_of(0) >> 5) * N + v] : 0;
+    while (s < own_lo) {
+        const int q = row_of(s) >> 5;
+        const int s_end = min(own_lo, FWD ? (q + 1) * 32 : N - q * 32);   // one past this block's last step
+        Bq = Bnext;
+        if (s_end < own_lo && row_ok) Bnext = Bg[(row_of(s_end) >> 5) * N + v];
+        while (s < s_end) {
+            if ((s & 3) == 0 && s + 4 <= s_end) {                   // a whole group: four columns per poll
+                wait_value(s + 3);                                   // values are published in order
+                cp_async_wait<AHEAD - 1>();
+                const int4* wp = &sW[idx_of(s)];
+                int4 w[4];
+                double kk[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    w[k] = wp[FWD ? k : -k];
+                    kk[k] = rp[k * RS];
+                }
+                if (((w[0].z ^ Eph) | (w[1].z ^ Eph) | (w[2].z ^ Eph) | (w[3].z ^ Eph)) == 0) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) acc = fma(kk[k], __hiloint2double(w[k].y, w[k].x), acc);
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) apply(w[k], kk[k]);
+                }
+                issue4();
+                s += 4;
+                advance(4);
+            } else {                                                 // ragged head / tail of a block (N % 4 != 0)
+                const int4 w = wait_value(s);
+                cp_async_wait<AHEAD - 1>();
+                apply(w, *rp);
+                if ((s & 3) == 3) issue4();
+                ++s;
+                advance(1);
+            }
+        }
+        fold();                                                      // the next block has its own scale
+    }
+    const long long t_own0 = a.dbg ? clock64() : 0;
+    long long t_loop0 = t_own0;
+    // ---- owner phase: the completing rows are my warp's; the chain runs lane to lane through shuffles
+    if (s <= own_hi) {
+        int s_resume = s;                 // first step whose result is NOT yet published
+        // Block-scaled fast path. Inside one 32-step owner phase every W is written as omega * 2^E with a common
+        // binary exponent E and a plain double omega, and every row keeps its sum in units of 2^(E + Bown) (Bown: the
+        // scale of the row's own factor block), so a step is ONE fma + ONE multiply + ONE shuffle (no exponent
+        // alignment, no normalisation on the chain). It is exact as long as every omega of the phase stays within
+        // 2^+-400 of the phase's first value and no accumulator starts above 2^600 on that scale: whatever a plain
+        // double then flushes to zero is < 2^-622 and negligible against the result. The moment a value leaves
+        // that window the phase is redone from the untouched extended-range accumulators (below); nothing out of
+        // range has been published by then. The loop is deliberately NOT unrolled: it runs once per warp, and
+        // straight-line code executed once is bound by instruction fetch.
+        // A published entry of such a phase is {omega (plain double), E, tag}: no normalisation work in the
+        // loop; entries are therefore NOT normalised in general (consumers treat them as mantissa * 2^E with a
+        // mantissa anywhere in 2^+-400), and each phase renormalises its first value so E does not drift.
+        const int4 w0 = wait_value(s);
+        const Ext n0 = ext_normalize(__hiloint2double(w0.y, w0.x), w0.z);
+        const int E = n0.e;
+        double om = n0.m;
+        const int d = ae - E - Bown;
+        double A = (am == 0.0) ? 0.0 : ext_to_double(am, min(d, 600));
+        bool exact = __any_sync(kFullMask, (am != 0.0) && (d > 600)) || !(om > 0.0);
+        // every group that holds an own-phase column has been issued (AHEAD * 4 >= 35); make sure they have landed
+        cp_async_wait<AHEAD - 9>();
+        if (a.dbg) t_loop0 = clock64();
+        if (!exact) {
+            // Measured on B200 (profiles/microbench2.cu): fma + mul + shuffle = 46 cycles per step; shared-memory
+            // operands loaded inside the step add 65, a compare-and-branch range check 55, a divergent publish 91.
+            // Hence: the factor is prefetched one step ahead, the weight 2^Bown / (v+1) is a per-lane constant (only
+            // the completing lane's product is used), the range check is an integer test on the exponent bits folded
+            // into a predicate (no branch; once it fails nothing more is published and the phase is redone
+            // below). The loop is software-pipelined by one step: iteration st issues the chain's fma and
+            // multiply first and only then checks and publishes the value the PREVIOUS iteration produced (every
+            // lane holds it after the broadcast shuffle), so the integer work and the store sit in the shadow of
+            // the FP64 latency. Every instruction here also costs one issue slot per co-resident consumer warp
+            // (in-order issue, 4 warps per scheduler), so the body is kept to ~25 instructions.
+            const double* kp = rp;                                       // own-phase slots do not wrap (see `off`)
+            double kcur = *kp;
+            const double myw = (FWD ? sInv[min(v + 1, N)] : 1.0) * pow2i(max(Bown, -1100));
+            bool okall = true;
+            int lane_o = row_of(s) & 31;
+            int4* wp = &sW[idx_of(s)];
+#pragma unroll 1
+            for (int st = s; st <= own_hi; ++st) {
+                kp += RS;
+                const double knext = *kp;
+                A = fma(kcur, om, A);                                     // K is 0 where a row takes no part
+                const double t = A * myw;
+                {   // value #st (st == s: re-stores the hand-off value, renormalised -- same number, same tag)
+                    const unsigned hi = (unsigned)__double2hiint(om);
+                    okall = okall && (hi - (623u << 20) < (800u << 20));   // positive, within 2^+-400, not NaN/inf/0
+                    if (okall && lane == 0) sts_volatile_v4(wp, make_int4(__double2loint(om), (int)hi, E, st + 1));
+                    s_resume = okall ? st : s_resume;
+                }
+                om = __shfl_sync(kFullMask, t, lane_o);
+                lane_o = (lane_o + (FWD ? 1 : -1)) & 31;
+                wp += FWD ? 1 : -1;
+                kcur = knext;
+            }
+            {   // the phase's last value, #(own_hi + 1)
+                const unsigned hi = (unsigned)__double2hiint(om);
+                okall = okall && (hi - (623u << 20) < (800u << 20));
+                if (okall && lane == 0) sts_volatile_v4(wp, make_int4(__double2loint(om), (int)hi, E, own_hi + 2));
+                s_resume = okall ? own_hi + 1 : s_resume;
+            }
+            exact = !okall;
+        }
+        if (exact) {
+            // Extended-range fallback: restarts the phase from the pre-phase accumulators, re-applies the already
+            // published columns without publishing them again (factors straight from global memory: rare), and
+            // continues from the first unpublished step; its entries are normalised {mantissa, exponent}.
+            const int4* Cg = FWD ? a.Cf : a.Cb;
+            double wm = __hiloint2double(w0.y, w0.x);
+            int we = w0.z;
+#pragma unroll 1
+            for (; s <= own_hi; ++s) {
+                if (s > own_lo && s <= s_resume) {
+                    const int4 w = wait_value(s);
+                    wm = __hiloint2double(w.y, w.x);
+                    we = w.z;
+                }
+                if (need(s)) {
+                    const int4 c = __ldg(&Cg[(long long)row_of(s) * N + v]);
+                    ext_fma(am, ae, ext_m(c), c.z, wm, we);
+                }
+                if (s >= s_resume) {
+                    const int lane_o = row_of(s) & 31;
+                    const Ext fin = ext_normalize(FWD ? am * sInv[s + 1] : am, ae);
+                    wm = __shfl_sync(kFullMask, fin.m, lane_o);
+                    we = __shfl_sync(kFullMask, fin.e, lane_o);
+                    if (lane == lane_o)
+                        sts_volatile_v4(&sW[idx_of(s + 1)], make_int4(__double2loint(fin.m), __double2hiint(fin.m), fin.e, s + 2));
+                }
+            }
+        }
+    }
+    if (a.dbg && lane == 0) {
+        long long* o = a.dbg + ((FWD ? 0 : 32) + warp) * 3;
+        o[0] = t_own0 - t_begin;            // cycles spent as a consumer (incl. waiting)
+        o[1] = clock64() - t_own0;          // cycles spent as the owner
+        o[2] = t_loop0 - t_own0;            // ... of which: hand-off wait + owner prologue
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+
+    // V = -(ln W)/beta in parallel; publish W (normalised) for the force kernel
+    const double LN2 = 0.6931471805599453;
+    double* Wm_g = FWD ? a.Wm : a.Wbm;
+    int* We_g = FWD ? a.We : a.Wbe;
+    double* V_g = FWD ? a.V : a.Vb;
+    for (int i = (FWD ? 0 : 1) + tid; i <= N; i += nt) {
+        const int4 w = sW[i];
+        const Ext wn = ext_normalize(__hiloint2double(w.y, w.x), w.z);
+        Wm_g[i] = wn.m;
+        We_g[i] = wn.e;
+        const double val = -(log(wn.m) + (double)wn.e * LN2) / a.beta;
+        if (!isfinite(val)) atomicOr(a.err, FWD ? kErrOverflowFwd : kErrOverflowBwd);
+        V_g[i] = (i == (FWD ? 0 : N)) ? 0.0 : val;
+    }
+}
+
+__global__ void __launch_bounds__(512) k_exch_recur_fast(ExArgs a) {
+    extern __shared__ __align__(16) double smem_d[];
+    if (blockIdx.x == 0) recur_fast<true>(a, smem_d);
+    else recur_fast<false>(a, smem_d);
+}
+
+template <int ST>
 __global__ void __launch_bounds__(1024) k_exch_recur_dec(ExArgs a) {
     extern __shared__ __align__(16) double smem_d[];
-    if (blockIdx.x == 0) recur_decoupled<true, ST, FAST>(a, smem_d);
-    else recur_decoupled<false, ST, FAST>(a, smem_d);
+    if (blockIdx.x == 0) recur_decoupled<true, ST>(a, smem_d);
+    else recur_decoupled<false, ST>(a, smem_d);
 }
 
 // ---------------------------------------------------------------- 4. exterior spring forces (K7 + K8)
@@ -810,6 +1057,8 @@ static ExArgs make_args(Sim* s) {
     a.A = s->exA;
     a.Inv = s->exA + s->N;
     a.Cf = s->exC; a.Cb = s->exC + NN;
+    a.Kf = s->exK; a.Kb = s->exK ? s->exK + NN + 512 : nullptr;
+    a.Bf = s->exB; a.Bb = s->exB ? s->exB + (size_t)((s->N + 31) / 32) * s->N : nullptr;
     a.Wm = s->exWm; a.Wbm = s->exWm + (s->N + 1);
     a.We = s->exWe; a.Wbe = s->exWe + (s->N + 1);
     a.V = s->exV; a.Vb = s->exVb; a.F = s->exF;
@@ -850,20 +1099,19 @@ static int run_recursion(Sim* s, const ExArgs& a, cudaStream_t st) {
         // coefficient ring: 16 rows in flight up to 512 rows per block, 8 beyond (shared-memory budget)
         const int ST = nt <= 512 ? 16 : 8;
         const size_t smem = (size_t)(s->N + 2) * (sizeof(int4) + sizeof(double)) + (size_t)ST * nt * sizeof(int4) + 16;
-        if (nt <= 512 && !getenv("PIMDB_EXCH_NOFAST")) {
-            // block-scaled fast owner phase: + a [32][nt] tile of plain-double factors, ring depth 8
-            const size_t smem_fast = (size_t)(s->N + 2) * (sizeof(int4) + sizeof(double)) + (size_t)8 * nt * sizeof(int4) +
-                                     (size_t)33 * nt * sizeof(double) + 16;
+        if (nt <= 512 && a.Kf && !getenv("PIMDB_EXCH_NOFAST")) {
+            // fast kernel: block-scaled factors, plain-double consumers and owner phase, 48-column factor ring
+            const size_t smem_fast = (size_t)(s->N + 2) * (sizeof(int4) + sizeof(double)) + (size_t)48 * 512 * sizeof(double) + 16;
             if (smem_fast > 48 * 1024)
-                cudaFuncSetAttribute(k_exch_recur_dec<8, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast);
-            k_exch_recur_dec<8, true><<<2, nt, smem_fast, st>>>(a);
+                cudaFuncSetAttribute(k_exch_recur_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast);
+            k_exch_recur_fast<<<2, nt, smem_fast, st>>>(a);
         } else if (ST == 16) {
             if (smem > 48 * 1024)
-                cudaFuncSetAttribute(k_exch_recur_dec<16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            k_exch_recur_dec<16, false><<<2, nt, smem, st>>>(a);
+                cudaFuncSetAttribute(k_exch_recur_dec<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k_exch_recur_dec<16><<<2, nt, smem, st>>>(a);
         } else {
-            cudaFuncSetAttribute(k_exch_recur_dec<8, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            k_exch_recur_dec<8, false><<<2, nt, smem, st>>>(a);
+            cudaFuncSetAttribute(k_exch_recur_dec<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            k_exch_recur_dec<8><<<2, nt, smem, st>>>(a);
         }
         return PIMDB_OK;
     }
@@ -887,7 +1135,12 @@ static int exchange_impl(Sim* s, cudaStream_t st, int part) {
     ExArgs a = make_args(s);
     if (part == 0) {
         k_exch_prefix<D><<<1, 1024, 0, st>>>(a);
-        k_exch_coeff<D><<<grid_for((size_t)s->N * s->N, 256, 16 * kNumSM), 256, 0, st>>>(a);
+        if (a.Kf) {
+            const int nb = (s->N + 31) / 32;
+            k_exch_coeff_tiles<D><<<nb * nb, 256, 0, st>>>(a);
+        } else {
+            k_exch_coeff<D><<<grid_for((size_t)s->N * s->N, 256, 16 * kNumSM), 256, 0, st>>>(a);
+        }
         s->launches += 2;
     } else {
         int rc = run_recursion(s, a, st);

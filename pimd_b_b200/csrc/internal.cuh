@@ -65,6 +65,7 @@ struct Sim {
     // exchange
     double *exA = nullptr, *exV = nullptr, *exVb = nullptr, *exF = nullptr;  // A[N], V[N+1], Vb[N+1], F[2][D][N]
     int4 *exC = nullptr;                                                   // Boltzmann factors [2][N][N], packed extended-range numbers
+    double *exK = nullptr; int *exB = nullptr;                             // block-scaled factors [2][N*N + 512], exponents [2][N/32][N] (N <= 512)
     double *exWm = nullptr; int *exWe = nullptr;                           // W/Wb [2][N+1]: mantissas, binary exponents
     long long* dbg_buf = nullptr;                                          // profiling aid (PIMDB_EXCH_DEBUG)
     double *exTab = nullptr; size_t exTabCap = 0;                          // on-demand E / prob tables

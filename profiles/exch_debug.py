@@ -22,3 +22,4 @@ for name, blk in zip(("fwd", "bwd"), d):
     nw = (n + 31) // 32
     print(name, "consumer cycles:", blk[:nw, 0].astype(int).tolist())
     print(name, "owner cycles:   ", blk[:nw, 1].astype(int).tolist())
+    print(name, "owner prologue: ", blk[:nw, 2].astype(int).tolist())
