@@ -192,59 +192,53 @@ __global__ void __launch_bounds__(256) k_exch_coeff(ExArgs a) {
 // doubles relative to 2^B. A factor more than 2^1022 below its block's largest becomes 0; it multiplies values that
 // the fast recurrence keeps within 2^+-400 of each other, so it could not have contributed.
 template <int D>
-__global__ void __launch_bounds__(256) k_exch_coeff_tiles(ExArgs a) {
-    __shared__ int s_ef[8][32], s_eb[8][32];
+__global__ void __launch_bounds__(1024) k_exch_coeff_tiles(ExArgs a) {
+    __shared__ int s_ef[32][33], s_eb[32][33];     // [step within the tile][column], padded: conflict-free both ways
+    __shared__ int s_mf[32], s_mb[32];
     const int N = a.N, nb = (N + 31) >> 5;
     const int rb = blockIdx.x / nb, sb = blockIdx.x % nb;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    const int sc = sb * 32 + tx;                       // column (the recurrence's row index v or l)
-    double mf[4], mb[4];
-    int ef[4], eb[4];
-    int maxf = kExtZeroExp, maxb = kExtZeroExp;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const int r = rb * 32 + ty + 8 * k;
-        mf[k] = 0.0; mb[k] = 0.0; ef[k] = kExtZeroExp; eb[k] = kExtZeroExp;
-        if (r < N && sc < N) {
-            const int u = min(r, sc), v = max(r, sc);
-            const double y = a.h * (a.A[v] - a.A[u] + dist2<D>(a, a.x1, u, a.xP, v));
-            const Ext c = ext_exp_neg(y < 0.0 ? 0.0 : y);   // (a NaN position stays NaN and is reported, like the reference)
-            const long long i = (long long)r * N + sc;
-            if (sc >= r) {
-                a.Cf[i] = ext_pack(c.m, c.e);
-                mf[k] = c.m; ef[k] = c.e;
-            }
-            if (sc <= r) {   // backward table: the 1/(p+1) weight of the sum (p = r) is folded in here, off the chain
-                const Ext cb = ext_normalize(c.m * a.Inv[r + 1], c.e);
-                a.Cb[i] = ext_pack(cb.m, cb.e);
-                mb[k] = cb.m; eb[k] = cb.e;
-            }
+    const int r = rb * 32 + ty, sc = sb * 32 + tx;   // one element per thread: 4x the parallelism of a 256-thread tile
+    double mf = 0.0, mb = 0.0;
+    int ef = kExtZeroExp, eb = kExtZeroExp;
+    const long long i = (long long)r * N + sc;
+    if (r < N && sc < N) {
+        const int u = min(r, sc), v = max(r, sc);
+        const double y = a.h * (a.A[v] - a.A[u] + dist2<D>(a, a.x1, u, a.xP, v));
+        const Ext c = ext_exp_neg(y < 0.0 ? 0.0 : y);   // (a NaN position stays NaN and is reported, like the reference)
+        if (sc >= r) {
+            a.Cf[i] = ext_pack(c.m, c.e);
+            mf = c.m; ef = c.e;
         }
-        maxf = max(maxf, ef[k]);
-        maxb = max(maxb, eb[k]);
+        if (sc <= r) {   // backward table: the 1/(p+1) weight of the sum (p = r) is folded in here, off the chain
+            const Ext cb = ext_normalize(c.m * a.Inv[r + 1], c.e);
+            a.Cb[i] = ext_pack(cb.m, cb.e);
+            mb = cb.m; eb = cb.e;
+        }
     }
-    s_ef[ty][tx] = maxf;
-    s_eb[ty][tx] = maxb;
+    s_ef[ty][tx] = ef;
+    s_eb[ty][tx] = eb;
     __syncthreads();
+    {   // warp ty reduces column ty over the 32 steps of the tile
+        int xf = s_ef[tx][ty], xb = s_eb[tx][ty];
 #pragma unroll
-    for (int w = 0; w < 8; ++w) {
-        maxf = max(maxf, s_ef[w][tx]);
-        maxb = max(maxb, s_eb[w][tx]);
+        for (int o = 16; o > 0; o >>= 1) {
+            xf = max(xf, __shfl_xor_sync(kFullMask, xf, o));
+            xb = max(xb, __shfl_xor_sync(kFullMask, xb, o));
+        }
+        if (tx == 0) { s_mf[ty] = xf; s_mb[ty] = xb; }
     }
+    __syncthreads();
+    const int maxf = s_mf[tx], maxb = s_mb[tx];
     if (sc < N) {
         if (ty == 0) {
             a.Bf[rb * N + sc] = maxf;
             a.Bb[rb * N + sc] = maxb;
         }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const int r = rb * 32 + ty + 8 * k;
-            if (r < N) {
-                const long long i = (long long)r * N + sc;
-                // (NaN mantissas propagate; an exact zero has exponent kExtZeroExp and scales to 0)
-                a.Kf[i] = mf[k] * pow2i(max(ef[k] - maxf, -1100));
-                a.Kb[i] = mb[k] * pow2i(max(eb[k] - maxb, -1100));
-            }
+        if (r < N) {
+            // (NaN mantissas propagate; an exact zero has exponent kExtZeroExp and scales to 0)
+            a.Kf[i] = mf * pow2i(max(ef - maxf, -1100));
+            a.Kb[i] = mb * pow2i(max(eb - maxb, -1100));
         }
     }
 }
@@ -638,7 +632,7 @@ __device__ __forceinline__ void recur_fast(const ExArgs& a, double* smem_d) {
         if (ip >= ring_me + ST * RS) ip -= ST * RS;
     };
     auto wait_value = [&](int s) {                                  // spin until value #s is published
-        int4 w;
+        int4 w;                     // (a __nanosleep(40 / 200) back-off between polls was measured: no gain / 1.5% slower)
         do { w = lds_volatile_v4(&sW[idx_of(s)]); } while (w.w != s + 1);
         return w;
     };
@@ -1137,7 +1131,7 @@ static int exchange_impl(Sim* s, cudaStream_t st, int part) {
         k_exch_prefix<D><<<1, 1024, 0, st>>>(a);
         if (a.Kf) {
             const int nb = (s->N + 31) / 32;
-            k_exch_coeff_tiles<D><<<nb * nb, 256, 0, st>>>(a);
+            k_exch_coeff_tiles<D><<<nb * nb, 1024, 0, st>>>(a);
         } else {
             k_exch_coeff<D><<<grid_for((size_t)s->N * s->N, 256, 16 * kNumSM), 256, 0, st>>>(a);
         }
