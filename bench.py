@@ -275,9 +275,11 @@ def main():
 
         # ---- e2e: the same step through the host-buffer API (upload x,p -> step -> download x,p,f)
         nloc = hi - lo
-        hx = np.ascontiguousarray(x[lo:hi])
-        hp = np.ascontiguousarray(p[lo:hi])
-        hf = np.empty_like(hx)
+        # page-locked host buffers (the library copies straight from / into them; pageable buffers are staged)
+        pin = [torch.empty(x[lo:hi].shape, dtype=torch.float64, pin_memory=True) for _ in range(3)]
+        hx, hp, hf = (t.numpy() for t in pin)
+        hx[...] = x[lo:hi]
+        hp[...] = p[lo:hi]
         sim.get("x", hx)
         sim.get("p", hp)
         Ke = max(20, min(K, 200))
@@ -301,7 +303,7 @@ def main():
         slab_bytes = nloc * cfg.natoms * cfg.ndim * 8
         e2e = {"value": 1.0 / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": 2 * slab_bytes * world,
                "d2h_bytes_per_step": 3 * slab_bytes * world, "steps": Ke,
-               "call": "pimdb_set_state(x,p) + pimdb_step(1) + pimdb_get_state(x,p,f)"}
+               "call": "pimdb_set_state(x,p) + pimdb_step(1) + pimdb_get_state(x,p,f), page-locked host buffers"}
 
         # ---- roofline of the dominant kernel (pair-force tiles), eager pass with CUDA events per launch
         roofline = None

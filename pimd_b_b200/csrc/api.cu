@@ -359,6 +359,16 @@ static double* array_ptr(Sim* s, int which, bool& halo) {
     }
 }
 
+// true when the caller's buffer is page-locked (cudaMallocHost / cudaHostRegister / torch pin_memory)
+static bool host_is_pinned(const void* ptr) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, ptr) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
+
 extern "C" int pimdb_set_state(pimdb_sim* sim, int which, const double* host) {
     Sim* s = reinterpret_cast<Sim*>(sim);
     if (!s || !host) return PIMDB_ERR_INVALID_ARGUMENT;
@@ -368,10 +378,15 @@ extern "C" int pimdb_set_state(pimdb_sim* sim, int which, const double* host) {
     PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
     if (which == PIMDB_P) s->p_shift_pending = false;   // the caller replaces the momenta: nothing left to settle
     const size_t bytes = s->S * s->Ploc * sizeof(double);
-    // the caller's buffer may be pageable: stage through pinned memory so the copy is truly asynchronous-safe
-    PIMDB_CUDA_TRY(s, cudaStreamSynchronize(s->stream));
-    memcpy(s->stage_h, host, bytes);
-    PIMDB_CUDA_TRY(s, cudaMemcpyAsync(s->stage_d, s->stage_h, bytes, cudaMemcpyHostToDevice, s->stream));
+    if (host_is_pinned(host)) {
+        // page-locked caller buffer: one asynchronous copy straight from it (stream order protects the device staging buffer)
+        PIMDB_CUDA_TRY(s, cudaMemcpyAsync(s->stage_d, host, bytes, cudaMemcpyHostToDevice, s->stream));
+    } else {
+        // pageable: stage through our pinned buffer so the copy is truly asynchronous-safe
+        PIMDB_CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+        memcpy(s->stage_h, host, bytes);
+        PIMDB_CUDA_TRY(s, cudaMemcpyAsync(s->stage_d, s->stage_h, bytes, cudaMemcpyHostToDevice, s->stream));
+    }
     API_TRY(launch_aos_to_soa(s, dst, halo));
     if (which == PIMDB_X && s->all_local) API_TRY(launch_fill_halos(s));
     return PIMDB_OK;
@@ -387,9 +402,14 @@ extern "C" int pimdb_get_state(pimdb_sim* sim, int which, double* host) {
     if (which == PIMDB_P) API_TRY(settle_momenta(s));
     const size_t bytes = s->S * s->Ploc * sizeof(double);
     API_TRY(launch_soa_to_aos(s, src, halo));
-    PIMDB_CUDA_TRY(s, cudaMemcpyAsync(s->stage_h, s->stage_d, bytes, cudaMemcpyDeviceToHost, s->stream));
-    PIMDB_CUDA_TRY(s, cudaStreamSynchronize(s->stream));
-    memcpy(host, s->stage_h, bytes);
+    if (host_is_pinned(host)) {
+        PIMDB_CUDA_TRY(s, cudaMemcpyAsync(host, s->stage_d, bytes, cudaMemcpyDeviceToHost, s->stream));
+        PIMDB_CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+    } else {
+        PIMDB_CUDA_TRY(s, cudaMemcpyAsync(s->stage_h, s->stage_d, bytes, cudaMemcpyDeviceToHost, s->stream));
+        PIMDB_CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+        memcpy(host, s->stage_h, bytes);
+    }
     return check_deferred(s);
 }
 
