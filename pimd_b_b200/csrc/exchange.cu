@@ -40,6 +40,7 @@ struct Ext {
 };
 
 constexpr int kExtZeroExp = -(1 << 29);
+constexpr int kExchFastMaxN = 512;     // largest N served by the block-scaled tables and the fast recurrence
 
 __device__ __forceinline__ double pow2i(int d) {   // 2^d for d in [-1022, 1023], 0 below
     return d < -1022 ? 0.0 : __hiloint2double((1023 + d) << 20, 0);
@@ -195,23 +196,56 @@ template <int D>
 __global__ void __launch_bounds__(1024) k_exch_coeff_tiles(ExArgs a) {
     __shared__ int s_ef[32][33], s_eb[32][33];     // [step within the tile][column], padded: conflict-free both ways
     __shared__ int s_mf[32], s_mb[32];
+    __shared__ double sA[kExchFastMaxN + 1];       // the prefix sums A(w), recomputed by every tile (N <= 512: one chunk)
+    __shared__ double warp_tot[32];
     const int N = a.N, nb = (N + 31) >> 5;
     const int rb = blockIdx.x / nb, sb = blockIdx.x % nb;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    {   // Same operations in the same order as k_exch_prefix (so A is bit-identical); fusing it here takes a 5 us
+        // single-block kernel and a launch gap off the step's critical path. Block 0 also publishes A and 1/i.
+        const int w = threadIdx.x;                     // produces A[w+1]
+        double v = (w < N - 1) ? dist2<D>(a, a.xP, w, a.x1, w + 1) : 0.0;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            double t = __shfl_up_sync(kFullMask, v, o);
+            if (tx >= o) v += t;
+        }
+        if (tx == 31) warp_tot[ty] = v;
+        __syncthreads();
+        if (ty == 0) {
+            double t = warp_tot[tx];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                double u = __shfl_up_sync(kFullMask, t, o);
+                if (tx >= o) t += u;
+            }
+            warp_tot[tx] = t;
+        }
+        __syncthreads();
+        const double incl = 0.0 + (ty > 0 ? warp_tot[ty - 1] : 0.0) + v;
+        if (w + 1 < N) sA[w + 1] = incl;
+        if (w == 0) sA[0] = 0.0;
+        if (blockIdx.x == 0) {
+            if (w + 1 < N) a.A[w + 1] = incl;
+            if (w == 0) a.A[0] = 0.0;
+            if (w <= N) a.Inv[w] = w > 0 ? 1.0 / (double)w : 0.0;
+        }
+        __syncthreads();
+    }
     const int r = rb * 32 + ty, sc = sb * 32 + tx;   // one element per thread: 4x the parallelism of a 256-thread tile
     double mf = 0.0, mb = 0.0;
     int ef = kExtZeroExp, eb = kExtZeroExp;
     const long long i = (long long)r * N + sc;
     if (r < N && sc < N) {
         const int u = min(r, sc), v = max(r, sc);
-        const double y = a.h * (a.A[v] - a.A[u] + dist2<D>(a, a.x1, u, a.xP, v));
+        const double y = a.h * (sA[v] - sA[u] + dist2<D>(a, a.x1, u, a.xP, v));
         const Ext c = ext_exp_neg(y < 0.0 ? 0.0 : y);   // (a NaN position stays NaN and is reported, like the reference)
         if (sc >= r) {
             a.Cf[i] = ext_pack(c.m, c.e);
             mf = c.m; ef = c.e;
         }
         if (sc <= r) {   // backward table: the 1/(p+1) weight of the sum (p = r) is folded in here, off the chain
-            const Ext cb = ext_normalize(c.m * a.Inv[r + 1], c.e);
+            const Ext cb = ext_normalize(c.m * (1.0 / (double)(r + 1)), c.e);
             a.Cb[i] = ext_pack(cb.m, cb.e);
             mb = cb.m; eb = cb.e;
         }
@@ -1128,14 +1162,15 @@ template <int D>
 static int exchange_impl(Sim* s, cudaStream_t st, int part) {
     ExArgs a = make_args(s);
     if (part == 0) {
-        k_exch_prefix<D><<<1, 1024, 0, st>>>(a);
-        if (a.Kf) {
+        if (a.Kf) {      // N <= 512: the tiles recompute the prefix sums themselves (one launch)
             const int nb = (s->N + 31) / 32;
             k_exch_coeff_tiles<D><<<nb * nb, 1024, 0, st>>>(a);
+            s->launches += 1;
         } else {
+            k_exch_prefix<D><<<1, 1024, 0, st>>>(a);
             k_exch_coeff<D><<<grid_for((size_t)s->N * s->N, 256, 16 * kNumSM), 256, 0, st>>>(a);
+            s->launches += 2;
         }
-        s->launches += 2;
     } else {
         int rc = run_recursion(s, a, st);
         if (rc != PIMDB_OK) return rc;

@@ -341,3 +341,26 @@ def test_error_paths(gpu_required):
         part.step(1)
     sim.close()
     part.close()
+
+
+def test_page_locked_host_buffers_take_the_direct_copy_path(gpu_required):
+    """pimdb_set_state / pimdb_get_state copy straight from / into page-locked caller buffers and stage pageable
+    ones; both must move the same bytes."""
+    import torch
+    cfg = wl.config("c1")
+    x, p = wl.initial_state(cfg, "c1")
+    sim = DeviceSim(cfg)
+    pinned = [torch.empty(x.shape, dtype=torch.float64, pin_memory=True) for _ in range(3)]
+    hx, hp, hout = (t.numpy() for t in pinned)
+    hx[...] = x
+    hp[...] = p
+    sim.set("x", hx)
+    sim.set("p", hp)
+    assert np.array_equal(sim.get("x"), x) and np.array_equal(sim.get("p"), p)      # pinned in, pageable out
+    sim.set("x", x)
+    sim.set("p", p)
+    assert np.array_equal(sim.get("x", hout), x)                                      # pageable in, pinned out
+    sim.step(3)
+    f_pageable = sim.get("f")
+    assert np.array_equal(sim.get("f", hout), f_pageable)
+    sim.close()

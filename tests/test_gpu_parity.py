@@ -233,10 +233,12 @@ def test_zero_momentum(gpu_required):
     sim.close()
 
 
-@pytest.mark.parametrize("natoms", [1100, 2100, 4200])
+@pytest.mark.parametrize("natoms", [129, 300, 512, 700, 1000, 1100, 2100, 4200])
 def test_exchange_large_n_paths(gpu_required, natoms):
-    """N > 1024 takes the multi-row recurrence kernels (2 rows per thread with cp.async staging, 4+ rows with direct
-    loads); compared with the oracle on V, V_backwards and the exterior forces."""
+    """Every recurrence kernel against the oracle on V, V_backwards and the exterior forces: N <= 512 the fast
+    block-scaled kernel (several owner warps, N not a multiple of 32 or 4), 512 < N <= 1024 the extended-range
+    warp-decoupled kernel, N > 1024 the multi-row kernels (2 rows per thread with cp.async staging, 4+ rows with
+    direct loads)."""
     cfg = trap(natoms, 3, temperature=1.0 * KELVIN, size=2000.0)
     rng = np.random.default_rng(natoms)
     centroid = rng.normal(0.0, 60.0, size=(1, natoms, 3))
