@@ -531,11 +531,13 @@ static double nh_chain_step(const orc_sim* s, double current_energy, double ndof
     return scale;
 }
 
-/* momentaUpdate of the three variants, src/thermostats/nose_hoover.cpp:69-91, 162-182, 207-222 (Cartesian coupling) */
-static void nose_hoover_step(orc_sim* s) {
+/* momentaUpdate of the three variants, src/thermostats/nose_hoover.cpp:69-91, 162-182, 207-222, on the momenta in
+ * `pall`: the Cartesian momenta (CartesianCoupling) or the normal-mode momenta (NMCoupling,
+ * src/thermostats/thermostat_coupling.cpp:29-47: rank k thermostats mode k with its own chains) */
+static void nose_hoover_apply(orc_sim* s, double* pall) {
     const int P = s->P, N = s->N, D = s->D, nc = s->c.nchains;
     for (int b = 0; b < P; ++b) {
-        double* pb = s->p + (size_t)b * slab(s);
+        double* pb = pall + (size_t)b * slab(s);
         size_t base = (size_t)b * s->nh_groups * nc;
         if (s->c.thermostat == ORC_THERMO_NOSE_HOOVER) {
             double e = 0.0;
@@ -590,7 +592,13 @@ static double nose_hoover_energy(const orc_sim* s) {
 
 void orc_thermostat_step(orc_sim* s) {
     if (s->c.thermostat >= ORC_THERMO_NOSE_HOOVER) {
-        nose_hoover_step(s);
+        if (!s->c.nmthermostat) {
+            nose_hoover_apply(s, s->p);
+        } else {   /* Thermostat::step, src/thermostats/thermostat.cpp:15-19: share, update mode momenta, transform back */
+            nm_apply(s, s->nm_fwd, s->p, s->scratch_p);
+            nose_hoover_apply(s, s->scratch_p);
+            nm_apply(s, s->nm_inv, s->scratch_p, s->p);
+        }
         return;
     }
     if (s->c.thermostat != ORC_THERMO_LANGEVIN) return;

@@ -57,10 +57,6 @@ static int validate(const pimdb_config* c, std::string& msg) {
             snprintf(buf, sizeof buf, "The specified number of Nose-Hoover chains (%d) is less than one!", c->nchains);
             msg = buf; return PIMDB_ERR_INVALID_ARGUMENT;
         }
-        if (c->nmthermostat) {
-            msg = "Nose-Hoover chains coupled to normal modes are not part of this build (Cartesian coupling only)";
-            return PIMDB_ERR_INVALID_ARGUMENT;
-        }
     }
     if (c->nmthermostat && c->thermostat == PIMDB_THERMO_NONE) {
         msg = "nmthermostat cannot be used in nve ensemble!"; return PIMDB_ERR_INVALID_ARGUMENT;
@@ -479,8 +475,12 @@ struct Fuser {
 
 static void thermostat_into(Sim* s, Fuser& fz) {
     if (s->cfg.thermostat >= PIMDB_THERMO_NOSE_HOOVER) {
+        // NMCoupling (src/thermostats/thermostat_coupling.cpp:29-47): the chains of "bead" k act on the momenta of
+        // normal mode k -- transform, run the same chain kernels on the mode momenta, transform back
         fz.flush();
+        if (s->cfg.nmthermostat && fz.rc == PIMDB_OK) fz.rc = launch_nm_momenta(s, true);
         if (fz.rc == PIMDB_OK) fz.rc = launch_nose_hoover(s);
+        if (s->cfg.nmthermostat && fz.rc == PIMDB_OK) fz.rc = launch_nm_momenta(s, false);
         return;
     }
     if (s->cfg.thermostat != PIMDB_THERMO_LANGEVIN) return;

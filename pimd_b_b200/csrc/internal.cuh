@@ -121,6 +121,7 @@ enum : unsigned { OP_SUBCM = 1, OP_O_PRE = 2, OP_B = 4, OP_O_POST = 8, OP_A = 16
 int launch_integrate(Sim* s, unsigned ops);
 int launch_nm_propagate(Sim* s);
 int launch_nm_thermostat(Sim* s);
+int launch_nm_momenta(Sim* s, bool forward);   // p <-> normal-mode momenta, in place
 int launch_obs_elementwise(Sim* s);
 int launch_nose_hoover(Sim* s);
 int launch_nose_hoover_energy(Sim* s, double* out_dev);

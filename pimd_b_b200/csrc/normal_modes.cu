@@ -28,7 +28,9 @@ struct NmArgs {
     unsigned long long seed;
 };
 
-// mode 0: propagator (x and p), mode 1: thermostat (p only)
+// mode 0: propagator (x and p), mode 1: Langevin thermostat on the mode momenta (p only),
+// mode 2 / 3: forward / inverse transform of p alone (in place) -- the two halves around a Nose-Hoover update of the
+// mode momenta, which needs a reduction over all particles of a mode and therefore its own kernels (nose_hoover.cu)
 template <int MODE>
 __global__ void __launch_bounds__(256) k_nm_fused(NmArgs a) {
     extern __shared__ double sm[];
@@ -64,10 +66,12 @@ __global__ void __launch_bounds__(256) k_nm_fused(NmArgs a) {
         for (int k = kg; k < P; k += KG, ++cnt) {
             const double* crow = a.C + (size_t)k * P;
             double xn = 0.0, pn = 0.0;
-            for (int j = 0; j < P; ++j) {
-                const double cj = __ldg(crow + j);
-                pn += cj * sp[j * TC + tc];
-                if (MODE == 0) xn += cj * sx[j * TC + tc];
+            if (MODE != 3) {
+                for (int j = 0; j < P; ++j) {
+                    const double cj = __ldg(crow + j);
+                    pn += cj * sp[j * TC + tc];
+                    if (MODE == 0) xn += cj * sx[j * TC + tc];
+                }
             }
             if (MODE == 0) {
                 const double cs = a.tab[k], sn = a.tab[P + k], mw = a.tab[2 * P + k];
@@ -81,6 +85,10 @@ __global__ void __launch_bounds__(256) k_nm_fused(NmArgs a) {
                 }
                 rn_x[cnt] = xo;
                 rn_p[cnt] = po;
+            } else if (MODE == 2) {
+                rn_p[cnt] = pn;
+            } else if (MODE == 3) {
+                rn_p[cnt] = sp[k * TC + tc];         // already mode momenta: pass through to the inverse transform
             } else {
                 // Langevin O step on mode k: noise stream row = mode k * D + axis (DESIGN.md "RNG")
                 const int axis = ok ? col / a.N : 0, n = ok ? col % a.N : 0;
@@ -100,10 +108,14 @@ __global__ void __launch_bounds__(256) k_nm_fused(NmArgs a) {
         for (int j = kg; j < P; j += KG) {
             const double* irow = a.Cinv + (size_t)j * P;
             double xc = 0.0, pc = 0.0;
-            for (int k = 0; k < P; ++k) {
-                const double ck = __ldg(irow + k);
-                pc += ck * sp[k * TC + tc];
-                if (MODE == 0) xc += ck * sx[k * TC + tc];
+            if (MODE == 2) {
+                pc = sp[j * TC + tc];                // forward only: row j now holds mode j
+            } else {
+                for (int k = 0; k < P; ++k) {
+                    const double ck = __ldg(irow + k);
+                    pc += ck * sp[k * TC + tc];
+                    if (MODE == 0) xc += ck * sx[k * TC + tc];
+                }
             }
             if (ok) {
                 a.p[(size_t)j * a.M + col] = pc;
@@ -145,6 +157,12 @@ static int launch_nm(Sim* s, int mode) {
     if (mode == 0) {
         if (smem > 48 * 1024) cudaFuncSetAttribute(k_nm_fused<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k_nm_fused<0><<<grid, 256, smem, s->stream>>>(a);
+    } else if (mode == 2) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k_nm_fused<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_nm_fused<2><<<grid, 256, smem, s->stream>>>(a);
+    } else if (mode == 3) {
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k_nm_fused<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k_nm_fused<3><<<grid, 256, smem, s->stream>>>(a);
     } else {
         if (smem > 48 * 1024) cudaFuncSetAttribute(k_nm_fused<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k_nm_fused<1><<<grid, 256, smem, s->stream>>>(a);
@@ -156,6 +174,7 @@ static int launch_nm(Sim* s, int mode) {
 
 int launch_nm_propagate(Sim* s) { return launch_nm(s, 0); }
 int launch_nm_thermostat(Sim* s) { return launch_nm(s, 1); }
+int launch_nm_momenta(Sim* s, bool forward) { return launch_nm(s, forward ? 2 : 3); }
 
 // ------------------------------------------------------------------------------------------------------
 // Element-wise estimator partials (K13): classical spring energy of the owned links, external potential and its

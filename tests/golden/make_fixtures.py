@@ -100,6 +100,14 @@ def probe_configs():
                   mass=2.0, size=50.0, interaction="harmonic", int_omega=2 * MEV, cutoff=20.0, external="free",
                   thermostat="none", seed=9, dt=FEMTOSECOND, obs_classical="kelvin", obs_bosonic="true")
     items["harmonic_pair_1d_pbc_cutoff"] = (c, rng.uniform(-25, 25, size=(5, 7, 1)), maxwell_momenta(c, rng))
+    # Nose-Hoover chains coupled to the normal modes (NMCoupling, src/thermostats/thermostat_coupling.cpp:29-47): no
+    # golden case of the reference covers them (appended last: the inputs of the cases above do not change)
+    for th in ("nose_hoover", "nose_hoover_np", "nose_hoover_np_dim"):
+        c = SimConfig(nbeads=6, natoms=9, ndim=3, bosonic=(th == "nose_hoover_np"), fixcom=True, pbc=False,
+                      temperature=5.802 * KELVIN, mass=1.0, size=300.0, interaction="harmonic", int_omega=1 * MEV,
+                      external="harmonic", ext_omega=3 * MEV, thermostat=th, nmthermostat=True, nchains=4, seed=11,
+                      dt=FEMTOSECOND, obs_classical="kelvin", obs_bosonic="true" if th == "nose_hoover_np" else "false")
+        items[f"{th}_nmcoupled"] = (c, rng.uniform(-30, 30, size=(6, 9, 3)), maxwell_momenta(c, rng))
     return items
 
 

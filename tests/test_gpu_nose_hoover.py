@@ -12,12 +12,14 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("thermostat", ["nose_hoover", "nose_hoover_np", "nose_hoover_np_dim"])
-@pytest.mark.parametrize("bosonic", [True, False])
-def test_nose_hoover_trajectory_and_conserved_quantity(gpu_required, thermostat, bosonic):
+@pytest.mark.parametrize("bosonic,nmcoupled", [(True, False), (False, False), (True, True), (False, True)])
+def test_nose_hoover_trajectory_and_conserved_quantity(gpu_required, thermostat, bosonic, nmcoupled):
+    """Cartesian coupling and coupling to the normal-mode momenta (nmthermostat = true; the oracle's NM-coupled chains
+    are bit-identical to the reference on tests/golden/refprobe.npz *_nmcoupled)."""
     cfg = SimConfig(nbeads=4, natoms=8, ndim=3, bosonic=bosonic, fixcom=False, pbc=False,
                     temperature=5.802 * KELVIN, mass=1.0, size=300.0, interaction="harmonic", int_omega=1 * MEV,
-                    external="harmonic", ext_omega=3 * MEV, thermostat=thermostat, nchains=4, seed=90846,
-                    dt=0.1 * FEMTOSECOND)
+                    external="harmonic", ext_omega=3 * MEV, thermostat=thermostat, nmthermostat=nmcoupled, nchains=4,
+                    seed=90846, dt=0.1 * FEMTOSECOND)
     rng = np.random.default_rng(8)
     x = rng.uniform(-30, 30, size=(4, 8, 3))
     p = maxwell_momenta(cfg, rng)
@@ -47,6 +49,17 @@ def test_nose_hoover_trajectory_and_conserved_quantity(gpu_required, thermostat,
     sim.close()
 
 
-def test_nose_hoover_with_normal_mode_coupling_is_rejected_loudly(gpu_required):
-    with pytest.raises(ValueError, match="Nose-Hoover chains coupled to normal modes"):
-        DeviceSim(SimConfig(nbeads=4, natoms=4, thermostat="nose_hoover", nmthermostat=True))
+@pytest.mark.parametrize("case", ["nose_hoover_nmcoupled", "nose_hoover_np_nmcoupled", "nose_hoover_np_dim_nmcoupled"])
+def test_nm_coupled_chains_match_the_reference_trajectory(gpu_required, case):
+    """12 iterations from the reference's own raw state dump (ref_probe, tests/golden/refprobe.npz)."""
+    import ast
+    from tests.helpers import GOLDEN_DIR
+    ref = np.load(GOLDEN_DIR / "refprobe.npz")
+    cfg = SimConfig(**ast.literal_eval(str(ref[f"{case}/cfg"])))
+    sim = DeviceSim(cfg)
+    sim.set("x", ref[f"{case}/x"])
+    sim.set("p", ref[f"{case}/p"])
+    sim.step(12)
+    for w in ("x", "p", "f"):
+        assert relerr(sim.get(w), ref[f"{case}/traj12_{w}"]) < 1e-9, (case, w)
+    sim.close()
