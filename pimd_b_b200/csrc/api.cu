@@ -140,7 +140,7 @@ static void free_all(Sim* s) {
     cudaFree(s->stage_d); cudaFreeHost(s->stage_h);
     cudaFree(s->tile_ij); cudaFree(s->pair_scratch);
     cudaFree(s->exA); cudaFree(s->exV); cudaFree(s->exVb); cudaFree(s->exF); cudaFree(s->exTab);
-    cudaFree(s->exC); cudaFree(s->exK); cudaFree(s->exB); cudaFree(s->exWm); cudaFree(s->exWe);
+    cudaFree(s->exC); cudaFree(s->exK); cudaFree(s->exB); cudaFree(s->exG); cudaFree(s->exGok); cudaFree(s->exSync); cudaFree(s->tl); cudaFree(s->exWm); cudaFree(s->exWe);
     cudaFree(s->com_part); cudaFree(s->com); cudaFree(s->tickets); cudaFree(s->draw);
     cudaFree(s->obs_d); cudaFreeHost(s->obs_h); cudaFree(s->obs_part);
     cudaFreeHost(s->err_h);
@@ -148,6 +148,8 @@ static void free_all(Sim* s) {
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     if (s->ev_join) cudaEventDestroy(s->ev_join);
     if (s->stream_x) cudaStreamDestroy(s->stream_x);
+    if (s->stream_r) cudaStreamDestroy(s->stream_r);
+    if (s->ev_join2) cudaEventDestroy(s->ev_join2);
     if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -227,6 +229,8 @@ extern "C" int pimdb_create(const pimdb_config* cfg, pimdb_sim** out) {
     CREATE_TRY(cudaStreamCreateWithPriority(&s->stream_x, cudaStreamNonBlocking, hi));
     CREATE_TRY(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
     CREATE_TRY(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
+    CREATE_TRY(cudaStreamCreateWithPriority(&s->stream_r, cudaStreamNonBlocking, hi));
+    CREATE_TRY(cudaEventCreateWithFlags(&s->ev_join2, cudaEventDisableTiming));
 
     const size_t slab_bytes = s->S * sizeof(double);
     const size_t own_bytes = slab_bytes * s->Ploc;
@@ -264,10 +268,23 @@ extern "C" int pimdb_create(const pimdb_config* cfg, pimdb_sim** out) {
         CREATE_TRY(cudaMalloc(&s->exA, sizeof(double) * (2 * s->N + 2)));   // A[N] | Inv[N+1]
         CREATE_TRY(cudaMalloc(&s->exC, sizeof(int4) * 2 * NN));
         if (s->N <= 512) {   // the fast recurrence's block-scaled copy (exchange.cu: k_exch_coeff_tiles)
-            CREATE_TRY(cudaMalloc(&s->exK, sizeof(double) * 2 * (NN + 512)));
-            CREATE_TRY(cudaMemset(s->exK, 0, sizeof(double) * 2 * (NN + 512)));
-            CREATE_TRY(cudaMalloc(&s->exB, sizeof(int) * 2 * (size_t)((s->N + 31) / 32) * s->N));
+            const size_t nbk = (size_t)((s->N + 31) / 32);
+            CREATE_TRY(cudaMalloc(&s->exK, sizeof(double) * 2 * nbk * nbk * 1024));      // 32 x 32 tiles, forward | backward
+            CREATE_TRY(cudaMemset(s->exK, 0, sizeof(double) * 2 * nbk * nbk * 1024));
+            CREATE_TRY(cudaMalloc(&s->exB, sizeof(int) * 2 * nbk * s->N));
+            CREATE_TRY(cudaMalloc(&s->exG, sizeof(double) * 2 * nbk * (1024 + 32)));     // G f|b, h f|b
+            CREATE_TRY(cudaMemset(s->exG, 0, sizeof(double) * 2 * nbk * (1024 + 32)));
+            CREATE_TRY(cudaMalloc(&s->exGok, sizeof(int) * 4 * (size_t)((s->N + 31) / 32)));   // Gok f|b, block status f|b
+            CREATE_TRY(cudaMemset(s->exGok, 0, sizeof(int) * 4 * (size_t)((s->N + 31) / 32)));
         }
+        if (getenv("PIMDB_TIMELINE")) {
+            CREATE_TRY(cudaMalloc(&s->tl, sizeof(unsigned long long) * 64));
+            std::vector<unsigned long long> init(64);
+            for (int i = 0; i < 32; ++i) { init[2 * i] = ~0ull; init[2 * i + 1] = 0ull; }
+            CREATE_TRY(cudaMemcpy(s->tl, init.data(), sizeof(unsigned long long) * 64, cudaMemcpyHostToDevice));
+        }
+        CREATE_TRY(cudaMalloc(&s->exSync, sizeof(int) * 4));
+        CREATE_TRY(cudaMemset(s->exSync, 0, sizeof(int) * 4));
         CREATE_TRY(cudaMalloc(&s->exWm, sizeof(double) * 2 * (s->N + 1)));
         CREATE_TRY(cudaMalloc(&s->exWe, sizeof(int) * 2 * (s->N + 1)));
         CREATE_TRY(cudaMemset(s->exWm, 0, sizeof(double) * 2 * (s->N + 1)));
@@ -319,6 +336,7 @@ extern "C" void pimdb_destroy(pimdb_sim* sim) {
     cudaSetDevice(s->device);
     cudaStreamSynchronize(s->stream);
     cudaStreamSynchronize(s->stream_x);
+    cudaStreamSynchronize(s->stream_r);
     free_all(s);
 }
 
@@ -327,6 +345,9 @@ static int check_deferred(Sim* s) {
     if (*s->err_h != 0) {
         const int e = *s->err_h;
         *s->err_h = 0;
+        if (e & kErrSyncTimeout)
+            return fail(s, PIMDB_ERR_RUNTIME, "exchange recurrence timed out waiting for its factor tiles (kernels serialised by a "
+                                              "profiler? set PIMDB_EXCH_SERIAL=1)");
         // same wording as the reference's std::overflow_error (quadratic_bosonic_exchange.cpp:92-97,119-124)
         return fail(s, PIMDB_ERR_OVERFLOW,
                     std::string("Invalid sig_denom / e_shift in bosonic exchange potential (non-finite ") +
@@ -413,29 +434,56 @@ extern "C" int pimdb_get_state(pimdb_sim* sim, int which, double* host) {
 // force evaluation: exchange on the high-priority side stream, pair tiles + assembly on the main stream
 static int enqueue_forces(Sim* s) {
     const bool ex = s->bosonic && (s->has_first || s->has_last);
+    bool early = false;
     if (ex) {
-        // Prefix sums + Boltzmann factors run on the main stream (wide, short). The two-block recurrence kernel is
-        // then launched on the high-priority side stream BEFORE the pair tiles, so its blocks are resident when
-        // the pair-force grid floods the SMs and the latency-bound chain overlaps the FP64-bound tiles.
-        API_TRY(launch_exchange_part(s, s->stream, 0));
-        PIMDB_CUDA_TRY(s, cudaEventRecord(s->ev_fork, s->stream));
-        PIMDB_CUDA_TRY(s, cudaStreamWaitEvent(s->stream_x, s->ev_fork, 0));
-        API_TRY(launch_exchange_part(s, s->stream_x, 1));
-        PIMDB_CUDA_TRY(s, cudaEventRecord(s->ev_join, s->stream_x));
+        // The exchange chain runs beside the pair tiles on two high-priority side streams. For N <= 512 (blocked
+        // recurrence) the two-block recurrence kernel is launched FIRST, on its own stream: its blocks need a whole SM
+        // each (512 threads x 126 registers), which they only get before the pair tiles flood the GPU; resident, they
+        // wait on a device-side counter for the factor tiles + block inverses (k_exch_coeff_tiles, launched second on the
+        // other side stream), so neither the tiles nor the inverses sit on the main stream ahead of the pair forces.
+        // Kernels serialised by a profiler would turn that wait into a time-out, so PIMDB_EXCH_SERIAL=1 (or a CUDA
+        // injection library in the environment: ncu, compute-sanitizer) selects the plain order: tiles on the main
+        // stream, then recurrences + exterior forces on the side stream.
+        static const bool serial = getenv("PIMDB_EXCH_SERIAL") || getenv("CUDA_INJECTION64_PATH") ||
+                                   getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR");
+        // Only inside a stream capture: in a graph every kernel is loaded when the graph is instantiated, whereas an
+        // eager first launch may have to load its kernel lazily, which waits for the device to go idle -- behind a
+        // recurrence kernel that is itself waiting for that very launch.
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(s->stream, &cap);
+        early = !serial && cap == cudaStreamCaptureStatusActive && s->exK && !getenv("PIMDB_EXCH_NOBLOCKED");
+        if (early) {
+            PIMDB_CUDA_TRY(s, cudaEventRecord(s->ev_fork, s->stream));
+            PIMDB_CUDA_TRY(s, cudaStreamWaitEvent(s->stream_r, s->ev_fork, 0));
+            PIMDB_CUDA_TRY(s, cudaStreamWaitEvent(s->stream_x, s->ev_fork, 0));
+            API_TRY(launch_exchange_part(s, s->stream_r, 1));      // recurrences (resident, waiting) + exterior forces
+            API_TRY(launch_exchange_part(s, s->stream_x, 0));      // factor tiles + block inverses
+            PIMDB_CUDA_TRY(s, cudaEventRecord(s->ev_join, s->stream_r));
+            PIMDB_CUDA_TRY(s, cudaEventRecord(s->ev_join2, s->stream_x));
+        } else {
+            API_TRY(launch_exchange_part(s, s->stream, 0));
+            PIMDB_CUDA_TRY(s, cudaEventRecord(s->ev_fork, s->stream));
+            PIMDB_CUDA_TRY(s, cudaStreamWaitEvent(s->stream_x, s->ev_fork, 0));
+            API_TRY(launch_exchange_part(s, s->stream_x, 1));
+            PIMDB_CUDA_TRY(s, cudaEventRecord(s->ev_join, s->stream_x));
+        }
     }
     bool joined = !ex;
+    auto join = [&]() -> int {
+        PIMDB_CUDA_TRY(s, cudaStreamWaitEvent(s->stream, s->ev_join, 0));
+        if (early) PIMDB_CUDA_TRY(s, cudaStreamWaitEvent(s->stream, s->ev_join2, 0));
+        joined = true;
+        return PIMDB_OK;
+    };
     if (s->pair_on) {
         for (int lo = 0; lo < s->Ploc; lo += s->bead_chunk) {
             const int nb = std::min(s->bead_chunk, s->Ploc - lo);
             API_TRY(launch_pair_chunk(s, lo, nb, false));
-            if (!joined) {
-                PIMDB_CUDA_TRY(s, cudaStreamWaitEvent(s->stream, s->ev_join, 0));
-                joined = true;
-            }
+            if (!joined) API_TRY(join());
             API_TRY(launch_assemble_chunk(s, lo, nb, true));
         }
     } else {
-        if (!joined) PIMDB_CUDA_TRY(s, cudaStreamWaitEvent(s->stream, s->ev_join, 0));
+        if (!joined) API_TRY(join());
         API_TRY(launch_assemble_chunk(s, 0, s->Ploc, false));
     }
     return PIMDB_OK;
@@ -639,6 +687,7 @@ extern "C" int pimdb_step(pimdb_sim* sim, int nsteps) {
     if (!s->graph_exec) {
         const unsigned long long before = s->launches;
         PIMDB_CUDA_TRY(s, cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+        s->tl_next = 0;
         int rc = enqueue_step(s, true);
         cudaGraph_t g = nullptr;
         cudaError_t ce = cudaStreamEndCapture(s->stream, &g);
@@ -892,6 +941,39 @@ extern "C" int pimdb_bench_fp64_peak(int device, double* tflops) {
 }
 
 // ----------------------------------------------------------------------------------------------------
+// Profiling aid (PIMDB_TIMELINE=1, not declared in pimdb200.h): [first block start, last block end] in ns of the
+// kernels of the captured step, in launch order, accumulated (min / max) since the last call; the slots are reset.
+extern "C" int pimdb_debug_timeline(pimdb_sim* sim, unsigned long long* out) {
+    Sim* s = reinterpret_cast<Sim*>(sim);
+    if (!s || !out || !s->tl) return 0;
+    cudaSetDevice(s->device);
+    cudaDeviceSynchronize();
+    cudaMemcpy(out, s->tl, sizeof(unsigned long long) * 64, cudaMemcpyDeviceToHost);
+    std::vector<unsigned long long> init(64);
+    for (int i = 0; i < 32; ++i) { init[2 * i] = ~0ull; init[2 * i + 1] = 0ull; }
+    cudaMemcpy(s->tl, init.data(), sizeof(unsigned long long) * 64, cudaMemcpyHostToDevice);
+    return s->tl_next;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// Test aid (not part of the reference surface, not declared in pimdb200.h): how the blocked exchange recurrence
+// solved each 32-row block in its last run, in step order. out[0 .. nb) forward, out[nb .. 2nb) backward:
+// 1 = one matrix-vector product with the precomputed block inverse, 2 = exact sequential extended-range steps,
+// 0 = block without steps. Returns the number of blocks per direction (0 when the blocked kernel does not apply).
+extern "C" int pimdb_debug_exchange_blocks(pimdb_sim* sim, int* out) {
+    Sim* s = reinterpret_cast<Sim*>(sim);
+    if (!s || !out || !s->bosonic || !s->exGok) return 0;
+    cudaSetDevice(s->device);
+    cudaStreamSynchronize(s->stream);
+    cudaStreamSynchronize(s->stream_x);
+    const int nb = (s->N + 31) / 32;
+    if (cudaMemcpy(out, s->exGok + 2 * nb, sizeof(int) * 2 * nb, cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+    if (!getenv("PIMDB_EXCH_REASONS"))
+        for (int i = 0; i < 2 * nb; ++i) out[i] &= 15;     // status only; the high bits say why a block went exact
+    return nb;
+}
+
+// ----------------------------------------------------------------------------------------------------
 // Profiling aid (not part of the reference surface, not declared in pimdb200.h): average warm duration in
 // microseconds of the two halves of the exchange chain, measured with CUDA events on the handle's stream.
 //   out[0] = prefix sums + Boltzmann factors, out[1] = recurrences + exterior forces
@@ -920,14 +1002,16 @@ extern "C" int pimdb_debug_exchange_timing(pimdb_sim* sim, int reps, double* out
     out[0] = acc[0] / reps * 1e3;
     out[1] = acc[1] / reps * 1e3;
     if (getenv("PIMDB_EXCH_DEBUG")) {   // per-warp clock64 stamps of one more run: out[2 + 3*(dir*32 + warp) + {0,1,2}]
-        if (!s->dbg_buf) cudaMalloc(&s->dbg_buf, sizeof(long long) * 64 * 3);
-        cudaMemset(s->dbg_buf, 0, sizeof(long long) * 64 * 3);
+        constexpr int kDbg = 64 * 3 + 2048 + 32;   // per-warp totals | per-(warp, block) stamps | owner-phase start
+        if (!s->dbg_buf) cudaMalloc(&s->dbg_buf, sizeof(long long) * kDbg);
+        cudaMemset(s->dbg_buf, 0, sizeof(long long) * kDbg);
         API_TRY(launch_exchange_part(s, s->stream, 0));
         API_TRY(launch_exchange_part(s, s->stream, 1));
         PIMDB_CUDA_TRY(s, cudaStreamSynchronize(s->stream));
-        long long h[64 * 3];
-        cudaMemcpy(h, s->dbg_buf, sizeof h, cudaMemcpyDeviceToHost);
-        for (int i = 0; i < 64 * 3; ++i) out[2 + i] = (double)h[i];
+        std::vector<long long> h(kDbg);
+        cudaMemcpy(h.data(), s->dbg_buf, sizeof(long long) * kDbg, cudaMemcpyDeviceToHost);
+        const int nout = getenv("PIMDB_EXCH_DEBUG_FULL") ? kDbg : 64 * 3;   // the caller sizes `out` accordingly
+        for (int i = 0; i < nout; ++i) out[2 + i] = (double)h[i];
         cudaFree(s->dbg_buf);
         s->dbg_buf = nullptr;
     }

@@ -119,6 +119,20 @@ __device__ __forceinline__ double rsqrt_fast(double x) {
     return fma(y * e, fma(0.375, e, 0.5), y);
 }
 
+// In-kernel timeline (PIMDB_TIMELINE=1, profiling aid): every block stamps %globaltimer into its kernel's slot,
+// [first start, last end] in ns -- the only way to see how the kernels of one captured step overlap on the device.
+__device__ __forceinline__ unsigned long long gtimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void tl_begin(unsigned long long* tl) {
+    if (tl && threadIdx.x == 0) atomicMin(tl, gtimer_ns());
+}
+__device__ __forceinline__ void tl_end(unsigned long long* tl) {
+    if (tl && threadIdx.x == 0) atomicMax(tl + 1, gtimer_ns());
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);

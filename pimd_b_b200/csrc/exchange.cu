@@ -28,6 +28,8 @@
 //          P(l->u) = W[u] c(u,l) Wb[l+1] / ((l+1) W[N]),
 //      evaluated on the fly in the exterior-force kernel (one warp per particle and exterior bead); the N x N
 //      matrix is only materialised when a caller asks for it (pimdb_exchange_get).
+#include <algorithm>
+
 #include "internal.cuh"
 #include "device_utils.cuh"
 
@@ -98,9 +100,19 @@ struct ExArgs {
     double* Inv;               // Inv[i] = 1/i, i = 0..N (Inv[0] = 0): no FP64 division in the O(N^2) loops
     int4 *Cf, *Cb;             // Boltzmann factors, packed {mantissa lo, hi, binary exponent, 0}, N x N each:
                                //   Cf[j][v] = c(j,v) (v >= j);  Cb[p][l] = c(l,p) / (p+1) (l <= p, backward weight folded in)
-    double *Kf, *Kb;           // the same factors block-scaled for the fast recurrence (N <= 512), or nullptr:
-                               //   K[r][v] = C[r][v] * 2^-B[r/32][v] as a plain double (0 outside the triangle)
+    double *Kf, *Kb;           // the same factors block-scaled for the blocked recurrence (N <= 512), or nullptr:
+                               //   K[r][v] = C[r][v] * 2^-B[r/32][v] as a plain double (0 outside the triangle), stored as
+                               //   32 x 32 tiles: K[(r/32 * nb + v/32) * 1024 + (r%32) * 32 + v%32], nb = ceil(N/32)
     int *Bf, *Bb;              //   B[rb][v] = largest binary exponent of C[32rb .. 32rb+31][v]
+    double *Gf, *Gb;           // inverses of the 32 x 32 diagonal blocks of the two triangular systems (blocked recurrence),
+                               //   G[q][k''][lane]: row k of block q lives in the lane that owns its particle row
+    double *Hf, *Hb;           //   H[q][lane] = (G kin)[k]: the block's response to the value handed over by the previous block
+    int *Gokf, *Gokb;          //   1 when every structural entry of G[q] is a normal double within the fast window
+    int* sync;                 // device counters that let the recurrence kernel start before the factor tiles are done:
+                               //   [0] tiles finished (ticket), [1] generations of tables completed, [2], [3] generations
+                               //   consumed by the forward / backward recurrence block
+    unsigned long long *tl0, *tl1, *tl2;   // timeline slots of the tile / recurrence / exterior-force kernels (or nullptr)
+    int *statf, *statb;        //   how the last run solved each block, in step order: 1 = G rho, 2 = exact sequential steps
     double *Wm, *Wbm;          // W[0..N], Wb[0..N] mantissas
     int *We, *Wbe;             // ... exponents
     double *V, *Vb, *F;        // V[N+1], Vb[N+1], F[2][D][N]
@@ -188,16 +200,134 @@ __global__ void __launch_bounds__(256) k_exch_coeff(ExArgs a) {
     }
 }
 
+// ---------------------------------------------------------------- inverses of the diagonal blocks (blocked recurrence)
+// Done by the diagonal tiles of k_exch_coeff_tiles. In step order (k = 0 .. n-1 within block q) the recurrence reads
+//     u_k = mu_k (rho_k + sum_{k'<k} T[k][k'] u_k'),   rho = what the earlier values contribute,
+// so  u = G rho  with  G = (I - diag(mu) T)^-1 diag(mu).  Every entry of T and mu is >= 0, hence G is a sum of products
+// of non-negative numbers: no cancellation, and an entry that stays a normal double is accurate to a few ulp. G is
+// built by recursive halving, G = [[G11, 0], [G22 T21 G11, G22]]: the four 8 x 8 diagonal blocks by substitution (28
+// dependent FMAs), then two levels of small matrix products -- ~80 dependent FMAs instead of 496. Both directions at
+// once (d = 0 forward, 1 backward). The block's response to the value handed over by the previous block (factor row
+// of step 0, `kin`) is folded into a vector h = G kin, so the owner needs no factor of its own block at run time:
+// u = G A + omega_0 h.
+// Called by all 1024 threads of a diagonal tile's block; `sX` is 2 x 16 x 17 doubles of scratch shared memory.
+__device__ __forceinline__ void diag_block_inverse(const ExArgs& a, int q, double kf, double kb, int maxf, int maxb,
+                                                   double (*sX)[16][17]) {
+    __shared__ double sT[2][32][33], sG[2][32][33];
+    __shared__ double sMu[2][32], sKin[2][32];
+    const int N = a.N;
+    const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
+    // forward: step k completes row 32q + k (tile column k) and uses factor row 32q + k (tile row k);
+    // backward: steps run downwards from `top` = min(N-1, 32q+31): step k completes row top - k, factor row top - k.
+    const int tt = min(N - 1, 32 * q + 31) - 32 * q;
+    const int nf = min(32, N - 32 * q), nbk = tt + 1 - (q == 0 ? 1 : 0);          // backward: row 0 is never computed
+    for (int i = tid; i < 2 * 32 * 33; i += 1024) { (&sT[0][0][0])[i] = 0.0; (&sG[0][0][0])[i] = 0.0; }
+    if (tid < 64) { (&sMu[0][0])[tid] = 0.0; (&sKin[0][0])[tid] = 0.0; }
+    __syncthreads();
+    // T[k][k'] = K[factor row of step k'+1][row of step k], k' < k < n
+    if (ty >= 1 && ty <= tx && tx < nf) sT[0][tx][ty - 1] = kf;                     // forward: tile (k'+1, k)
+    if (ty == 0 && tx < nf) {
+        sKin[0][tx] = kf;
+        sMu[0][tx] = (1.0 / (double)(32 * q + tx + 1)) * pow2i(max(maxf, -1100));
+    }
+    if (tx <= tt && ty >= tx && ty <= tt - 1 && tt - tx < nbk) sT[1][tt - tx][tt - ty - 1] = kb;   // backward: tile (top-k'-1, top-k)
+    if (ty == tt && tx <= tt && tt - tx < nbk) sKin[1][tt - tx] = kb;
+    if (ty == 1 && tx <= tt && tt - tx < nbk) sMu[1][tt - tx] = pow2i(max(maxb, -1100));
+    __syncthreads();
+    if (tid < 64) {   // level 0: the 8 x 8 diagonal blocks, lane = (block b, column j)
+        const int d = tid >> 5, b = (tid & 31) >> 3, j = tid & 7;
+        double g[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            double sum = (k == j) ? 1.0 : 0.0;
+#pragma unroll
+            for (int kp = 0; kp < k; ++kp) sum = fma(sT[d][8 * b + k][8 * b + kp], g[kp], sum);
+            g[k] = (k < j) ? 0.0 : sMu[d][8 * b + k] * sum;
+            sG[d][8 * b + k][8 * b + j] = g[k];
+        }
+    }
+    __syncthreads();
+    {   // level 1: 16 x 16 blocks out of 8 x 8 ones; 2 directions x 2 pairs x 64 elements
+        const int d = tid >> 7, pr = (tid >> 6) & 1, i = (tid >> 3) & 7, j = tid & 7;
+        const int r0 = 16 * pr, r1 = r0 + 8;
+        if (tid < 256) {
+            double x = 0.0;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) x = fma(sT[d][r1 + i][r0 + m], sG[d][r0 + m][r0 + j], x);
+            sX[d][8 * pr + i][j] = x;
+        }
+        __syncthreads();
+        if (tid < 256) {
+            double x = 0.0;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) x = fma(sG[d][r1 + i][r1 + m], sX[d][8 * pr + m][j], x);
+            sG[d][r1 + i][r0 + j] = x;
+        }
+    }
+    __syncthreads();
+    {   // level 2: the 32 x 32 block; 2 directions x 256 elements
+        const int d = tid >> 8, i = (tid >> 4) & 15, j = tid & 15;
+        if (tid < 512) {
+            double x0 = 0.0, x1 = 0.0;
+#pragma unroll
+            for (int m = 0; m < 16; m += 2) {
+                x0 = fma(sT[d][16 + i][m], sG[d][m][j], x0);
+                x1 = fma(sT[d][16 + i][m + 1], sG[d][m + 1][j], x1);
+            }
+            sX[d][i][j] = x0 + x1;
+        }
+        __syncthreads();
+        if (tid < 512) {
+            double x0 = 0.0, x1 = 0.0;
+#pragma unroll
+            for (int m = 0; m < 16; m += 2) {
+                x0 = fma(sG[d][16 + i][16 + m], sX[d][m][j], x0);
+                x1 = fma(sG[d][16 + i][16 + m + 1], sX[d][m + 1][j], x1);
+            }
+            sG[d][16 + i][j] = x0 + x1;
+        }
+    }
+    __syncthreads();
+    // validity: every structural entry (k'' <= k < n) and h_k must be a normal positive double in [2^-700, 2^300]
+    auto in_window = [](double g) { return (unsigned)__double2hiint(g) - (323u << 20) < (1000u << 20); };
+    bool okf = !(tx <= ty && ty < nf) || in_window(sG[0][ty][tx]);
+    bool okb = !(tx <= ty && ty < nbk) || in_window(sG[1][ty][tx]);
+    if (tid < 64) {   // h = G kin, lane = row k; the result goes to the lane that owns row k in the recurrence
+        const int d = tid >> 5, k = tid & 31;
+        double h0 = 0.0, h1 = 0.0;
+#pragma unroll 8
+        for (int c = 0; c < 32; c += 2) {
+            h0 = fma(sG[d][k][c], sKin[d][c], h0);
+            h1 = fma(sG[d][k][c + 1], sKin[d][c + 1], h1);
+        }
+        const double h = h0 + h1;
+        const int n = d == 0 ? nf : nbk;
+        if (k < n && !in_window(h)) { if (d == 0) okf = false; else okb = false; }
+        const int ln = d == 0 ? k : (tt - k) & 31;
+        (d == 0 ? a.Hf : a.Hb)[q * 32 + ln] = h;
+    }
+    okf = __syncthreads_and(okf);
+    okb = __syncthreads_and(okb);
+    {   // G[q][k''][lane]: row k lives in the lane that owns its particle row (rows k >= n: the lanes without a row, zeros)
+        const int c = ty, ln = tx;
+        a.Gf[(size_t)q * 1024 + c * 32 + ln] = sG[0][ln][c];
+        a.Gb[(size_t)q * 1024 + c * 32 + ln] = sG[1][(tt - ln) & 31][c];
+    }
+    if (tid == 0) { a.Gokf[q] = okf ? 1 : 0; a.Gokb[q] = okb ? 1 : 0; }
+}
+
 // Tile version for N <= 512: one block per 32 x 32 tile of the index square also emits the block-scaled copy the
 // fast recurrence consumes -- per (32-row block rb, column v) the largest binary exponent B and the factors as plain
 // doubles relative to 2^B. A factor more than 2^1022 below its block's largest becomes 0; it multiplies values that
 // the fast recurrence keeps within 2^+-400 of each other, so it could not have contributed.
 template <int D>
 __global__ void __launch_bounds__(1024) k_exch_coeff_tiles(ExArgs a) {
-    __shared__ int s_ef[32][33], s_eb[32][33];     // [step within the tile][column], padded: conflict-free both ways
+    __shared__ __align__(16) int s_e2[2][32][33];  // [step within the tile][column], padded: conflict-free both ways
+    int (*s_ef)[33] = s_e2[0], (*s_eb)[33] = s_e2[1];
     __shared__ int s_mf[32], s_mb[32];
     __shared__ double sA[kExchFastMaxN + 1];       // the prefix sums A(w), recomputed by every tile (N <= 512: one chunk)
     __shared__ double warp_tot[32];
+    tl_begin(a.tl0);
     const int N = a.N, nb = (N + 31) >> 5;
     const int rb = blockIdx.x / nb, sb = blockIdx.x % nb;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -264,17 +394,36 @@ __global__ void __launch_bounds__(1024) k_exch_coeff_tiles(ExArgs a) {
     }
     __syncthreads();
     const int maxf = s_mf[tx], maxb = s_mb[tx];
-    if (sc < N) {
-        if (ty == 0) {
-            a.Bf[rb * N + sc] = maxf;
-            a.Bb[rb * N + sc] = maxb;
-        }
-        if (r < N) {
-            // (NaN mantissas propagate; an exact zero has exponent kExtZeroExp and scales to 0)
-            a.Kf[i] = mf * pow2i(max(ef - maxf, -1100));
-            a.Kb[i] = mb * pow2i(max(eb - maxb, -1100));
+    // (NaN mantissas propagate; an exact zero has exponent kExtZeroExp and scales to 0)
+    const double kf = mf * pow2i(max(ef - maxf, -1100)), kb = mb * pow2i(max(eb - maxb, -1100));
+    if (sc < N && ty == 0) {
+        a.Bf[rb * N + sc] = maxf;
+        a.Bb[rb * N + sc] = maxb;
+    }
+    // tiled layout: the 32 x 32 tile (factor-row block rb, accumulating-row block sb) is one contiguous 8 KB piece
+    // [factor row][accumulating row], so that a warp of the recurrence fetches it with two bulk copies
+    {
+        const size_t t = ((size_t)rb * nb + sb) * 1024 + ty * 32 + tx;
+        a.Kf[t] = kf;
+        a.Kb[t] = kb;
+    }
+    if (rb == sb) {
+        __syncthreads();                             // s_e2 is free now: it becomes the scratch of the inversion
+        static_assert(sizeof(s_e2) >= 2 * 16 * 17 * sizeof(double), "scratch too small");
+        diag_block_inverse(a, rb, kf, kb, maxf, maxb, reinterpret_cast<double (*)[16][17]>(&s_e2[0][0][0]));
+    }
+    // The recurrence kernel is already resident and polls sync[1] (it is launched first so that its two large blocks
+    // get their SMs before the pair tiles flood the GPU): the last tile to finish publishes this generation of tables.
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&a.sync[0], 1) == (int)gridDim.x - 1) {
+            a.sync[0] = 0;
+            __threadfence();
+            atomicAdd(&a.sync[1], 1);
         }
     }
+    tl_end(a.tl0);
 }
 
 // ---------------------------------------------------------------- 3. the two recurrences
@@ -605,251 +754,301 @@ static __device__ __noinline__ void ext_fold(double& am, int& ae, double acc, in
     }
 }
 
-// ---------------------------------------------------------------- 3c. fast warp-decoupled recurrence (N <= 512)
-// Same protocol as recur_decoupled (tagged 16-byte entries, one owner warp on the chain, everybody else consuming),
-// with both sides of the work made cheap enough that the chain itself is what is left:
-//   * consumers read the BLOCK-SCALED factors K (plain doubles, k_exch_coeff_tiles) through an 8-byte cp.async ring and
-//     accumulate a 32-column phase as a plain dot product, acc += K * omega -- one FP64 instruction per column instead
-//     of an extended-range multiply-add (~25 instructions). Published entries of a fast phase share one binary exponent
-//     E, so the partial sum is folded into the extended-range accumulator once per phase (and whenever an entry's
-//     exponent differs, which is what entries of the exact fallback path do -- then every column is folded
-//     separately, still correct). This matters twice: a consumer shares its scheduler with the owner (in-order issue,
-//     4 warps each), and the NEXT owner cannot start before it has applied every earlier column.
-//   * the owner phase is the block-scaled loop described below (operands prefetched, publish software-pipelined).
-// smem: entries int4[N+2] | factor ring double[48][512] | sInv[N+2]
+template <int ST>
+__global__ void __launch_bounds__(1024) k_exch_recur_dec(ExArgs a) {
+    extern __shared__ __align__(16) double smem_d[];
+    if (blockIdx.x == 0) recur_decoupled<true, ST>(a, smem_d);
+    else recur_decoupled<false, ST>(a, smem_d);
+}
+
+// ---------------------------------------------------------------- 3d. blocked recurrence (N <= 512)
+// The two recurrences are triangular linear systems. The scalar kernels walk them one unknown at a time: N dependent
+// steps of ~100-200 cycles. Here the system is solved 32 unknowns at a time: k_exch_coeff_tiles has already inverted
+// every 32 x 32 diagonal block (G and h, positions only -- off the chain), so the owner warp of block q turns "what
+// the earlier values contribute to my 32 rows" (A, one plain double per lane) into its 32 new values with ONE 32 x 32
+// matrix-vector product, u = G A + omega_0 h: lane k keeps row k of G in registers, A travels through 256 bytes of
+// shared memory. The dependency chain is N/32 block steps instead of N scalar steps.
+//   * value #s in step order is W[s] (forward) / Wb[N-s] (backward); block q covers the steps [lo_q, hi_q] whose
+//     completing rows are 32q .. 32q+31, consumes the values #lo_q .. #hi_q and produces #lo_q+1 .. #hi_q+1. A value
+//     is stored under the factor row it multiplies (r = s forward, N-1-s backward), so block q's 32 entries are
+//     sOm[32q .. 32q+31] in either direction.
+//   * the owner publishes its block as plain doubles omega relative to ONE binary exponent E_q (sOm / sEx), hands its
+//     last value to the next owner (sHand), fences, and raises the block's flag; every later warp then applies the
+//     block's 32 columns to its own rows as a plain dot product with the block-scaled factor tile K[q][warp] and folds
+//     it into its extended-range accumulator once.
+//   * factor tiles are contiguous 8 KB pieces (k_exch_coeff_tiles), fetched by TMA bulk copies (cp.async.bulk +
+//     mbarrier transaction counts) as 4 KB half tiles into a private 3-slot ring per warp: one copy instruction per
+//     16 columns instead of 16 LDGSTS (8 cycles each at the SM's load/store unit -- that, not the arithmetic, bounded
+//     the per-thread cp.async ring of the scalar kernel at ~4000 cycles per block, measured).
+//   * fast-path validity, checked where it is cheap: G's structural entries and h are normal doubles in
+//     [2^-700, 2^300] (flag from the tile kernel), the accumulators entering the block are <= 2^600 on the block's
+//     scale, every new omega is a normal double in [2^-700, 2^300]. All terms are non-negative, so whatever underflows
+//     on the way is at least 2^-322 below the result it was added to. If any check fails the block is redone exactly:
+//     sequential extended-range steps from the untouched accumulators (the recur_decoupled arithmetic), flag value 2,
+//     and the consumers apply such a block column by column from the extended-range table.
+// smem: ring double[nb][3][512] | sOm double[32 nb] | sRho double[nb][32] | sHandOm double[nb+2] | mbarriers u64[nb][3]
+//       | sEx int[32 nb] | sHandE int[nb+2] | sFlag int[nb+2]
+__device__ __forceinline__ int lds_volatile_s32(const int* p) {
+    int r;
+    unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(r) : "r"(a) : "memory");
+    return r;
+}
+__device__ __forceinline__ void sts_volatile_s32(int* p, int v) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+__device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned mbar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(mbar), "r"(parity) : "memory");
+    } while (!ok);
+}
+// one 1-D bulk copy global -> shared, completion counted in bytes on the mbarrier
+__device__ __forceinline__ void bulk_load(unsigned dst, const void* src, unsigned bytes, unsigned mbar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mbar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
+}
+
 template <bool FWD>
-__device__ __forceinline__ void recur_fast(const ExArgs& a, double* smem_d) {
-    constexpr int ST = 48;                           // ring depth: 12 groups of 4 columns per thread
-    constexpr int AHEAD = 11;                        // groups in flight ahead of the consumer (global latency ~1000+ cycles
-                                                     // against ~100 cycles per column: 12 columns ahead was measured too few)
-    constexpr int RS = 512;                          // row stride of the ring: a compile-time constant, so every
-                                                     // shared-memory address in the loops is base + immediate
-    int tid;   // read %tid.x once into a register (the compiler otherwise re-reads the special register inside the chain loop)
+__device__ __forceinline__ void recur_blocked(const ExArgs& a, double* smem_d) {
+    constexpr int SLOTS = 3, HALF = 512;             // ring: 3 half tiles (16 factor rows x 32 lanes) per warp
+    int tid;
     asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
-    const int nt = blockDim.x, N = a.N, lane = tid & 31, warp = tid >> 5;
-    int4* sW = (int4*)smem_d;                        // {omega.lo, omega.hi, e, tag}
-    double* ring = (double*)(sW + (N + 2));
-    double* sInv = ring + (size_t)ST * RS;
+    const int nt = blockDim.x, N = a.N, lane = tid & 31, warp = tid >> 5, nb = nt >> 5;
     const int nsteps = FWD ? N : N - 1;
-    const int dstep = FWD ? N : -N;
+    const int npos = nsteps > 0 ? nb : 0;            // blocks that own at least one step
+    const int nb2 = (nb + 3) & ~1;
+    double* ring = smem_d;
+    double* sOm = ring + (size_t)nb * SLOTS * HALF;
+    double* sRho = sOm + 32 * nb;
+    double* sHandOm = sRho + 32 * nb;
+    unsigned long long* sBar = reinterpret_cast<unsigned long long*>(sHandOm + nb2);
+    int* sEx = reinterpret_cast<int*>(sBar + nb * SLOTS + (nb & 1));
+    int* sHandE = sEx + 32 * nb;
+    int* sFlag = sHandE + nb2;
+    int* sReason = sFlag + nb2;                      // why a block left the fast path (test aid): 1 accumulator range,
+                                                     // 2 hand-off value, 4 block inverse out of window, 8 new values out of window
+
+    auto g_lo = [&](int q) { return FWD ? 32 * q : max(0, N - 32 * (q + 1)); };
+    auto g_hi = [&](int q) { return min(nsteps - 1, FWD ? 32 * q + 31 : N - 1 - 32 * q); };
+    auto row_of = [&](int st) { return FWD ? st : (N - 1 - st); };  // factor row used by step st = row it completes
     const int v = tid;                                              // my row
     const bool row_ok = FWD ? (v < N) : (v >= 1 && v < N);
-    // steps in which my warp owns the completing row; they use the factor rows r = 32 warp .. 32 warp + 31
-    const int own_lo = FWD ? 32 * warp : max(0, N - 1 - (32 * warp + 31));
-    const int own_hi = min(nsteps - 1, FWD ? 32 * warp + 31 : N - 1 - 32 * warp);
+    const int own_lo = g_lo(warp), own_hi = g_hi(warp), n_own = own_hi - own_lo + 1;
+    const int mypos = FWD ? warp : nb - 1 - warp;                   // my block's position in step order
     const int last_need = row_ok ? (FWD ? v : N - 1 - v) : -1;
     auto need = [&](int s) { return s <= last_need; };
-    auto idx_of = [&](int s) { return FWD ? s : N - s; };           // where value #s lives
-    auto row_of = [&](int st) { return FWD ? st : (N - 1 - st); };  // factor row used by step st
-    const double* Kg = FWD ? a.Kf : a.Kb;
     const int* Bg = FWD ? a.Bf : a.Bb;
-    // Factor ring, private per thread: column s of my row lives in slot (s + off) % 48, with `off` chosen per warp so
-    // that the 32 columns of the warp's OWN phase sit in slots 0..34 without wrapping -- the owner loop then walks a
-    // plain pointer. Columns travel in aligned groups of four (one cp.async group each), AHEAD groups ahead of the
-    // consumer; the copies run on through the own phase (s <= own_hi), whose factors are read from the same ring.
-    // A group may reach up to three columns past own_hi (or past the table: the allocation is padded) -- never read.
-    const int off = (ST * 1024 - (own_lo & ~3)) % ST;
-    double* const ring_me = ring + tid;
-    auto slot_ptr = [&](int s) { return ring_me + ((s + off) % ST) * RS; };
-    const double* gk = Kg + (FWD ? 0 : (long long)(N - 1) * N) + tid;
-    int s_issue = 0;
-    double* ip = slot_ptr(0);                                       // slot of column s_issue
-    auto issue4 = [&]() {
-        if (s_issue <= own_hi && row_ok) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) cp_async8(ip + k * RS, gk + (long long)k * dstep);
-        }
-        cp_async_commit();
-        s_issue += 4;
-        gk += 4 * (long long)dstep;
-        ip += 4 * RS;
-        if (ip >= ring_me + ST * RS) ip -= ST * RS;
-    };
-    auto wait_value = [&](int s) {                                  // spin until value #s is published
-        int4 w;                     // (a __nanosleep(40 / 200) back-off between polls was measured: no gain / 1.5% slower)
-        do { w = lds_volatile_v4(&sW[idx_of(s)]); } while (w.w != s + 1);
-        return w;
+    const int4* Cg = FWD ? a.Cf : a.Cb;
+    // my warp's factor tiles, one per earlier block in step order: K[q][warp], q = pos (forward) / nb-1-pos (backward)
+    const double* Ktile = (FWD ? a.Kf : a.Kb) + (size_t)warp * 1024;
+    const size_t tile_stride = (size_t)nb * 1024;
+    const int ntile_half = 2 * min(mypos, npos);                    // half tiles this warp consumes
+    double* const ring_w = ring + (size_t)warp * SLOTS * HALF;
+    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring_w);
+    const unsigned bar_s = (unsigned)__cvta_generic_to_shared(sBar + warp * SLOTS);
+    auto issue_half = [&](int i) {                                  // lane 0 only: half tile #i -> slot i % 3
+        const int pos = i >> 1, q = FWD ? pos : nb - 1 - pos, slot = i % SLOTS;
+        bulk_load(ring_s + slot * HALF * 8, Ktile + (size_t)q * tile_stride + (i & 1) * HALF, HALF * 8, bar_s + slot * 8);
     };
 
-    if (!row_ok) {                             // rows outside the recurrence never copy: their ring slots stay 0
-#pragma unroll 4
-        for (int k = 0; k < ST; ++k) ring_me[k * RS] = 0.0;
+    for (int i = tid; i < 32 * nb; i += nt) { sOm[i] = 0.0; sEx[i] = 0; }
+    for (int i = tid; i < nb2; i += nt) sFlag[i] = 0;
+    if (tid == 0) {
+        sHandOm[0] = 1.0; sHandE[0] = 0;
+        // wait for this generation of factor tiles and block inverses (k_exch_coeff_tiles may still be running: this
+        // kernel is launched ahead of it on its own stream). Bounded: a missing producer becomes an error, not a hang.
+        const int used = a.sync[FWD ? 2 : 3];
+        int done, spins = 0;
+        do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(done) : "l"(a.sync + 1) : "memory");
+        } while (done - used <= 0 && ++spins < (1 << 22));
+        if (done - used <= 0) atomicOr(a.err, kErrSyncTimeout);
     }
-    for (int i = tid; i <= N + 1; i += nt) sW[i] = make_int4(0, 0, 0, 0);
-    for (int i = tid; i <= N; i += nt) sInv[i] = i > 0 ? 1.0 / (double)i : 0.0;
-#pragma unroll 1
-    for (int g = 0; g < AHEAD; ++g) issue4();
-    // my own block's scale: the owner phase works on factors K (relative to 2^Bown) and folds 2^Bown into the weight
+    __syncthreads();
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < SLOTS; ++k) mbar_init(bar_s + k * 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async;" ::: "memory");      // shared (barrier init) and global (tiles written by a running kernel)
+        for (int i = 0; i < SLOTS && i < ntile_half; ++i) issue_half(i);
+    }
+    // row `lane`'s row of G (zero beyond the diagonal and for lanes without a row), h, and the block's validity flag
+    double Grow[32];
+    {
+        const double* Gg = (FWD ? a.Gf : a.Gb) + (size_t)warp * 1024 + lane;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) Grow[k] = Gg[k * 32];
+    }
+    const double hrow = (FWD ? a.Hf : a.Hb)[warp * 32 + lane];
+    const int Gok = (FWD ? a.Gokf : a.Gokb)[warp];
     const int Bown = row_ok ? Bg[warp * N + v] : kExtZeroExp;
     __syncthreads();
-    if (tid == 0) sts_volatile_v4(&sW[idx_of(0)], make_int4(__double2loint(1.0), __double2hiint(1.0), 0, 1));
 
     double am = 0.0;                                 // extended-range accumulator of my row (normalised)
     int ae = kExtZeroExp;
-    double acc = 0.0;                                // plain partial sum of the current run of columns, scale 2^(Bq + Eph)
-    int Eph = 0, Bq = 0;
-    auto fold = [&]() {                              // am * 2^ae += acc * 2^(Bq + Eph)
-        ext_fold(am, ae, acc, Bq + Eph);
-        acc = 0.0;
-    };
-    auto apply = [&](const int4& w, double kk) {     // one column the careful way (warp-uniform branch: w is broadcast)
-        if (w.z != Eph) { fold(); Eph = w.z; }
-        acc = fma(kk, __hiloint2double(w.y, w.x), acc);
-    };
-    int s = 0;
-    double* rp = slot_ptr(0);                        // slot of column s
-    auto advance = [&](int n) {
-        rp += n * RS;
-        if (rp >= ring_me + ST * RS) rp -= ST * RS;
-    };
     const long long t_begin = a.dbg ? clock64() : 0;
-    // ---- consumer phases: columns owned by earlier warps, one 32-row factor block q at a time
-    // invariant: issued groups = floor(s / 4) + AHEAD, so "all but the AHEAD-1 newest groups" covers the group of column s
-    int Bnext = (own_lo > 0 && row_ok) ? Bg[(row_of(0) >> 5) * N + v] : 0;
-    while (s < own_lo) {
-        const int q = row_of(s) >> 5;
-        const int s_end = min(own_lo, FWD ? (q + 1) * 32 : N - q * 32);   // one past this block's last step
-        Bq = Bnext;
-        if (s_end < own_lo && row_ok) Bnext = Bg[(row_of(s_end) >> 5) * N + v];
-        while (s < s_end) {
-            if ((s & 3) == 0 && s + 4 <= s_end) {                   // a whole group: four columns per poll
-                wait_value(s + 3);                                   // values are published in order
-                cp_async_wait<AHEAD - 1>();
-                const int4* wp = &sW[idx_of(s)];
-                int4 w[4];
-                double kk[4];
+    // ---- consumer phases: the blocks before mine in step order, each applied as soon as its flag is up
+    int Bnext = (mypos > 0 && row_ok) ? Bg[(FWD ? 0 : nb - 1) * N + v] : 0;
+#pragma unroll 1
+    for (int pos = 0; pos < mypos && pos < npos; ++pos) {
+        const int q = FWD ? pos : nb - 1 - pos;
+        const int Bq = Bnext;
+        if (pos + 1 < mypos && row_ok) Bnext = Bg[(FWD ? pos + 1 : nb - 2 - pos) * N + v];
+        int fl;
+        do { fl = lds_volatile_s32(&sFlag[pos]); } while (fl == 0);
+        long long* stamp = (a.dbg && lane == 0) ? a.dbg + 192 + (((FWD ? 0 : 16) + warp) * 16 + pos) * 4 : nullptr;
+        if (stamp) stamp[0] = clock64();             // flag seen
+        const double* om = sOm + 32 * q;
+        double acc0 = 0.0, acc1 = 0.0;
+#pragma unroll 1
+        for (int h = 0; h < 2; ++h) {
+            const int i = 2 * pos + h, slot = i % SLOTS;
+            mbar_wait(bar_s + slot * 8, (unsigned)(i / SLOTS) & 1u);
+            if (stamp) stamp[1 + h] = clock64();     // half tile landed
+            if (fl == 1) {
+                const double* kp = ring_w + slot * HALF + lane;
+                const double* op = om + 16 * h;
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    w[k] = wp[FWD ? k : -k];
-                    kk[k] = rp[k * RS];
+                for (int c = 0; c < 16; c += 4) {
+                    const double2 w01 = *reinterpret_cast<const double2*>(op + c);
+                    const double2 w23 = *reinterpret_cast<const double2*>(op + c + 2);
+                    acc0 = fma(kp[(c + 0) * 32], w01.x, acc0);
+                    acc1 = fma(kp[(c + 1) * 32], w01.y, acc1);
+                    acc0 = fma(kp[(c + 2) * 32], w23.x, acc0);
+                    acc1 = fma(kp[(c + 3) * 32], w23.y, acc1);
                 }
-                if (((w[0].z ^ Eph) | (w[1].z ^ Eph) | (w[2].z ^ Eph) | (w[3].z ^ Eph)) == 0) {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) acc = fma(kk[k], __hiloint2double(w[k].y, w[k].x), acc);
-                } else {
-#pragma unroll
-                    for (int k = 0; k < 4; ++k) apply(w[k], kk[k]);
-                }
-                issue4();
-                s += 4;
-                advance(4);
-            } else {                                                 // ragged head / tail of a block (N % 4 != 0)
-                const int4 w = wait_value(s);
-                cp_async_wait<AHEAD - 1>();
-                apply(w, *rp);
-                if ((s & 3) == 3) issue4();
-                ++s;
-                advance(1);
+            }
+            __syncwarp();
+            if (lane == 0 && i + SLOTS < ntile_half) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue_half(i + SLOTS);
             }
         }
-        fold();                                                      // the next block has its own scale
-    }
-    const long long t_own0 = a.dbg ? clock64() : 0;
-    long long t_loop0 = t_own0;
-    // ---- owner phase: the completing rows are my warp's; the chain runs lane to lane through shuffles
-    if (s <= own_hi) {
-        int s_resume = s;                 // first step whose result is NOT yet published
-        // Block-scaled fast path. Inside one 32-step owner phase every W is written as omega * 2^E with a common
-        // binary exponent E and a plain double omega, and every row keeps its sum in units of 2^(E + Bown) (Bown: the
-        // scale of the row's own factor block), so a step is ONE fma + ONE multiply + ONE shuffle (no exponent
-        // alignment, no normalisation on the chain). It is exact as long as every omega of the phase stays within
-        // 2^+-400 of the phase's first value and no accumulator starts above 2^600 on that scale: whatever a plain
-        // double then flushes to zero is < 2^-622 and negligible against the result. The moment a value leaves
-        // that window the phase is redone from the untouched extended-range accumulators (below); nothing out of
-        // range has been published by then. The loop is deliberately NOT unrolled: it runs once per warp, and
-        // straight-line code executed once is bound by instruction fetch.
-        // A published entry of such a phase is {omega (plain double), E, tag}: no normalisation work in the
-        // loop; entries are therefore NOT normalised in general (consumers treat them as mantissa * 2^E with a
-        // mantissa anywhere in 2^+-400), and each phase renormalises its first value so E does not drift.
-        const int4 w0 = wait_value(s);
-        const Ext n0 = ext_normalize(__hiloint2double(w0.y, w0.x), w0.z);
-        const int E = n0.e;
-        double om = n0.m;
-        const int d = ae - E - Bown;
-        double A = (am == 0.0) ? 0.0 : ext_to_double(am, min(d, 600));
-        bool exact = __any_sync(kFullMask, (am != 0.0) && (d > 600)) || !(om > 0.0);
-        // every group that holds an own-phase column has been issued (AHEAD * 4 >= 35); make sure they have landed
-        cp_async_wait<AHEAD - 9>();
-        if (a.dbg) t_loop0 = clock64();
-        if (!exact) {
-            // Measured on B200 (profiles/microbench2.cu): fma + mul + shuffle = 46 cycles per step; shared-memory
-            // operands loaded inside the step add 65, a compare-and-branch range check 55, a divergent publish 91.
-            // Hence: the factor is prefetched one step ahead, the weight 2^Bown / (v+1) is a per-lane constant (only
-            // the completing lane's product is used), the range check is an integer test on the exponent bits folded
-            // into a predicate (no branch; once it fails nothing more is published and the phase is redone
-            // below). The loop is software-pipelined by one step: iteration st issues the chain's fma and
-            // multiply first and only then checks and publishes the value the PREVIOUS iteration produced (every
-            // lane holds it after the broadcast shuffle), so the integer work and the store sit in the shadow of
-            // the FP64 latency. Every instruction here also costs one issue slot per co-resident consumer warp
-            // (in-order issue, 4 warps per scheduler), so the body is kept to ~25 instructions.
-            const double* kp = rp;                                       // own-phase slots do not wrap (see `off`)
-            double kcur = *kp;
-            const double myw = (FWD ? sInv[min(v + 1, N)] : 1.0) * pow2i(max(Bown, -1100));
-            bool okall = true;
-            int lane_o = row_of(s) & 31;
-            int4* wp = &sW[idx_of(s)];
+        if (stamp) stamp[3] = clock64();             // both halves applied
+        if (fl == 1) {
+            ext_fold(am, ae, acc0 + acc1, Bq + sEx[32 * q]);
+        } else {                                     // the block was solved exactly: entries are {mantissa, exponent} per value
+            const int s0 = g_lo(q), s1 = g_hi(q);
 #pragma unroll 1
-            for (int st = s; st <= own_hi; ++st) {
-                kp += RS;
-                const double knext = *kp;
-                A = fma(kcur, om, A);                                     // K is 0 where a row takes no part
-                const double t = A * myw;
-                {   // value #st (st == s: re-stores the hand-off value, renormalised -- same number, same tag)
-                    const unsigned hi = (unsigned)__double2hiint(om);
-                    okall = okall && (hi - (623u << 20) < (800u << 20));   // positive, within 2^+-400, not NaN/inf/0
-                    if (okall && lane == 0) sts_volatile_v4(wp, make_int4(__double2loint(om), (int)hi, E, st + 1));
-                    s_resume = okall ? st : s_resume;
-                }
-                om = __shfl_sync(kFullMask, t, lane_o);
-                lane_o = (lane_o + (FWD ? 1 : -1)) & 31;
-                wp += FWD ? 1 : -1;
-                kcur = knext;
-            }
-            {   // the phase's last value, #(own_hi + 1)
-                const unsigned hi = (unsigned)__double2hiint(om);
-                okall = okall && (hi - (623u << 20) < (800u << 20));
-                if (okall && lane == 0) sts_volatile_v4(wp, make_int4(__double2loint(om), (int)hi, E, own_hi + 2));
-                s_resume = okall ? own_hi + 1 : s_resume;
-            }
-            exact = !okall;
-        }
-        if (exact) {
-            // Extended-range fallback: restarts the phase from the pre-phase accumulators, re-applies the already
-            // published columns without publishing them again (factors straight from global memory: rare), and
-            // continues from the first unpublished step; its entries are normalised {mantissa, exponent}.
-            const int4* Cg = FWD ? a.Cf : a.Cb;
-            double wm = __hiloint2double(w0.y, w0.x);
-            int we = w0.z;
-#pragma unroll 1
-            for (; s <= own_hi; ++s) {
-                if (s > own_lo && s <= s_resume) {
-                    const int4 w = wait_value(s);
-                    wm = __hiloint2double(w.y, w.x);
-                    we = w.z;
-                }
+            for (int s = s0; s <= s1; ++s) {
                 if (need(s)) {
-                    const int4 c = __ldg(&Cg[(long long)row_of(s) * N + v]);
+                    const int r = row_of(s);
+                    const int4 c = __ldg(&Cg[(long long)r * N + v]);
+                    ext_fma(am, ae, ext_m(c), c.z, sOm[r], sEx[r]);
+                }
+            }
+        }
+    }
+    if (!row_ok) { am = 0.0; ae = kExtZeroExp; }     // (the tiles also hold factors of rows that take no part: backward row 0)
+    const long long t_own0 = a.dbg ? clock64() : 0;
+    // ---- owner phase
+    if (n_own > 0) {
+        const double hm = sHandOm[mypos];
+        const int he = sHandE[mypos];
+        const Ext n0 = ext_normalize(hm, he);
+        const int E = n0.e;
+        const double om0 = n0.m;
+        const int d = ae - E - Bown;
+        const double A = (am == 0.0) ? 0.0 : ext_to_double(am, min(d, 600));
+        bool exact = __any_sync(kFullMask, (am != 0.0) && (d > 600)) || !(om0 > 0.0) || !Gok;
+        int reason = (__any_sync(kFullMask, (am != 0.0) && (d > 600)) ? 1 : 0) | (!(om0 > 0.0) ? 2 : 0) | (!Gok ? 4 : 0);
+        // step index of my row inside the block = slot of my A (lanes without a row fill the unused slots with 0)
+        const int tt = FWD ? 0 : row_of(own_lo) & 31;
+        const int kslot = FWD ? lane : (tt - lane) & 31;
+        if (!exact) {
+            double* rho_w = sRho + warp * 32;
+            rho_w[kslot] = A;
+            __syncwarp();
+            double u0 = om0 * hrow, u1 = 0.0, u2 = 0.0, u3 = 0.0;
+#pragma unroll
+            for (int k = 0; k < 32; k += 4) {
+                const double2 r01 = *reinterpret_cast<const double2*>(rho_w + k);
+                const double2 r23 = *reinterpret_cast<const double2*>(rho_w + k + 2);
+                u0 = fma(Grow[k], r01.x, u0);
+                u1 = fma(Grow[k + 1], r01.y, u1);
+                u2 = fma(Grow[k + 2], r23.x, u2);
+                u3 = fma(Grow[k + 3], r23.y, u3);
+            }
+            const double u = (u0 + u1) + (u2 + u3);
+            const bool mine = kslot < n_own;
+            const unsigned hi = (unsigned)__double2hiint(u);
+            const bool okall = __all_sync(kFullMask, !mine || (hi - (323u << 20) < (1000u << 20)));
+            if (okall) {
+                if (mine) {
+                    if (kslot < n_own - 1) {
+                        const int r = row_of(own_lo + kslot + 1);
+                        sOm[r] = u;
+                        sEx[r] = E;
+                    } else {
+                        sHandOm[mypos + 1] = u;
+                        sHandE[mypos + 1] = E;
+                    }
+                }
+                if (lane == 0) {
+                    const int r = row_of(own_lo);
+                    sOm[r] = om0;
+                    sEx[r] = E;
+                }
+                __syncwarp();
+                __threadfence_block();
+                if (lane == 0) sts_volatile_s32(&sFlag[mypos], 1);
+            } else {
+                exact = true;
+                reason |= 8;
+            }
+        }
+        if (lane == 0) sReason[mypos] = reason;
+        if (exact) {
+            double wm = n0.m;                                         // (normalised: ext_fma wants moderate mantissas)
+            int we = n0.e;
+            if (lane == 0) {
+                const int r = row_of(own_lo);
+                sOm[r] = wm;
+                sEx[r] = we;
+            }
+#pragma unroll 1
+            for (int st = own_lo; st <= own_hi; ++st) {
+                if (need(st)) {
+                    const int4 c = __ldg(&Cg[(long long)row_of(st) * N + v]);
                     ext_fma(am, ae, ext_m(c), c.z, wm, we);
                 }
-                if (s >= s_resume) {
-                    const int lane_o = row_of(s) & 31;
-                    const Ext fin = ext_normalize(FWD ? am * sInv[s + 1] : am, ae);
-                    wm = __shfl_sync(kFullMask, fin.m, lane_o);
-                    we = __shfl_sync(kFullMask, fin.e, lane_o);
-                    if (lane == lane_o)
-                        sts_volatile_v4(&sW[idx_of(s + 1)], make_int4(__double2loint(fin.m), __double2hiint(fin.m), fin.e, s + 2));
+                const int lane_o = row_of(st) & 31;
+                const Ext fin = ext_normalize(FWD ? am * a.Inv[st + 1] : am, ae);
+                wm = __shfl_sync(kFullMask, fin.m, lane_o);
+                we = __shfl_sync(kFullMask, fin.e, lane_o);
+                if (lane == lane_o) {
+                    if (st < own_hi) {
+                        const int r = row_of(st + 1);
+                        sOm[r] = fin.m;
+                        sEx[r] = fin.e;
+                    } else {
+                        sHandOm[mypos + 1] = fin.m;
+                        sHandE[mypos + 1] = fin.e;
+                    }
                 }
             }
+            __syncwarp();
+            __threadfence_block();
+            if (lane == 0) sts_volatile_s32(&sFlag[mypos], 2);
         }
     }
     if (a.dbg && lane == 0) {
         long long* o = a.dbg + ((FWD ? 0 : 32) + warp) * 3;
         o[0] = t_own0 - t_begin;            // cycles spent as a consumer (incl. waiting)
         o[1] = clock64() - t_own0;          // cycles spent as the owner
-        o[2] = t_loop0 - t_own0;            // ... of which: hand-off wait + owner prologue
+        o[2] = t_begin;
+        a.dbg[192 + 2048 + (FWD ? 0 : 16) + warp] = t_own0;
     }
-    cp_async_wait<0>();
     __syncthreads();
+    if (tid < nb) (FWD ? a.statf : a.statb)[tid] = tid < npos ? sFlag[tid] + 16 * sReason[tid] : 0;
+    if (tid == 0) a.sync[FWD ? 2 : 3] += 1;          // this generation is consumed
 
     // V = -(ln W)/beta in parallel; publish W (normalised) for the force kernel
     const double LN2 = 0.6931471805599453;
@@ -857,8 +1056,9 @@ __device__ __forceinline__ void recur_fast(const ExArgs& a, double* smem_d) {
     int* We_g = FWD ? a.We : a.Wbe;
     double* V_g = FWD ? a.V : a.Vb;
     for (int i = (FWD ? 0 : 1) + tid; i <= N; i += nt) {
-        const int4 w = sW[i];
-        const Ext wn = ext_normalize(__hiloint2double(w.y, w.x), w.z);
+        const int sv = FWD ? i : N - i;                              // value number
+        const int r = row_of(sv);
+        const Ext wn = sv < nsteps ? ext_normalize(sOm[r], sEx[r]) : ext_normalize(sHandOm[npos], sHandE[npos]);
         Wm_g[i] = wn.m;
         We_g[i] = wn.e;
         const double val = -(log(wn.m) + (double)wn.e * LN2) / a.beta;
@@ -867,120 +1067,116 @@ __device__ __forceinline__ void recur_fast(const ExArgs& a, double* smem_d) {
     }
 }
 
-__global__ void __launch_bounds__(512) k_exch_recur_fast(ExArgs a) {
+__global__ void __launch_bounds__(512, 1) k_exch_recur_blocked(ExArgs a) {
     extern __shared__ __align__(16) double smem_d[];
-    if (blockIdx.x == 0) recur_fast<true>(a, smem_d);
-    else recur_fast<false>(a, smem_d);
-}
-
-template <int ST>
-__global__ void __launch_bounds__(1024) k_exch_recur_dec(ExArgs a) {
-    extern __shared__ __align__(16) double smem_d[];
-    if (blockIdx.x == 0) recur_decoupled<true, ST>(a, smem_d);
-    else recur_decoupled<false, ST>(a, smem_d);
+    tl_begin(a.tl1);
+    if (blockIdx.x == 0) recur_blocked<true>(a, smem_d);
+    else recur_blocked<false>(a, smem_d);
+    tl_end(a.tl1);
 }
 
 // ---------------------------------------------------------------- 4. exterior spring forces (K7 + K8)
-// one block of kFT threads per (exterior bead, particle l): the u-sum is latency-bound (a handful of dependent
-// global loads per term), so it is spread over 4 warps and the partials are combined in a fixed order
-constexpr int kFT = 128;
-template <int D>
-__device__ __forceinline__ void block_reduce_store(double (&acc)[D], double* sred) {
+// The kernel runs beside the pair tiles, and every block it needs has to wait for a pair-tile block to retire
+// (in-kernel timeline: 1024 blocks of a block-per-particle version took 22 us to trickle in). So: 128 blocks of 4
+// warps, one WARP per (exterior bead, particle l) and two such tasks per warp at N = 512. What a term needs besides
+// its Boltzmann factor -- the other recurrence's weights and one bead slice -- is staged in shared memory once per
+// block (even blocks serve the first bead, odd blocks the last), and a task issues all of its factor loads (16 B each,
+// L2) before it uses the first one, so a task costs one L2 round trip instead of one per term.
+constexpr int kFW = 4;                       // warps per block (127 registers x 128 threads: fits where ONE pair-tile block retired)
+constexpr int kFU = 16;                      // terms per lane held in flight (covers N <= 512)
+template <int D, bool STAGE>
+__global__ void __launch_bounds__(32 * kFW) k_exch_forces(ExArgs a) {
+    extern __shared__ __align__(16) double fsm[];
+    tl_begin(a.tl2);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-    for (int c = 0; c < D; ++c) acc[c] = warp_sum(acc[c]);
-    if (lane == 0) {
-#pragma unroll
-        for (int c = 0; c < D; ++c) sred[warp * D + c] = acc[c];
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-#pragma unroll
-        for (int c = 0; c < D; ++c) {
-            double t = 0.0;
-            for (int k = 0; k < kFT / 32; ++k) t += sred[k * D + c];
-            acc[c] = t;
-        }
-    }
-}
-
-template <int D>
-__global__ void __launch_bounds__(kFT) k_exch_forces(ExArgs a) {
-    __shared__ double sred[(kFT / 32) * D];
-    const int lane = threadIdx.x;          // position in the u-stride of this block
-    const int w = blockIdx.x;
     const int N = a.N;
-    const int which = w / N, l = w % N;   // 0: first bead, 1: last bead
-    if ((which == 0 && !a.do_first) || (which == 1 && !a.do_last)) return;
+    const int which = blockIdx.x & 1;         // 0: first bead, 1: last bead
+    const int nblk = gridDim.x >> 1, blk = blockIdx.x >> 1;
+    // per-u operands: weight mantissa gm[u], exponent ge[u], slice xo[c][u]
+    //   first bead (sum over u >= l-1): g = Wb[u+1] / (u+1), xo = bead P;   last bead (sum over u <= l+1): g = W[u], xo = bead 1
+    double* gm = fsm;
+    int* ge = reinterpret_cast<int*>(fsm + N + 1);
+    double* xo = fsm + N + 1 + ((N + 2) >> 1);
+    const double* xo_g = which == 0 ? a.xP : a.x1;
+    if (STAGE) {
+        for (int u = threadIdx.x; u < N; u += blockDim.x) {
+            if (which == 0) { gm[u] = a.Wbm[u + 1] * a.Inv[u + 1]; ge[u] = a.Wbe[u + 1]; }
+            else { gm[u] = a.Wm[u]; ge[u] = a.We[u]; }
+#pragma unroll
+            for (int c = 0; c < D; ++c) xo[c * N + u] = xo_g[(size_t)c * N + u];
+        }
+        __syncthreads();
+    }
+    auto g_of = [&](int u, int& e) {
+        if (STAGE) { e = ge[u]; return gm[u]; }
+        if (which == 0) { e = a.Wbe[u + 1]; return a.Wbm[u + 1] * a.Inv[u + 1]; }
+        e = a.We[u];
+        return a.Wm[u];
+    };
+    auto xo_of = [&](int c, int u) { return STAGE ? xo[c * N + u] : xo_g[(size_t)c * N + u]; };
+    const bool active = which == 0 ? a.do_first : a.do_last;
     const double iWN = 1.0 / a.Wm[N];
     const int eWN = a.We[N];
-    double acc[D];
+    const int4* Ctab = which == 0 ? a.Cf : a.Cb;
+    for (int l = blk * kFW + warp; active && l < N; l += nblk * kFW) {
+        // first bead: f_l = k [ sum_{u=max(0,l-1)}^{N-1} P(u->l) mi(r^P_u - r^1_l) + mi(r^2_l - r^1_l) ]
+        //             P(u->l) = W[l] c(l,u) Wb[u+1] / ((u+1) W[N]),  P(l-1->l) = 1 - W[l] Wb[l] / W[N]
+        // last bead:  f_l = k [ sum_{u=0}^{min(l+1,N-1)} P(l->u) mi(r^1_u - r^P_l) + mi(r^{P-1}_l - r^P_l) ]
+        //             P(l->u) = W[u] [c(u,l)/(l+1)] Wb[l+1] / W[N],  P(l->l+1) = 1 - W[l+1] Wb[l+1] / W[N]
+        const double wl = (which == 0 ? a.Wm[l] : a.Wbm[l + 1]) * iWN;
+        const int el = (which == 0 ? a.We[l] : a.Wbe[l + 1]) - eWN;
+        const int ulo = which == 0 ? max(0, l - 1) : 0, uhi = which == 0 ? N - 1 : min(l + 1, N - 1);
+        const int special = which == 0 ? l - 1 : l + 1;               // the neighbour term (1 - ...), no factor
+        const double* xs = which == 0 ? a.x1 : a.xP;
+        double xl[D], acc[D];
 #pragma unroll
-    for (int c = 0; c < D; ++c) acc[c] = 0.0;
-
-    if (which == 0) {
-        // f_l = k [ sum_{u=max(0,l-1)}^{N-1} P(u->l) mi(r^P_u - r^1_l) + mi(r^2_l - r^1_l) ]
-        const double wl = a.Wm[l] * iWN;
-        const int el = a.We[l] - eWN;
-#pragma unroll 2
-        for (int u = max(0, l - 1) + lane; u < N; u += kFT) {
-            double pr;
-            if (u == l - 1) {
-                pr = 1.0 - ext_to_double(wl * a.Wbm[l], el + a.Wbe[l]);
-            } else {
-                const size_t ci = (size_t)l * N + u;
-                const int4 c = __ldg(&a.Cf[ci]);
-                pr = ext_to_double(wl * ext_m(c) * a.Wbm[u + 1] * a.Inv[u + 1], el + c.z + a.Wbe[u + 1]);
+        for (int c = 0; c < D; ++c) { xl[c] = xs[(size_t)c * N + l]; acc[c] = 0.0; }
+        const int4* Crow = Ctab + (size_t)l * N;
+        for (int u0 = ulo + lane; u0 <= uhi; u0 += 32 * kFU) {
+            int4 cv[kFU];
+#pragma unroll
+            for (int k = 0; k < kFU; ++k) {
+                const int u = u0 + 32 * k;
+                cv[k] = (u <= uhi && u != special) ? __ldg(Crow + u) : make_int4(0, 0, 0, 0);
             }
 #pragma unroll
-            for (int c = 0; c < D; ++c) {
-                double dx = a.xP[(size_t)c * N + u] - a.x1[(size_t)c * N + l];
-                if (a.pbc) dx = min_image(dx, a.L, a.invL);
-                acc[c] = fma(pr, dx, acc[c]);
+            for (int k = 0; k < kFU; ++k) {
+                const int u = u0 + 32 * k;
+                if (u <= uhi) {
+                    double pr;
+                    if (u == special) {
+                        pr = which == 0 ? 1.0 - ext_to_double(wl * a.Wbm[l], el + a.Wbe[l])
+                                        : 1.0 - ext_to_double(wl * a.Wm[l + 1], el + a.We[l + 1]);
+                    } else {
+                        int e;
+                        const double g = g_of(u, e);
+                        pr = ext_to_double(wl * ext_m(cv[k]) * g, el + cv[k].z + e);
+                    }
+                    if (pr != 0.0) {   // most connection probabilities underflow to exactly 0: skip their separations
+#pragma unroll
+                        for (int c = 0; c < D; ++c) {
+                            double dx = xo_of(c, u) - xl[c];
+                            if (a.pbc) dx = min_image(dx, a.L, a.invL);
+                            acc[c] = fma(pr, dx, acc[c]);
+                        }
+                    }
+                }
             }
         }
-        block_reduce_store<D>(acc, sred);
+#pragma unroll
+        for (int c = 0; c < D; ++c) acc[c] = warp_sum(acc[c]);
         if (lane == 0) {
+            const double* xn = which == 0 ? a.x2 : a.xPm1;            // the interior neighbour bead
 #pragma unroll
             for (int c = 0; c < D; ++c) {
-                double dx = a.x2[(size_t)c * N + l] - a.x1[(size_t)c * N + l];
+                double dx = xn[(size_t)c * N + l] - xl[c];
                 if (a.pbc) dx = min_image(dx, a.L, a.invL);
-                a.F[(size_t)c * N + l] = (acc[c] + dx) * a.k;
-            }
-        }
-    } else {
-        // f_l = k [ sum_{u=0}^{min(l+1,N-1)} P(l->u) mi(r^1_u - r^P_l) + mi(r^{P-1}_l - r^P_l) ]
-        const double wb = a.Wbm[l + 1] * iWN;
-        const int eb = a.Wbe[l + 1] - eWN;
-        const int uend = min(l + 1, N - 1);
-#pragma unroll 2
-        for (int u = lane; u <= uend; u += kFT) {
-            double pr;
-            if (u == l + 1) {
-                pr = 1.0 - ext_to_double(wb * a.Wm[l + 1], eb + a.We[l + 1]);
-            } else {
-                const size_t ci = (size_t)l * N + u;
-                const int4 c = __ldg(&a.Cb[ci]);                       // = c(u,l) / (l+1)
-                pr = ext_to_double(wb * ext_m(c) * a.Wm[u], eb + c.z + a.We[u]);
-            }
-#pragma unroll
-            for (int c = 0; c < D; ++c) {
-                double dx = a.x1[(size_t)c * N + u] - a.xP[(size_t)c * N + l];
-                if (a.pbc) dx = min_image(dx, a.L, a.invL);
-                acc[c] = fma(pr, dx, acc[c]);
-            }
-        }
-        block_reduce_store<D>(acc, sred);
-        if (lane == 0) {
-#pragma unroll
-            for (int c = 0; c < D; ++c) {
-                double dx = a.xPm1[(size_t)c * N + l] - a.xP[(size_t)c * N + l];
-                if (a.pbc) dx = min_image(dx, a.L, a.invL);
-                a.F[(size_t)(D + c) * N + l] = (acc[c] + dx) * a.k;
+                a.F[(size_t)(which * D + c) * N + l] = (acc[c] + dx) * a.k;
             }
         }
     }
-    if (w == 0 && lane == 0) a.Vb[0] = a.V[N];   // V_backwards[0] = V[N] (quadratic_bosonic_exchange.cpp:127)
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.Vb[0] = a.V[N];   // V_backwards[0] = V[N] (quadratic_bosonic_exchange.cpp:127)
+    tl_end(a.tl2);
 }
 
 // ---------------------------------------------------------------- estimators (bead-0 owner only), one block
@@ -1085,8 +1281,16 @@ static ExArgs make_args(Sim* s) {
     a.A = s->exA;
     a.Inv = s->exA + s->N;
     a.Cf = s->exC; a.Cb = s->exC + NN;
-    a.Kf = s->exK; a.Kb = s->exK ? s->exK + NN + 512 : nullptr;
+    const size_t nbk = (size_t)((s->N + 31) / 32);
+    a.Kf = s->exK; a.Kb = s->exK ? s->exK + nbk * nbk * 1024 : nullptr;
     a.Bf = s->exB; a.Bb = s->exB ? s->exB + (size_t)((s->N + 31) / 32) * s->N : nullptr;
+    a.Gf = s->exG; a.Gb = s->exG ? s->exG + nbk * 1024 : nullptr;
+    a.Hf = s->exG ? s->exG + 2 * nbk * 1024 : nullptr; a.Hb = s->exG ? s->exG + 2 * nbk * 1024 + nbk * 32 : nullptr;
+    a.Gokf = s->exGok; a.Gokb = s->exGok ? s->exGok + (s->N + 31) / 32 : nullptr;
+    a.sync = s->exSync;
+    a.tl0 = a.tl1 = a.tl2 = nullptr;
+    a.statf = s->exGok ? s->exGok + 2 * ((s->N + 31) / 32) : nullptr;
+    a.statb = s->exGok ? s->exGok + 3 * ((s->N + 31) / 32) : nullptr;
     a.Wm = s->exWm; a.Wbm = s->exWm + (s->N + 1);
     a.We = s->exWe; a.Wbe = s->exWe + (s->N + 1);
     a.V = s->exV; a.Vb = s->exVb; a.F = s->exF;
@@ -1127,12 +1331,14 @@ static int run_recursion(Sim* s, const ExArgs& a, cudaStream_t st) {
         // coefficient ring: 16 rows in flight up to 512 rows per block, 8 beyond (shared-memory budget)
         const int ST = nt <= 512 ? 16 : 8;
         const size_t smem = (size_t)(s->N + 2) * (sizeof(int4) + sizeof(double)) + (size_t)ST * nt * sizeof(int4) + 16;
-        if (nt <= 512 && a.Kf && !getenv("PIMDB_EXCH_NOFAST")) {
-            // fast kernel: block-scaled factors, plain-double consumers and owner phase, 48-column factor ring
-            const size_t smem_fast = (size_t)(s->N + 2) * (sizeof(int4) + sizeof(double)) + (size_t)48 * 512 * sizeof(double) + 16;
-            if (smem_fast > 48 * 1024)
-                cudaFuncSetAttribute(k_exch_recur_fast, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_fast);
-            k_exch_recur_fast<<<2, nt, smem_fast, st>>>(a);
+        if (nt <= 512 && a.Kf && !getenv("PIMDB_EXCH_NOBLOCKED")) {
+            // blocked kernel: 32 unknowns per chain step through the precomputed diagonal-block inverses
+            const int nb = nt / 32, nb2 = (nb + 3) & ~1;
+            const size_t smem_blk = sizeof(double) * ((size_t)nb * 3 * 512 + 64 * nb + nb2) + 8 * ((size_t)nb * 3 + (nb & 1))
+                                    + sizeof(int) * ((size_t)32 * nb + 3 * nb2) + 16;
+            if (smem_blk > 48 * 1024)
+                cudaFuncSetAttribute(k_exch_recur_blocked, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_blk);
+            k_exch_recur_blocked<<<2, nt, smem_blk, st>>>(a);
         } else if (ST == 16) {
             if (smem > 48 * 1024)
                 cudaFuncSetAttribute(k_exch_recur_dec<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1161,6 +1367,8 @@ static int run_recursion(Sim* s, const ExArgs& a, cudaStream_t st) {
 template <int D>
 static int exchange_impl(Sim* s, cudaStream_t st, int part) {
     ExArgs a = make_args(s);
+    if (part == 0) a.tl0 = tl_slot(s);
+    else { a.tl1 = tl_slot(s); a.tl2 = tl_slot(s); }
     if (part == 0) {
         if (a.Kf) {      // N <= 512: the tiles recompute the prefix sums themselves (one launch)
             const int nb = (s->N + 31) / 32;
@@ -1174,7 +1382,15 @@ static int exchange_impl(Sim* s, cudaStream_t st, int part) {
     } else {
         int rc = run_recursion(s, a, st);
         if (rc != PIMDB_OK) return rc;
-        k_exch_forces<D><<<2 * s->N, kFT, 0, st>>>(a);
+        {
+            const int per_kind = std::max(1, std::min((s->N + 2 * kFW - 1) / (2 * kFW), 4 * kNumSM));   // 2 tasks per warp
+            if (s->N <= 512) {
+                const size_t smem = sizeof(double) * ((size_t)s->N + 1 + ((s->N + 2) >> 1) + (size_t)D * s->N);
+                k_exch_forces<D, true><<<2 * per_kind, 32 * kFW, smem, st>>>(a);
+            } else {
+                k_exch_forces<D, false><<<2 * per_kind, 32 * kFW, 0, st>>>(a);
+            }
+        }
         s->launches += 2;
     }
     PIMDB_CUDA_TRY(s, cudaGetLastError());

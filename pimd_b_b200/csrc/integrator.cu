@@ -24,11 +24,13 @@ struct AssembleArgs {
     size_t S;
     double k, kext, L, invL;
     int pbc, ext_pot, write_split;
+    unsigned long long* tl;
     double ext_a, ext_b, mass;     // double_well: strength, location ; cosine: amplitude, phase
 };
 
 template <int D>
 __global__ void __launch_bounds__(256) k_assemble(AssembleArgs a) {
+    tl_begin(a.tl);
     const long long total = (long long)a.nb * a.N;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -98,6 +100,7 @@ __global__ void __launch_bounds__(256) k_assemble(AssembleArgs a) {
             }
         }
     }
+    tl_end(a.tl);
 }
 
 int launch_assemble_chunk(Sim* s, int bead_lo, int nb, bool with_pair) {
@@ -113,6 +116,7 @@ int launch_assemble_chunk(Sim* s, int bead_lo, int nb, bool with_pair) {
     a.k = s->kspring; a.kext = s->kext; a.L = s->L; a.invL = 1.0 / s->L;
     a.pbc = s->cfg.pbc; a.ext_pot = s->cfg.ext_potential; a.write_split = 1;
     a.mass = s->cfg.mass;
+    a.tl = tl_slot(s);
     if (s->cfg.ext_potential == PIMDB_POT_DOUBLE_WELL) { a.ext_a = s->cfg.ext_strength; a.ext_b = s->cfg.ext_location; }
     else { a.ext_a = s->cfg.ext_amplitude; a.ext_b = s->cfg.ext_phase; }
     const int grid = grid_for((size_t)nb * s->N, 256);
@@ -143,9 +147,11 @@ struct IntArgs {
     double c1, c2, hdt, dt_over_m, inv_np;
     unsigned long long seed;
     unsigned ops;
+    unsigned long long* tl;
 };
 
 __global__ void __launch_bounds__(256) k_integrate(IntArgs a) {
+    tl_begin(a.tl);
     __shared__ double sm[3 * 32];
     __shared__ bool is_last;
     const int Q = (a.N + 1) >> 1;
@@ -239,6 +245,7 @@ __global__ void __launch_bounds__(256) k_integrate(IntArgs a) {
             }
         }
     }
+    tl_end(a.tl);
 }
 
 int launch_integrate(Sim* s, unsigned ops) {
@@ -252,6 +259,7 @@ int launch_integrate(Sim* s, unsigned ops) {
     a.inv_np = 1.0 / ((double)s->N * (double)s->P);
     a.seed = s->cfg.seed;
     a.ops = ops;
+    a.tl = tl_slot(s);
     const size_t items = (size_t)s->Ploc * s->D * ((s->N + 1) / 2);
     const int grid = grid_for(items, 256, kMaxPartials);
     k_integrate<<<grid, 256, 0, s->stream>>>(a);

@@ -20,7 +20,7 @@ constexpr double kAzRm = 5.60738, kAzA = 0.5448504e6, kAzEps = 3.42016E-5, kAzAl
                  kAzD = 1.241314, kAzC6 = 1.3732412, kAzC8 = 0.4253785, kAzC10 = 0.1781;
 
 // device-side error flags (host-mapped)
-enum : int { kErrOverflowFwd = 1, kErrOverflowBwd = 2 };
+enum : int { kErrOverflowFwd = 1, kErrOverflowBwd = 2, kErrSyncTimeout = 4 };
 
 struct DevObs {  // partial sums produced on device; assembled into pimdb_observables on the host
     double spring_e[1];      // sum over owned classical links of 0.5 k |x_b - x_{b-1}|^2 (exterior link excluded for bosons)
@@ -66,6 +66,9 @@ struct Sim {
     double *exA = nullptr, *exV = nullptr, *exVb = nullptr, *exF = nullptr;  // A[N], V[N+1], Vb[N+1], F[2][D][N]
     int4 *exC = nullptr;                                                   // Boltzmann factors [2][N][N], packed extended-range numbers
     double *exK = nullptr; int *exB = nullptr;                             // block-scaled factors [2][N*N + 512], exponents [2][N/32][N] (N <= 512)
+    int* exSync = nullptr;                                                 // tiles -> recurrence hand-shake counters (exchange.cu)
+    cudaStream_t stream_r = nullptr; cudaEvent_t ev_join2 = nullptr;       // recurrence stream (resident early) + its join
+    double *exG = nullptr; int *exGok = nullptr;                           // diagonal-block inverses [2][N/32][32][32] + validity flags (N <= 512)
     double *exWm = nullptr; int *exWe = nullptr;                           // W/Wb [2][N+1]: mantissas, binary exponents
     long long* dbg_buf = nullptr;                                          // profiling aid (PIMDB_EXCH_DEBUG)
     double *exTab = nullptr; size_t exTabCap = 0;                          // on-demand E / prob tables
@@ -82,6 +85,7 @@ struct Sim {
     double *nmFreq = nullptr;          // [P] cos/sin tables: [3][P] = cos(w dt), sin(w dt), m*w
     // Nose-Hoover chains: eta | eta_dot | eta_dot_dot, each [bead][group][nchains]
     double *nh_state = nullptr; size_t nh_len = 0;
+    unsigned long long* tl = nullptr; int tl_next = 0;   // in-kernel timeline slots [32][2] (PIMDB_TIMELINE=1), next slot
     // graph
     cudaGraph_t graph = nullptr; cudaGraphExec_t graph_exec = nullptr;
     unsigned long long graph_kernels = 0;
@@ -92,6 +96,8 @@ struct Sim {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pair, ev_step;
     std::string err;
 };
+
+inline unsigned long long* tl_slot(Sim* s) { return s->tl ? s->tl + 2 * (s->tl_next++ % 32) : nullptr; }
 
 // launch helpers --------------------------------------------------------------------------------------
 inline int grid_for(size_t items, int block, int max_blocks = 8 * kNumSM) {

@@ -42,6 +42,7 @@ struct PairArgs {
     //   az_k2 = -alpha log2(e) / rm, az_drm = D rm, az_ca = -(eps/rm) A alpha,
     //   az_h{0,1,2} = (eps/rm) rm^{7,9,11} {6 C6, 8 C8, 10 C10}
     double az_k2, az_drm, az_ca, az_h0, az_h1, az_h2;
+    unsigned long long* tl;   // timeline slot (profiling aid) or nullptr
 };
 
 // dV/dr / r (so that grad V = g * r_vec) and optionally V, from r^2.
@@ -144,6 +145,7 @@ __device__ __forceinline__ void pair_rotation(const PairArgs& a, int t, int lane
 template <int D, int POT, bool PBC, bool CUT, bool OBS>
 __global__ void __launch_bounds__(32 * kPairWarps, PIMDB_PAIR_MINBLOCKS) k_pair_tiles(PairArgs a) {
     __shared__ double s_x[kPairWarps][D * 32], s_f[kPairWarps][D * 32];
+    tl_begin(a.tl);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sp = a.split;
     const long long gw = (long long)blockIdx.x * kPairWarps + warp;
@@ -226,6 +228,7 @@ __global__ void __launch_bounds__(32 * kPairWarps, PIMDB_PAIR_MINBLOCKS) k_pair_
             a.obs_part[2 * gw + 1] = live ? virsum : 0.0;
         }
     }
+    tl_end(a.tl);
 }
 
 // Deterministic final reduction of the per-warp (V, virial) partials: one block, fixed order.
@@ -286,6 +289,7 @@ static int launch_chunk(Sim* s, int bead_lo, int nb, bool with_obs) {
     // `split` > 1 cuts a tile pair's rotations over 2 or 4 warps. Measured on B200 at C3 (2.45 waves of tile pairs):
     // 52.0 / 52.2 / 58.3 us for split 1 / 2 / 4 -- the tail is not what limits the kernel, so the default stays 1.
     a.split = 1;
+    a.tl = with_obs ? nullptr : tl_slot(s);
     if (const char* e = getenv("PIMDB_PAIR_SPLIT")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) a.split = v; }
     const long long gwarps = items * a.split;
     const int grid = (int)((gwarps + kPairWarps - 1) / kPairWarps);
