@@ -1075,6 +1075,340 @@ __global__ void __launch_bounds__(512, 1) k_exch_recur_blocked(ExArgs a) {
     tl_end(a.tl1);
 }
 
+// ---------------------------------------------------------------- 3e. blocked recurrence on a thread-block cluster
+// recur_blocked keeps all 16 consumer warps of a direction on ONE SM: every factor crosses that SM's shared-memory
+// pipe twice (TMA write + LDS read, ~2200 cycles per block with 15 consumers; measured with clock64 stamps) and the
+// owner's own shared-memory traffic queues behind it, so a block step costs ~2700 cycles although the chain itself
+// needs ~900. Here one recurrence is a CLUSTER of 8 thread blocks (one or two warps each, 8 SMs): each block keeps
+// the rings, accumulators and G rows of its own row blocks, and a full copy of the published values. The owner of
+// row block q writes its 32 new values straight into the shared memory of every block that still needs them
+// (st.shared::cluster over the SM-to-SM network, ~215 cycles), orders them with one cluster-scope fence and raises
+// the block's flag in each of those copies; consumers poll their LOCAL flag. Per SM the factor traffic drops 8-fold,
+// so the chain is what is left. Small blocks also fit wherever a pair-tile block retires.
+// Arithmetic, validity checks and the exact fallback are those of recur_blocked.
+__device__ __forceinline__ unsigned cluster_ctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned map_to_cta(const void* smem_ptr, unsigned cta) {
+    unsigned a = (unsigned)__cvta_generic_to_shared(smem_ptr), r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void st_cluster_f64(unsigned addr, double v) {
+    asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+__device__ __forceinline__ void st_cluster_s32(unsigned addr, int v) {
+    asm volatile("st.shared::cluster.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ int ld_acquire_cluster_s32(const int* p) {
+    int r;
+    unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("ld.acquire.cluster.shared::cta.s32 %0, [%1];" : "=r"(r) : "r"(a) : "memory");
+    return r;
+}
+
+constexpr int kClusterSize = 8;
+
+__device__ __forceinline__ void st_cluster_b64(unsigned addr, unsigned long long v) {
+    asm volatile("st.relaxed.cluster.shared::cluster.b64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long lds_volatile_b64(const void* p) {
+    unsigned long long r;
+    unsigned a = (unsigned)__cvta_generic_to_shared(p);
+    asm volatile("ld.volatile.shared.b64 %0, [%1];" : "=l"(r) : "r"(a) : "memory");
+    return r;
+}
+
+// Publication protocol (no fence on the chain): every published word is 8 bytes, naturally aligned -- single-copy atomic
+// -- and carries its own validity: an omega of a fast block is a strictly positive double (0 = not there yet), the
+// block word is {mode, E} with mode != 0. A consumer waits for the block word, then for the block's omegas (one lane
+// per entry, one vote), and needs no ordering between different words. Only an EXACT block (per-value exponents in
+// separate words) orders its stores with a cluster-scope fence before it raises its block word.
+template <bool FWD>
+__device__ __forceinline__ void recur_cluster(const ExArgs& a, double* smem_d) {
+    constexpr int SLOTS = 3, HALF = 512;
+    int tid;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+    const int nt = blockDim.x, N = a.N, lane = tid & 31, lw = tid >> 5, wpc = nt >> 5;
+    const int nb = (N + 31) >> 5;
+    const int crank = (int)cluster_ctarank();
+    const int warp = crank * wpc + lw;               // = the row block this warp owns (if < nb)
+    const bool has_block = warp < nb;
+    const int nsteps = FWD ? N : N - 1;
+    const int npos = nsteps > 0 ? nb : 0;
+    const int nb2 = (nb + 3) & ~1;
+    double* ring = smem_d;
+    double* sOm = ring + (size_t)wpc * SLOTS * HALF;                 // value table, by factor row; 0 = not published
+    double* sRho = sOm + 32 * nb;
+    double* sHandOm = sRho + 32 * wpc;                               // hand-off value per position; 0 = not published
+    unsigned long long* sWord = reinterpret_cast<unsigned long long*>(sHandOm + nb2);   // block word per position
+    unsigned long long* sBar = sWord + nb2;
+    int* sEx = reinterpret_cast<int*>(sBar + wpc * SLOTS + (wpc & 1));   // per-value exponents (exact blocks only)
+    int* sHandE = sEx + 32 * nb;
+
+    auto g_lo = [&](int q) { return FWD ? 32 * q : max(0, N - 32 * (q + 1)); };
+    auto g_hi = [&](int q) { return min(nsteps - 1, FWD ? 32 * q + 31 : N - 1 - 32 * q); };
+    auto row_of = [&](int st) { return FWD ? st : (N - 1 - st); };
+    const int v = 32 * warp + lane;                                 // my row
+    const bool row_ok = has_block && (FWD ? (v < N) : (v >= 1 && v < N));
+    const int own_lo = has_block ? g_lo(warp) : 0, own_hi = has_block ? g_hi(warp) : -1, n_own = own_hi - own_lo + 1;
+    const int mypos = FWD ? warp : nb - 1 - warp;
+    const int last_need = row_ok ? (FWD ? v : N - 1 - v) : -1;
+    auto need = [&](int s) { return s <= last_need; };
+    const int* Bg = FWD ? a.Bf : a.Bb;
+    const int4* Cg = FWD ? a.Cf : a.Cb;
+    const double* Ktile = (FWD ? a.Kf : a.Kb) + (size_t)warp * 1024;
+    const size_t tile_stride = (size_t)nb * 1024;
+    const int ntile_half = has_block ? 2 * min(mypos, npos) : 0;
+    double* const ring_w = ring + (size_t)lw * SLOTS * HALF;
+    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring_w);
+    const unsigned bar_s = (unsigned)__cvta_generic_to_shared(sBar + lw * SLOTS);
+    auto issue_half = [&](int i) {
+        const int pos = i >> 1, q = FWD ? pos : nb - 1 - pos, slot = i % SLOTS;
+        bulk_load(ring_s + slot * HALF * 8, Ktile + (size_t)q * tile_stride + (i & 1) * HALF, HALF * 8, bar_s + slot * 8);
+    };
+    // the blocks that still need the values of my row block: those holding a later position (my own included)
+    const int dst_lo = FWD ? crank : 0, dst_hi = FWD ? kClusterSize - 1 : crank;
+
+    for (int i = tid; i < 32 * nb; i += nt) { sOm[i] = 0.0; sEx[i] = 0; }
+    for (int i = tid; i < nb2; i += nt) { sWord[i] = 0ull; sHandOm[i] = 0.0; sHandE[i] = 0; }
+    __syncthreads();
+    if (tid == 0) {
+        sHandOm[0] = 1.0;
+        const int used = a.sync[FWD ? 2 : 3];
+        int done, spins = 0;
+        do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(done) : "l"(a.sync + 1) : "memory");
+        } while (done - used <= 0 && ++spins < (1 << 22));
+        if (done - used <= 0) atomicOr(a.err, kErrSyncTimeout);
+    }
+    __syncthreads();
+    if (lane == 0 && has_block) {
+#pragma unroll
+        for (int k = 0; k < SLOTS; ++k) mbar_init(bar_s + k * 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async;" ::: "memory");
+        for (int i = 0; i < SLOTS && i < ntile_half; ++i) issue_half(i);
+    }
+    double Grow[32];
+    double hrow = 0.0;
+    int Gok = 0, Bown = kExtZeroExp;
+    if (has_block) {
+        const double* Gg = (FWD ? a.Gf : a.Gb) + (size_t)warp * 1024 + lane;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) Grow[k] = Gg[k * 32];
+        hrow = (FWD ? a.Hf : a.Hb)[warp * 32 + lane];
+        Gok = (FWD ? a.Gokf : a.Gokb)[warp];
+        if (row_ok) Bown = Bg[warp * N + v];
+    } else {
+#pragma unroll
+        for (int k = 0; k < 32; ++k) Grow[k] = 0.0;
+    }
+    cluster_sync_all();                              // every copy is initialised before anybody writes into it
+
+    double am = 0.0;
+    int ae = kExtZeroExp;
+    long long* stamp = (a.dbg && lane == 0 && has_block) ? a.dbg + 192 + ((FWD ? 0 : 16) + warp) * 64 : nullptr;
+    if (stamp) stamp[5] = clock64();                                  // start (after the cluster barrier)
+    int Eprev = 0, mode_prev = 1;                                     // block word of the block before mine
+    // ---- consumer phases
+    int Bnext = (has_block && mypos > 0 && row_ok) ? Bg[(FWD ? 0 : nb - 1) * N + v] : 0;
+#pragma unroll 1
+    for (int pos = 0; has_block && pos < mypos && pos < npos; ++pos) {
+        const int q = FWD ? pos : nb - 1 - pos;
+        const int Bq = Bnext;
+        if (pos + 1 < mypos && row_ok) Bnext = Bg[(FWD ? pos + 1 : nb - 2 - pos) * N + v];
+        unsigned long long word;
+        do { word = lds_volatile_b64(&sWord[pos]); } while (word == 0ull);
+        const int fl = (int)(word >> 32), Eq = (int)(unsigned)word;
+        Eprev = Eq; mode_prev = fl;
+        const double* om = sOm + 32 * q;
+        if (fl == 1) {   // lane k vouches for entry k of the block (entries without a value stay 0 and multiply K = 0)
+            const int r = 32 * q + lane;
+            const bool expect = r >= (FWD ? 0 : 1) && r < N;
+            while (!__all_sync(kFullMask, !expect || lds_volatile_b64(&om[lane]) != 0ull)) {}
+        } else {
+            asm volatile("fence.acq_rel.cluster;" ::: "memory");
+        }
+        if (stamp && pos + 1 == mypos) stamp[0] = clock64();          // the previous block's values are here
+        const int i0 = 2 * pos;
+        mbar_wait(bar_s + (i0 % SLOTS) * 8, (unsigned)(i0 / SLOTS) & 1u);
+        mbar_wait(bar_s + ((i0 + 1) % SLOTS) * 8, (unsigned)((i0 + 1) / SLOTS) & 1u);
+        if (fl == 1) {
+            double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const double* kp = ring_w + ((i0 + h) % SLOTS) * HALF + lane;
+                const double* op = om + 16 * h;
+#pragma unroll
+                for (int c = 0; c < 16; c += 4) {
+                    const double2 w01 = *reinterpret_cast<const double2*>(op + c);
+                    const double2 w23 = *reinterpret_cast<const double2*>(op + c + 2);
+                    acc0 = fma(kp[(c + 0) * 32], w01.x, acc0);
+                    acc1 = fma(kp[(c + 1) * 32], w01.y, acc1);
+                    acc2 = fma(kp[(c + 2) * 32], w23.x, acc2);
+                    acc3 = fma(kp[(c + 3) * 32], w23.y, acc3);
+                }
+            }
+            ext_fold(am, ae, (acc0 + acc1) + (acc2 + acc3), Bq + Eq);
+        } else {
+            const int s0 = g_lo(q), s1 = g_hi(q);
+#pragma unroll 1
+            for (int s = s0; s <= s1; ++s) {
+                if (need(s)) {
+                    const int r = row_of(s);
+                    const int4 c = __ldg(&Cg[(long long)r * N + v]);
+                    ext_fma(am, ae, ext_m(c), c.z, sOm[r], sEx[r]);
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0 && i0 + SLOTS < ntile_half) {   // both slots are free again (the warp has read them: __syncwarp above)
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue_half(i0 + SLOTS);
+            if (i0 + 1 + SLOTS < ntile_half) issue_half(i0 + 1 + SLOTS);
+        }
+    }
+    if (!row_ok) { am = 0.0; ae = kExtZeroExp; }
+    if (stamp) stamp[1] = clock64();                                  // every earlier block applied
+    // ---- owner phase
+    if (n_own > 0) {
+        // value #s goes to every block that needs it: s <= own_hi into the value table under its factor row, the
+        // block's last value into the hand-off slot of the next owner
+        auto publish = [&](int s, double m) {
+            const void* pm = (s == own_hi + 1) ? (const void*)&sHandOm[mypos + 1] : (const void*)&sOm[row_of(s)];
+            for (int d = dst_lo; d <= dst_hi; ++d) st_cluster_b64(map_to_cta(pm, (unsigned)d), (unsigned long long)__double_as_longlong(m));
+        };
+        auto publish_exp = [&](int s, int e) {                        // exact blocks: per-value exponent
+            const void* pe = (s == own_hi + 1) ? (const void*)&sHandE[mypos + 1] : (const void*)&sEx[row_of(s)];
+            for (int d = dst_lo; d <= dst_hi; ++d) st_cluster_s32(map_to_cta(pe, (unsigned)d), e);
+        };
+        auto publish_word = [&](int mode, int E) {
+            const unsigned long long w = ((unsigned long long)(unsigned)mode << 32) | (unsigned long long)(unsigned)E;
+            for (int d = dst_lo; d <= dst_hi; ++d) st_cluster_b64(map_to_cta(&sWord[mypos], (unsigned)d), w);
+        };
+        // the same value for the force kernel and the caller: W / Wb (normalised) and V = -(ln W)/beta
+        auto emit = [&](int s, double m, int e) {
+            const Ext wn = ext_normalize(m, e);
+            const int i = FWD ? s : N - s;
+            (FWD ? a.Wm : a.Wbm)[i] = wn.m;
+            (FWD ? a.We : a.Wbe)[i] = wn.e;
+            const double val = -(log(wn.m) + (double)wn.e * 0.6931471805599453) / a.beta;
+            if (!isfinite(val)) atomicOr(a.err, FWD ? kErrOverflowFwd : kErrOverflowBwd);
+            (FWD ? a.V : a.Vb)[i] = (s == 0) ? 0.0 : val;
+        };
+        // the value handed over by the previous owner (its exponent: the block word's E, or its own word after an exact block)
+        unsigned long long hbits;
+        do { hbits = lds_volatile_b64(&sHandOm[mypos]); } while (hbits == 0ull);
+        const double hm = __longlong_as_double((long long)hbits);
+        const int he = mypos == 0 ? 0 : (mode_prev == 1 ? Eprev : sHandE[mypos]);
+        const Ext n0 = ext_normalize(hm, he);
+        const int E = n0.e;
+        const double om0 = n0.m;
+        const int d = ae - E - Bown;
+        const double A = (am == 0.0) ? 0.0 : ext_to_double(am, min(d, 600));
+        bool exact = __any_sync(kFullMask, (am != 0.0) && (d > 600)) || !(om0 > 0.0) || !Gok;
+        const int tt = FWD ? 0 : row_of(own_lo) & 31;
+        const int kslot = FWD ? lane : (tt - lane) & 31;
+        int mode = 2;
+        if (!exact) {
+            double* rho_w = sRho + lw * 32;
+            rho_w[kslot] = A;
+            __syncwarp();
+            double u0 = om0 * hrow, u1 = 0.0, u2 = 0.0, u3 = 0.0;
+#pragma unroll
+            for (int k = 0; k < 32; k += 4) {
+                const double2 r01 = *reinterpret_cast<const double2*>(rho_w + k);
+                const double2 r23 = *reinterpret_cast<const double2*>(rho_w + k + 2);
+                u0 = fma(Grow[k], r01.x, u0);
+                u1 = fma(Grow[k + 1], r01.y, u1);
+                u2 = fma(Grow[k + 2], r23.x, u2);
+                u3 = fma(Grow[k + 3], r23.y, u3);
+            }
+            const double u = (u0 + u1) + (u2 + u3);
+            const bool mine = kslot < n_own;
+            const unsigned hi = (unsigned)__double2hiint(u);
+            const bool okall = __all_sync(kFullMask, !mine || (hi - (323u << 20) < (1000u << 20)));
+            if (stamp) stamp[2] = clock64();                          // new values computed
+            if (okall) {
+                // destination by destination, the next owner's block first: it is the only one in a hurry
+                const void* pm = !mine ? nullptr : (kslot == n_own - 1) ? (const void*)&sHandOm[mypos + 1]
+                                                                       : (const void*)&sOm[row_of(own_lo + kslot + 1)];
+                const unsigned long long ub = (unsigned long long)__double_as_longlong(u);
+                const unsigned long long ob = (unsigned long long)__double_as_longlong(om0);
+                const unsigned long long wb = (1ull << 32) | (unsigned long long)(unsigned)E;
+                for (int k = 0; k <= dst_hi - dst_lo; ++k) {
+                    const unsigned dd = (unsigned)(FWD ? dst_lo + k : dst_hi - k);
+                    if (mine) st_cluster_b64(map_to_cta(pm, dd), ub);
+                    if (lane == 0) {
+                        st_cluster_b64(map_to_cta(&sOm[row_of(own_lo)], dd), ob);
+                        st_cluster_b64(map_to_cta(&sWord[mypos], dd), wb);
+                    }
+                    if (stamp && k == 0) stamp[3] = clock64();        // the next owner's copy is on its way
+                }
+                if (stamp) stamp[4] = clock64();                      // all remote stores issued
+                mode = 1;
+                if (mine) emit(own_lo + kslot + 1, u, E);
+                if (lane == 0 && mypos == 0) emit(0, om0, E);
+            } else {
+                exact = true;
+            }
+        }
+        if (exact) {
+            double wm = n0.m;
+            int we = n0.e;
+            if (lane == 0) {
+                publish(own_lo, wm);
+                publish_exp(own_lo, we);
+                if (mypos == 0) emit(0, wm, we);
+            }
+#pragma unroll 1
+            for (int st = own_lo; st <= own_hi; ++st) {
+                if (need(st)) {
+                    const int4 c = __ldg(&Cg[(long long)row_of(st) * N + v]);
+                    ext_fma(am, ae, ext_m(c), c.z, wm, we);
+                }
+                const int lane_o = row_of(st) & 31;
+                const Ext fin = ext_normalize(FWD ? am * a.Inv[st + 1] : am, ae);
+                wm = __shfl_sync(kFullMask, fin.m, lane_o);
+                we = __shfl_sync(kFullMask, fin.e, lane_o);
+                if (lane == lane_o) {
+                    publish_exp(st + 1, fin.e);
+                    publish(st + 1, fin.m);                           // (a zero here is caught as a non-finite V below)
+                    emit(st + 1, fin.m, fin.e);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) {
+                asm volatile("fence.acq_rel.cluster;" ::: "memory");
+                publish_word(2, 0);
+            }
+        }
+        if (lane == 0) (FWD ? a.statf : a.statb)[mypos] = mode;
+    }
+    if (has_block && n_own <= 0 && lane == 0) {
+        (FWD ? a.statf : a.statb)[mypos] = 0;
+        if (nsteps == 0 && warp == 0) {                 // backward recurrence of a single particle: Wb[1] = 1
+            a.Wbm[N] = 1.0; a.Wbe[N] = 0; a.Vb[N] = 0.0;
+        }
+    }
+    cluster_sync_all();                              // nobody leaves while its shared memory may still be written
+    if (crank == 0 && tid == 0) a.sync[FWD ? 2 : 3] += 1;
+}
+
+__global__ void __launch_bounds__(64, 1) k_exch_recur_cluster(ExArgs a) {
+    extern __shared__ __align__(16) double smem_d[];
+    tl_begin(a.tl1);
+    if (blockIdx.x < kClusterSize) recur_cluster<true>(a, smem_d);
+    else recur_cluster<false>(a, smem_d);
+    tl_end(a.tl1);
+}
+
 // ---------------------------------------------------------------- 4. exterior spring forces (K7 + K8)
 // The kernel runs beside the pair tiles, and every block it needs has to wait for a pair-tile block to retire
 // (in-kernel timeline: 1024 blocks of a block-per-particle version took 22 us to trickle in). So: 128 blocks of 4
@@ -1132,17 +1466,39 @@ __global__ void __launch_bounds__(32 * kFW) k_exch_forces(ExArgs a) {
 #pragma unroll
         for (int c = 0; c < D; ++c) { xl[c] = xs[(size_t)c * N + l]; acc[c] = 0.0; }
         const int4* Crow = Ctab + (size_t)l * N;
-        for (int u0 = ulo + lane; u0 <= uhi; u0 += 32 * kFU) {
+        // Upper bound of a term's binary exponent from the block-scaled tables: B[l/32][u] >= exponent of the factor
+        // (l, u), so  e(term) <= el + B + e(g_u) + 3.  Below -1080 the connection probability is exactly 0 (the same
+        // cut ext_to_double applies); a 32-wide chunk whose lanes are all below it is skipped before its factors are
+        // loaded -- in a cold liquid that is everything but the chunks next to l.
+        const int* Brow = STAGE ? (which == 0 ? a.Bf : a.Bb) + (size_t)(l >> 5) * N : nullptr;
+        for (int ub = ulo; ub <= uhi; ub += 32 * kFU) {     // warp-uniform trip count (votes inside)
+            const int u0 = ub + lane;
             int4 cv[kFU];
+            unsigned live = ~0u;                  // bit k: chunk k of this batch may hold a non-zero probability
+            if (STAGE) {
+                int bexp[kFU];
 #pragma unroll
-            for (int k = 0; k < kFU; ++k) {
-                const int u = u0 + 32 * k;
-                cv[k] = (u <= uhi && u != special) ? __ldg(Crow + u) : make_int4(0, 0, 0, 0);
+                for (int k = 0; k < kFU; ++k) {
+                    const int u = u0 + 32 * k;
+                    bexp[k] = (u <= uhi) ? __ldg(Brow + u) : kExtZeroExp;
+                }
+                live = 0u;
+#pragma unroll
+                for (int k = 0; k < kFU; ++k) {
+                    const int u = u0 + 32 * k;
+                    const bool maybe = (u <= uhi) && (u == special || el + bexp[k] + ge[u] >= -1080);
+                    if (__any_sync(kFullMask, maybe)) live |= 1u << k;
+                }
             }
 #pragma unroll
             for (int k = 0; k < kFU; ++k) {
                 const int u = u0 + 32 * k;
-                if (u <= uhi) {
+                cv[k] = ((live >> k) & 1u) && (u <= uhi && u != special) ? __ldg(Crow + u) : make_int4(0, 0, 0, kExtZeroExp);
+            }
+#pragma unroll
+            for (int k = 0; k < kFU; ++k) {
+                const int u = u0 + 32 * k;
+                if (((live >> k) & 1u) && u <= uhi) {
                     double pr;
                     if (u == special) {
                         pr = which == 0 ? 1.0 - ext_to_double(wl * a.Wbm[l], el + a.Wbe[l])
@@ -1331,7 +1687,25 @@ static int run_recursion(Sim* s, const ExArgs& a, cudaStream_t st) {
         // coefficient ring: 16 rows in flight up to 512 rows per block, 8 beyond (shared-memory budget)
         const int ST = nt <= 512 ? 16 : 8;
         const size_t smem = (size_t)(s->N + 2) * (sizeof(int4) + sizeof(double)) + (size_t)ST * nt * sizeof(int4) + 16;
-        if (nt <= 512 && a.Kf && !getenv("PIMDB_EXCH_NOBLOCKED")) {
+        if (nt <= 512 && a.Kf && !getenv("PIMDB_EXCH_NOBLOCKED") && !getenv("PIMDB_EXCH_NOCLUSTER")) {
+            // blocked recurrence on two clusters of 8 thread blocks (forward, backward), one or two warps each
+            const int nb = nt / 32, nb2 = (nb + 3) & ~1, wpc = (nb + kClusterSize - 1) / kClusterSize;
+            const size_t smem_cl = sizeof(double) * ((size_t)wpc * 3 * 512 + 32 * nb + 32 * wpc + nb2) + 8 * ((size_t)nb2 + wpc * 3 + (wpc & 1))
+                                   + sizeof(int) * ((size_t)32 * nb + nb2) + 16;
+            if (smem_cl > 48 * 1024)
+                cudaFuncSetAttribute(k_exch_recur_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cl);
+            cudaLaunchConfig_t lc = {};
+            lc.gridDim = dim3(2 * kClusterSize);
+            lc.blockDim = dim3(32 * wpc);
+            lc.dynamicSmemBytes = smem_cl;
+            lc.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = kClusterSize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            lc.attrs = at;
+            lc.numAttrs = 1;
+            cudaLaunchKernelEx(&lc, k_exch_recur_cluster, a);
+        } else if (nt <= 512 && a.Kf && !getenv("PIMDB_EXCH_NOBLOCKED")) {
             // blocked kernel: 32 unknowns per chain step through the precomputed diagonal-block inverses
             const int nb = nt / 32, nb2 = (nb + 3) & ~1;
             const size_t smem_blk = sizeof(double) * ((size_t)nb * 3 * 512 + 64 * nb + nb2) + 8 * ((size_t)nb * 3 + (nb & 1))
