@@ -99,6 +99,7 @@ struct orc_sim {
     double *nm_fwd, *nm_inv;                     /* [P][P] rows: fwd[k][j] = C_kj ; inv[j][k] as the reference stores them */
     double *nm_ext;                              /* NormalModesPropagator::ext_forces (zero before the first step) */
     double *scratch_x, *scratch_p;               /* [P][N][D] NM-space copies */
+    double *scratch_slab;                        /* [N][D] external gradient of one bead (observables) */
     /* Nose-Hoover chains, one thermostat object per bead (rank): eta, eta_dot, eta_dot_dot [P][groups][nchains] */
     double *nh_eta, *nh_ed, *nh_edd;
     int nh_groups;
@@ -189,11 +190,73 @@ static double separation(const orc_sim* s, const double* xb, int i, int j, doubl
     return sqrt(r2);
 }
 
+/* gradient of the external potential on one bead slice, written the way the reference's gradV does:
+ * free -> 0 (include/potentials/potential.h:12-24); harmonic k x (src/potentials/harmonic.cpp:21-23);
+ * double_well 4 m lambda (|x|^2 - a^2) x, the prefactor summed over the axes first (src/potentials/double_well.cpp:22-40);
+ * cosine -A k sin(k x + phase) per component, k = 2 pi / wavelength, wavelength = box size
+ * (src/potentials/cosine.cpp:4-35, src/simulation.cpp:634-638). */
+static void external_gradient(const orc_sim* s, const double* xb, double* g) {
+    const int N = s->N, D = s->D;
+    switch (s->c.ext_pot) {
+        case ORC_POT_HARMONIC: {
+            const double kext = s->c.mass * s->c.ext_omega * s->c.ext_omega;
+            for (size_t q = 0; q < slab(s); ++q) g[q] = kext * xb[q];
+            break;
+        }
+        case ORC_POT_DOUBLE_WELL: {
+            const double loc2 = s->c.ext_location * s->c.ext_location;
+            for (int i = 0; i < N; ++i) {
+                double prefactor = 0;
+                for (int a = 0; a < D; ++a) prefactor += xb[(size_t)i * D + a] * xb[(size_t)i * D + a];
+                prefactor = 4 * s->c.mass * s->c.ext_strength * (prefactor - loc2);
+                for (int a = 0; a < D; ++a) g[(size_t)i * D + a] = prefactor * xb[(size_t)i * D + a];
+            }
+            break;
+        }
+        case ORC_POT_COSINE: {
+            const double k = 2 * 3.141592653589793238462643383279502884 / s->c.size;   /* std::numbers::pi */
+            const double prefactor = -s->c.ext_amplitude * k;
+            for (size_t q = 0; q < slab(s); ++q) g[q] = prefactor * sin(k * xb[q] + s->c.ext_phase);
+            break;
+        }
+        default:
+            for (size_t q = 0; q < slab(s); ++q) g[q] = 0.0;
+    }
+}
+
+/* V_ext of one bead slice: harmonic (k/2) sum x^2 (src/potentials/harmonic.cpp:3-19); double_well
+ * m lambda sum over particles AND axes of (x_c^2 - a^2)^2 (src/potentials/double_well.cpp:6-20 -- per component, unlike
+ * its gradient); cosine A sum cos(k x_c + phase) (src/potentials/cosine.cpp:9-21). */
+static double external_energy(const orc_sim* s, const double* xb) {
+    switch (s->c.ext_pot) {
+        case ORC_POT_HARMONIC: {
+            const double kext = s->c.mass * s->c.ext_omega * s->c.ext_omega;
+            double v = 0;
+            for (size_t q = 0; q < slab(s); ++q) v += xb[q] * xb[q];
+            return v * (0.5 * kext);
+        }
+        case ORC_POT_DOUBLE_WELL: {
+            const double loc2 = s->c.ext_location * s->c.ext_location;
+            double v = 0;
+            for (size_t q = 0; q < slab(s); ++q) v += (xb[q] * xb[q] - loc2) * (xb[q] * xb[q] - loc2);
+            return v * (s->c.mass * s->c.ext_strength);
+        }
+        case ORC_POT_COSINE: {
+            const double k = 2 * 3.141592653589793238462643383279502884 / s->c.size;
+            double v = 0;
+            for (size_t q = 0; q < slab(s); ++q) v += cos(k * xb[q] + s->c.ext_phase);
+            return v * s->c.ext_amplitude;
+        }
+        default:
+            return 0.0;
+    }
+}
+
 /* src/simulation.cpp:428-455 — external force then the i<j pair loop with strict '<' cutoff */
 static void physical_forces(const orc_sim* s, const double* xb, double* out) {
     const int N = s->N, D = s->D;
-    double kext = (s->c.ext_pot == ORC_POT_HARMONIC) ? s->c.mass * s->c.ext_omega * s->c.ext_omega : 0.0;
-    for (size_t q = 0; q < slab(s); ++q) out[q] = (-1.0) * (kext * xb[q]);
+    external_gradient(s, xb, out);
+    for (size_t q = 0; q < slab(s); ++q) out[q] = (-1.0) * out[q];
     if (s->rc == 0.0) return;
     double d[3];
     for (int i = 0; i < N; ++i) {
@@ -659,7 +722,6 @@ void orc_observables_calc(orc_sim* s, orc_observables* o) {
     const int bos = bosonic_active(s);
     memset(o, 0, sizeof *o);
     if (bos) exchange_prepare(s);
-    double kext = (s->c.ext_pot == ORC_POT_HARMONIC) ? s->c.mass * s->c.ext_omega * s->c.ext_omega : 0.0;
     for (int b = 0; b < P; ++b) {
         const double* xb = s->x + (size_t)b * slab(s);
         /* kinetic (primitive estimator) */
@@ -672,11 +734,10 @@ void orc_observables_calc(orc_sim* s, orc_observables* o) {
         /* potential + "virial" */
         double pot = 0, vir = 0, ipot = 0, epot = 0;
         if (s->c.ext_pot != ORC_POT_FREE) {
-            double v = 0;
-            for (size_t q = 0; q < slab(s); ++q) v += xb[q] * xb[q];
-            epot = v * (0.5 * kext);
+            epot = external_energy(s, xb);
             pot += epot;
-            for (size_t q = 0; q < slab(s); ++q) vir -= xb[q] * ((-1.0) * (kext * xb[q]));
+            external_gradient(s, xb, s->scratch_slab);
+            for (size_t q = 0; q < slab(s); ++q) vir -= xb[q] * ((-1.0) * s->scratch_slab[q]);
         }
         if (s->rc != 0.0) {
             double d[3];
@@ -743,6 +804,7 @@ orc_sim* orc_create(const orc_config* cfg) {
     s->nm_ext = calloc(n, sizeof(double));
     s->scratch_x = calloc(n, sizeof(double));
     s->scratch_p = calloc(n, sizeof(double));
+    s->scratch_slab = calloc((size_t)s->N * s->D, sizeof(double));
     size_t N = s->N;
     s->E_kn = calloc(N * (N + 1) / 2, sizeof(double));
     s->V = calloc(N + 1, sizeof(double));
@@ -770,7 +832,7 @@ void orc_destroy(orc_sim* s) {
     for (int b = 0; b < s->P; ++b) orc_ranmars_free(s->rng[b]);
     free(s->rng);
     free(s->x); free(s->p); free(s->f); free(s->f_spring); free(s->f_phys); free(s->nm_ext);
-    free(s->scratch_x); free(s->scratch_p);
+    free(s->scratch_x); free(s->scratch_p); free(s->scratch_slab);
     free(s->E_kn); free(s->V); free(s->Vb); free(s->prob); free(s->tmp); free(s->prim);
     free(s->nm_fwd); free(s->nm_inv);
     free(s->nh_eta); free(s->nh_ed); free(s->nh_edd);

@@ -25,7 +25,8 @@
 extern "C" {
 #endif
 
-enum { ORC_POT_FREE = 0, ORC_POT_AZIZ = 1, ORC_POT_HARMONIC = 2, ORC_POT_DIPOLE = 3 };
+enum { ORC_POT_FREE = 0, ORC_POT_AZIZ = 1, ORC_POT_HARMONIC = 2, ORC_POT_DIPOLE = 3, ORC_POT_DOUBLE_WELL = 4,
+       ORC_POT_COSINE = 5 };
 enum { ORC_PROP_CARTESIAN = 0, ORC_PROP_NORMAL_MODES = 1 };
 enum { ORC_THERMO_NONE = 0, ORC_THERMO_LANGEVIN = 1, ORC_THERMO_NOSE_HOOVER = 2, ORC_THERMO_NOSE_HOOVER_NP = 3,
        ORC_THERMO_NOSE_HOOVER_NP_DIM = 4 };
@@ -34,7 +35,7 @@ typedef struct {
     int natoms, nbeads, ndim;
     int bosonic, fixcom, pbc;
     int propagator, thermostat, nmthermostat;
-    int int_pot, ext_pot;        /* ORC_POT_* (ext: FREE or HARMONIC) */
+    int int_pot, ext_pot;        /* ORC_POT_* (ext: FREE, HARMONIC, DOUBLE_WELL or COSINE) */
     double int_omega;            /* harmonic pair: omega (energy units == a.u. frequency) */
     double int_strength;         /* dipole strength */
     double ext_omega;            /* harmonic trap omega */
@@ -42,6 +43,8 @@ typedef struct {
     double mass, temperature, dt, gamma, size;
     unsigned int seed;
     int nchains;                 /* Nose-Hoover chain length ([simulation] nchains, default 4) */
+    double ext_strength, ext_location;   /* double_well: strength (energy), location (length), src/params.cpp:238-242 */
+    double ext_amplitude, ext_phase;     /* cosine: amplitude (energy), phase; wavelength = box size (src/simulation.cpp:634-638) */
 } orc_config;
 
 typedef struct orc_sim orc_sim;

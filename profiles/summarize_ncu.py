@@ -9,7 +9,7 @@ from pathlib import Path
 tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
 ROOT = Path(__file__).resolve().parent.parent
 OUT = ROOT / "gpurun_out"
-KERNELS = ["k_pair_tiles", "k_exch_recur", "k_exch_forces", "k_integrate", "k_assemble"]
+KERNELS = ["k_pair_tiles", "k_exch_recur_cluster", "k_exch_coeff_tiles", "k_exch_forces", "k_integrate", "k_assemble"]
 METRICS = {
     "gpu__time_duration.sum": "duration_us",
     "dram__bytes_read.sum": "dram_read_bytes",

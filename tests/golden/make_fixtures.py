@@ -108,6 +108,16 @@ def probe_configs():
                       external="harmonic", ext_omega=3 * MEV, thermostat=th, nmthermostat=True, nchains=4, seed=11,
                       dt=FEMTOSECOND, obs_classical="kelvin", obs_bosonic="true" if th == "nose_hoover_np" else "false")
         items[f"{th}_nmcoupled"] = (c, rng.uniform(-30, 30, size=(6, 9, 3)), maxwell_momenta(c, rng))
+    # external double-well and cosine potentials (src/potentials/double_well.cpp, cosine.cpp): no golden case of the
+    # reference uses them (appended last again)
+    base = dict(nbeads=4, natoms=9, ndim=3, bosonic=False, fixcom=False, pbc=False, temperature=5.802 * KELVIN,
+                mass=1.0, size=300.0, interaction="free", thermostat="none", seed=3, dt=FEMTOSECOND,
+                obs_classical="kelvin")
+    c = SimConfig(**base, external="double_well", ext_strength=1e-6, ext_location=3.0)
+    items["double_well_ext"] = (c, rng.uniform(-8, 8, size=(4, 9, 3)), maxwell_momenta(c, rng))
+    c = SimConfig(**{**base, "bosonic": True, "obs_bosonic": "true", "interaction": "harmonic", "int_omega": 1 * MEV},
+                  external="cosine", ext_amplitude=1e-3, ext_phase=0.3)
+    items["cosine_ext_bosonic_pair"] = (c, rng.uniform(-100, 100, size=(4, 9, 3)), maxwell_momenta(c, rng))
     return items
 
 

@@ -21,7 +21,7 @@ ORACLE_DIR = ROOT / "oracle"
 REF_DIR = ORACLE_DIR / "_ref"
 GOLDEN_DIR = ROOT / "tests" / "golden"
 
-POT_ID = {"free": 0, "aziz": 1, "harmonic": 2, "dipole": 3}
+POT_ID = {"free": 0, "aziz": 1, "harmonic": 2, "dipole": 3, "double_well": 4, "cosine": 5}
 PROP_ID = {"cartesian": 0, "normal_modes": 1}
 THERMO_ID = {"none": 0, "langevin": 1, "nose_hoover": 2, "nose_hoover_np": 3, "nose_hoover_np_dim": 4}
 
@@ -38,6 +38,8 @@ class OrcConfig(C.Structure):
         ("size", C.c_double),
         ("seed", C.c_uint),
         ("nchains", C.c_int),
+        ("ext_strength", C.c_double), ("ext_location", C.c_double),
+        ("ext_amplitude", C.c_double), ("ext_phase", C.c_double),
     ]
 
 
@@ -99,7 +101,9 @@ def to_orc_config(cfg: SimConfig) -> OrcConfig:
         int_pot=POT_ID[cfg.interaction], ext_pot=POT_ID[cfg.external],
         int_omega=cfg.int_omega, int_strength=cfg.int_strength, ext_omega=cfg.ext_omega,
         cutoff=cfg.cutoff, mass=cfg.mass, temperature=cfg.temperature, dt=cfg.dt, gamma=cfg.gamma,
-        size=cfg.size, seed=cfg.seed, nchains=cfg.nchains)
+        size=cfg.size, seed=cfg.seed, nchains=cfg.nchains,
+        ext_strength=cfg.ext_strength, ext_location=cfg.ext_location,
+        ext_amplitude=cfg.ext_amplitude, ext_phase=cfg.ext_phase)
 
 
 class Oracle:

@@ -77,7 +77,7 @@ FORCE_CASES = {
 }
 
 
-@pytest.mark.parametrize("name", [k for k in FORCE_CASES if "double_well" not in k and "cosine" not in k])
+@pytest.mark.parametrize("name", list(FORCE_CASES))
 def test_forces_match_oracle(gpu_required, name):
     cfg, kind = FORCE_CASES[name]
     x, p = make_inputs(cfg, 7, kind)
