@@ -123,7 +123,10 @@ typedef struct pimdb_observables {
     double temperature, cl_kinetic, cl_spring;
     double prob_dist, prob_all;
     double nh_energy;        /* Nose-Hoover: sum over beads of getAdditionToH() (src/thermostats/nose_hoover.cpp:37-67) */
-    double reserved[5];
+    double w_gsf, pot_gsf;   /* GSF action observable (src/observables/gsf_action.cpp:21-73), free interaction only:
+                                with an interaction potential the reference reads past a one-row gradient (:36), which
+                                cannot be reproduced -- both fields are NaN then. w_gsf is dimensionless. */
+    double reserved[3];
 } pimdb_observables;
 
 typedef struct pimdb_sim pimdb_sim;

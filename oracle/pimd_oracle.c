@@ -761,6 +761,28 @@ void orc_observables_calc(orc_sim* s, orc_observables* o) {
             o->potential += pot / P;
             o->virial += vir * (0.5 / P);
         }
+        /* gsf: src/observables/gsf_action.cpp:21-73, per bead, summed by the logger. With an interaction potential
+         * the reference adds a one-row gradient to an N-row array and reads past its end (:36): not restated. */
+        if (s->c.int_pot == ORC_POT_FREE) {
+            const double alpha = 0.0;
+            double total_potential = external_energy(s, xb);
+            external_gradient(s, xb, s->scratch_slab);
+            double total_force_squared = 0.0;
+            for (size_t q = 0; q < slab(s); ++q) total_force_squared += s->scratch_slab[q] * s->scratch_slab[q];
+            double sp_constant = s->k_spring / P;                      /* IPI_CONVENTION (include/common.h:40-42) */
+            double potential_term = total_potential / (3 * P);
+            double force_squared_term = total_force_squared / (9 * sp_constant * P * P);
+            double w;
+            if (b % 2 != 0) {
+                w = (-1.0) * potential_term + alpha * force_squared_term;
+                o->pot_gsf += total_potential / (0.5 * P);
+            } else {
+                w = potential_term + (1 - alpha) * force_squared_term;
+            }
+            o->w_gsf += w * ((-1.0) * s->beta);
+        } else {
+            o->w_gsf = o->pot_gsf = NAN;
+        }
         /* classical */
         double ke = 0;
         const double* pb = s->p + (size_t)b * slab(s);

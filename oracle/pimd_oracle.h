@@ -56,6 +56,7 @@ typedef struct {
     double temperature, cl_kinetic, cl_spring;             /* classical          */
     double prob_dist, prob_all;                            /* bosonic            */
     double nh_energy;                                      /* classical, Nose-Hoover runs only */
+    double w_gsf, pot_gsf;                                 /* gsf (free interaction only; NaN otherwise) */
 } orc_observables;
 
 orc_sim* orc_create(const orc_config* cfg);

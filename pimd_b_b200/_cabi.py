@@ -45,7 +45,8 @@ class PimdbConfig(C.Structure):
 class PimdbObservables(C.Structure):
     _fields_ = [(n, C.c_double) for n in (
         "kinetic", "potential", "ext_pot", "int_pot", "virial",
-        "temperature", "cl_kinetic", "cl_spring", "prob_dist", "prob_all", "nh_energy")] + [("reserved", C.c_double * 5)]
+        "temperature", "cl_kinetic", "cl_spring", "prob_dist", "prob_all", "nh_energy", "w_gsf", "pot_gsf")] + [
+            ("reserved", C.c_double * 3)]
 
 
 OBS_FIELDS = tuple(n for n, _ in PimdbObservables._fields_ if n != "reserved")

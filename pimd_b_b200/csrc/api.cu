@@ -824,6 +824,17 @@ extern "C" int pimdb_observables_calc(pimdb_sim* sim, pimdb_observables* out) {
     out->temperature = 2.0 * out->cl_kinetic / (D * N * P) / P;
     out->cl_spring = o.spring_e[0] + ((s->bosonic && s->has_first) ? o.v_n : 0.0);
     out->nh_energy = o.nh_energy;   // classical.cpp:24-26
+    // gsf_action.cpp:21-73 (alpha = 0, IPI convention: spring constant / P): an odd bead contributes
+    // -beta (-V_b/(3P) + alpha F2_b/(9 k P^2)) and V_b/(P/2) to pot_gsf, an even bead -beta (V_b/(3P) + (1-alpha) F2_b/(9 k P^2))
+    if (!int_on) {
+        const double alpha = 0.0, sp = s->kspring / P;
+        const double w_odd = (-1.0) * (o.gsf[0] / (3 * P)) + alpha * (o.gsf[2] / (9 * sp * P * P));
+        const double w_even = o.gsf[1] / (3 * P) + (1 - alpha) * (o.gsf[3] / (9 * sp * P * P));
+        out->w_gsf = (-1.0) * s->beta * (w_odd + w_even);
+        out->pot_gsf = o.gsf[0] / (0.5 * P);
+    } else {
+        out->w_gsf = out->pot_gsf = std::nan("");
+    }
     // bosonic.cpp:17-22, quadratic_bosonic_exchange.cpp:222-240
     if (s->bosonic && s->has_first) {
         out->prob_dist = std::exp(-s->exch_beta * (o.e_diag_sum - o.v_n) - std::lgamma(N + 1.0));

@@ -34,7 +34,8 @@ struct DevObs {  // partial sums produced on device; assembled into pimdb_observ
     double e_diag_sum;       // sum_m E^{[m..m]}
     double e_full;           // E^{[0..N-1]}
     double nh_energy;        // Nose-Hoover addition to the conserved quantity, owned beads
-    double pad[5];
+    double gsf[4];           // GSF observable: sum of V_ext over odd / even beads, sum of |grad V_ext|^2 over odd / even beads
+    double pad[1];
 };
 
 struct Sim {

@@ -189,13 +189,16 @@ struct ObsArgs {
     double k, kext, L, invL, mass;
     int pbc, ext_pot;
     double ext_a, ext_b;
+    int bead_begin;
 };
 
 __global__ void __launch_bounds__(256) k_obs_elementwise(ObsArgs a) {
-    __shared__ double sm[4 * 32];
+    __shared__ double sm[8 * 32];
     __shared__ bool is_last;
     const long long total = (long long)a.Ploc * a.N;
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};   // spring d^2, ext V, ext virial, p^2
+    // spring d^2, ext V, ext virial, p^2 | GSF (src/observables/gsf_action.cpp:21-73): V_ext on odd / even beads,
+    // |grad V_ext|^2 on odd / even beads (bead parity is that of the GLOBAL bead index, `this_bead`)
+    double acc[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
         const int b = (int)(idx / a.N), n = (int)(idx % a.N);
@@ -215,27 +218,39 @@ __global__ void __launch_bounds__(256) k_obs_elementwise(ObsArgs a) {
             pp = fma(pi, pi, pp);
         }
         if (b != a.skip_link) acc[0] += d2;
+        double vext = 0.0, g2 = 0.0;      // this particle's V_ext and |grad V_ext|^2 (GSF)
         if (a.ext_pot == PIMDB_POT_HARMONIC) {
             acc[1] += r2;                 // V = k/2 sum x^2 ; virial -x.F = k sum x^2 (scaled at the end)
+            vext = 0.5 * a.kext * r2;
+            g2 = a.kext * a.kext * r2;
         } else if (a.ext_pot == PIMDB_POT_DOUBLE_WELL) {
             // reference src/potentials/double_well.cpp:6-40: V = m lambda sum_c (x_c^2 - a^2)^2 ; grad = 4 m lambda (|x|^2 - a^2) x
             double v = 0.0;
             for (int c = 0; c < a.D; ++c) { double t = xv[c] * xv[c] - a.ext_b * a.ext_b; v += t * t; }
-            acc[1] += a.mass * a.ext_a * v;
-            acc[2] += 4.0 * a.mass * a.ext_a * (r2 - a.ext_b * a.ext_b) * r2;
+            vext = a.mass * a.ext_a * v;
+            acc[1] += vext;
+            const double pref = 4.0 * a.mass * a.ext_a * (r2 - a.ext_b * a.ext_b);
+            acc[2] += pref * r2;
+            g2 = pref * pref * r2;
         } else if (a.ext_pot == PIMDB_POT_COSINE) {
             // reference src/potentials/cosine.cpp:9-35
             const double kk = 2.0 * M_PI / a.L;
             for (int c = 0; c < a.D; ++c) {
-                acc[1] += a.ext_a * cos(kk * xv[c] + a.ext_b);
-                acc[2] += -xv[c] * (a.ext_a * kk * sin(kk * xv[c] + a.ext_b));
+                const double vc = a.ext_a * cos(kk * xv[c] + a.ext_b), gc = -a.ext_a * kk * sin(kk * xv[c] + a.ext_b);
+                acc[1] += vc;
+                acc[2] += xv[c] * gc;
+                vext += vc;
+                g2 += gc * gc;
             }
         }
         acc[3] += pp;
+        const int odd = (a.bead_begin + b) & 1;
+        acc[odd ? 4 : 5] += vext;
+        acc[odd ? 6 : 7] += g2;
     }
-    block_sum<4>(acc, sm);
+    block_sum<8>(acc, sm);
     if (threadIdx.x == 0) {
-        for (int c = 0; c < 4; ++c) a.part[blockIdx.x * 4 + c] = acc[c];
+        for (int c = 0; c < 8; ++c) a.part[blockIdx.x * 8 + c] = acc[c];
         __threadfence();
         unsigned int t = atomicAdd(a.ticket, 1u);
         is_last = (t == gridDim.x - 1);
@@ -243,10 +258,10 @@ __global__ void __launch_bounds__(256) k_obs_elementwise(ObsArgs a) {
     __syncthreads();
     if (is_last) {
         __threadfence();
-        double tot[4] = {0.0, 0.0, 0.0, 0.0};
+        double tot[8] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
         for (int blk = threadIdx.x; blk < (int)gridDim.x; blk += blockDim.x)
-            for (int c = 0; c < 4; ++c) tot[c] += __ldcg(&a.part[blk * 4 + c]);
-        block_sum<4>(tot, sm);
+            for (int c = 0; c < 8; ++c) tot[c] += __ldcg(&a.part[blk * 8 + c]);
+        block_sum<8>(tot, sm);
         if (threadIdx.x == 0) {
             a.obs->spring_e[0] = 0.5 * a.k * tot[0];
             if (a.ext_pot == PIMDB_POT_HARMONIC) {
@@ -257,6 +272,7 @@ __global__ void __launch_bounds__(256) k_obs_elementwise(ObsArgs a) {
                 a.obs->ext_vir = tot[2];
             }
             a.obs->p2 = tot[3];
+            for (int c = 0; c < 4; ++c) a.obs->gsf[c] = tot[4 + c];
             *a.ticket = 0u;
         }
     }
@@ -269,6 +285,7 @@ int launch_obs_elementwise(Sim* s) {
     a.skip_link = (s->bosonic && s->has_first) ? 0 : -1;
     a.S = s->S; a.k = s->kspring; a.kext = s->kext; a.L = s->L; a.invL = 1.0 / s->L; a.mass = s->cfg.mass;
     a.pbc = s->cfg.pbc; a.ext_pot = s->cfg.ext_potential;
+    a.bead_begin = s->b0;
     if (s->cfg.ext_potential == PIMDB_POT_DOUBLE_WELL) { a.ext_a = s->cfg.ext_strength; a.ext_b = s->cfg.ext_location; }
     else { a.ext_a = s->cfg.ext_amplitude; a.ext_b = s->cfg.ext_phase; }
     const int grid = grid_for((size_t)s->Ploc * s->N, 256, kMaxPartials);

@@ -348,6 +348,15 @@ void BosonicObservable::calculate() {
     q("prob_all") = o.prob_all;
 }
 
+GSFActionObservable::GSFActionObservable(Simulation& s, const std::string& u) : Observable(s, u) {   // gsf_action.cpp:9-13
+    initialize({"w_gsf", "pot_gsf"});
+}
+void GSFActionObservable::calculate() {
+    const pimdb_observables& o = sim.deviceObservables();
+    q("w_gsf") = o.w_gsf;                                                    // dimensionless (gsf_action.cpp:72)
+    q("pot_gsf") = Units::convertToUser("energy", out_unit, o.pot_gsf);      // gsf_action.cpp:66
+}
+
 ObservablesLogger::ObservablesLogger(const std::string& filename, const std::vector<std::unique_ptr<Observable>>& obs)
     : observables(obs) {
     file.open("output/" + filename, std::ios::out | std::ios::app);
@@ -455,7 +464,13 @@ Simulation::Simulation(Params& p, int device) : params(p) {
     if (p.obs_energy != "off") observables.push_back(std::make_unique<EnergyObservable>(*this, unit_of(p.obs_energy)));
     if (p.obs_classical != "off") observables.push_back(std::make_unique<ClassicalObservable>(*this, unit_of(p.obs_classical)));
     if (bosonic && p.obs_bosonic != "off") observables.push_back(std::make_unique<BosonicObservable>(*this, unit_of(p.obs_bosonic)));
-    if (p.obs_gsf != "off") throw std::invalid_argument("The gsf observable is not part of the B200 hot path (DESIGN.md, out of scope)");
+    if (p.obs_gsf != "off") {
+        // With an interaction potential the reference's GSF observable adds a one-row gradient to an N-row array and
+        // reads past its end (src/observables/gsf_action.cpp:36): there is nothing well-defined to reproduce.
+        if (interaction_potential_name != "free")
+            throw std::invalid_argument("The gsf observable is only supported with a free interaction potential");
+        observables.push_back(std::make_unique<GSFActionObservable>(*this, unit_of(p.obs_gsf)));
+    }
 }
 
 Simulation::~Simulation() {

@@ -153,6 +153,12 @@ public:
     void calculate() override;
 };
 
+class GSFActionObservable : public Observable {  // src/observables/gsf_action.cpp (free interaction only)
+public:
+    GSFActionObservable(Simulation& sim, const std::string& out_unit);
+    void calculate() override;
+};
+
 class ObservablesLogger {                        // src/observables/observable.cpp:61-116
 public:
     ObservablesLogger(const std::string& filename, const std::vector<std::unique_ptr<Observable>>& observables);

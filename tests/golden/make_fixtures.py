@@ -118,6 +118,14 @@ def probe_configs():
     c = SimConfig(**{**base, "bosonic": True, "obs_bosonic": "true", "interaction": "harmonic", "int_omega": 1 * MEV},
                   external="cosine", ext_amplitude=1e-3, ext_phase=0.3)
     items["cosine_ext_bosonic_pair"] = (c, rng.uniform(-100, 100, size=(4, 9, 3)), maxwell_momenta(c, rng))
+    # GSF action observable (src/observables/gsf_action.cpp), free interaction: odd bead count so that odd and even
+    # time slices differ in number; harmonic trap (bosonic) and double well
+    gs = dict(nbeads=5, natoms=6, ndim=3, fixcom=False, pbc=False, temperature=5.802 * KELVIN, mass=1.0, size=300.0,
+              interaction="free", thermostat="none", seed=4, dt=FEMTOSECOND, obs_classical="kelvin", obs_gsf="atomic_unit")
+    c = SimConfig(**gs, bosonic=True, obs_bosonic="true", external="harmonic", ext_omega=3 * MEV)
+    items["gsf_trap_bosonic"] = (c, rng.uniform(-30, 30, size=(5, 6, 3)), maxwell_momenta(c, rng))
+    c = SimConfig(**gs, bosonic=False, external="double_well", ext_strength=1e-6, ext_location=3.0)
+    items["gsf_double_well"] = (c, rng.uniform(-8, 8, size=(5, 6, 3)), maxwell_momenta(c, rng))
     return items
 
 

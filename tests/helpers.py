@@ -46,7 +46,7 @@ class OrcConfig(C.Structure):
 class OrcObservables(C.Structure):
     _fields_ = [(n, C.c_double) for n in (
         "kinetic", "potential", "ext_pot", "int_pot", "virial",
-        "temperature", "cl_kinetic", "cl_spring", "prob_dist", "prob_all", "nh_energy")]
+        "temperature", "cl_kinetic", "cl_spring", "prob_dist", "prob_all", "nh_energy", "w_gsf", "pot_gsf")]
 
 
 _lib = None

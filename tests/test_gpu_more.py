@@ -59,10 +59,10 @@ def test_reference_raw_outputs(gpu_required, case):
     obs = sim.observables()
     kelvin = convert_to_internal("temperature", "kelvin", 1.0)
     ref = dict(zip(map(str, REFPROBE[f"{case}/obs_names"]), REFPROBE[f"{case}/obs_values"]))
-    scale = max(abs(v) for k, v in ref.items() if k not in ("temperature", "prob_dist", "prob_all"))
+    scale = max(abs(v) for k, v in ref.items() if k not in ("temperature", "prob_dist", "prob_all", "w_gsf"))
     for name, val in ref.items():
         mine = obs[name] / kelvin if name == "temperature" else obs[name]
-        tol = 1e-10 * (abs(val) if name in ("temperature", "cl_kinetic") else max(scale / cfg.nbeads, abs(val)))
+        tol = 1e-10 * (abs(val) if name in ("temperature", "cl_kinetic", "w_gsf") else max(scale / cfg.nbeads, abs(val)))
         if name in ("prob_dist", "prob_all"):
             tol = 1e-9 * abs(val) + 1e-300
         assert abs(mine - val) <= tol, (name, mine, val)
@@ -247,6 +247,9 @@ def test_two_sharded_handles_equal_one_handle(gpu_required, fixcom):
     ow = whole.observables()
     o0, o1 = shards[0].observables(), shards[1].observables()
     for k in ow:
+        if np.isnan(ow[k]):   # the GSF columns are undefined with an interaction potential (include/pimdb200.h)
+            assert k in ("w_gsf", "pot_gsf") and np.isnan(o0[k]) and np.isnan(o1[k])
+            continue
         assert abs(o0[k] + o1[k] - ow[k]) <= 1e-11 * max(abs(ow[k]), abs(ow["cl_spring"])), k
     for s in shards + [whole]:
         s.close()

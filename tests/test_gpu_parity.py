@@ -127,8 +127,6 @@ def test_exchange_tables_match_oracle(gpu_required, name):
 @pytest.mark.parametrize("name", list(FORCE_CASES))
 def test_observables_match_oracle(gpu_required, name):
     cfg, kind = FORCE_CASES[name]
-    if cfg.external in ("double_well", "cosine"):
-        pytest.skip("oracle restates harmonic/free external potentials only (SURVEY.md 8f rank 3)")
     x, p = make_inputs(cfg, 13, kind)
     orc = Oracle(cfg)
     orc.set("x", x)
@@ -148,6 +146,11 @@ def test_observables_match_oracle(gpu_required, name):
         assert abs(got[key] - ref[key]) <= ENERGY_TOL * abs(ref[key]), (key, got[key], ref[key])
     for key in ("prob_dist", "prob_all"):
         assert abs(got[key] - ref[key]) <= 1e-9 * max(abs(ref[key]), 1e-300) + 1e-300, (key, got[key], ref[key])
+    for key in ("w_gsf", "pot_gsf"):   # GSF action observable: defined for a free interaction only
+        if cfg.interaction == "free":
+            assert abs(got[key] - ref[key]) <= ENERGY_TOL * max(abs(ref[key]), 1e-300), (key, got[key], ref[key])
+        else:
+            assert np.isnan(got[key]) and np.isnan(ref[key])
     sim.close()
 
 
