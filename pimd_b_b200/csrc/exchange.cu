@@ -321,7 +321,10 @@ __device__ __forceinline__ void diag_block_inverse(const ExArgs& a, int q, doubl
 // doubles relative to 2^B. A factor more than 2^1022 below its block's largest becomes 0; it multiplies values that
 // the fast recurrence keeps within 2^+-400 of each other, so it could not have contributed.
 template <int D>
-__global__ void __launch_bounds__(1024) k_exch_coeff_tiles(ExArgs a) {
+// (2 blocks per SM, 32 registers: all 256 tiles of N = 512 are dispatched in ONE wave. The block scheduler does not
+// start the pair-tile grid, launched right behind, before every block of this grid has been dispatched -- with one block
+// per SM the pair tiles started 6 us late, measured with the in-kernel timeline.)
+__global__ void __launch_bounds__(1024, 2) k_exch_coeff_tiles(ExArgs a) {
     __shared__ __align__(16) int s_e2[2][32][33];  // [step within the tile][column], padded: conflict-free both ways
     int (*s_ef)[33] = s_e2[0], (*s_eb)[33] = s_e2[1];
     __shared__ int s_mf[32], s_mb[32];
