@@ -63,6 +63,13 @@ enum pimdb_thermostat {
     PIMDB_THERMO_NOSE_HOOVER_NP_DIM = 4
 };
 
+/* noise stream of the Langevin thermostat. The reference draws from one RANMAR generator per rank, seed + rank
+ * (src/simulation.cpp:58-59, libs/random_mars.cpp, src/thermostats/langevin.cpp:15-27). */
+enum pimdb_rng {
+    PIMDB_RNG_PHILOX = 0,   /* counter-based Philox4x32-10, parallel (DESIGN.md "Noise stream"): statistical agreement */
+    PIMDB_RNG_RANMARS = 1   /* the reference's own stream, sequential per bead: trajectory-level agreement, slow     */
+};
+
 /* which state array (include/simulation.h:59-60; the split forces are the two locals of
  * Simulation::updateForces, src/simulation.cpp:357-361) */
 enum pimdb_array {
@@ -111,7 +118,8 @@ typedef struct pimdb_config {
        Single GPU: 0 and nbeads. */
     int bead_begin, bead_end;
     int device;              /* CUDA device ordinal */
-    int reserved[4];
+    int rng;                 /* enum pimdb_rng: noise stream of the Langevin thermostat (0 = default)                  */
+    int reserved[3];
 } pimdb_config;
 
 /* Columns of output/simulation.out (src/observables/energy.cpp, classical.cpp, bosonic.cpp), summed over the

@@ -18,6 +18,7 @@ PIMDB_OK, ERR_INVALID_ARGUMENT, ERR_OVERFLOW, ERR_RUNTIME, ERR_CUDA = range(5)
 
 POTENTIAL = {"free": 0, "aziz": 1, "harmonic": 2, "dipole": 3, "double_well": 4, "cosine": 5}
 PROPAGATOR = {"cartesian": 0, "normal_modes": 1}
+RNG = {"philox": 0, "ranmars": 1}
 THERMOSTAT = {"none": 0, "langevin": 1, "nose_hoover": 2, "nose_hoover_np": 3, "nose_hoover_np_dim": 4}
 ARRAY = {"x": 0, "p": 1, "f": 2, "f_spring": 3, "f_phys": 4}
 EXCH_TABLE = {"V": 0, "Vb": 1, "E": 2, "prob": 3}
@@ -38,7 +39,8 @@ class PimdbConfig(C.Structure):
         ("seed", C.c_ulonglong),
         ("bead_begin", C.c_int), ("bead_end", C.c_int),
         ("device", C.c_int),
-        ("reserved", C.c_int * 4),
+        ("rng", C.c_int),
+        ("reserved", C.c_int * 3),
     ]
 
 

@@ -130,6 +130,9 @@ class SimConfig:
     obs_classical: str = "off"
     obs_bosonic: str = "off"
     obs_gsf: str = "off"
+    # not an INI key: noise stream of the Langevin thermostat on the GPU, "philox" (parallel, default) or "ranmars"
+    # (the reference's own generator, one sequential stream per bead: trajectory-level parity, slow)
+    rng: str = "philox"
 
     def __post_init__(self):
         if self.gamma < 0:

@@ -140,7 +140,7 @@ static void free_all(Sim* s) {
     cudaFree(s->stage_d); cudaFreeHost(s->stage_h);
     cudaFree(s->tile_ij); cudaFree(s->pair_scratch);
     cudaFree(s->exA); cudaFree(s->exV); cudaFree(s->exVb); cudaFree(s->exF); cudaFree(s->exTab);
-    cudaFree(s->exC); cudaFree(s->exK); cudaFree(s->exB); cudaFree(s->exG); cudaFree(s->exGok); cudaFree(s->exSync); cudaFree(s->tl); cudaFree(s->exWm); cudaFree(s->exWe);
+    cudaFree(s->exC); cudaFree(s->exK); cudaFree(s->exB); cudaFree(s->exG); cudaFree(s->exGok); cudaFree(s->exSync); cudaFree(s->tl); cudaFree(s->rm_state); cudaFree(s->rm_noise); cudaFree(s->exWm); cudaFree(s->exWe);
     cudaFree(s->com_part); cudaFree(s->com); cudaFree(s->tickets); cudaFree(s->draw);
     cudaFree(s->obs_d); cudaFreeHost(s->obs_h); cudaFree(s->obs_part);
     cudaFreeHost(s->err_h);
@@ -295,6 +295,10 @@ extern "C" int pimdb_create(const pimdb_config* cfg, pimdb_sim** out) {
         CREATE_TRY(cudaMemset(s->exV, 0, sizeof(double) * (s->N + 1)));
         CREATE_TRY(cudaMemset(s->exVb, 0, sizeof(double) * (s->N + 1)));
         CREATE_TRY(cudaMemset(s->exF, 0, sizeof(double) * 2 * s->S));
+    }
+    if (cfg->rng == PIMDB_RNG_RANMARS && cfg->thermostat == PIMDB_THERMO_LANGEVIN) {
+        const int rc = ranmars_create(s);
+        if (rc != PIMDB_OK) { g_create_error = s->err; free_all(s); return rc; }
     }
     CREATE_TRY(cudaMalloc(&s->com_part, sizeof(double) * 4 * kMaxPartials));
     CREATE_TRY(cudaMalloc(&s->com, sizeof(double) * 4));

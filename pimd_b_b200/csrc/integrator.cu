@@ -147,6 +147,7 @@ struct IntArgs {
     double c1, c2, hdt, dt_over_m, inv_np;
     unsigned long long seed;
     unsigned ops;
+    const double* noise;   // reference-compatible stream: [Ploc][N][D] gaussians of this half-step, or nullptr (Philox)
     unsigned long long* tl;
 };
 
@@ -178,7 +179,14 @@ __global__ void __launch_bounds__(256) k_integrate(IntArgs a) {
             p0 -= cmc; p1 -= cmc;
         }
         double z0 = 0.0, z1 = 0.0;
-        if (do_o) gaussian_pair((uint32_t)q, (uint32_t)((a.bead_begin + b) * a.D + c), draw, a.seed, z0, z1);
+        if (do_o) {
+            if (a.noise) {   // particle-major, axis-minor within a bead: the order langevin.cpp:18-26 consumes them
+                z0 = a.noise[((size_t)b * a.N + n0) * a.D + c];
+                z1 = two ? a.noise[((size_t)b * a.N + n0 + 1) * a.D + c] : 0.0;
+            } else {
+                gaussian_pair((uint32_t)q, (uint32_t)((a.bead_begin + b) * a.D + c), draw, a.seed, z0, z1);
+            }
+        }
         if (a.ops & OP_O_PRE) { p0 = a.c1 * p0 + a.c2 * z0; p1 = a.c1 * p1 + a.c2 * z1; }
         if (a.ops & (OP_B | OP_B_PHYS)) {
             p0 += a.hdt * a.f[o];
@@ -207,7 +215,8 @@ __global__ void __launch_bounds__(256) k_integrate(IntArgs a) {
             }
         }
         if (a.ops & OP_SUM) {
-            const double ps = p0 + p1;
+            // (odd N: the second slot of the last pair is no particle, but SUBCM and the Langevin step have acted on it)
+            const double ps = p0 + (two ? p1 : 0.0);
             acc[0] += c == 0 ? ps : 0.0;
             acc[1] += c == 1 ? ps : 0.0;
             acc[2] += c == 2 ? ps : 0.0;
@@ -259,6 +268,12 @@ int launch_integrate(Sim* s, unsigned ops) {
     a.inv_np = 1.0 / ((double)s->N * (double)s->P);
     a.seed = s->cfg.seed;
     a.ops = ops;
+    a.noise = nullptr;
+    if (s->rm_state && (ops & (OP_O_PRE | OP_O_POST))) {
+        int rc = launch_ranmars_fill(s);
+        if (rc != PIMDB_OK) return rc;
+        a.noise = s->rm_noise;
+    }
     a.tl = tl_slot(s);
     const size_t items = (size_t)s->Ploc * s->D * ((s->N + 1) / 2);
     const int grid = grid_for(items, 256, kMaxPartials);

@@ -38,6 +38,13 @@ struct DevObs {  // partial sums produced on device; assembled into pimdb_observ
     double pad[1];
 };
 
+// RANMAR state of one bead (reference libs/random_mars.h): u[1..97], c, the lag indices and the cached second gaussian
+struct RanMarsState {
+    double u[98];
+    double c, spare;
+    int i97, j97, have_spare, pad;
+};
+
 struct Sim {
     pimdb_config cfg{};
     int N = 0, P = 0, D = 0, Ploc = 0, b0 = 0, b1 = 0;
@@ -86,6 +93,7 @@ struct Sim {
     double *nmFreq = nullptr;          // [P] cos/sin tables: [3][P] = cos(w dt), sin(w dt), m*w
     // Nose-Hoover chains: eta | eta_dot | eta_dot_dot, each [bead][group][nchains]
     double *nh_state = nullptr; size_t nh_len = 0;
+    RanMarsState* rm_state = nullptr; double* rm_noise = nullptr;   // reference-compatible noise mode (ranmars.cu): [Ploc], [Ploc][N][D]
     unsigned long long* tl = nullptr; int tl_next = 0;   // in-kernel timeline slots [32][2] (PIMDB_TIMELINE=1), next slot
     // graph
     cudaGraph_t graph = nullptr; cudaGraphExec_t graph_exec = nullptr;
@@ -130,6 +138,8 @@ int launch_nm_propagate(Sim* s);
 int launch_nm_thermostat(Sim* s);
 int launch_nm_momenta(Sim* s, bool forward);   // p <-> normal-mode momenta, in place
 int launch_obs_elementwise(Sim* s);
+int ranmars_create(Sim* s);
+int launch_ranmars_fill(Sim* s);   // the next thermostat half-step's gaussians, all owned beads
 int launch_nose_hoover(Sim* s);
 int launch_nose_hoover_energy(Sim* s, double* out_dev);
 int launch_aos_to_soa(Sim* s, double* dst_soa, bool dst_has_halo);

@@ -26,6 +26,7 @@ struct NmArgs {
     int P, M, N, D, TC;
     double hdt, dt_over_m, c1, c2;
     unsigned long long seed;
+    const double* noise;       // reference-compatible stream: [mode][N][D] gaussians of this half-step, or nullptr (Philox)
 };
 
 // mode 0: propagator (x and p), mode 1: Langevin thermostat on the mode momenta (p only),
@@ -92,9 +93,15 @@ __global__ void __launch_bounds__(256) k_nm_fused(NmArgs a) {
             } else {
                 // Langevin O step on mode k: noise stream row = mode k * D + axis (DESIGN.md "RNG")
                 const int axis = ok ? col / a.N : 0, n = ok ? col % a.N : 0;
-                double z0, z1;
-                gaussian_pair((uint32_t)(n >> 1), (uint32_t)(k * a.D + axis), draw, a.seed, z0, z1);
-                rn_p[cnt] = a.c1 * pn + a.c2 * ((n & 1) ? z1 : z0);
+                double z;
+                if (a.noise) {   // the generator of rank k acts on mode k (thermostat_coupling.cpp:29-47), particle-major order
+                    z = ok ? a.noise[((size_t)k * a.N + n) * a.D + axis] : 0.0;
+                } else {
+                    double z0, z1;
+                    gaussian_pair((uint32_t)(n >> 1), (uint32_t)(k * a.D + axis), draw, a.seed, z0, z1);
+                    z = (n & 1) ? z1 : z0;
+                }
+                rn_p[cnt] = a.c1 * pn + a.c2 * z;
             }
         }
         __syncthreads();
@@ -152,6 +159,12 @@ static int launch_nm(Sim* s, int mode) {
     a.TC = TC;
     a.hdt = 0.5 * s->cfg.dt; a.dt_over_m = s->cfg.dt / s->cfg.mass; a.c1 = s->c1; a.c2 = s->c2;
     a.seed = s->cfg.seed;
+    a.noise = nullptr;
+    if (mode == 1 && s->rm_state) {
+        int rc = launch_ranmars_fill(s);
+        if (rc != PIMDB_OK) return rc;
+        a.noise = s->rm_noise;
+    }
     const size_t smem = (size_t)2 * s->P * TC * sizeof(double);
     const int grid = grid_for((a.M + TC - 1) / TC, 1, 4 * kNumSM);
     if (mode == 0) {

@@ -28,7 +28,8 @@ def make_c_config(cfg: SimConfig, bead_begin: int = 0, bead_end: Optional[int] =
         ext_amplitude=cfg.ext_amplitude, ext_phase=cfg.ext_phase,
         cutoff=cfg.cutoff, mass=cfg.mass, temperature=cfg.temperature, dt=cfg.dt, gamma=cfg.gamma,
         size=cfg.size, seed=cfg.seed,
-        bead_begin=bead_begin, bead_end=cfg.nbeads if bead_end is None else bead_end, device=device)
+        bead_begin=bead_begin, bead_end=cfg.nbeads if bead_end is None else bead_end, device=device,
+        rng=_cabi.RNG[getattr(cfg, "rng", "philox")])
 
 
 class DeviceSim:

@@ -1,8 +1,11 @@
 // pimdb_gpu: the reference's `pimdb` entry point (src/pimdb.cpp:31-68) on top of the B200 hot path.
-//   pimdb_gpu [-in config.ini] [--dim D] [--device K] [--bosonic_alg]
+//   pimdb_gpu [-in config.ini] [--dim D] [--device K] [--rng philox|ranmars] [--bosonic_alg]
+// --rng ranmars (or PIMDB_RNG=ranmars) draws the Langevin noise from the reference's own generator, one sequential
+// RANMAR stream per bead (libs/random_mars.cpp): thermostatted runs then follow the reference's trajectories.
 // Same INI schema, same output/ files (simulation.out, position_b.xyz, velocity_b.dat, force_b.dat, report.txt),
 // same error reporting ("[X] <kind>: <message>", exit code 0 like the reference). NDIM is a run-time flag here
 // (compile-time in the reference, CMakeLists.txt:44-48).
+#include <cstdlib>
 #include <cstring>
 #include <iostream>
 #include <string>
@@ -12,6 +15,7 @@
 int main(int argc, char** argv) {
     std::string config = "config.ini";
     int ndim = 3, device = 0;
+    std::string rng = std::getenv("PIMDB_RNG") ? std::getenv("PIMDB_RNG") : "philox";
     bool info = false;
     try {
         for (int i = 1; i < argc; ++i) {
@@ -23,6 +27,8 @@ int main(int argc, char** argv) {
                 info = true;
             } else if (!std::strcmp(argv[i], "--device")) {
                 if (i + 1 < argc) device = std::atoi(argv[++i]);
+            } else if (!std::strcmp(argv[i], "--rng")) {
+                if (i + 1 < argc) rng = argv[++i];
             } else if (!std::strcmp(argv[i], "-in")) {
                 if (i + 1 < argc) config = argv[++i];
                 else throw std::invalid_argument("-in option requires a filename argument");
@@ -31,6 +37,8 @@ int main(int argc, char** argv) {
         if (!info) {
             std::cout << "[*] Initializing the simulation parameters\n";
             pimdb_host::Params params(config, ndim);
+            if (rng == "ranmars") params.cfg.rng = PIMDB_RNG_RANMARS;
+            else if (rng != "philox") throw std::invalid_argument("--rng takes philox or ranmars");
             pimdb_host::Simulation sim(params, device);
             sim.run();
         }

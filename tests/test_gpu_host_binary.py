@@ -83,6 +83,35 @@ def test_pimdb_gpu_passes_the_reference_golden_nose_hoover_cases(gpu_required, c
         assert frames.shape[0] == 101
 
 
+LANGEVIN_CASES = ["bosonic_quadratic_harmonic", "bosonic_quadratic_harmonic_dynamics", "bosonic_quadratic_harmonic_gsf",
+                  "bosonic_quadratic_harmonic_nmthermostat_dynamics", "dist_harmonic", "dist_harmonic_dynamics",
+                  "dist_harmonic_nm_propagation_dynamics"]
+
+
+@pytest.mark.parametrize("case", LANGEVIN_CASES)
+def test_pimdb_gpu_passes_the_reference_golden_langevin_cases(gpu_required, case, tmp_path):
+    """The reference's thermostatted regression cases (tests/cases/<case>/, 100 000 Langevin steps, Cartesian and
+    normal-mode coupling, normal-mode propagator, bosons and distinguishable particles, the GSF observable) run
+    unchanged through pimdb_gpu with the reference's own noise generator (--rng ranmars: one RANMAR stream per bead,
+    libs/random_mars.cpp) and are judged by the reference's own rule (tests/main.py:77-107: every column of
+    simulation.out, np.allclose with rtol 1e-5)."""
+    (tmp_path / "config.ini").write_text(str(REFCASES[f"{case}/ini"]))
+    r = subprocess.run([str(BIN), "-in", "config.ini", "--dim", "3", "--rng", "ranmars"], cwd=tmp_path,
+                       capture_output=True, text=True, timeout=900)
+    assert "finished running successfully" in r.stdout, r.stdout + r.stderr
+    got = pio.read_simulation_out(str(tmp_path / "output" / "simulation.out"))
+    cols = [str(c) for c in REFCASES[f"{case}/simout_columns"]]
+    ref = REFCASES[f"{case}/simout"]
+    # like tests/main.py:92-105 the columns of the ACTUAL output are the ones compared (some expected files still carry
+    # the ext_pot / int_pot columns of an older EnergyObservable; src/observables/energy.cpp:10-19 no longer prints them
+    # when one of the potentials is free)
+    assert set(got.keys()) <= set(cols) and {"step", "kinetic"} <= set(got.keys())
+    for c in got:
+        i = cols.index(c)
+        assert got[c].shape == ref[:, i].shape
+        assert np.allclose(got[c], ref[:, i], rtol=1e-5), (c, np.max(np.abs(got[c] - ref[:, i])))
+
+
 def test_pimdb_gpu_reports_config_errors_like_the_reference(gpu_required, tmp_path):
     (tmp_path / "config.ini").write_text("[simulation]\nnbeads = 4\nbosonic = true\npropagator = normal_modes\n"
                                          "thermostat = langevin\n")

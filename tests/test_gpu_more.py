@@ -66,6 +66,15 @@ def test_reference_raw_outputs(gpu_required, case):
         if name in ("prob_dist", "prob_all"):
             tol = 1e-9 * abs(val) + 1e-300
         assert abs(mine - val) <= tol, (name, mine, val)
+    if cfg.thermostat == "langevin":   # the reference's own noise stream (one RANMAR generator per bead): its trajectory
+        import dataclasses
+        sim2 = DeviceSim(dataclasses.replace(cfg, rng="ranmars"))
+        sim2.set("x", x)
+        sim2.set("p", p)
+        sim2.step(12)
+        for w in ("x", "p", "f"):
+            assert relerr(sim2.get(w), REFPROBE[f"{case}/traj12_{w}"]) < 1e-9, (case, w)
+        sim2.close()
     if cfg.thermostat == "none":   # deterministic: trajectory-level parity with the reference itself
         sim2 = DeviceSim(cfg)
         sim2.set("x", x)
@@ -367,3 +376,26 @@ def test_page_locked_host_buffers_take_the_direct_copy_path(gpu_required):
     f_pageable = sim.get("f")
     assert np.array_equal(sim.get("f", hout), f_pageable)
     sim.close()
+
+
+@pytest.mark.parametrize("rng", ["philox", "ranmars"])
+def test_fixcom_with_odd_particle_count_in_the_fused_step(gpu_required, rng):
+    """Regression: the fused integrator handles particles in pairs; with an odd particle count the empty second slot of
+    the last pair must not enter the centre-of-mass sum after the COM shift / Langevin step of the same kernel have
+    acted on it. pimdb_step (fused, deferred COM shift) must equal the call-by-call order of Simulation::run
+    (src/simulation.cpp:246-259) and leave no centre-of-mass momentum (Simulation::zeroMomentum :581-603)."""
+    import dataclasses
+    case = "aziz_pbc_bosonic"          # N = 27, fixcom, Langevin
+    cfg = dataclasses.replace(SimConfig(**ast.literal_eval(str(REFPROBE[f"{case}/cfg"]))), rng=rng)
+    assert cfg.natoms % 2 == 1 and cfg.fixcom and cfg.thermostat == "langevin"
+    x, p = REFPROBE[f"{case}/x"], REFPROBE[f"{case}/p"]
+    a = DeviceSim(cfg); a.set("x", x); a.set("p", p)
+    a.step(7)
+    b = DeviceSim(cfg); b.set("x", x); b.set("p", p)
+    for _ in range(7):
+        b.thermostat_step(); b.zero_momentum(); b.propagator_step(); b.thermostat_step(); b.zero_momentum()
+    pa = a.get("p")
+    assert np.max(np.abs(pa.sum(axis=(0, 1)))) < 1e-12 * np.abs(pa).sum()
+    for w in ("x", "p", "f"):
+        assert relerr(a.get(w), b.get(w)) < 1e-12, w
+    a.close(); b.close()
