@@ -34,6 +34,8 @@ OUT = Path(__file__).resolve().parent
 CASES = ["bosonic_quadratic_harmonic_dynamics", "dist_harmonic_dynamics",
          "bosonic_quadratic_harmonic_nmthermostat_dynamics", "dist_harmonic_nm_propagation_dynamics",
          "bosonic_quadratic_harmonic", "dist_harmonic", "bosonic_quadratic_harmonic_gsf",
+         # (the two bosonic_factorial_* cases belong to the reference's factorial build: the sum over all N! permutations is
+         # a pointwise different potential from the Feldman-Hirshberg one -- same partition function, other forces)
          # deterministic after initialisation (Nose-Hoover chains): whole simulation.out is a known-answer test
          "bosonic_quadratic_harmonic_nh_dynamics", "bosonic_quadratic_harmonic_nh_np_dynamics",
          "bosonic_quadratic_harmonic_nh_np_dim_dynamics"]
