@@ -267,7 +267,7 @@ extern "C" int pimdb_create(const pimdb_config* cfg, pimdb_sim** out) {
         const size_t NN = (size_t)s->N * s->N;
         CREATE_TRY(cudaMalloc(&s->exA, sizeof(double) * (2 * s->N + 2)));   // A[N] | Inv[N+1]
         CREATE_TRY(cudaMalloc(&s->exC, sizeof(int4) * 2 * NN));
-        if (s->N <= 512) {   // the fast recurrence's block-scaled copy (exchange.cu: k_exch_coeff_tiles)
+        if (s->N <= 2048) {  // block-scaled factor tiles + diagonal-block inverses of the blocked recurrence (exchange.cu)
             const size_t nbk = (size_t)((s->N + 31) / 32);
             CREATE_TRY(cudaMalloc(&s->exK, sizeof(double) * 2 * nbk * nbk * 1024));      // 32 x 32 tiles, forward | backward
             CREATE_TRY(cudaMemset(s->exK, 0, sizeof(double) * 2 * nbk * nbk * 1024));
@@ -455,7 +455,9 @@ static int enqueue_forces(Sim* s) {
         // recurrence kernel that is itself waiting for that very launch.
         cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
         cudaStreamIsCapturing(s->stream, &cap);
-        early = !serial && cap == cudaStreamCaptureStatusActive && s->exK && !getenv("PIMDB_EXCH_NOBLOCKED");
+        // N <= 512 only: beyond that the tiles follow a prefix-sum kernel on their stream and would be dispatched behind
+        // the (much larger) pair-tile grid, which delays the whole chain to the end of the pair forces (measured at C4)
+        early = !serial && cap == cudaStreamCaptureStatusActive && s->exK && s->N <= 512 && !getenv("PIMDB_EXCH_NOBLOCKED");
         if (early) {
             PIMDB_CUDA_TRY(s, cudaEventRecord(s->ev_fork, s->stream));
             PIMDB_CUDA_TRY(s, cudaStreamWaitEvent(s->stream_r, s->ev_fork, 0));

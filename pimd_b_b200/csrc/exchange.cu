@@ -42,7 +42,8 @@ struct Ext {
 };
 
 constexpr int kExtZeroExp = -(1 << 29);
-constexpr int kExchFastMaxN = 512;     // largest N served by the block-scaled tables and the fast recurrence
+constexpr int kExchFastMaxN = 512;     // largest N for which every factor tile recomputes the prefix sums itself
+constexpr int kExchBlockedMaxN = 2048; // largest N served by the block-scaled tiles and the blocked (cluster) recurrence
 
 __device__ __forceinline__ double pow2i(int d) {   // 2^d for d in [-1022, 1023], 0 below
     return d < -1022 ? 0.0 : __hiloint2double((1023 + d) << 20, 0);
@@ -334,7 +335,9 @@ __global__ void __launch_bounds__(1024, 2) k_exch_coeff_tiles(ExArgs a) {
     const int N = a.N, nb = (N + 31) >> 5;
     const int rb = blockIdx.x / nb, sb = blockIdx.x % nb;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-    {   // Same operations in the same order as k_exch_prefix (so A is bit-identical); fusing it here takes a 5 us
+    const bool own_prefix = N <= kExchFastMaxN;      // beyond that k_exch_prefix has run before this kernel
+    if (own_prefix) {
+        // Same operations in the same order as k_exch_prefix (so A is bit-identical); fusing it here takes a 5 us
         // single-block kernel and a launch gap off the step's critical path. Block 0 also publishes A and 1/i.
         const int w = threadIdx.x;                     // produces A[w+1]
         double v = (w < N - 1) ? dist2<D>(a, a.xP, w, a.x1, w + 1) : 0.0;
@@ -371,7 +374,8 @@ __global__ void __launch_bounds__(1024, 2) k_exch_coeff_tiles(ExArgs a) {
     const long long i = (long long)r * N + sc;
     if (r < N && sc < N) {
         const int u = min(r, sc), v = max(r, sc);
-        const double y = a.h * (sA[v] - sA[u] + dist2<D>(a, a.x1, u, a.xP, v));
+        const double Av = own_prefix ? sA[v] : a.A[v], Au = own_prefix ? sA[u] : a.A[u];
+        const double y = a.h * (Av - Au + dist2<D>(a, a.x1, u, a.xP, v));
         const Ext c = ext_exp_neg(y < 0.0 ? 0.0 : y);   // (a NaN position stays NaN and is reported, like the reference)
         if (sc >= r) {
             a.Cf[i] = ext_pack(c.m, c.e);
@@ -1216,7 +1220,7 @@ __device__ __forceinline__ void recur_cluster(const ExArgs& a, double* smem_d) {
 
     double am = 0.0;
     int ae = kExtZeroExp;
-    long long* stamp = (a.dbg && lane == 0 && has_block) ? a.dbg + 192 + ((FWD ? 0 : 16) + warp) * 64 : nullptr;
+    long long* stamp = (a.dbg && lane == 0 && has_block && nb <= 16) ? a.dbg + 192 + ((FWD ? 0 : 16) + warp) * 64 : nullptr;
     if (stamp) stamp[5] = clock64();                                  // start (after the cluster barrier)
     int Eprev = 0, mode_prev = 1;                                     // block word of the block before mine
     // ---- consumer phases
@@ -1404,7 +1408,7 @@ __device__ __forceinline__ void recur_cluster(const ExArgs& a, double* smem_d) {
     if (crank == 0 && tid == 0) a.sync[FWD ? 2 : 3] += 1;
 }
 
-__global__ void __launch_bounds__(64, 1) k_exch_recur_cluster(ExArgs a) {
+__global__ void __launch_bounds__(256, 1) k_exch_recur_cluster(ExArgs a) {
     extern __shared__ __align__(16) double smem_d[];
     tl_begin(a.tl1);
     if (blockIdx.x < kClusterSize) recur_cluster<true>(a, smem_d);
@@ -1686,13 +1690,12 @@ static int launch_recur(Sim* s, const ExArgs& a, cudaStream_t st, int nt) {
 static int run_recursion(Sim* s, const ExArgs& a, cudaStream_t st) {
     int nt;
     const int R = rows_per_thread(s->N, nt);
-    if (R == 1 && !getenv("PIMDB_EXCH_BARRIER")) {           // N <= 1024: warp-decoupled kernel
-        // coefficient ring: 16 rows in flight up to 512 rows per block, 8 beyond (shared-memory budget)
-        const int ST = nt <= 512 ? 16 : 8;
-        const size_t smem = (size_t)(s->N + 2) * (sizeof(int4) + sizeof(double)) + (size_t)ST * nt * sizeof(int4) + 16;
-        if (nt <= 512 && a.Kf && !getenv("PIMDB_EXCH_NOBLOCKED") && !getenv("PIMDB_EXCH_NOCLUSTER")) {
-            // blocked recurrence on two clusters of 8 thread blocks (forward, backward), one or two warps each
-            const int nb = nt / 32, nb2 = (nb + 3) & ~1, wpc = (nb + kClusterSize - 1) / kClusterSize;
+    const int nblk = (s->N + 31) / 32;                       // 32-row blocks
+    const bool blocked_ok = a.Kf && !getenv("PIMDB_EXCH_NOBLOCKED");
+    if (blocked_ok && (nblk > 16 || !getenv("PIMDB_EXCH_NOCLUSTER"))) {
+        {
+            // blocked recurrence on two clusters of 8 thread blocks (forward, backward), 1..8 warps each (N <= 2048)
+            const int nb = nblk, nb2 = (nb + 3) & ~1, wpc = (nb + kClusterSize - 1) / kClusterSize;
             const size_t smem_cl = sizeof(double) * ((size_t)wpc * 3 * 512 + 32 * nb + 32 * wpc + nb2) + 8 * ((size_t)nb2 + wpc * 3 + (wpc & 1))
                                    + sizeof(int) * ((size_t)32 * nb + nb2) + 16;
             if (smem_cl > 48 * 1024)
@@ -1708,7 +1711,14 @@ static int run_recursion(Sim* s, const ExArgs& a, cudaStream_t st) {
             lc.attrs = at;
             lc.numAttrs = 1;
             cudaLaunchKernelEx(&lc, k_exch_recur_cluster, a);
-        } else if (nt <= 512 && a.Kf && !getenv("PIMDB_EXCH_NOBLOCKED")) {
+        }
+        return PIMDB_OK;
+    }
+    if (R == 1 && !getenv("PIMDB_EXCH_BARRIER")) {           // N <= 1024: single-block kernels
+        // coefficient ring: 16 rows in flight up to 512 rows per block, 8 beyond (shared-memory budget)
+        const int ST = nt <= 512 ? 16 : 8;
+        const size_t smem = (size_t)(s->N + 2) * (sizeof(int4) + sizeof(double)) + (size_t)ST * nt * sizeof(int4) + 16;
+        if (nt <= 512 && blocked_ok) {
             // blocked kernel: 32 unknowns per chain step through the precomputed diagonal-block inverses
             const int nb = nt / 32, nb2 = (nb + 3) & ~1;
             const size_t smem_blk = sizeof(double) * ((size_t)nb * 3 * 512 + 64 * nb + nb2) + 8 * ((size_t)nb * 3 + (nb & 1))
@@ -1747,8 +1757,12 @@ static int exchange_impl(Sim* s, cudaStream_t st, int part) {
     if (part == 0) a.tl0 = tl_slot(s);
     else { a.tl1 = tl_slot(s); a.tl2 = tl_slot(s); }
     if (part == 0) {
-        if (a.Kf) {      // N <= 512: the tiles recompute the prefix sums themselves (one launch)
+        if (a.Kf) {      // N <= 2048: factor tiles + diagonal-block inverses; up to N = 512 the tiles recompute the prefix sums
             const int nb = (s->N + 31) / 32;
+            if (s->N > kExchFastMaxN) {
+                k_exch_prefix<D><<<1, 1024, 0, st>>>(a);
+                s->launches += 1;
+            }
             k_exch_coeff_tiles<D><<<nb * nb, 1024, 0, st>>>(a);
             s->launches += 1;
         } else {
@@ -1761,8 +1775,10 @@ static int exchange_impl(Sim* s, cudaStream_t st, int part) {
         if (rc != PIMDB_OK) return rc;
         {
             const int per_kind = std::max(1, std::min((s->N + 2 * kFW - 1) / (2 * kFW), 4 * kNumSM));   // 2 tasks per warp
-            if (s->N <= 512) {
+            if (a.Kf) {
                 const size_t smem = sizeof(double) * ((size_t)s->N + 1 + ((s->N + 2) >> 1) + (size_t)D * s->N);
+                if (smem > 48 * 1024)
+                    cudaFuncSetAttribute(k_exch_forces<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 k_exch_forces<D, true><<<2 * per_kind, 32 * kFW, smem, st>>>(a);
             } else {
                 k_exch_forces<D, false><<<2 * per_kind, 32 * kFW, 0, st>>>(a);

@@ -22,7 +22,7 @@ def block_status(sim):
     fn = sim.lib.pimdb_debug_exchange_blocks
     fn.restype = C.c_int
     fn.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
-    buf = (C.c_int * 64)()
+    buf = (C.c_int * 256)()
     nb = fn(sim.h, buf)
     return list(buf[:nb]), list(buf[nb:2 * nb])
 
@@ -50,10 +50,12 @@ def check(cfg, x, expect=None):
     return fwd, bwd
 
 
-@pytest.mark.parametrize("natoms", [1, 2, 3, 5, 31, 32, 33, 34, 63, 64, 65, 95, 97, 128, 129, 255, 257, 300, 449, 481, 511, 512])
+@pytest.mark.parametrize("natoms", [1, 2, 3, 5, 31, 32, 33, 34, 63, 64, 65, 95, 97, 128, 129, 255, 257, 300, 449, 481, 511, 512,
+                                    513, 700, 1023, 1024, 1025, 1500, 2047, 2048])
 def test_blocked_recurrence_sizes(gpu_required, natoms):
     """Correlated ring polymers in a trap: every block takes the matrix-vector path. Sizes straddle the 32-row block
-    and 4-column copy-group boundaries (ragged first / last blocks in either direction)."""
+    boundaries (ragged first / last blocks in either direction), the 512-particle limit of the tiles' own prefix sums and
+    the warps-per-cluster-block steps (1 .. 8 warps, N <= 2048)."""
     cfg = trap(natoms, 3, temperature=1.0 * KELVIN, size=2000.0)
     rng = np.random.default_rng(natoms)
     centroid = rng.normal(0.0, 60.0, size=(1, natoms, 3))
@@ -61,7 +63,7 @@ def test_blocked_recurrence_sizes(gpu_required, natoms):
     check(cfg, x, expect=1)
 
 
-@pytest.mark.parametrize("natoms,pbc", [(80, False), (200, True), (333, False), (512, True)])
+@pytest.mark.parametrize("natoms,pbc", [(80, False), (200, True), (333, False), (512, True), (1100, False)])
 def test_blocked_recurrence_exact_blocks(gpu_required, natoms, pbc):
     """Stiff springs + uncorrelated beads (beta*E ~ 1e3-1e4 per link): the block inverses or the new values leave the
     plain-double window and the blocks are redone exactly; consumers then apply them column by column."""
