@@ -81,10 +81,14 @@ class CudaShard:
 class ShardedSimulation:
     """Runs Simulation::run's loop body (src/simulation.cpp:246-259) over bead shards."""
 
-    def __init__(self, cfg, shard, group=None):
+    def __init__(self, cfg, shard, group=None, halo: str = "p2p"):
         self.cfg = cfg
         self.shard = shard
         self.group = group
+        if halo not in ("p2p", "allgather"):
+            raise ValueError("halo must be 'p2p' or 'allgather'")
+        self.halo = halo
+        self._gather_send = self._gather_recv = None
         self.rank = dist.get_rank(group)
         self.world = dist.get_world_size(group)
         self.prev = (self.rank - 1) % self.world
@@ -96,6 +100,20 @@ class ShardedSimulation:
         if self.world == 1:
             s.halo_before.copy_(s.send_last)
             s.halo_after.copy_(s.send_first)
+            return
+        if self.halo == "allgather":
+            # One collective instead of four point-to-point operations: every rank contributes its first and last bead
+            # slice and picks its two neighbours' out of the result. More bytes than the ring needs (2 G slices), but
+            # they are tiny, and a collective can be captured into a CUDA graph together with the kernels of the step.
+            n = s.send_first.numel()
+            if self._gather_send is None:
+                self._gather_send = torch.empty(2 * n, dtype=s.send_first.dtype, device=s.send_first.device)
+                self._gather_recv = torch.empty(self.world * 2 * n, dtype=s.send_first.dtype, device=s.send_first.device)
+            self._gather_send[:n].copy_(s.send_first)
+            self._gather_send[n:].copy_(s.send_last)
+            dist.all_gather_into_tensor(self._gather_recv, self._gather_send, group=self.group)
+            s.halo_before.copy_(self._gather_recv[(2 * self.prev + 1) * n:(2 * self.prev + 2) * n])   # prev's last slice
+            s.halo_after.copy_(self._gather_recv[2 * self.next * n:(2 * self.next + 1) * n])          # next's first slice
             return
         # Order matters when prev == next (two ranks): the k-th send to a peer pairs with its k-th receive.
         ops = [
@@ -119,6 +137,7 @@ class ShardedSimulation:
             return True
         if not torch.cuda.is_available() or not hasattr(self.shard, "stream"):
             return False
+        self.halo = "allgather"                       # point-to-point NCCL calls inside a capture hung on this stack
         try:
             self._step_eager(2)                       # warm-up: NCCL communicators, lazy allocations
             torch.cuda.synchronize()

@@ -75,14 +75,14 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, cfg_dict, x, p, steps, out_dir):
+def _worker(rank, world, port, cfg_dict, x, p, steps, out_dir, halo="p2p"):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     cfg = SimConfig(**cfg_dict)
     lo, hi = bead_range(cfg.nbeads, world, rank)
     shard = NumpyShard(cfg, x, p, lo, hi)
-    sim = ShardedSimulation(cfg, shard)
+    sim = ShardedSimulation(cfg, shard, halo=halo)
     sim.exchange_halos()
     sim.step(steps)
     obs = sim.observables()
@@ -107,8 +107,9 @@ def test_bead_range_partitions():
             assert max(sizes) - min(sizes) <= 1 and min(sizes) >= 1
 
 
-@pytest.mark.parametrize("world,nbeads", [(2, 8), (3, 8), (2, 2)])
-def test_sharded_steps_equal_single_process_oracle(world, nbeads, tmp_path):
+@pytest.mark.parametrize("world,nbeads,halo", [(2, 8, "p2p"), (3, 8, "p2p"), (2, 2, "p2p"), (2, 8, "allgather"),
+                                               (3, 7, "allgather")])
+def test_sharded_steps_equal_single_process_oracle(world, nbeads, halo, tmp_path):
     cfg = SimConfig(nbeads=nbeads, natoms=6, ndim=3, bosonic=False, fixcom=True, pbc=False,
                     temperature=5.802 * KELVIN, mass=1.0, size=300.0, interaction="free", external="harmonic",
                     ext_omega=3 * MEV, thermostat="none", seed=3, dt=FEMTOSECOND)
@@ -117,7 +118,7 @@ def test_sharded_steps_equal_single_process_oracle(world, nbeads, tmp_path):
     p = maxwell_momenta(cfg, rng) + 0.01
     steps = 7
     port = _free_port()
-    mp.start_processes(_worker, args=(world, port, cfg.as_dict(), x, p, steps, str(tmp_path)), nprocs=world,
+    mp.start_processes(_worker, args=(world, port, cfg.as_dict(), x, p, steps, str(tmp_path), halo), nprocs=world,
                        join=True, start_method="spawn")
     orc = Oracle(cfg)
     orc.set("x", x)
