@@ -18,12 +18,15 @@
 //   3. With W[m] = exp(-beta V[m]) and Wb[l] = exp(-beta Vb[l]) the two N-step recursions become linear
 //      triangular recurrences
 //          W[v+1] = 1/(v+1) sum_{j<=v} c(j,v) W[j],          Wb[l] = sum_{p>=l} c(l,p) Wb[p+1] / (p+1),
-//      evaluated column-wise in extended-range arithmetic: when W[j] is known every row v >= j adds its term.
-//      The dependency chain of a step is one multiply-add, one normalisation and one barrier -- no exp, no log,
-//      no block reduction. Mathematically this is the reference's shifted log-sum-exp with the shift carried
-//      exactly in the binary exponent, so it is robust for any positions the reference handles.
-//      V[m] = -(ln W[m])/beta is recovered in parallel afterwards. Forward and backward recursions are
-//      independent and run as two concurrent thread blocks; coefficient rows are prefetched with cp.async.
+//      i.e. triangular linear systems: no exp, no log, no reduction on the chain. Mathematically this is the
+//      reference's shifted log-sum-exp with the shift carried exactly in the binary exponent, so it is robust for
+//      any positions the reference handles. They are solved 32 unknowns at a time (N <= 2048): the 32 x 32 diagonal
+//      blocks are inverted ahead of the chain (positions only), the owner warp of a block turns what the earlier
+//      values contribute to its rows into its 32 new values with one matrix-vector product, and every later row
+//      applies the block as a plain dot product with block-scaled factor tiles (TMA bulk copies). One recurrence is
+//      one thread-block cluster; new values are pushed into the other blocks' shared memory (section 3e). Larger N
+//      falls back to scalar column-wise kernels in extended-range arithmetic (sections 3, 3b).
+//      V[m] = -(ln W[m])/beta is recovered as the values are published.
 //   4. Connection probabilities are products of known extended-range numbers,
 //          P(l->u) = W[u] c(u,l) Wb[l+1] / ((l+1) W[N]),
 //      evaluated on the fly in the exterior-force kernel (one warp per particle and exterior bead); the N x N
