@@ -267,7 +267,7 @@ extern "C" int pimdb_create(const pimdb_config* cfg, pimdb_sim** out) {
         const size_t NN = (size_t)s->N * s->N;
         CREATE_TRY(cudaMalloc(&s->exA, sizeof(double) * (2 * s->N + 2)));   // A[N] | Inv[N+1]
         CREATE_TRY(cudaMalloc(&s->exC, sizeof(int4) * 2 * NN));
-        if (s->N <= 2048) {  // block-scaled factor tiles + diagonal-block inverses of the blocked recurrence (exchange.cu)
+        if (s->N <= 8192) {  // block-scaled factor tiles + diagonal-block inverses of the blocked recurrence (exchange.cu)
             const size_t nbk = (size_t)((s->N + 31) / 32);
             CREATE_TRY(cudaMalloc(&s->exK, sizeof(double) * 2 * nbk * nbk * 1024));      // 32 x 32 tiles, forward | backward
             CREATE_TRY(cudaMemset(s->exK, 0, sizeof(double) * 2 * nbk * nbk * 1024));

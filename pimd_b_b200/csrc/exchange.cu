@@ -46,7 +46,7 @@ struct Ext {
 
 constexpr int kExtZeroExp = -(1 << 29);
 constexpr int kExchFastMaxN = 512;     // largest N for which every factor tile recomputes the prefix sums itself
-constexpr int kExchBlockedMaxN = 2048; // largest N served by the block-scaled tiles and the blocked (cluster) recurrence
+constexpr int kExchBlockedMaxN = 8192; // largest N served by the block-scaled tiles and the blocked (cluster) recurrence
 
 __device__ __forceinline__ double pow2i(int d) {   // 2^d for d in [-1022, 1023], 0 below
     return d < -1022 ? 0.0 : __hiloint2double((1023 + d) << 20, 0);
@@ -1411,11 +1411,346 @@ __device__ __forceinline__ void recur_cluster(const ExArgs& a, double* smem_d) {
     if (crank == 0 && tid == 0) a.sync[FWD ? 2 : 3] += 1;
 }
 
+// ---------------------------------------------------------------- 3f. the same, several row blocks per warp (N <= 8192)
+// Beyond 64 row blocks a direction still runs on ONE cluster of 8 thread blocks x 8 warps, and warp g owns the row
+// blocks g, g + 64, g + 128, ... (up to 4): consecutive blocks belong to consecutive warps, so the chain hops from
+// warp to warp exactly as before, and every warp keeps consuming for the blocks it has not solved yet. Per published
+// block a warp applies up to 4 factor tiles (one per block it still owns), the one of its NEXT own block first. The
+// row of G of the next own block is fetched right after the previous own block has been solved (64 chain steps of
+// slack). Shared memory per thread block: 96 KB of tile rings + 64 KB for the value table of N = 8192.
+constexpr int kMultiM = 4;        // row blocks per warp
+constexpr int kMultiWpc = 8;      // warps per thread block (8 blocks per cluster: 64 owner warps per direction)
+
+template <bool FWD>
+__device__ __forceinline__ void recur_cluster_multi(const ExArgs& a, double* smem_d) {
+    constexpr int SLOTS = 3, HALF = 512, WPC = kMultiWpc, NW = kClusterSize * kMultiWpc, M = kMultiM;
+    constexpr int kSpinMax = 1 << 26;            // every wait is bounded: a protocol error becomes an error code, not a hang
+    int tid;
+    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
+    const int nt = blockDim.x, N = a.N, lane = tid & 31, lw = tid >> 5;
+    const int nb = (N + 31) >> 5;
+    const int crank = (int)cluster_ctarank();
+    const int gwarp = crank * WPC + lw;
+    const int nsteps = FWD ? N : N - 1;
+    const int npos = nb;                                             // (N > 2048: every block owns steps)
+    const int nb2 = (nb + 3) & ~1;
+    double* ring = smem_d;
+    double* sOm = ring + (size_t)WPC * SLOTS * HALF;
+    double* sRho = sOm + 32 * nb;
+    double* sHandOm = sRho + 32 * WPC;
+    unsigned long long* sWord = reinterpret_cast<unsigned long long*>(sHandOm + nb2);
+    unsigned long long* sBar = sWord + nb2;
+    int* sEx = reinterpret_cast<int*>(sBar + WPC * SLOTS + (WPC & 1));
+    int* sHandE = sEx + 32 * nb;
+
+    auto g_lo = [&](int q) { return FWD ? 32 * q : max(0, N - 32 * (q + 1)); };
+    auto g_hi = [&](int q) { return min(nsteps - 1, FWD ? 32 * q + 31 : N - 1 - 32 * q); };
+    auto row_of = [&](int st) { return FWD ? st : (N - 1 - st); };
+    auto pos_of = [&](int q) { return FWD ? q : nb - 1 - q; };
+    auto blk_at = [&](int pos) { return FWD ? pos : nb - 1 - pos; };
+    const int* Bg = FWD ? a.Bf : a.Bb;
+    const int4* Cg = FWD ? a.Cf : a.Cb;
+    const double* Kall = FWD ? a.Kf : a.Kb;
+
+    // my row blocks q_j = gwarp + j NW and my row in each of them
+    auto q_of = [&](int j) { return gwarp + j * NW; };
+    auto own_valid = [&](int j) { return q_of(j) < nb; };
+    auto row_v = [&](int j) { return 32 * q_of(j) + lane; };
+    auto row_ok = [&](int j) { const int v = row_v(j); return own_valid(j) && (FWD ? v < N : (v >= 1 && v < N)); };
+    double am[M];
+    int ae[M];
+#pragma unroll
+    for (int j = 0; j < M; ++j) { am[j] = 0.0; ae[j] = kExtZeroExp; }
+
+    // consumption order = (position ascending, my later blocks nearest first); the ring runs SLOTS half tiles ahead of it
+    struct Cur { int pos, k; };      // k-th of my blocks that lie after `pos`, in step order
+    // my blocks in step order: forward j ascending, backward j descending
+    auto jth = [&](int k) { return FWD ? k : M - 1 - k; };
+    auto later_than = [&](int j, int pos) { return own_valid(j) && pos_of(q_of(j)) > pos; };
+    auto cur_valid = [&](const Cur& c) { return c.pos < npos && c.k < M && later_than(jth(c.k), c.pos); };
+    auto cur_norm = [&](Cur& c) {    // move to the next existing (pos, block) pair at or after c
+        while (c.pos < npos) {
+            while (c.k < M && !later_than(jth(c.k), c.pos)) ++c.k;
+            if (c.k < M) return;
+            ++c.pos; c.k = 0;
+        }
+    };
+    auto cur_next = [&](Cur& c) { ++c.k; cur_norm(c); };
+    double* const ring_w = ring + (size_t)lw * SLOTS * HALF;
+    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring_w);
+    const unsigned bar_s = (unsigned)__cvta_generic_to_shared(sBar + lw * SLOTS);
+    Cur prod{0, 0};                  // next tile to fetch
+    int prod_half = 0, n_issued = 0;
+    auto issue_one = [&]() {         // fetch the next half tile into slot n_issued % SLOTS (every lane runs the cursor, lane 0 copies)
+        if (prod.pos >= npos) return false;
+        if (lane == 0) {
+            const int qs = blk_at(prod.pos), qd = q_of(jth(prod.k)), slot = n_issued % SLOTS;
+            bulk_load(ring_s + slot * HALF * 8, Kall + ((size_t)qs * nb + qd) * 1024 + prod_half * HALF, HALF * 8, bar_s + slot * 8);
+        }
+        ++n_issued;
+        if (++prod_half == 2) { prod_half = 0; cur_next(prod); }
+        return true;
+    };
+
+    for (int i = tid; i < 32 * nb; i += nt) { sOm[i] = 0.0; sEx[i] = 0; }
+    for (int i = tid; i < nb2; i += nt) { sWord[i] = 0ull; sHandOm[i] = 0.0; sHandE[i] = 0; }
+    __syncthreads();
+    if (tid == 0) {
+        sHandOm[0] = 1.0;
+        const int used = a.sync[FWD ? 2 : 3];
+        int done, spins = 0;
+        do {
+            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(done) : "l"(a.sync + 1) : "memory");
+        } while (done - used <= 0 && ++spins < (1 << 22));
+        if (done - used <= 0) atomicOr(a.err, kErrSyncTimeout);
+    }
+    __syncthreads();
+    cur_norm(prod);
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < SLOTS; ++k) mbar_init(bar_s + k * 8, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async;" ::: "memory");
+    }
+    __syncwarp();
+    for (int k = 0; k < SLOTS; ++k) if (!issue_one()) break;
+    // G row / h / flags of my first own block in step order
+    double Grow[32];
+    double hrow = 0.0;
+    int Gok = 0, Bown = kExtZeroExp, jown = -1;
+    auto load_own = [&](int j) {     // prepare the owner phase of block q_j
+        jown = j;
+        const int q = q_of(j);
+        const double* Gg = (FWD ? a.Gf : a.Gb) + (size_t)q * 1024 + lane;
+#pragma unroll
+        for (int k = 0; k < 32; ++k) Grow[k] = Gg[k * 32];
+        hrow = (FWD ? a.Hf : a.Hb)[q * 32 + lane];
+        Gok = (FWD ? a.Gokf : a.Gokb)[q];
+        Bown = row_ok(j) ? Bg[(size_t)q * N + row_v(j)] : kExtZeroExp;
+    };
+#pragma unroll
+    for (int k = 0; k < 32; ++k) Grow[k] = 0.0;
+    {
+        int first = -1;
+        for (int k = 0; k < M; ++k) if (first < 0 && own_valid(jth(k))) first = jth(k);
+        if (first >= 0) load_own(first);
+    }
+    cluster_sync_all();
+
+    int n_consumed = 0;              // half tiles taken out of the ring so far
+#pragma unroll 1
+    for (int pos = 0; pos < npos; ++pos) {
+        const int q = blk_at(pos);
+        const bool mine = (q % NW) == gwarp;
+        bool any_later = false;
+#pragma unroll
+        for (int j = 0; j < M; ++j) any_later = any_later || later_than(j, pos);
+        if (!mine && !any_later) break;          // nothing of mine lies at or after this position
+        int mode = 0, Eq = 0;
+        const int own_lo = g_lo(q), own_hi = g_hi(q), n_own = own_hi - own_lo + 1;
+        if (mine) {
+            // ---- owner phase of block q (= my block jown)
+            double amo = 0.0; int aeo = kExtZeroExp;
+#pragma unroll
+            for (int j = 0; j < M; ++j) if (j == jown) { amo = am[j]; aeo = ae[j]; }
+            const int v = row_v(jown);
+            const bool rok = row_ok(jown);
+            if (!rok) { amo = 0.0; aeo = kExtZeroExp; }
+            const int last_need = rok ? (FWD ? v : N - 1 - v) : -1;
+            auto dest = [&](int k) {             // destination blocks, the next owner's first
+                const int nxt = ((FWD ? gwarp + 1 : gwarp + NW - 1) % NW) / WPC;
+                return (unsigned)((nxt + k) % kClusterSize);
+            };
+            auto emit = [&](int s_, double m, int e) {
+                const Ext wn = ext_normalize(m, e);
+                const int i = FWD ? s_ : N - s_;
+                (FWD ? a.Wm : a.Wbm)[i] = wn.m;
+                (FWD ? a.We : a.Wbe)[i] = wn.e;
+                const double val = -(log(wn.m) + (double)wn.e * 0.6931471805599453) / a.beta;
+                if (!isfinite(val)) atomicOr(a.err, FWD ? kErrOverflowFwd : kErrOverflowBwd);
+                (FWD ? a.V : a.Vb)[i] = (s_ == 0) ? 0.0 : val;
+            };
+            unsigned long long hbits;
+            { int spins = 0; do { hbits = lds_volatile_b64(&sHandOm[pos]); } while (hbits == 0ull && ++spins < kSpinMax);
+              if (hbits == 0ull) atomicOr(a.err, kErrSyncTimeout); }
+            const double hm = __longlong_as_double((long long)hbits);
+            int he = 0;
+            if (pos > 0) {
+                const unsigned long long wprev = lds_volatile_b64(&sWord[pos - 1]);   // (seen non-zero as a consumer)
+                he = ((int)(wprev >> 32) == 1) ? (int)(unsigned)wprev : sHandE[pos];
+            }
+            const Ext n0 = ext_normalize(hm, he);
+            const int E = n0.e;
+            const double om0 = n0.m;
+            const int d = aeo - E - Bown;
+            const double A = (amo == 0.0) ? 0.0 : ext_to_double(amo, min(d, 600));
+            bool exact = __any_sync(kFullMask, (amo != 0.0) && (d > 600)) || !(om0 > 0.0) || !Gok;
+            const int tt = FWD ? 0 : row_of(own_lo) & 31;
+            const int kslot = FWD ? lane : (tt - lane) & 31;
+            mode = 2;
+            if (!exact) {
+                double* rho_w = sRho + lw * 32;
+                rho_w[kslot] = A;
+                __syncwarp();
+                double u0 = om0 * hrow, u1 = 0.0, u2 = 0.0, u3 = 0.0;
+#pragma unroll
+                for (int k = 0; k < 32; k += 4) {
+                    const double2 r01 = *reinterpret_cast<const double2*>(rho_w + k);
+                    const double2 r23 = *reinterpret_cast<const double2*>(rho_w + k + 2);
+                    u0 = fma(Grow[k], r01.x, u0);
+                    u1 = fma(Grow[k + 1], r01.y, u1);
+                    u2 = fma(Grow[k + 2], r23.x, u2);
+                    u3 = fma(Grow[k + 3], r23.y, u3);
+                }
+                const double u = (u0 + u1) + (u2 + u3);
+                const bool have = kslot < n_own;
+                const unsigned hi = (unsigned)__double2hiint(u);
+                const bool okall = __all_sync(kFullMask, !have || (hi - (323u << 20) < (1000u << 20)));
+                if (okall) {
+                    const void* pm = !have ? nullptr : (kslot == n_own - 1) ? (const void*)&sHandOm[pos + 1]
+                                                                           : (const void*)&sOm[row_of(own_lo + kslot + 1)];
+                    const unsigned long long ub = (unsigned long long)__double_as_longlong(u);
+                    const unsigned long long ob = (unsigned long long)__double_as_longlong(om0);
+                    const unsigned long long wb = (1ull << 32) | (unsigned long long)(unsigned)E;
+                    for (int k = 0; k < kClusterSize; ++k) {
+                        const unsigned dd = dest(k);
+                        if (have) st_cluster_b64(map_to_cta(pm, dd), ub);
+                        if (lane == 0) {
+                            st_cluster_b64(map_to_cta(&sOm[row_of(own_lo)], dd), ob);
+                            st_cluster_b64(map_to_cta(&sWord[pos], dd), wb);
+                        }
+                    }
+                    mode = 1; Eq = E;
+                    if (have) emit(own_lo + kslot + 1, u, E);
+                    if (lane == 0 && pos == 0) emit(0, om0, E);
+                } else {
+                    exact = true;
+                }
+            }
+            if (exact) {
+                double wm = n0.m;
+                int we = n0.e;
+                auto push = [&](int s_, double m, int e) {
+                    const bool last = s_ == own_hi + 1;
+                    const void* pm = last ? (const void*)&sHandOm[pos + 1] : (const void*)&sOm[row_of(s_)];
+                    const void* pe = last ? (const void*)&sHandE[pos + 1] : (const void*)&sEx[row_of(s_)];
+                    for (int k = 0; k < kClusterSize; ++k) {
+                        st_cluster_s32(map_to_cta(pe, dest(k)), e);
+                        st_cluster_b64(map_to_cta(pm, dest(k)), (unsigned long long)__double_as_longlong(m));
+                    }
+                };
+                if (lane == 0) { push(own_lo, wm, we); if (pos == 0) emit(0, wm, we); }
+#pragma unroll 1
+                for (int st = own_lo; st <= own_hi; ++st) {
+                    if (st <= last_need) {
+                        const int4 c = __ldg(&Cg[(long long)row_of(st) * N + v]);
+                        ext_fma(amo, aeo, ext_m(c), c.z, wm, we);
+                    }
+                    const int lane_o = row_of(st) & 31;
+                    const Ext fin = ext_normalize(FWD ? amo * a.Inv[st + 1] : amo, aeo);
+                    wm = __shfl_sync(kFullMask, fin.m, lane_o);
+                    we = __shfl_sync(kFullMask, fin.e, lane_o);
+                    if (lane == lane_o) { push(st + 1, fin.m, fin.e); emit(st + 1, fin.m, fin.e); }
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    asm volatile("fence.acq_rel.cluster;" ::: "memory");
+                    const unsigned long long wb = 2ull << 32;
+                    for (int k = 0; k < kClusterSize; ++k) st_cluster_b64(map_to_cta(&sWord[pos], dest(k)), wb);
+                }
+            }
+            if (lane == 0) (FWD ? a.statf : a.statb)[pos] = mode;
+            // the next block I own, if any: fetch its row of G now
+            int nxt = -1;
+            for (int k = 0; k < M; ++k) if (nxt < 0 && later_than(jth(k), pos)) nxt = jth(k);
+            if (nxt >= 0) load_own(nxt);
+        }
+        if (!any_later) continue;
+        // ---- consume block q for my later blocks (my own publication included: it is in my table like any other)
+        {
+            unsigned long long word;
+            { int spins = 0; do { word = lds_volatile_b64(&sWord[pos]); } while (word == 0ull && ++spins < kSpinMax);
+              if (word == 0ull) { atomicOr(a.err, kErrSyncTimeout); word = 2ull << 32; } }
+            mode = (int)(word >> 32); Eq = (int)(unsigned)word;
+            const double* om = sOm + 32 * q;
+            if (mode == 1) {
+                const int r = 32 * q + lane;
+                const bool expect = r >= (FWD ? 0 : 1) && r < N;
+                int spins = 0;
+                while (!__all_sync(kFullMask, !expect || lds_volatile_b64(&om[lane]) != 0ull) && ++spins < kSpinMax) {}
+            } else {
+                asm volatile("fence.acq_rel.cluster;" ::: "memory");
+            }
+#pragma unroll
+            for (int k = 0; k < M; ++k) {
+                const int j = jth(k);
+                if (!later_than(j, pos)) continue;
+                const int vj = row_v(j);
+                const bool rok = row_ok(j);
+                const int Bq = rok ? Bg[(size_t)q * N + vj] : kExtZeroExp;
+                const int i0 = n_consumed;
+                mbar_wait(bar_s + (i0 % SLOTS) * 8, (unsigned)(i0 / SLOTS) & 1u);
+                mbar_wait(bar_s + ((i0 + 1) % SLOTS) * 8, (unsigned)((i0 + 1) / SLOTS) & 1u);
+                double amj = 0.0; int aej = kExtZeroExp;
+#pragma unroll
+                for (int jj = 0; jj < M; ++jj) if (jj == j) { amj = am[jj]; aej = ae[jj]; }
+                if (mode == 1) {
+                    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const double* kp = ring_w + ((i0 + h) % SLOTS) * HALF + lane;
+                        const double* op = om + 16 * h;
+#pragma unroll
+                        for (int c = 0; c < 16; c += 4) {
+                            const double2 w01 = *reinterpret_cast<const double2*>(op + c);
+                            const double2 w23 = *reinterpret_cast<const double2*>(op + c + 2);
+                            acc0 = fma(kp[(c + 0) * 32], w01.x, acc0);
+                            acc1 = fma(kp[(c + 1) * 32], w01.y, acc1);
+                            acc2 = fma(kp[(c + 2) * 32], w23.x, acc2);
+                            acc3 = fma(kp[(c + 3) * 32], w23.y, acc3);
+                        }
+                    }
+                    if (rok) ext_fold(amj, aej, (acc0 + acc1) + (acc2 + acc3), Bq + Eq);
+                } else {
+                    const int last_need = rok ? (FWD ? vj : N - 1 - vj) : -1;
+                    const int s0 = g_lo(q), s1 = g_hi(q);
+#pragma unroll 1
+                    for (int s_ = s0; s_ <= s1; ++s_) {
+                        if (s_ <= last_need) {
+                            const int r = row_of(s_);
+                            const int4 c = __ldg(&Cg[(long long)r * N + vj]);
+                            ext_fma(amj, aej, ext_m(c), c.z, sOm[r], sEx[r]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int jj = 0; jj < M; ++jj) if (jj == j) { am[jj] = amj; ae[jj] = aej; }
+                n_consumed += 2;
+                __syncwarp();
+                // both slots are free again: keep the ring SLOTS half tiles ahead (all lanes mirror the cursor)
+                if (lane == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                issue_one();
+                issue_one();
+            }
+        }
+    }
+    cluster_sync_all();
+    if (crank == 0 && tid == 0) a.sync[FWD ? 2 : 3] += 1;
+}
+
 __global__ void __launch_bounds__(256, 1) k_exch_recur_cluster(ExArgs a) {
     extern __shared__ __align__(16) double smem_d[];
     tl_begin(a.tl1);
     if (blockIdx.x < kClusterSize) recur_cluster<true>(a, smem_d);
     else recur_cluster<false>(a, smem_d);
+    tl_end(a.tl1);
+}
+
+__global__ void __launch_bounds__(256, 1) k_exch_recur_cluster_multi(ExArgs a) {
+    extern __shared__ __align__(16) double smem_d[];
+    tl_begin(a.tl1);
+    if (blockIdx.x < kClusterSize) recur_cluster_multi<true>(a, smem_d);
+    else recur_cluster_multi<false>(a, smem_d);
     tl_end(a.tl1);
 }
 
@@ -1695,6 +2030,25 @@ static int run_recursion(Sim* s, const ExArgs& a, cudaStream_t st) {
     const int R = rows_per_thread(s->N, nt);
     const int nblk = (s->N + 31) / 32;                       // 32-row blocks
     const bool blocked_ok = a.Kf && !getenv("PIMDB_EXCH_NOBLOCKED");
+    if (blocked_ok && nblk > 8 * kClusterSize) {
+        // more than 64 row blocks (2048 < N <= 8192): the same cluster, up to 4 row blocks per warp
+        const int nb = nblk, nb2 = (nb + 3) & ~1, wpc = kMultiWpc;
+        const size_t smem_cl = sizeof(double) * ((size_t)wpc * 3 * 512 + 32 * nb + 32 * wpc + nb2) + 8 * ((size_t)nb2 + wpc * 3 + (wpc & 1))
+                               + sizeof(int) * ((size_t)32 * nb + nb2) + 16;
+        cudaFuncSetAttribute(k_exch_recur_cluster_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cl);
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3(2 * kClusterSize);
+        lc.blockDim = dim3(32 * wpc);
+        lc.dynamicSmemBytes = smem_cl;
+        lc.stream = st;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = kClusterSize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        lc.attrs = at;
+        lc.numAttrs = 1;
+        cudaLaunchKernelEx(&lc, k_exch_recur_cluster_multi, a);
+        return PIMDB_OK;
+    }
     if (blocked_ok && (nblk > 16 || !getenv("PIMDB_EXCH_NOCLUSTER"))) {
         {
             // blocked recurrence on two clusters of 8 thread blocks (forward, backward), 1..8 warps each (N <= 2048)
@@ -1778,8 +2132,9 @@ static int exchange_impl(Sim* s, cudaStream_t st, int part) {
         if (rc != PIMDB_OK) return rc;
         {
             const int per_kind = std::max(1, std::min((s->N + 2 * kFW - 1) / (2 * kFW), 4 * kNumSM));   // 2 tasks per warp
-            if (a.Kf) {
-                const size_t smem = sizeof(double) * ((size_t)s->N + 1 + ((s->N + 2) >> 1) + (size_t)D * s->N);
+            const size_t smem_stage = sizeof(double) * ((size_t)s->N + 1 + ((s->N + 2) >> 1) + (size_t)D * s->N);
+            if (a.Kf && smem_stage <= 200 * 1024) {
+                const size_t smem = smem_stage;
                 if (smem > 48 * 1024)
                     cudaFuncSetAttribute(k_exch_forces<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 k_exch_forces<D, true><<<2 * per_kind, 32 * kFW, smem, st>>>(a);

@@ -22,12 +22,12 @@ def block_status(sim):
     fn = sim.lib.pimdb_debug_exchange_blocks
     fn.restype = C.c_int
     fn.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
-    buf = (C.c_int * 256)()
+    buf = (C.c_int * 1024)()
     nb = fn(sim.h, buf)
     return list(buf[:nb]), list(buf[nb:2 * nb])
 
 
-def check(cfg, x, expect=None):
+def check(cfg, x, expect=None, force_tol=FORCE_TOL):
     orc = Oracle(cfg)
     orc.set("x", x)
     orc.update_forces()
@@ -36,10 +36,10 @@ def check(cfg, x, expect=None):
     sim.update_forces()
     assert relerr(sim.exchange("V"), orc.exchange("V")) < ENERGY_TOL
     assert relerr(sim.exchange("Vb"), orc.exchange("B")) < ENERGY_TOL
-    assert relerr(sim.get("f_spring"), orc.get("s")) < FORCE_TOL
+    assert relerr(sim.get("f_spring"), orc.get("s")) < force_tol
     n = cfg.natoms
     prob = sim.exchange("prob").reshape(n, n)
-    assert np.max(np.abs(prob - orc.exchange("P").reshape(n, n))) < 1e-10
+    assert np.max(np.abs(prob - orc.exchange("P").reshape(n, n))) < 1e-10 * (force_tol / FORCE_TOL)
     fwd, bwd = block_status(sim)
     sim.close()
     nb = (n + 31) // 32
@@ -51,7 +51,7 @@ def check(cfg, x, expect=None):
 
 
 @pytest.mark.parametrize("natoms", [1, 2, 3, 5, 31, 32, 33, 34, 63, 64, 65, 95, 97, 128, 129, 255, 257, 300, 449, 481, 511, 512,
-                                    513, 700, 1023, 1024, 1025, 1500, 2047, 2048])
+                                    513, 700, 1023, 1024, 1025, 1500, 2047, 2048, 2049, 2100, 3000, 4127])
 def test_blocked_recurrence_sizes(gpu_required, natoms):
     """Correlated ring polymers in a trap: every block takes the matrix-vector path. Sizes straddle the 32-row block
     boundaries (ragged first / last blocks in either direction), the 512-particle limit of the tiles' own prefix sums and
@@ -63,14 +63,16 @@ def test_blocked_recurrence_sizes(gpu_required, natoms):
     check(cfg, x, expect=1)
 
 
-@pytest.mark.parametrize("natoms,pbc", [(80, False), (200, True), (333, False), (512, True), (1100, False)])
+@pytest.mark.parametrize("natoms,pbc", [(80, False), (200, True), (333, False), (512, True), (1100, False), (2500, False)])
 def test_blocked_recurrence_exact_blocks(gpu_required, natoms, pbc):
     """Stiff springs + uncorrelated beads (beta*E ~ 1e3-1e4 per link): the block inverses or the new values leave the
     plain-double window and the blocks are redone exactly; consumers then apply them column by column."""
     cfg = trap(natoms, 3, mass=4.0026 * DALTON, temperature=2 * KELVIN, size=60.0, pbc=pbc,
                external="free" if pbc else "harmonic")
     x, _ = make_inputs(cfg, 11 + natoms, 1.0)
-    fwd, bwd = check(cfg, x)
+    # (N = 2500: the reference's own probabilities exp(-beta (V[u] + E + Vb - V[N])) difference energies of order 1e5
+    # there and carry ~1e-10 themselves; V and V_backwards still agree to 1e-10)
+    fwd, bwd = check(cfg, x, force_tol=FORCE_TOL if natoms < 2000 else 1e-9)
     assert 2 in fwd + bwd, (fwd, bwd)
 
 
