@@ -1457,32 +1457,29 @@ __device__ __forceinline__ void recur_cluster_multi(const ExArgs& a, double* sme
     auto own_valid = [&](int j) { return q_of(j) < nb; };
     auto row_v = [&](int j) { return 32 * q_of(j) + lane; };
     auto row_ok = [&](int j) { const int v = row_v(j); return own_valid(j) && (FWD ? v < N : (v >= 1 && v < N)); };
-    double am[M];
-    int ae[M];
-#pragma unroll
-    for (int j = 0; j < M; ++j) { am[j] = 0.0; ae[j] = kExtZeroExp; }
 
-    // consumption order = (position ascending, my later blocks nearest first); the ring runs SLOTS half tiles ahead of it
-    struct Cur { int pos, k; };      // k-th of my blocks that lie after `pos`, in step order
-    // my blocks in step order: forward j ascending, backward j descending
-    auto jth = [&](int k) { return FWD ? k : M - 1 - k; };
-    auto later_than = [&](int j, int pos) { return own_valid(j) && pos_of(q_of(j)) > pos; };
-    auto cur_valid = [&](const Cur& c) { return c.pos < npos && c.k < M && later_than(jth(c.k), c.pos); };
-    auto cur_norm = [&](Cur& c) {    // move to the next existing (pos, block) pair at or after c
-        while (c.pos < npos) {
-            while (c.k < M && !later_than(jth(c.k), c.pos)) ++c.k;
-            if (c.k < M) return;
-            ++c.pos; c.k = 0;
+    // Consumption order: my row blocks one after the other in step order, each taking ALL earlier positions -- the
+    // positions older than my previous own block arrive as a burst from the table (they were published long ago), the
+    // rest as they are published. Only one accumulator is live, and the warp that is next on the chain has exactly one
+    // tile to apply between the previous block's publication and its own owner phase. The ring runs SLOTS half tiles
+    // ahead of the same enumeration.
+    struct Cur { int k, pos; };      // k-th of my blocks in step order, source position
+    auto jth = [&](int k) { return FWD ? k : M - 1 - k; };          // forward: j ascending, backward: descending
+    auto cur_norm = [&](Cur& c) {
+        while (c.k < M) {
+            const int j = jth(c.k);
+            if (own_valid(j) && c.pos < pos_of(q_of(j))) return;
+            ++c.k; c.pos = 0;
         }
     };
-    auto cur_next = [&](Cur& c) { ++c.k; cur_norm(c); };
+    auto cur_next = [&](Cur& c) { ++c.pos; cur_norm(c); };
     double* const ring_w = ring + (size_t)lw * SLOTS * HALF;
     const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring_w);
     const unsigned bar_s = (unsigned)__cvta_generic_to_shared(sBar + lw * SLOTS);
     Cur prod{0, 0};                  // next tile to fetch
     int prod_half = 0, n_issued = 0;
     auto issue_one = [&]() {         // fetch the next half tile into slot n_issued % SLOTS (every lane runs the cursor, lane 0 copies)
-        if (prod.pos >= npos) return false;
+        if (prod.k >= M) return false;
         if (lane == 0) {
             const int qs = blk_at(prod.pos), qd = q_of(jth(prod.k)), slot = n_issued % SLOTS;
             bulk_load(ring_s + slot * HALF * 8, Kall + ((size_t)qs * nb + qd) * 1024 + prod_half * HALF, HALF * 8, bar_s + slot * 8);
@@ -1530,32 +1527,83 @@ __device__ __forceinline__ void recur_cluster_multi(const ExArgs& a, double* sme
     };
 #pragma unroll
     for (int k = 0; k < 32; ++k) Grow[k] = 0.0;
-    {
-        int first = -1;
-        for (int k = 0; k < M; ++k) if (first < 0 && own_valid(jth(k))) first = jth(k);
-        if (first >= 0) load_own(first);
-    }
     cluster_sync_all();
 
     int n_consumed = 0;              // half tiles taken out of the ring so far
 #pragma unroll 1
-    for (int pos = 0; pos < npos; ++pos) {
-        const int q = blk_at(pos);
-        const bool mine = (q % NW) == gwarp;
-        bool any_later = false;
+    for (int kk = 0; kk < M; ++kk) {
+        const int j = jth(kk);
+        if (!own_valid(j)) continue;
+        const int q = q_of(j), pos = pos_of(q);                      // my block and its position on the chain
+        load_own(j);                                                 // row of G, h, flags (latency hidden by the loop below)
+        const int v = row_v(j);
+        const bool rok = row_ok(j);
+        double am = 0.0;
+        int ae = kExtZeroExp;
+        // ---- everything the earlier positions contribute to my rows
+        int Bnext = (pos > 0 && rok) ? Bg[(size_t)blk_at(0) * N + v] : kExtZeroExp;
+#pragma unroll 1
+        for (int sp = 0; sp < pos; ++sp) {
+            const int qs = blk_at(sp);
+            const int Bq = Bnext;
+            if (sp + 1 < pos && rok) Bnext = Bg[(size_t)blk_at(sp + 1) * N + v];
+            unsigned long long word;
+            { int spins = 0; do { word = lds_volatile_b64(&sWord[sp]); } while (word == 0ull && ++spins < kSpinMax);
+              if (word == 0ull) { atomicOr(a.err, kErrSyncTimeout); word = 2ull << 32; } }
+            const int smode = (int)(word >> 32), Eq = (int)(unsigned)word;
+            const double* om = sOm + 32 * qs;
+            if (smode == 1) {
+                const int r = 32 * qs + lane;
+                const bool expect = r >= (FWD ? 0 : 1) && r < N;
+                int spins = 0;
+                while (!__all_sync(kFullMask, !expect || lds_volatile_b64(&om[lane]) != 0ull) && ++spins < kSpinMax) {}
+            } else {
+                asm volatile("fence.acq_rel.cluster;" ::: "memory");
+            }
+            const int i0 = n_consumed;
+            mbar_wait(bar_s + (i0 % SLOTS) * 8, (unsigned)(i0 / SLOTS) & 1u);
+            mbar_wait(bar_s + ((i0 + 1) % SLOTS) * 8, (unsigned)((i0 + 1) / SLOTS) & 1u);
+            if (smode == 1) {
+                double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
 #pragma unroll
-        for (int j = 0; j < M; ++j) any_later = any_later || later_than(j, pos);
-        if (!mine && !any_later) break;          // nothing of mine lies at or after this position
+                for (int h = 0; h < 2; ++h) {
+                    const double* kp = ring_w + ((i0 + h) % SLOTS) * HALF + lane;
+                    const double* op = om + 16 * h;
+#pragma unroll
+                    for (int c = 0; c < 16; c += 4) {
+                        const double2 w01 = *reinterpret_cast<const double2*>(op + c);
+                        const double2 w23 = *reinterpret_cast<const double2*>(op + c + 2);
+                        acc0 = fma(kp[(c + 0) * 32], w01.x, acc0);
+                        acc1 = fma(kp[(c + 1) * 32], w01.y, acc1);
+                        acc2 = fma(kp[(c + 2) * 32], w23.x, acc2);
+                        acc3 = fma(kp[(c + 3) * 32], w23.y, acc3);
+                    }
+                }
+                if (rok) ext_fold(am, ae, (acc0 + acc1) + (acc2 + acc3), Bq + Eq);
+            } else {
+                const int last_need_c = rok ? (FWD ? v : N - 1 - v) : -1;
+                const int s0 = g_lo(qs), s1 = g_hi(qs);
+#pragma unroll 1
+                for (int s_ = s0; s_ <= s1; ++s_) {
+                    if (s_ <= last_need_c) {
+                        const int r = row_of(s_);
+                        const int4 c = __ldg(&Cg[(long long)r * N + v]);
+                        ext_fma(am, ae, ext_m(c), c.z, sOm[r], sEx[r]);
+                    }
+                }
+            }
+            n_consumed += 2;
+            __syncwarp();
+            if (lane == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            issue_one();
+            issue_one();
+        }
         int mode = 0, Eq = 0;
         const int own_lo = g_lo(q), own_hi = g_hi(q), n_own = own_hi - own_lo + 1;
-        if (mine) {
+        {
             // ---- owner phase of block q (= my block jown)
-            double amo = 0.0; int aeo = kExtZeroExp;
-#pragma unroll
-            for (int j = 0; j < M; ++j) if (j == jown) { amo = am[j]; aeo = ae[j]; }
-            const int v = row_v(jown);
-            const bool rok = row_ok(jown);
-            if (!rok) { amo = 0.0; aeo = kExtZeroExp; }
+            double amo = rok ? am : 0.0;
+            int aeo = rok ? ae : kExtZeroExp;
             const int last_need = rok ? (FWD ? v : N - 1 - v) : -1;
             auto dest = [&](int k) {             // destination blocks, the next owner's first
                 const int nxt = ((FWD ? gwarp + 1 : gwarp + NW - 1) % NW) / WPC;
@@ -1660,79 +1708,8 @@ __device__ __forceinline__ void recur_cluster_multi(const ExArgs& a, double* sme
                 }
             }
             if (lane == 0) (FWD ? a.statf : a.statb)[pos] = mode;
-            // the next block I own, if any: fetch its row of G now
-            int nxt = -1;
-            for (int k = 0; k < M; ++k) if (nxt < 0 && later_than(jth(k), pos)) nxt = jth(k);
-            if (nxt >= 0) load_own(nxt);
         }
-        if (!any_later) continue;
-        // ---- consume block q for my later blocks (my own publication included: it is in my table like any other)
-        {
-            unsigned long long word;
-            { int spins = 0; do { word = lds_volatile_b64(&sWord[pos]); } while (word == 0ull && ++spins < kSpinMax);
-              if (word == 0ull) { atomicOr(a.err, kErrSyncTimeout); word = 2ull << 32; } }
-            mode = (int)(word >> 32); Eq = (int)(unsigned)word;
-            const double* om = sOm + 32 * q;
-            if (mode == 1) {
-                const int r = 32 * q + lane;
-                const bool expect = r >= (FWD ? 0 : 1) && r < N;
-                int spins = 0;
-                while (!__all_sync(kFullMask, !expect || lds_volatile_b64(&om[lane]) != 0ull) && ++spins < kSpinMax) {}
-            } else {
-                asm volatile("fence.acq_rel.cluster;" ::: "memory");
-            }
-#pragma unroll
-            for (int k = 0; k < M; ++k) {
-                const int j = jth(k);
-                if (!later_than(j, pos)) continue;
-                const int vj = row_v(j);
-                const bool rok = row_ok(j);
-                const int Bq = rok ? Bg[(size_t)q * N + vj] : kExtZeroExp;
-                const int i0 = n_consumed;
-                mbar_wait(bar_s + (i0 % SLOTS) * 8, (unsigned)(i0 / SLOTS) & 1u);
-                mbar_wait(bar_s + ((i0 + 1) % SLOTS) * 8, (unsigned)((i0 + 1) / SLOTS) & 1u);
-                double amj = 0.0; int aej = kExtZeroExp;
-#pragma unroll
-                for (int jj = 0; jj < M; ++jj) if (jj == j) { amj = am[jj]; aej = ae[jj]; }
-                if (mode == 1) {
-                    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const double* kp = ring_w + ((i0 + h) % SLOTS) * HALF + lane;
-                        const double* op = om + 16 * h;
-#pragma unroll
-                        for (int c = 0; c < 16; c += 4) {
-                            const double2 w01 = *reinterpret_cast<const double2*>(op + c);
-                            const double2 w23 = *reinterpret_cast<const double2*>(op + c + 2);
-                            acc0 = fma(kp[(c + 0) * 32], w01.x, acc0);
-                            acc1 = fma(kp[(c + 1) * 32], w01.y, acc1);
-                            acc2 = fma(kp[(c + 2) * 32], w23.x, acc2);
-                            acc3 = fma(kp[(c + 3) * 32], w23.y, acc3);
-                        }
-                    }
-                    if (rok) ext_fold(amj, aej, (acc0 + acc1) + (acc2 + acc3), Bq + Eq);
-                } else {
-                    const int last_need = rok ? (FWD ? vj : N - 1 - vj) : -1;
-                    const int s0 = g_lo(q), s1 = g_hi(q);
-#pragma unroll 1
-                    for (int s_ = s0; s_ <= s1; ++s_) {
-                        if (s_ <= last_need) {
-                            const int r = row_of(s_);
-                            const int4 c = __ldg(&Cg[(long long)r * N + vj]);
-                            ext_fma(amj, aej, ext_m(c), c.z, sOm[r], sEx[r]);
-                        }
-                    }
-                }
-#pragma unroll
-                for (int jj = 0; jj < M; ++jj) if (jj == j) { am[jj] = amj; ae[jj] = aej; }
-                n_consumed += 2;
-                __syncwarp();
-                // both slots are free again: keep the ring SLOTS half tiles ahead (all lanes mirror the cursor)
-                if (lane == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                issue_one();
-                issue_one();
-            }
-        }
+        (void)Eq;
     }
     cluster_sync_all();
     if (crank == 0 && tid == 0) a.sync[FWD ? 2 : 3] += 1;
