@@ -1740,7 +1740,9 @@ __global__ void __launch_bounds__(256, 1) k_exch_recur_cluster_multi(ExArgs a) {
 // L2) before it uses the first one, so a task costs one L2 round trip instead of one per term.
 constexpr int kFW = 4;                       // warps per block (127 registers x 128 threads: fits where ONE pair-tile block retired)
 constexpr int kFU = 16;                      // terms per lane held in flight (covers N <= 512)
-template <int D, bool STAGE>
+// STAGE: 1 = weights, exponents and the bead slice in shared memory (N <= ~5000), 2 = weights and exponents only (the
+// slice is read from global memory; N <= 8192), 0 = nothing staged and no chunk skipping (larger N)
+template <int D, int STAGE>
 __global__ void __launch_bounds__(32 * kFW) k_exch_forces(ExArgs a) {
     extern __shared__ __align__(16) double fsm[];
     tl_begin(a.tl2);
@@ -1758,8 +1760,10 @@ __global__ void __launch_bounds__(32 * kFW) k_exch_forces(ExArgs a) {
         for (int u = threadIdx.x; u < N; u += blockDim.x) {
             if (which == 0) { gm[u] = a.Wbm[u + 1] * a.Inv[u + 1]; ge[u] = a.Wbe[u + 1]; }
             else { gm[u] = a.Wm[u]; ge[u] = a.We[u]; }
+            if (STAGE == 1) {
 #pragma unroll
-            for (int c = 0; c < D; ++c) xo[c * N + u] = xo_g[(size_t)c * N + u];
+                for (int c = 0; c < D; ++c) xo[c * N + u] = xo_g[(size_t)c * N + u];
+            }
         }
         __syncthreads();
     }
@@ -1769,7 +1773,7 @@ __global__ void __launch_bounds__(32 * kFW) k_exch_forces(ExArgs a) {
         e = a.We[u];
         return a.Wm[u];
     };
-    auto xo_of = [&](int c, int u) { return STAGE ? xo[c * N + u] : xo_g[(size_t)c * N + u]; };
+    auto xo_of = [&](int c, int u) { return STAGE == 1 ? xo[c * N + u] : xo_g[(size_t)c * N + u]; };
     const bool active = which == 0 ? a.do_first : a.do_last;
     const double iWN = 1.0 / a.Wm[N];
     const int eWN = a.We[N];
@@ -2109,14 +2113,18 @@ static int exchange_impl(Sim* s, cudaStream_t st, int part) {
         if (rc != PIMDB_OK) return rc;
         {
             const int per_kind = std::max(1, std::min((s->N + 2 * kFW - 1) / (2 * kFW), 4 * kNumSM));   // 2 tasks per warp
-            const size_t smem_stage = sizeof(double) * ((size_t)s->N + 1 + ((s->N + 2) >> 1) + (size_t)D * s->N);
-            if (a.Kf && smem_stage <= 200 * 1024) {
-                const size_t smem = smem_stage;
-                if (smem > 48 * 1024)
-                    cudaFuncSetAttribute(k_exch_forces<D, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-                k_exch_forces<D, true><<<2 * per_kind, 32 * kFW, smem, st>>>(a);
+            const size_t smem_w = sizeof(double) * ((size_t)s->N + 1 + ((s->N + 2) >> 1));            // weights + exponents
+            const size_t smem_full = smem_w + sizeof(double) * (size_t)D * s->N;                         // + the bead slice
+            if (a.Kf && smem_full <= 200 * 1024) {
+                if (smem_full > 48 * 1024)
+                    cudaFuncSetAttribute(k_exch_forces<D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_full);
+                k_exch_forces<D, 1><<<2 * per_kind, 32 * kFW, smem_full, st>>>(a);
+            } else if (a.Kf && smem_w <= 200 * 1024) {
+                if (smem_w > 48 * 1024)
+                    cudaFuncSetAttribute(k_exch_forces<D, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w);
+                k_exch_forces<D, 2><<<2 * per_kind, 32 * kFW, smem_w, st>>>(a);
             } else {
-                k_exch_forces<D, false><<<2 * per_kind, 32 * kFW, 0, st>>>(a);
+                k_exch_forces<D, 0><<<2 * per_kind, 32 * kFW, 0, st>>>(a);
             }
         }
         s->launches += 2;
