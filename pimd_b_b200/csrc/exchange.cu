@@ -413,9 +413,11 @@ __global__ void __launch_bounds__(1024, 2) k_exch_coeff_tiles(ExArgs a) {
     // tiled layout: the 32 x 32 tile (factor-row block rb, accumulating-row block sb) is one contiguous 8 KB piece
     // [factor row][accumulating row], so that a warp of the recurrence fetches it with two bulk copies
     {
+        // (tiles on the wrong side of the diagonal are never fetched -- the forward recurrence reads tiles with sb >= rb,
+        // the backward one tiles with sb <= rb -- and stay as allocated: zero)
         const size_t t = ((size_t)rb * nb + sb) * 1024 + ty * 32 + tx;
-        a.Kf[t] = kf;
-        a.Kb[t] = kb;
+        if (sb >= rb) a.Kf[t] = kf;
+        if (sb <= rb) a.Kb[t] = kb;
     }
     if (rb == sb) {
         __syncthreads();                             // s_e2 is free now: it becomes the scratch of the inversion
