@@ -152,26 +152,47 @@ class ShardedSimulation:
             torch.cuda.synchronize()
             return False
 
-    def step(self, nsteps: int = 1):
+    def step(self, nsteps: int = 1, finalize: bool = True):
+        """``finalize=False`` leaves the closing zeroMomentum of the last iteration pending (see ``_step_eager``); it is
+        carried out by ``flush()``, which ``observables()`` calls, or made redundant by the next ``step``."""
         g = getattr(self, "_graph", None)
         if g is not None:
             for _ in range(nsteps):
                 g.replay()
             return
-        self._step_eager(nsteps)
+        self._step_eager(nsteps, finalize)
 
-    def _step_eager(self, nsteps: int = 1):
+    def _step_eager(self, nsteps: int = 1, finalize: bool = True):
+        """One iteration of Simulation::run is  O, Z, B, A, forces, B, O, Z  (O: thermostat half step, Z: zeroMomentum).
+        Z is the projection p -> p - mean(p) and O is affine with the same coefficients for every degree of freedom
+        (p -> c1 p + c2 xi), so  Z O Z = Z O:  the closing Z of an iteration is subsumed by the first Z of the next one,
+        and between consecutive iterations its all-reduce and its kernel are skipped (the positions are updated after
+        a Z either way). Only the last iteration before the momenta are looked at carries it out (``flush``). Other
+        thermostats do not commute with Z like that, so they keep both."""
         s = self.shard
-        for _ in range(nsteps):
+        skip_closing = self.cfg.fixcom and self.cfg.thermostat in ("langevin", "none") and not self.cfg.nmthermostat
+        for it in range(nsteps):
+            self._com_pending = False    # a pending closing Z is subsumed by this iteration's first Z
             s.step_phase(0)          # thermostat half step (+ local momentum sums)
             self._allreduce_com()
             s.step_phase(1)          # COM removal, B, A
             self.exchange_halos()
             s.step_phase(2)          # forces, B, thermostat half step (+ local momentum sums)
+            if skip_closing and (it + 1 < nsteps or not finalize):
+                self._com_pending = True
+                continue
             self._allreduce_com()
             s.step_phase(3)          # COM removal
 
+    def flush(self):
+        """Carry out a closing zeroMomentum that ``step(..., finalize=False)`` left pending."""
+        if getattr(self, "_com_pending", False):
+            self._allreduce_com()
+            self.shard.step_phase(3)
+            self._com_pending = False
+
     def observables(self) -> dict:
+        self.flush()
         part = self.shard.observables_partial()
         if self.world > 1:
             dist.all_reduce(part, op=dist.ReduceOp.SUM, group=self.group)

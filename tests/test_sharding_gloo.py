@@ -84,7 +84,13 @@ def _worker(rank, world, port, cfg_dict, x, p, steps, out_dir, halo="p2p"):
     shard = NumpyShard(cfg, x, p, lo, hi)
     sim = ShardedSimulation(cfg, shard, halo=halo)
     sim.exchange_halos()
-    sim.step(steps)
+    if halo == "allgather":        # also exercise the pending closing zeroMomentum: left open, subsumed, flushed
+        sim.step(2, finalize=False)
+        sim.step(steps - 3, finalize=False)
+        sim.step(1, finalize=False)
+        sim.flush()
+    else:
+        sim.step(steps)
     obs = sim.observables()
     n = hi - lo
     np.savez(os.path.join(out_dir, f"rank{rank}.npz"), x=shard.x[1:n + 1].numpy(), p=shard.p.numpy(),
