@@ -65,7 +65,22 @@ __global__ void __launch_bounds__(256) k_assemble(AssembleArgs a) {
         if (a.scratch) {
             const int K = n / kTile, lane = n % kTile;
             const double* s = a.scratch + ((size_t)bl * a.T + K) * a.T * D * kTile + lane;
-            for (int m = 0; m < a.T; ++m) {
+            // (loads of 8 partials in flight at a time; the additions keep their order m = 0..T-1: bit-reproducible)
+            int m = 0;
+            for (; m + 8 <= a.T; m += 8) {
+                double v[8][D];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+#pragma unroll
+                    for (int c = 0; c < D; ++c) v[k][c] = s[((size_t)(m + k) * D + c) * kTile];
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+#pragma unroll
+                    for (int c = 0; c < D; ++c) phys[c] += v[k][c];
+                }
+            }
+            for (; m < a.T; ++m) {
 #pragma unroll
                 for (int c = 0; c < D; ++c) phys[c] += s[((size_t)m * D + c) * kTile];
             }
