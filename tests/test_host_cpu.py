@@ -153,3 +153,31 @@ def test_philox_known_answer_vectors():
     assert philox4x32_10((0xffffffff,) * 4, (0xffffffff,) * 2) == (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)
     assert philox4x32_10((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0)) == \
         (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """pimdb_config / pimdb_observables as declared in include/pimdb200.h (compiled with gcc) and as mirrored in
+    pimd_b_b200/_cabi.py must agree in size and in the offset of every field."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    from pimd_b_b200 import _cabi
+    gcc = shutil.which("gcc") or shutil.which("cc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    fields_cfg = [n for n, _ in _cabi.PimdbConfig._fields_]
+    fields_obs = [n for n, _ in _cabi.PimdbObservables._fields_]
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "pimdb200.h"', 'int main(void) {',
+           'printf("config %zu\\n", sizeof(pimdb_config));', 'printf("observables %zu\\n", sizeof(pimdb_observables));']
+    src += [f'printf("config.{n} %zu\\n", offsetof(pimdb_config, {n}));' for n in fields_cfg]
+    src += [f'printf("observables.{n} %zu\\n", offsetof(pimdb_observables, {n}));' for n in fields_obs]
+    src += ['return 0; }']
+    (tmp_path / "t.c").write_text("\n".join(src))
+    subprocess.check_call([gcc, "-I", str(ROOT / "include"), "-o", str(tmp_path / "t"), str(tmp_path / "t.c")])
+    out = dict(line.split() for line in subprocess.check_output([str(tmp_path / "t")], text=True).splitlines())
+    assert int(out["config"]) == C.sizeof(_cabi.PimdbConfig)
+    assert int(out["observables"]) == C.sizeof(_cabi.PimdbObservables)
+    for n in fields_cfg:
+        assert int(out[f"config.{n}"]) == getattr(_cabi.PimdbConfig, n).offset, n
+    for n in fields_obs:
+        assert int(out[f"observables.{n}"]) == getattr(_cabi.PimdbObservables, n).offset, n
