@@ -7,9 +7,13 @@
   Simulation::run (thermostat half step, COM removal, B, A, forces = pair + exchange + springs, B, thermostat half
   step, COM removal) on the headline system (He-4 Aziz, N=512, P=64, PBC); estimators are evaluated every `sfreq`
   steps inside the timed region. State is resident in HBM for `value`; `e2e` drives the same step through the
-  host-buffer API (upload x,p / step / download x,p,f every step).
-* N>1 (torchrun): beads are sharded over the ranks (pimd_b_b200.distributed), halo slices and the momentum sums
-  move over NCCL; time = max over ranks; the system is the same, so scaling is "strong".
+  host-buffer API (upload x,p / step / download x,p,f every step, page-locked host buffers).
+* N>1 (torchrun): beads are sharded over the ranks (pimd_b_b200.distributed.PeerShardedSimulation): halo slices and the
+  momentum sums are stored into the peers' memory over NVLink by the step's own kernels, one CUDA-graph replay per rank
+  and step, no host collective inside the timed region; time = max over ranks; the system is the same at every N, so
+  scaling is "strong". PIMDB_SHARD_MODE=nccl selects the host-driven NCCL choreography of round 1 for comparison.
+* The line also carries `c4`: the same measurement on He-4 N=2048 P=128 (BASELINE configs[3], the configuration that
+  names bead sharding), at every N.
 * --impl reference: the reference's own CPU implementation (oracle/_ref/pimdb_ndim3, unmodified sources, one
   process per bead on all host cores) on the same configuration and initial state.
 Prints ONE JSON line on rank 0.
@@ -46,6 +50,7 @@ def parse_args():
     ap.add_argument("--sfreq", type=int, default=1000, help="estimators every sfreq steps (reference default 1000)")
     ap.add_argument("--cpu-seconds", type=float, default=20.0, help="budget of the cpu_baseline leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-c4", action="store_true", help="skip the extra C4 measurement")
     ap.add_argument("--no-flush", action="store_true", help="do not flush L2 between timed steps (diagnostic)")
     return ap.parse_args()
 
@@ -59,6 +64,11 @@ def load_peaks():
         except Exception:
             pass
     return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def config_dict(name, cfg):
+    """Identical in both arms (the driver compares them)."""
+    return {"workload": workloads.DESCRIPTION[name], "natoms": cfg.natoms, "nbeads": cfg.nbeads, "ndim": cfg.ndim}
 
 
 # ------------------------------------------------------------------------------------------- clocks
@@ -137,8 +147,8 @@ def reference_main(args):
         "metric": METRIC, "value": sps, "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * res["sec_per_step"], "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
-        "config": {"workload": workloads.DESCRIPTION[args.workload], "natoms": cfg.natoms, "nbeads": cfg.nbeads,
-                   "ndim": cfg.ndim, "observables": "off"},
+        "config": config_dict(args.workload, cfg),
+        "details": {"observables": "off"},
         "cpu_baseline": {"value": sps, "unit": "steps/s", "cores": res["cores"], "kind": res["kind"],
                          "sample": f"{n} MD steps of the full workload after a 2-step warm-up run; "
                                    f"{res['ranks']} processes (one per bead) on {res['cores']} host cores, observables off"},
@@ -149,6 +159,205 @@ def reference_main(args):
 
 
 # ------------------------------------------------------------------------------------------- GPU arm
+class Runner:
+    """One workload on this rank's GPU: a full ring (world 1) or this rank's bead shard."""
+
+    def __init__(self, name, world, rank, local_rank, mode):
+        import torch
+        from pimd_b_b200.engine import DeviceSim
+        self.torch = torch
+        self.name, self.world, self.rank = name, world, rank
+        self.cfg = workloads.config(name)
+        self.x, self.p = workloads.initial_state(self.cfg, name)
+        self.dev = torch.device("cuda", local_rank)
+        self.mode = mode if world > 1 else "single"
+        cfg = self.cfg
+        if world == 1:
+            self.stream = torch.cuda.Stream(device=self.dev)
+            self.sim = DeviceSim(cfg, device=local_rank)
+            self.sim.set_stream(self.stream.cuda_stream)
+            self.lo, self.hi = 0, cfg.nbeads
+            self.sim.upload(self.x, self.p)
+            self.step = self.sim.step
+            self.observe = self.sim.observables
+            self.finish = lambda: None
+            self.launch_note = "CUDA graph replay (pimdb_step)"
+        elif self.mode == "peer":
+            from pimd_b_b200.distributed import PeerShardedSimulation
+            self.ps = PeerShardedSimulation(cfg, rank, world, local_rank)
+            self.sim, self.stream = self.ps.sim, self.ps.stream
+            self.lo, self.hi = self.ps.lo, self.ps.hi
+            self.ps.set_state(self.x, self.p)
+            self.step = self.ps.step
+            self.observe = self.ps.observables
+            self.finish = lambda: None   # the closing zeroMomentum left open between steps is carried out by whatever reads p
+            self.launch_note = ("one CUDA graph replay per rank and step; halo slices and momentum sums stored into the "
+                                "peers' memory by the step's kernels (no NCCL / host call inside the step)")
+        else:   # round-1 choreography: host-driven phases + NCCL
+            from pimd_b_b200.distributed import CudaShard, ShardedSimulation, bead_range
+            shard = CudaShard(cfg, rank, world, local_rank)
+            self.stream, self.sim = shard.stream, shard.sim
+            self.lo, self.hi = bead_range(cfg.nbeads, world, rank)
+            self.sim.set("x", self.x[self.lo:self.hi])
+            self.sim.set("p", self.p[self.lo:self.hi])
+            self.driver = ShardedSimulation(cfg, shard, halo=os.environ.get("PIMDB_SHARD_HALO", "p2p"))
+            with torch.cuda.stream(self.stream):
+                self.driver.exchange_halos()
+            self.step = lambda n=1: self.driver.step(n, finalize=False)
+            self.observe = self.driver.observables
+            self.finish = self.driver.flush
+            self.launch_note = "eager phases + NCCL point-to-point halos and all-reduces (PIMDB_SHARD_MODE=nccl)"
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, v: float) -> float:
+        if self.world == 1:
+            return v
+        import torch.distributed as dist
+        t = self.torch.tensor([v], dtype=self.torch.float64, device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def close(self):
+        self.barrier()
+        self.sim.close()
+
+
+def measure(run: Runner, K: int, W: int, sfreq: int, flush, clocks_rank0: bool, do_e2e: bool):
+    """W untimed steps, exactly K timed steps (CUDA events per step on the launching stream, L2 flushed in between),
+    a back-to-back pass, and the end-to-end pass through the host-buffer API."""
+    torch = run.torch
+    sim, stream = run.sim, run.stream
+    out = {}
+    with torch.cuda.stream(stream):
+        run.step(W)
+        run.observe()
+        run.barrier()
+        clocks = ClockSampler(run.dev.index) if clocks_rank0 and run.rank == 0 else None
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+        l0 = sim.launch_count
+        run.barrier()
+        wall0 = time.perf_counter()
+        for i in range(K):
+            if flush is not None:
+                flush.zero_()
+            ev[i][0].record(stream)
+            run.step(1)
+            if (i + 1) % sfreq == 0:
+                run.observe()
+            if i == K - 1:
+                run.finish()
+            ev[i][1].record(stream)
+        run.barrier()
+        wall1 = time.perf_counter()
+        out["gpu_launches"] = int(sim.launch_count - l0)
+        total_ms = run.max_over_ranks(sum(a.elapsed_time(b) for a, b in ev))
+        out["clocks"] = clocks.stop() if clocks else None
+        out["ms_per_step"] = total_ms / K
+        out["value"] = 1e3 * K / total_ms
+        out["wall_s_timed_region"] = wall1 - wall0
+
+        # back-to-back replay without flushes (diagnostic: what a production trajectory sees)
+        run.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        run.step(K)
+        e1.record(stream)
+        run.barrier()
+        out["ms_per_step_back_to_back"] = run.max_over_ranks(e0.elapsed_time(e1) / K)
+        out["steps_per_s_back_to_back"] = 1e3 / out["ms_per_step_back_to_back"]
+
+        if do_e2e:
+            # the same step through the host-buffer API: upload x,p -> step -> download x,p,f, page-locked host buffers
+            # (the library copies straight from / into them), one transpose kernel and one synchronisation per direction
+            shape = run.x[run.lo:run.hi].shape
+            pin = [torch.empty(shape, dtype=torch.float64, pin_memory=True) for _ in range(3)]
+            hx, hp, hf = (t.numpy() for t in pin)
+            sim.download(hx, hp, None)
+            Ke = max(20, min(K, 300))
+            for _ in range(3):
+                sim.upload(hx, hp); run.step(1); sim.download(hx, hp, hf)
+            run.barrier()
+            t0 = time.perf_counter()
+            for i in range(Ke):
+                sim.upload(hx, hp)
+                run.step(1)
+                sim.download(hx, hp, hf)
+            run.barrier()
+            e2e_s = run.max_over_ranks((time.perf_counter() - t0) / Ke)
+            slab = int(np.prod(shape)) * 8
+            out["e2e"] = {"value": 1.0 / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": 2 * slab * run.world,
+                          "d2h_bytes_per_step": 3 * slab * run.world, "steps": Ke,
+                          "call": "pimdb_upload_state(x,p) + pimdb_step(1) + pimdb_download_state(x,p,f), page-locked host buffers"}
+    return out
+
+
+def rooflines(run: Runner, hbm_peak, peak_src, fp64_peak):
+    """Pair-force kernel (FP64 pipe) and fused integrator (HBM), from an eager pass with CUDA events around every
+    launch of those kernels (every rank takes part: the steps are collective; rank 0 reports its own kernels)."""
+    torch, sim, cfg = run.torch, run.sim, run.cfg
+    nsteps = 40
+    with torch.cuda.stream(run.stream):
+        sim.timing_enable(True)
+        run.step(nsteps)
+        run.barrier()
+        pair_ms, npair = sim.timing_get(0)
+        step_ms, _ = sim.timing_get(1)
+        integ_ms, ninteg = sim.timing_get(2)
+        integ_bytes = sim.timing_integrator_bytes()
+        sim.timing_enable(False)
+    nloc = run.hi - run.lo
+    roofline = None
+    if cfg.interaction != "free" and npair:
+        flops = workloads.pair_flops_per_step(cfg) * nloc / cfg.nbeads / max(1, npair // nsteps)
+        ach = flops / (pair_ms * 1e-3) * 1e-12
+        traffic, fp64_pipe = None, {}
+        try:
+            prof = json.loads((ROOT / "profiles" / "r02_ncu_summary.json").read_text())
+            if run.name == "c3" and run.world == 1:
+                traffic = prof["kernels"]["k_pair_tiles"]["dram_traffic_bytes"]
+            fp64_pipe = {k: v.get("fp64_pipe_pct") for k, v in prof["kernels"].items()}
+        except Exception:
+            pass
+        roofline = {"kernel": "k_pair_tiles", "bound": "fp64", "achieved": ach, "peak": fp64_peak, "unit": "TFLOP/s",
+                    "frac": ach / fp64_peak if fp64_peak else None, "traffic": traffic,
+                    "traffic_source": "profiles/r02_ncu_summary.json (ncu --set full, bytes per launch, N=1 C3 capture)",
+                    "peak_source": "DFMA micro-benchmark in this run (MEASURED_PEAKS.json has no FP64 figure)",
+                    "flops_per_launch": flops, "ms_per_launch": pair_ms, "launches_timed": npair,
+                    "share_of_step": pair_ms * (npair / nsteps) / step_ms if step_ms else None,
+                    "eager_step_ms": step_ms, "fp64_pipe_pct_ncu": fp64_pipe}
+    ach_gbs = integ_bytes / (integ_ms * 1e-3) * 1e-9 if integ_ms else None
+    integ = {"kernel": "k_integrate", "bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
+             "frac": ach_gbs / hbm_peak if ach_gbs else None, "peak_source": peak_src,
+             "bytes_per_launch": integ_bytes, "ms_per_launch": integ_ms, "launches_per_step": ninteg / nsteps,
+             "note": "algorithmic bytes (p, f, x once per stage group + pair partials where the closing kick assembles the "
+                     "forces) / CUDA-event time per launch; at C3 the state is L2-resident and a launch is bounded by "
+                     "launch latency (~2 us), not by HBM",
+             "bytes_per_step_survey": workloads.integrator_bytes_per_step(cfg) * nloc / cfg.nbeads}
+    return roofline, integ
+
+
+def scrambled_pair_time(name, local_rank, torch):
+    """The pair kernel's far-rotation shortcut depends on how well particle order follows space: time it again with the
+    particle order scrambled (same positions, random labels)."""
+    from pimd_b_b200.engine import DeviceSim
+    cfg = workloads.config(name)
+    x, p = workloads.initial_state(cfg, name)
+    perm = np.random.default_rng(7).permutation(cfg.natoms)
+    sim = DeviceSim(cfg, device=local_rank)
+    sim.upload(np.ascontiguousarray(x[:, perm]), np.ascontiguousarray(p[:, perm]))
+    sim.timing_enable(True)
+    sim.step(20)
+    ms, n = sim.timing_get(0)
+    sim.timing_enable(False)
+    sim.close()
+    return ms
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -157,7 +366,6 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from pimd_b_b200.engine import DeviceSim
     from pimd_b_b200 import _cabi
     import ctypes as C
 
@@ -171,183 +379,52 @@ def main():
         raise RuntimeError("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    mode = os.environ.get("PIMDB_SHARD_MODE", "peer")
 
-    cfg = workloads.config(args.workload)
-    x, p = workloads.initial_state(cfg, args.workload)
     hbm_peak, peak_src = load_peaks()
     K, W = args.steps, max(args.warmup, 3)
-
     flush = None if args.no_flush else torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=dev)
+    lib = _cabi.load()
+    pk = C.c_double()
+    lib.pimdb_bench_fp64_peak(local_rank, C.byref(pk))
+    fp64_peak = pk.value
 
-    if world == 1:
-        stream = torch.cuda.Stream(device=dev)
-        sim = DeviceSim(cfg, device=local_rank)
-        sim.set_stream(stream.cuda_stream)
-        sim.set("x", x)
-        sim.set("p", p)
-        stepper = lambda n=1: sim.step(n)
-        observe = sim.observables
-        launch_count = lambda: sim.launch_count
-        lo, hi = 0, cfg.nbeads
-    else:
-        from pimd_b_b200.distributed import CudaShard, ShardedSimulation, bead_range
-        shard = CudaShard(cfg, rank, world, local_rank)
-        stream = shard.stream
-        sim = shard.sim
-        lo, hi = bead_range(cfg.nbeads, world, rank)
-        sim.set("x", x[lo:hi])
-        sim.set("p", p[lo:hi])
-        driver = ShardedSimulation(cfg, shard, halo=os.environ.get("PIMDB_SHARD_HALO", "p2p"))
-        with torch.cuda.stream(stream):
-            driver.exchange_halos()
-        # between consecutive steps the closing zeroMomentum of an iteration is subsumed by the first one of the next
-        # (distributed.py: Z O Z = Z O); it is carried out before anything looks at the momenta (observables, the end
-        # of the timed region)
-        stepper = lambda n=1: driver.step(n, finalize=False)
-        observe = driver.observables
-        launch_count = lambda: sim.launch_count
+    # ---- headline workload
+    run = Runner(args.workload, world, rank, local_rank, mode)
+    cfg = run.cfg
+    m = measure(run, K, W, args.sfreq, flush, clocks_rank0=True, do_e2e=True)
+    roofline, integ = rooflines(run, hbm_peak, peak_src, fp64_peak) if mode != "nccl" or world == 1 else (None, None)
+    launch_note = run.launch_note
+    x0, p0 = run.x, run.p
+    run.close()
+    if roofline is not None and world == 1 and rank == 0:
+        try:
+            ms_scr = scrambled_pair_time(args.workload, local_rank, torch)
+            roofline["ms_per_launch_scrambled_order"] = ms_scr
+            roofline["frac_scrambled_order"] = roofline["flops_per_launch"] / (ms_scr * 1e-3) * 1e-12 / fp64_peak
+        except Exception as exc:
+            roofline["ms_per_launch_scrambled_order"] = f"failed: {exc}"
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    graph_note = "CUDA graph replay (pimdb_step)"
-    launches_per_step = None
-    with torch.cuda.stream(stream):
-        # ---- warm-up (W >= 3 untimed steps; also captures the CUDA graph)
-        stepper(W)
-        observe()
-        barrier()
-        if world > 1:
-            l_a = launch_count()
-            stepper(1)
-            launches_per_step = launch_count() - l_a      # kernels of one sharded step (NCCL kernels not counted)
-            # Capturing the NCCL point-to-point calls hung on this pool's boxes (round 1): opt-in only.
-            ok = driver.enable_graph() if os.environ.get("PIMDB_SHARD_GRAPH") == "1" else False
-            if not ok and not hasattr(driver, "_graph_error"):
-                driver._graph_error = "disabled (set PIMDB_SHARD_GRAPH=1 to try)"
-            flags = torch.tensor([1.0 if ok else 0.0], device=dev)
-            dist.all_reduce(flags, op=dist.ReduceOp.MIN)
-            if flags.item() < 0.5:
-                driver._graph = None
-            graph_note = ("torch CUDA graph of the sharded step incl. NCCL halo + all-reduce" if flags.item() > 0.5
-                          else "eager phases + NCCL (graph capture unavailable: %s)" % getattr(driver, "_graph_error", "?"))
-            barrier()
-
-        # ---- timed region: exactly K steps, L2 flushed between steps, CUDA events on the launching stream
-        clocks = ClockSampler(local_rank) if rank == 0 else None
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
-        l0 = launch_count()
-        barrier()
-        wall0 = time.perf_counter()
-        for i in range(K):
-            if flush is not None:
-                flush.zero_()
-            ev[i][0].record(stream)
-            stepper(1)
-            if (i + 1) % args.sfreq == 0:
-                observe()
-            if i == K - 1 and world > 1:
-                driver.flush()       # the pending closing zeroMomentum belongs to the timed region
-            ev[i][1].record(stream)
-        barrier()
-        wall1 = time.perf_counter()
-        gpu_launches = launch_count() - l0
-        if launches_per_step is not None and getattr(driver, "_graph", None) is not None:
-            gpu_launches = launches_per_step * K + (launch_count() - l0)   # graph replays do not pass through the library's counter
-        total_ms = sum(a.elapsed_time(b) for a, b in ev)
-        clk = clocks.stop() if clocks else None
-        if world > 1:
-            t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            total_ms = float(t.item())
-        ms_per_step = total_ms / K
-        value = 1e3 / ms_per_step
-
-        # ---- back-to-back replay without flushes (diagnostic: what a production trajectory sees)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(stream)
-        stepper(K)
-        e1.record(stream)
-        barrier()
-        b2b_ms = e0.elapsed_time(e1) / K
-        if world > 1:
-            t = torch.tensor([b2b_ms], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            b2b_ms = float(t.item())
-
-        # ---- e2e: the same step through the host-buffer API (upload x,p -> step -> download x,p,f)
-        nloc = hi - lo
-        # page-locked host buffers (the library copies straight from / into them; pageable buffers are staged)
-        pin = [torch.empty(x[lo:hi].shape, dtype=torch.float64, pin_memory=True) for _ in range(3)]
-        hx, hp, hf = (t.numpy() for t in pin)
-        hx[...] = x[lo:hi]
-        hp[...] = p[lo:hi]
-        sim.get("x", hx)
-        sim.get("p", hp)
-        Ke = max(20, min(K, 200))
-        barrier()
-        t0 = time.perf_counter()
-        for i in range(Ke):
-            sim.set("x", hx)
-            sim.set("p", hp)
-            if world > 1:
-                driver.exchange_halos()
-            stepper(1)
-            sim.get("x", hx)
-            sim.get("p", hp)
-            sim.get("f", hf)
-        barrier()
-        e2e_s = (time.perf_counter() - t0) / Ke
-        if world > 1:
-            t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = float(t.item())
-        slab_bytes = nloc * cfg.natoms * cfg.ndim * 8
-        e2e = {"value": 1.0 / e2e_s, "unit": "steps/s", "h2d_bytes_per_step": 2 * slab_bytes * world,
-               "d2h_bytes_per_step": 3 * slab_bytes * world, "steps": Ke,
-               "call": "pimdb_set_state(x,p) + pimdb_step(1) + pimdb_get_state(x,p,f), page-locked host buffers"}
-
-        # ---- roofline of the dominant kernel (pair-force tiles), eager pass with CUDA events per launch
-        roofline = None
-        integ = None
-        if rank == 0:
-            lib = _cabi.load()
-            pk = C.c_double()
-            lib.pimdb_bench_fp64_peak(local_rank, C.byref(pk))
-            fp64_peak = pk.value
-            if world == 1 and cfg.interaction != "free":
-                sim.timing_enable(True)
-                sim.step(50)
-                pair_ms, npair = sim.timing_get(0)
-                step_ms, _ = sim.timing_get(1)
-                sim.timing_enable(False)
-                flops = workloads.pair_flops_per_step(cfg) / max(1, (npair // 50))
-                ach = flops / (pair_ms * 1e-3) * 1e-12
-                traffic = None   # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture
-                try:
-                    prof = json.loads((ROOT / "profiles" / "r01_ncu_summary.json").read_text())
-                    if args.workload == "c3":
-                        traffic = prof["kernels"]["k_pair_tiles"]["dram_traffic_bytes"]
-                except Exception:
-                    pass
-                roofline = {"kernel": "k_pair_tiles", "bound": "fp64", "achieved": ach, "peak": fp64_peak,
-                            "unit": "TFLOP/s", "frac": ach / fp64_peak if fp64_peak else None, "traffic": traffic,
-                            "traffic_source": "profiles/r01_ncu_summary.json (ncu --set full, bytes per launch)",
-                            "peak_source": "DFMA micro-benchmark in this run (MEASURED_PEAKS.json has no FP64 figure)",
-                            "flops_per_launch": flops, "ms_per_launch": pair_ms, "launches_timed": npair,
-                            "share_of_step": pair_ms * (npair / 50) / step_ms if step_ms else None,
-                            "eager_step_ms": step_ms}
-            integ = {"bound": "hbm", "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_src,
-                     "bytes_per_step": workloads.integrator_bytes_per_step(cfg)}
+    # ---- C4 (the configuration that names bead sharding), at every N
+    c4 = None
+    if args.workload == "c3" and not args.no_c4:
+        try:
+            run4 = Runner("c4", world, rank, local_rank, mode)
+            K4 = max(20, min(K, 200))
+            m4 = measure(run4, K4, 5, 10 ** 9, flush, clocks_rank0=False, do_e2e=False)
+            r4, i4 = rooflines(run4, hbm_peak, peak_src, fp64_peak) if mode != "nccl" or world == 1 else (None, None)
+            c4 = {"config": config_dict("c4", run4.cfg), "steps_per_s": m4["value"], "ms_per_step": m4["ms_per_step"], "steps": K4,
+                  "steps_per_s_back_to_back": m4["steps_per_s_back_to_back"], "gpu_launches": m4["gpu_launches"],
+                  "frac": r4["frac"] if r4 else None, "roofline": r4, "roofline_integrator": i4}
+            run4.close()
+        except Exception as exc:   # never lose the headline line to the extra measurement
+            c4 = {"failed": repr(exc)}
 
     # ---- CPU baseline (rank 0, N=1 only): the reference's own implementation on the host cores
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
-            res, n = run_reference(args, cfg, x, p, budget_s=args.cpu_seconds)
+            res, n = run_reference(args, cfg, x0, p0, budget_s=args.cpu_seconds)
             cpu_baseline = {"value": 1.0 / res["sec_per_step"], "unit": "steps/s", "cores": res["cores"],
                             "kind": res["kind"],
                             "sample": f"{n} MD steps of the full workload (same config and initial state), "
@@ -358,18 +435,18 @@ def main():
 
     if rank == 0:
         line = {
-            "metric": METRIC, "value": value, "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "metric": METRIC, "value": m["value"], "unit": "steps/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workloads.DESCRIPTION[args.workload], "natoms": cfg.natoms, "nbeads": cfg.nbeads,
-                       "ndim": cfg.ndim, "parallelism": f"bead-sharded x{world}" if world > 1 else "single GPU",
-                       "l2": "flushed between timed steps (256 MiB write)" if flush is not None else "not flushed",
-                       "estimators_every": args.sfreq, "timing": "CUDA events per step on the launching stream, max over ranks",
-                       "launch": graph_note},
-            "ms_per_step_back_to_back": b2b_ms, "steps_per_s_back_to_back": 1e3 / b2b_ms,
-            "wall_s_timed_region": wall1 - wall0,
-            "e2e": e2e, "gpu_launches": int(gpu_launches), "clocks": clk,
-            "roofline": roofline, "roofline_integrator": integ, "cpu_baseline": cpu_baseline,
+            "config": config_dict(args.workload, cfg),
+            "details": {"parallelism": f"bead-sharded x{world}" if world > 1 else "single GPU",
+                        "l2": "flushed between timed steps (256 MiB write)" if flush is not None else "not flushed",
+                        "estimators_every": args.sfreq,
+                        "timing": "CUDA events per step on the launching stream, max over ranks", "launch": launch_note},
+            "ms_per_step_back_to_back": m["ms_per_step_back_to_back"], "steps_per_s_back_to_back": m["steps_per_s_back_to_back"],
+            "wall_s_timed_region": m["wall_s_timed_region"],
+            "e2e": m["e2e"], "gpu_launches": m["gpu_launches"], "clocks": m["clocks"],
+            "roofline": roofline, "roofline_integrator": integ, "c4": c4, "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PIMDB_ABI_VERSION 1
+#define PIMDB_ABI_VERSION 2
 
 enum pimdb_status {
     PIMDB_OK = 0,
@@ -158,6 +158,13 @@ const char* pimdb_last_error(const pimdb_sim* sim);
 int pimdb_set_state(pimdb_sim* sim, int which, const double* host);
 int pimdb_get_state(pimdb_sim* sim, int which, double* host);
 
+/* Several arrays per call: one PCIe copy per array back to back and ONE transpose kernel (upload), one transpose kernel,
+ * the copies and ONE synchronisation (download). NULL = skip that array. Same layout and buffer rules as above; the
+ * caller's buffers may be reused as soon as the call returns. What a host loop that keeps its own copy of the state
+ * pays per step (bench.py's e2e figure). */
+int pimdb_upload_state(pimdb_sim* sim, const double* x, const double* p);
+int pimdb_download_state(pimdb_sim* sim, double* x, double* p, double* f);
+
 /* ---- the reference's per-step calls, one by one (so its loop order can be driven call by call) ------- */
 /* Simulation::updateNeighboringCoordinates (src/simulation.cpp:379-382, getPrev/NextCoords :299-347).
  * With all beads on one handle it fills the two halo slices by ring wrap; with bead sharding the host
@@ -212,12 +219,33 @@ void* pimdb_com_ptr(pimdb_sim* sim);
  *   3: COM removal */
 int pimdb_step_phase(pimdb_sim* sim, int phase);
 
+/* ---- bead sharding over peer memory (one handle per GPU; NVLink peer stores instead of host-driven collectives) ----
+ * Replaces the MPI_Sendrecv of getPrev/NextCoords (src/simulation.cpp:299-347) and the MPI_Allreduce of zeroMomentum
+ * (:595) by stores into the peers' memory issued by the step's own kernels. Start-up, on every rank:
+ *     pimdb_create(cfg with this rank's [bead_begin, bead_end))  ->  pimdb_peer_export(blob)
+ *     gather the blobs of all ranks in rank order (any transport: torch.distributed, MPI, a pipe; a single process that
+ *     drives several GPUs just concatenates them)  ->  pimdb_peer_attach(world, rank, blobs)
+ * After that pimdb_step, the call-by-call entry points, pimdb_update_forces and pimdb_observables_calc work on the shard
+ * (observables stay per-handle partial sums). Every rank must make the same sequence of calls; device-side waits are
+ * bounded (PIMDB_PEER_TIMEOUT_MS, default 20 s) and a peer that never shows up surfaces as PIMDB_ERR_RUNTIME at the next
+ * synchronising call. With fixcom and a Langevin thermostat (or none) the closing zeroMomentum of an iteration is
+ * subsumed by the first one of the next (Z O Z = Z O); it is carried out when the momenta are read, so reading them is a
+ * collective operation too. Cartesian propagator / thermostat coupling only. */
+#define PIMDB_PEER_BLOB_BYTES 256
+int pimdb_peer_export(pimdb_sim* sim, void* blob_out /* PIMDB_PEER_BLOB_BYTES */);
+int pimdb_peer_attach(pimdb_sim* sim, int world, int rank, const void* blobs /* world x PIMDB_PEER_BLOB_BYTES */);
+int pimdb_peer_attached(const pimdb_sim* sim);
+
 /* Number of kernels this handle has launched (graph replays count their kernel nodes). */
 unsigned long long pimdb_launch_count(const pimdb_sim* sim);
-/* Average duration in ms of the pair-force kernel / of whole steps over the launches recorded since
+/* Average duration in ms of the pair-force kernel (what = 0) / of whole steps (1) over the launches recorded since
  * pimdb_timing_reset, measured with CUDA events on the handle's stream (bench.py's roofline). */
 int pimdb_timing_enable(pimdb_sim* sim, int on);
 int pimdb_timing_get(pimdb_sim* sim, int what, double* ms_avg, unsigned long long* count);
+/* what = 2 of pimdb_timing_get averages over the fused integrator launches; this returns their algorithmic bytes per
+ * launch (p, f, x read / written once per stage group, plus the pair partials when the closing kick
+ * assembles the forces), so that achieved GB/s = bytes / time. */
+int pimdb_timing_integrator_bytes(pimdb_sim* sim, double* bytes_per_launch);
 /* Measured FP64 FMA throughput of the device (TFLOP/s, dependent-FMA micro-benchmark): the denominator of the
  * pair-force roofline, which MEASURED_PEAKS.json does not provide. Not part of the reference surface. */
 int pimdb_bench_fp64_peak(int device, double* tflops);

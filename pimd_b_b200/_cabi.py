@@ -15,6 +15,8 @@ from pathlib import Path
 LIB_PATH = Path(os.environ.get("PIMDB200_LIB") or Path(__file__).resolve().parent / "libpimdb200.so")
 
 PIMDB_OK, ERR_INVALID_ARGUMENT, ERR_OVERFLOW, ERR_RUNTIME, ERR_CUDA = range(5)
+ABI_VERSION = 2
+PEER_BLOB_BYTES = 256
 
 POTENTIAL = {"free": 0, "aziz": 1, "harmonic": 2, "dipole": 3, "double_well": 4, "cosine": 5}
 PROPAGATOR = {"cartesian": 0, "normal_modes": 1}
@@ -62,6 +64,8 @@ SYMBOLS = {
     "pimdb_last_error": (C.c_char_p, [_VP]),
     "pimdb_set_state": (C.c_int, [_VP, C.c_int, _VP]),
     "pimdb_get_state": (C.c_int, [_VP, C.c_int, _VP]),
+    "pimdb_upload_state": (C.c_int, [_VP, _VP, _VP]),
+    "pimdb_download_state": (C.c_int, [_VP, _VP, _VP, _VP]),
     "pimdb_update_neighbors": (C.c_int, [_VP]),
     "pimdb_update_forces": (C.c_int, [_VP]),
     "pimdb_moment_step": (C.c_int, [_VP]),
@@ -79,9 +83,13 @@ SYMBOLS = {
     "pimdb_halo_ptr": (_VP, [_VP, C.c_int, C.POINTER(C.c_size_t)]),
     "pimdb_com_ptr": (_VP, [_VP]),
     "pimdb_step_phase": (C.c_int, [_VP, C.c_int]),
+    "pimdb_peer_export": (C.c_int, [_VP, _VP]),
+    "pimdb_peer_attach": (C.c_int, [_VP, C.c_int, C.c_int, _VP]),
+    "pimdb_peer_attached": (C.c_int, [_VP]),
     "pimdb_launch_count": (C.c_ulonglong, [_VP]),
     "pimdb_timing_enable": (C.c_int, [_VP, C.c_int]),
     "pimdb_timing_get": (C.c_int, [_VP, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]),
+    "pimdb_timing_integrator_bytes": (C.c_int, [_VP, C.POINTER(C.c_double)]),
     "pimdb_bench_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double)]),
 }
 

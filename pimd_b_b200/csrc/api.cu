@@ -4,6 +4,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <new>
+#include <unistd.h>
 
 #include "internal.cuh"
 
@@ -134,8 +135,8 @@ static void free_all(Sim* s) {
     cudaSetDevice(s->device);
     if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
     if (s->graph) cudaGraphDestroy(s->graph);
-    for (auto& e : s->ev_pair) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
-    for (auto& e : s->ev_step) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+    for (auto* v : {&s->ev_pair, &s->ev_step, &s->ev_integ})
+        for (auto& e : *v) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     cudaFree(s->x); cudaFree(s->p); cudaFree(s->f); cudaFree(s->fs); cudaFree(s->fp);
     cudaFree(s->stage_d); cudaFreeHost(s->stage_h);
     cudaFree(s->tile_ij); cudaFree(s->pair_scratch);
@@ -145,8 +146,11 @@ static void free_all(Sim* s) {
     cudaFree(s->obs_d); cudaFreeHost(s->obs_h); cudaFree(s->obs_part);
     cudaFreeHost(s->err_h);
     cudaFree(s->nmC); cudaFree(s->nmFreq); cudaFree(s->nh_state);
+    for (void* m : s->ipc_opened) cudaIpcCloseMemHandle(m);
+    cudaFree(s->mailbox); cudaFree(s->peer_seq);
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     if (s->ev_join) cudaEventDestroy(s->ev_join);
+    if (s->ev_copy) cudaEventDestroy(s->ev_copy);
     if (s->stream_x) cudaStreamDestroy(s->stream_x);
     if (s->stream_r) cudaStreamDestroy(s->stream_r);
     if (s->ev_join2) cudaEventDestroy(s->ev_join2);
@@ -239,8 +243,9 @@ extern "C" int pimdb_create(const pimdb_config* cfg, pimdb_sim** out) {
     CREATE_TRY(cudaMalloc(&s->f, own_bytes));
     CREATE_TRY(cudaMalloc(&s->fs, own_bytes));
     CREATE_TRY(cudaMalloc(&s->fp, own_bytes));
-    CREATE_TRY(cudaMalloc(&s->stage_d, own_bytes));
-    CREATE_TRY(cudaHostAlloc(&s->stage_h, own_bytes, cudaHostAllocDefault));
+    CREATE_TRY(cudaMalloc(&s->stage_d, 3 * own_bytes));
+    CREATE_TRY(cudaHostAlloc(&s->stage_h, 3 * own_bytes, cudaHostAllocDefault));
+    CREATE_TRY(cudaEventCreateWithFlags(&s->ev_copy, cudaEventDisableTiming));
     CREATE_TRY(cudaMemset(s->x, 0, slab_bytes * (s->Ploc + 2)));
     CREATE_TRY(cudaMemset(s->p, 0, own_bytes));
     CREATE_TRY(cudaMemset(s->f, 0, own_bytes));    // forces start at zero like the reference's (App. A-1)
@@ -300,6 +305,12 @@ extern "C" int pimdb_create(const pimdb_config* cfg, pimdb_sim** out) {
         const int rc = ranmars_create(s);
         if (rc != PIMDB_OK) { g_create_error = s->err; free_all(s); return rc; }
     }
+    if (!s->all_local) {   // mailbox + counters of the peer-memory sharding protocol (pimdb_peer_export / _attach)
+        CREATE_TRY(cudaMalloc(&s->mailbox, sizeof(PeerMailbox)));
+        CREATE_TRY(cudaMemset(s->mailbox, 0, sizeof(PeerMailbox)));
+        CREATE_TRY(cudaMalloc(&s->peer_seq, sizeof(unsigned int) * 4));
+        CREATE_TRY(cudaMemset(s->peer_seq, 0, sizeof(unsigned int) * 4));
+    }
     CREATE_TRY(cudaMalloc(&s->com_part, sizeof(double) * 4 * kMaxPartials));
     CREATE_TRY(cudaMalloc(&s->com, sizeof(double) * 4));
     CREATE_TRY(cudaMemset(s->com, 0, sizeof(double) * 4));
@@ -349,6 +360,9 @@ static int check_deferred(Sim* s) {
     if (*s->err_h != 0) {
         const int e = *s->err_h;
         *s->err_h = 0;
+        if (e & kErrPeerTimeout)
+            return fail(s, PIMDB_ERR_RUNTIME, "bead shard timed out waiting for a peer GPU (halo slice / momentum sums); every rank must "
+                                              "make the same sequence of calls");
         if (e & kErrSyncTimeout)
             return fail(s, PIMDB_ERR_RUNTIME, "exchange recurrence timed out waiting for its factor tiles (kernels serialised by a "
                                               "profiler? set PIMDB_EXCH_SERIAL=1)");
@@ -390,53 +404,106 @@ static bool host_is_pinned(const void* ptr) {
     return at.type == cudaMemoryTypeHost;
 }
 
+// f_spring / f_phys after a step that assembled the forces inside its closing integrator kernel: rebuilt on request from
+// the pair partials and exterior forces of that evaluation, which are still in place
+static int refresh_split_forces(Sim* s) {
+    if (!s->split_stale) return PIMDB_OK;
+    return launch_assemble_chunk(s, 0, s->Ploc, s->pair_on);
+}
+
+// One upload = one asynchronous PCIe copy per array (straight from a page-locked caller buffer, through the pinned
+// staging buffer otherwise) + ONE transpose kernel for all of them.
+static int upload_arrays(Sim* s, int n, const int* which, const double* const* host) {
+    const size_t count = s->S * s->Ploc, bytes = count * sizeof(double);
+    double* dst[3]; bool halo[3];
+    if (n < 1 || n > 3) return fail(s, PIMDB_ERR_INVALID_ARGUMENT, "1 to 3 arrays per transfer");
+    bool all_pinned = true;
+    for (int i = 0; i < n; ++i) {
+        dst[i] = array_ptr(s, which[i], halo[i]);
+        if (!dst[i] || !host[i]) return fail(s, PIMDB_ERR_INVALID_ARGUMENT, "unknown state array");
+        all_pinned = all_pinned && host_is_pinned(host[i]);
+        if (which[i] == PIMDB_P) { s->p_shift_pending = false; s->z_owed = false; }   // the caller replaces the momenta
+    }
+    if (!all_pinned) PIMDB_CUDA_TRY(s, cudaStreamSynchronize(s->stream));   // the pinned staging buffer is about to be rewritten
+    for (int i = 0; i < n; ++i) {
+        const double* src = host[i];
+        if (!all_pinned) { memcpy(s->stage_h + i * count, host[i], bytes); src = s->stage_h + i * count; }
+        PIMDB_CUDA_TRY(s, cudaMemcpyAsync(s->stage_d + i * count, src, bytes, cudaMemcpyHostToDevice, s->stream));
+    }
+    // The caller may reuse its buffers as soon as the call returns (pageable and page-locked alike): wait for the copies,
+    // not for the transpose.
+    PIMDB_CUDA_TRY(s, cudaEventRecord(s->ev_copy, s->stream));
+    API_TRY(launch_aos_to_soa(s, n, dst, halo));
+    bool x_changed = false;
+    for (int i = 0; i < n; ++i) x_changed = x_changed || which[i] == PIMDB_X;
+    if (x_changed && s->all_local) API_TRY(launch_fill_halos(s));
+    if (x_changed && s->peer_on) API_TRY(launch_peer_push_halos(s));
+    PIMDB_CUDA_TRY(s, cudaEventSynchronize(s->ev_copy));
+    return PIMDB_OK;
+}
+
+static int download_arrays(Sim* s, int n, const int* which, double* const* host) {
+    const size_t count = s->S * s->Ploc, bytes = count * sizeof(double);
+    const double* src[3]; bool halo[3];
+    if (n < 1 || n > 3) return fail(s, PIMDB_ERR_INVALID_ARGUMENT, "1 to 3 arrays per transfer");
+    bool all_pinned = true;
+    for (int i = 0; i < n; ++i) {
+        src[i] = array_ptr(s, which[i], halo[i]);
+        if (!src[i] || !host[i]) return fail(s, PIMDB_ERR_INVALID_ARGUMENT, "unknown state array");
+        all_pinned = all_pinned && host_is_pinned(host[i]);
+        if (which[i] == PIMDB_P) API_TRY(settle_momenta(s));
+        if (which[i] == PIMDB_F_SPRING || which[i] == PIMDB_F_PHYS) API_TRY(refresh_split_forces(s));
+    }
+    API_TRY(launch_soa_to_aos(s, n, src, halo));
+    for (int i = 0; i < n; ++i)
+        PIMDB_CUDA_TRY(s, cudaMemcpyAsync(all_pinned ? host[i] : s->stage_h + i * count, s->stage_d + i * count, bytes,
+                                          cudaMemcpyDeviceToHost, s->stream));
+    PIMDB_CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+    if (!all_pinned)
+        for (int i = 0; i < n; ++i) memcpy(host[i], s->stage_h + i * count, bytes);
+    return check_deferred(s);
+}
+
 extern "C" int pimdb_set_state(pimdb_sim* sim, int which, const double* host) {
     Sim* s = reinterpret_cast<Sim*>(sim);
     if (!s || !host) return PIMDB_ERR_INVALID_ARGUMENT;
-    bool halo;
-    double* dst = array_ptr(s, which, halo);
-    if (!dst) return fail(s, PIMDB_ERR_INVALID_ARGUMENT, "unknown state array");
     PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
-    if (which == PIMDB_P) s->p_shift_pending = false;   // the caller replaces the momenta: nothing left to settle
-    const size_t bytes = s->S * s->Ploc * sizeof(double);
-    if (host_is_pinned(host)) {
-        // page-locked caller buffer: one asynchronous copy straight from it (stream order protects the device staging buffer)
-        PIMDB_CUDA_TRY(s, cudaMemcpyAsync(s->stage_d, host, bytes, cudaMemcpyHostToDevice, s->stream));
-    } else {
-        // pageable: stage through our pinned buffer so the copy is truly asynchronous-safe
-        PIMDB_CUDA_TRY(s, cudaStreamSynchronize(s->stream));
-        memcpy(s->stage_h, host, bytes);
-        PIMDB_CUDA_TRY(s, cudaMemcpyAsync(s->stage_d, s->stage_h, bytes, cudaMemcpyHostToDevice, s->stream));
-    }
-    API_TRY(launch_aos_to_soa(s, dst, halo));
-    if (which == PIMDB_X && s->all_local) API_TRY(launch_fill_halos(s));
-    return PIMDB_OK;
+    return upload_arrays(s, 1, &which, &host);
 }
 
 extern "C" int pimdb_get_state(pimdb_sim* sim, int which, double* host) {
     Sim* s = reinterpret_cast<Sim*>(sim);
     if (!s || !host) return PIMDB_ERR_INVALID_ARGUMENT;
-    bool halo;
-    double* src = array_ptr(s, which, halo);
-    if (!src) return fail(s, PIMDB_ERR_INVALID_ARGUMENT, "unknown state array");
     PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
-    if (which == PIMDB_P) API_TRY(settle_momenta(s));
-    const size_t bytes = s->S * s->Ploc * sizeof(double);
-    API_TRY(launch_soa_to_aos(s, src, halo));
-    if (host_is_pinned(host)) {
-        PIMDB_CUDA_TRY(s, cudaMemcpyAsync(host, s->stage_d, bytes, cudaMemcpyDeviceToHost, s->stream));
-        PIMDB_CUDA_TRY(s, cudaStreamSynchronize(s->stream));
-    } else {
-        PIMDB_CUDA_TRY(s, cudaMemcpyAsync(s->stage_h, s->stage_d, bytes, cudaMemcpyDeviceToHost, s->stream));
-        PIMDB_CUDA_TRY(s, cudaStreamSynchronize(s->stream));
-        memcpy(host, s->stage_h, bytes);
-    }
-    return check_deferred(s);
+    return download_arrays(s, 1, &which, &host);
+}
+
+extern "C" int pimdb_upload_state(pimdb_sim* sim, const double* x, const double* p) {
+    Sim* s = reinterpret_cast<Sim*>(sim);
+    if (!s || (!x && !p)) return PIMDB_ERR_INVALID_ARGUMENT;
+    PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
+    int which[2]; const double* host[2]; int n = 0;
+    if (x) { which[n] = PIMDB_X; host[n++] = x; }
+    if (p) { which[n] = PIMDB_P; host[n++] = p; }
+    return upload_arrays(s, n, which, host);
+}
+
+extern "C" int pimdb_download_state(pimdb_sim* sim, double* x, double* p, double* f) {
+    Sim* s = reinterpret_cast<Sim*>(sim);
+    if (!s || (!x && !p && !f)) return PIMDB_ERR_INVALID_ARGUMENT;
+    PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
+    int which[3]; double* host[3]; int n = 0;
+    if (x) { which[n] = PIMDB_X; host[n++] = x; }
+    if (p) { which[n] = PIMDB_P; host[n++] = p; }
+    if (f) { which[n] = PIMDB_F; host[n++] = f; }
+    return download_arrays(s, n, which, host);
 }
 
 // ----------------------------------------------------------------------------------------------------
 // force evaluation: exchange on the high-priority side stream, pair tiles + assembly on the main stream
-static int enqueue_forces(Sim* s) {
+// `assemble_later`: the caller's next k_integrate launch forms f itself (OP_ASSEMBLE) -- one pass over the pair partials
+// and one launch fewer on the step's critical path.
+static int enqueue_forces(Sim* s, bool assemble_later = false) {
     const bool ex = s->bosonic && (s->has_first || s->has_last);
     bool early = false;
     if (ex) {
@@ -486,13 +553,30 @@ static int enqueue_forces(Sim* s) {
             const int nb = std::min(s->bead_chunk, s->Ploc - lo);
             API_TRY(launch_pair_chunk(s, lo, nb, false));
             if (!joined) API_TRY(join());
-            API_TRY(launch_assemble_chunk(s, lo, nb, true));
+            if (!assemble_later) API_TRY(launch_assemble_chunk(s, lo, nb, true));
         }
     } else {
         if (!joined) API_TRY(join());
-        API_TRY(launch_assemble_chunk(s, 0, s->Ploc, false));
+        if (!assemble_later) API_TRY(launch_assemble_chunk(s, 0, s->Ploc, false));
     }
     return PIMDB_OK;
+}
+
+// The closing kick of a Cartesian step can assemble the forces itself when the pair partials of all owned beads are in
+// the scratch slab at once. (PIMDB_NO_FUSED_ASSEMBLE=1: separate k_assemble, for A/B timing.)
+static bool fuse_assembly(const Sim* s) {
+    static const bool off = getenv("PIMDB_NO_FUSED_ASSEMBLE") != nullptr;
+    return !off && s->cfg.propagator == PIMDB_PROP_CARTESIAN && (!s->pair_on || s->bead_chunk >= s->Ploc);
+}
+
+// Bead shards over peer memory: one iteration is O Z B A forces B O Z (O thermostat half step, Z zeroMomentum). Z is the
+// projection p -> p - mean(p) and a Langevin O is affine with the same coefficients for every degree of freedom, so
+// Z O Z = Z O (and Z Z = Z without a thermostat): the closing Z of an iteration is subsumed by the first Z of the next,
+// and between iterations its exchange of momentum sums is skipped. It is carried out before anything reads the momenta
+// (settle_momenta). Other thermostats do not commute with Z like that and keep both.
+static bool lazy_closing_com(const Sim* s) {
+    return s->peer_on && s->cfg.fixcom && !s->cfg.nmthermostat &&
+           (s->cfg.thermostat == PIMDB_THERMO_LANGEVIN || s->cfg.thermostat == PIMDB_THERMO_NONE);
 }
 
 // Fuses consecutive element-wise stages into as few k_integrate launches as their fixed in-kernel order
@@ -519,11 +603,11 @@ struct Fuser {
         if (ops & (OP_B | OP_B_PHYS)) put(OP_O_POST, 3);
         else put(OP_O_PRE, 1);
     }
-    void kick(bool phys_only) {
-        if (ops & (OP_B | OP_B_PHYS)) flush();
-        put(phys_only ? OP_B_PHYS : OP_B, 2);
+    void kick(bool phys_only, bool assemble = false) {
+        if (assemble || (ops & (OP_B | OP_B_PHYS))) flush();
+        put((phys_only ? OP_B_PHYS : OP_B) | (assemble ? OP_ASSEMBLE : 0u), 2);
     }
-    void drift() { put(OP_A | (s->all_local ? OP_HALO : 0u), 4); }
+    void drift() { put(OP_A | ((s->all_local || s->peer_on) ? OP_HALO : 0u), 4); }
     void sum() { put(OP_SUM, 5); }
 };
 
@@ -551,9 +635,10 @@ static void propagator_into(Sim* s, Fuser& fz) {
         fz.kick(false);
         fz.drift();
         fz.flush();
-        if (!s->all_local) return;   // sharded: the host exchanges halos, then calls phase 2
-        if (fz.rc == PIMDB_OK) fz.rc = enqueue_forces(s);
-        fz.kick(false);
+        if (!s->all_local && !s->peer_on) return;   // host-driven sharding: the host exchanges halos, then calls phase 2
+        const bool fuse = fuse_assembly(s);
+        if (fz.rc == PIMDB_OK) fz.rc = enqueue_forces(s, fuse);
+        fz.kick(false, fuse);
     } else {
         fz.flush();
         if (fz.rc == PIMDB_OK) fz.rc = launch_nm_propagate(s);   // half kick (physical forces) + exact ring rotation
@@ -567,6 +652,11 @@ static void propagator_into(Sim* s, Fuser& fz) {
 // the second zeroMomentum of an iteration in this state so that the subtraction rides in the first kernel of the next
 // iteration instead of costing a launch; every other entry point settles it first, so callers never see it.
 static int settle_momenta(Sim* s) {
+    if (s->z_owed) {   // peer mode: the closing zeroMomentum that consecutive iterations skip (collective: every rank gets here)
+        s->z_owed = false;
+        API_TRY(launch_integrate(s, OP_SUM));
+        s->p_shift_pending = true;
+    }
     if (!s->p_shift_pending) return PIMDB_OK;
     s->p_shift_pending = false;
     return launch_integrate(s, OP_SUBCM);
@@ -575,15 +665,20 @@ static int settle_momenta(Sim* s) {
 // body of Simulation::run, src/simulation.cpp:246-259
 static int enqueue_step(Sim* s, bool defer_last_com) {
     Fuser fz(s);
-    if (s->p_shift_pending) { fz.subcm(); s->p_shift_pending = false; }
+    const bool lazy = lazy_closing_com(s);
+    if (lazy) { s->p_shift_pending = false; s->z_owed = false; }   // whatever Z is outstanding is subsumed by this iteration's first
+    else if (s->p_shift_pending) { fz.subcm(); s->p_shift_pending = false; }
     thermostat_into(s, fz);
     if (s->cfg.fixcom) { fz.sum(); fz.subcm(); }
     propagator_into(s, fz);
     thermostat_into(s, fz);
     if (s->cfg.fixcom) {
-        fz.sum();
-        if (defer_last_com) s->p_shift_pending = true;
-        else fz.subcm();
+        if (lazy) s->z_owed = true;
+        else {
+            fz.sum();
+            if (defer_last_com) s->p_shift_pending = true;
+            else fz.subcm();
+        }
     }
     fz.flush();
     return fz.rc;
@@ -592,16 +687,19 @@ static int enqueue_step(Sim* s, bool defer_last_com) {
 // pimdb_step replays one captured iteration, so every iteration must start in the same state: with fixcom that is
 // "a shift is pending". A pending shift of zero is a no-op (p - 0.0 == p bit for bit).
 static int make_entry_state_uniform(Sim* s) {
+    if (lazy_closing_com(s)) return PIMDB_OK;   // an iteration starts the same way whether or not a Z is outstanding
     if (s->cfg.fixcom && !s->p_shift_pending) {
-        PIMDB_CUDA_TRY(s, cudaMemsetAsync(s->com, 0, sizeof(double) * 4, s->stream));
+        if (s->peer_on) API_TRY(launch_integrate(s, OP_ZERO_SUM));   // every rank publishes zero sums
+        else PIMDB_CUDA_TRY(s, cudaMemsetAsync(s->com, 0, sizeof(double) * 4, s->stream));
         s->p_shift_pending = true;
     }
     return PIMDB_OK;
 }
 
 static int require_all_local(Sim* s, const char* what) {
-    if (!s->all_local)
-        return fail(s, PIMDB_ERR_INVALID_ARGUMENT, std::string(what) + " needs all beads on this handle; use pimdb_step_phase with bead sharding");
+    if (!s->all_local && !s->peer_on)
+        return fail(s, PIMDB_ERR_INVALID_ARGUMENT, std::string(what) + " needs all beads on this handle, or a bead shard attached to its "
+                                                   "peers (pimdb_peer_attach); host-driven sharding uses pimdb_step_phase");
     return PIMDB_OK;
 }
 
@@ -610,7 +708,7 @@ extern "C" int pimdb_update_neighbors(pimdb_sim* sim) {
     if (!s) return PIMDB_ERR_INVALID_ARGUMENT;
     API_TRY(require_all_local(s, "pimdb_update_neighbors"));
     PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
-    return launch_fill_halos(s);
+    return s->peer_on ? launch_peer_push_halos(s) : launch_fill_halos(s);
 }
 
 extern "C" int pimdb_update_forces(pimdb_sim* sim) {
@@ -633,7 +731,7 @@ extern "C" int pimdb_coords_step(pimdb_sim* sim) {
     if (!s) return PIMDB_ERR_INVALID_ARGUMENT;
     PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
     API_TRY(settle_momenta(s));
-    return launch_integrate(s, OP_A | (s->all_local ? OP_HALO : 0u));
+    return launch_integrate(s, OP_A | ((s->all_local || s->peer_on) ? OP_HALO : 0u));
 }
 
 extern "C" int pimdb_propagator_step(pimdb_sim* sim) {
@@ -689,15 +787,20 @@ extern "C" int pimdb_step(pimdb_sim* sim, int nsteps) {
         }
         return PIMDB_OK;
     }
-    if (nsteps > 0) API_TRY(make_entry_state_uniform(s));
+    if (nsteps == 0) return PIMDB_OK;   // nothing to enqueue (and nothing to capture: the entry state below belongs to a real step)
+    API_TRY(make_entry_state_uniform(s));
     if (!s->graph_exec) {
         const unsigned long long before = s->launches;
+        const bool pending0 = s->p_shift_pending, owed0 = s->z_owed, stale0 = s->split_stale;
         PIMDB_CUDA_TRY(s, cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
         s->tl_next = 0;
         int rc = enqueue_step(s, true);
         cudaGraph_t g = nullptr;
         cudaError_t ce = cudaStreamEndCapture(s->stream, &g);
+        // nothing has run yet: the host-side flags go back to what they were; the replays below set them
+        s->p_shift_pending = pending0; s->z_owed = owed0; s->split_stale = stale0;
         if (rc != PIMDB_OK) { if (g) cudaGraphDestroy(g); return rc; }
+        if (ce != cudaSuccess) s->launches = before;
         PIMDB_CUDA_TRY(s, ce);
         s->graph = g;
         s->graph_kernels = s->launches - before;
@@ -708,6 +811,12 @@ extern "C" int pimdb_step(pimdb_sim* sim, int nsteps) {
         PIMDB_CUDA_TRY(s, cudaGraphLaunch(s->graph_exec, s->stream));
         s->launches += s->graph_kernels;
     }
+    // host-side state after an iteration (what enqueue_step leaves behind)
+    if (s->cfg.fixcom) {
+        if (lazy_closing_com(s)) { s->z_owed = true; s->p_shift_pending = false; }
+        else s->p_shift_pending = true;
+    }
+    if (s->cfg.propagator == PIMDB_PROP_CARTESIAN && fuse_assembly(s)) s->split_stale = true;
     return PIMDB_OK;
 }
 
@@ -744,6 +853,118 @@ extern "C" int pimdb_step_phase(pimdb_sim* sim, int phase) {
     }
     fz.flush();
     return fz.rc;
+}
+
+// ----------------------------------------------------------------------------------------------------
+// Bead sharding over peer memory. Each handle exports a blob (cudaIpc handles of its coordinate array and of its mailbox
+// + what a peer in the same process needs to use the pointers directly); the host gathers the blobs of all ranks (one
+// torch.distributed all-gather at start-up, or plainly in a single process driving several GPUs) and hands every handle
+// the whole table. From then on halo slices and momentum sums travel inside the step's own kernels (integrator.cu), and
+// pimdb_step works on a shard exactly as on a full ring: one CUDA graph per rank, no host call between its kernels.
+namespace {
+struct PeerBlob {
+    unsigned int magic, version;
+    long long pid;
+    unsigned long long boot_tag;       // distinguishes handles of different processes with recycled pids (create-time stamp)
+    int device, natoms, nbeads, ndim, bead_begin, bead_end;
+    void* x;                           // device pointers, meaningful inside the exporting process only
+    void* mailbox;
+    cudaIpcMemHandle_t x_ipc, mailbox_ipc;
+};
+static_assert(sizeof(PeerBlob) <= PIMDB_PEER_BLOB_BYTES, "blob does not fit");
+constexpr unsigned int kBlobMagic = 0x50494d44u;   // "PIMD"
+}  // namespace
+
+extern "C" int pimdb_peer_export(pimdb_sim* sim, void* blob_out) {
+    Sim* s = reinterpret_cast<Sim*>(sim);
+    if (!s || !blob_out) return PIMDB_ERR_INVALID_ARGUMENT;
+    if (s->all_local) return fail(s, PIMDB_ERR_INVALID_ARGUMENT, "this handle owns every bead: there is nothing to share");
+    PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
+    PeerBlob b;
+    memset(&b, 0, sizeof b);
+    b.magic = kBlobMagic; b.version = PIMDB_ABI_VERSION;
+    b.pid = (long long)getpid();
+    b.device = s->device; b.natoms = s->N; b.nbeads = s->P; b.ndim = s->D; b.bead_begin = s->b0; b.bead_end = s->b1;
+    b.x = s->x; b.mailbox = s->mailbox;
+    PIMDB_CUDA_TRY(s, cudaIpcGetMemHandle(&b.x_ipc, s->x));
+    PIMDB_CUDA_TRY(s, cudaIpcGetMemHandle(&b.mailbox_ipc, s->mailbox));
+    memset(blob_out, 0, PIMDB_PEER_BLOB_BYTES);
+    memcpy(blob_out, &b, sizeof b);
+    return PIMDB_OK;
+}
+
+static int map_peer(Sim* s, const PeerBlob& b, bool want_x, void** x_out, void** mailbox_out) {
+    *x_out = nullptr;
+    if (b.pid == (long long)getpid()) {          // same process: the pointers are valid as they are
+        if (b.device != s->device) {
+            int can = 0;
+            PIMDB_CUDA_TRY(s, cudaDeviceCanAccessPeer(&can, s->device, b.device));
+            if (!can) return fail(s, PIMDB_ERR_CUDA, "GPUs " + std::to_string(s->device) + " and " + std::to_string(b.device) + " cannot access each other's memory");
+            const cudaError_t e = cudaDeviceEnablePeerAccess(b.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) PIMDB_CUDA_TRY(s, e);
+            cudaGetLastError();
+        }
+        *mailbox_out = b.mailbox;
+        if (want_x) *x_out = b.x;
+        return PIMDB_OK;
+    }
+    PIMDB_CUDA_TRY(s, cudaIpcOpenMemHandle(mailbox_out, b.mailbox_ipc, cudaIpcMemLazyEnablePeerAccess));
+    s->ipc_opened.push_back(*mailbox_out);
+    if (want_x) {
+        PIMDB_CUDA_TRY(s, cudaIpcOpenMemHandle(x_out, b.x_ipc, cudaIpcMemLazyEnablePeerAccess));
+        s->ipc_opened.push_back(*x_out);
+    }
+    return PIMDB_OK;
+}
+
+extern "C" int pimdb_peer_attach(pimdb_sim* sim, int world, int rank, const void* blobs) {
+    Sim* s = reinterpret_cast<Sim*>(sim);
+    if (!s || !blobs) return PIMDB_ERR_INVALID_ARGUMENT;
+    if (s->peer_on) return fail(s, PIMDB_ERR_INVALID_ARGUMENT, "handle is already attached to its peers");
+    if (world < 2 || world > kMaxPeers || rank < 0 || rank >= world)
+        return fail(s, PIMDB_ERR_INVALID_ARGUMENT, "peer sharding supports 2.." + std::to_string(kMaxPeers) + " ranks");
+    if (s->cfg.propagator != PIMDB_PROP_CARTESIAN || s->cfg.nmthermostat)
+        return fail(s, PIMDB_ERR_INVALID_ARGUMENT, "bead shards support the cartesian propagator / thermostat coupling only");
+    PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
+    std::vector<PeerBlob> tab(world);
+    int expect = 0;
+    for (int r = 0; r < world; ++r) {
+        memcpy(&tab[r], (const char*)blobs + (size_t)r * PIMDB_PEER_BLOB_BYTES, sizeof(PeerBlob));
+        const PeerBlob& b = tab[r];
+        if (b.magic != kBlobMagic || b.version != PIMDB_ABI_VERSION) return fail(s, PIMDB_ERR_INVALID_ARGUMENT, "not a pimdb peer blob (rank " + std::to_string(r) + ")");
+        if (b.natoms != s->N || b.nbeads != s->P || b.ndim != s->D) return fail(s, PIMDB_ERR_INVALID_ARGUMENT, "peer " + std::to_string(r) + " holds a different system");
+        if (b.bead_begin != expect || b.bead_end <= b.bead_begin) return fail(s, PIMDB_ERR_INVALID_ARGUMENT, "bead ranges must tile [0, nbeads) in rank order");
+        expect = b.bead_end;
+    }
+    if (expect != s->P || tab[rank].bead_begin != s->b0 || tab[rank].bead_end != s->b1)
+        return fail(s, PIMDB_ERR_INVALID_ARGUMENT, "bead ranges must tile [0, nbeads) in rank order (and blobs[rank] must be this handle's)");
+    PeerDev pd{};
+    pd.world = world; pd.rank = rank;
+    pd.prev = (rank + world - 1) % world; pd.next = (rank + 1) % world;
+    pd.mine = s->mailbox; pd.seq = s->peer_seq;
+    unsigned long long ms = 20000;
+    if (const char* e = getenv("PIMDB_PEER_TIMEOUT_MS")) ms = (unsigned long long)std::max(1, atoi(e));
+    pd.timeout_ns = ms * 1000000ull;
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) { pd.box[r] = s->mailbox; continue; }
+        void *x = nullptr, *mb = nullptr;
+        API_TRY(map_peer(s, tab[r], r == pd.prev || r == pd.next, &x, &mb));
+        pd.box[r] = reinterpret_cast<PeerMailbox*>(mb);
+        const size_t ploc_r = (size_t)(tab[r].bead_end - tab[r].bead_begin);
+        if (r == pd.prev) pd.halo_to_prev = reinterpret_cast<double*>(x) + (ploc_r + 1) * s->S;   // its trailing halo slab
+        if (r == pd.next) pd.halo_to_next = reinterpret_cast<double*>(x);                          // its leading halo slab
+    }
+    s->peer = pd;
+    s->peer_on = true;
+    if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }
+    if (s->graph) { cudaGraphDestroy(s->graph); s->graph = nullptr; }
+    // Simulation::updateNeighboringCoordinates for whatever coordinates the handle holds now
+    return launch_peer_push_halos(s);
+}
+
+extern "C" int pimdb_peer_attached(const pimdb_sim* sim) {
+    const Sim* s = reinterpret_cast<const Sim*>(sim);
+    return s && s->peer_on ? 1 : 0;
 }
 
 // ----------------------------------------------------------------------------------------------------
@@ -793,6 +1014,7 @@ extern "C" int pimdb_observables_calc(pimdb_sim* sim, pimdb_observables* out) {
     if (!s || !out) return PIMDB_ERR_INVALID_ARGUMENT;
     PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
     API_TRY(settle_momenta(s));
+    API_TRY(launch_peer_wait_halos(s));
     PIMDB_CUDA_TRY(s, cudaMemsetAsync(s->obs_d, 0, sizeof(DevObs), s->stream));
     API_TRY(launch_obs_elementwise(s));
     if (s->pair_on) {
@@ -894,21 +1116,22 @@ extern "C" int pimdb_timing_enable(pimdb_sim* sim, int on) {
     if (!s) return PIMDB_ERR_INVALID_ARGUMENT;
     PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
     PIMDB_CUDA_TRY(s, cudaStreamSynchronize(s->stream));
-    for (auto& e : s->ev_pair) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
-    for (auto& e : s->ev_step) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
-    s->ev_pair.clear();
-    s->ev_step.clear();
+    for (auto* v : {&s->ev_pair, &s->ev_step, &s->ev_integ}) {
+        for (auto& e : *v) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
+        v->clear();
+    }
+    s->integ_bytes = 0.0;
     s->timing = on != 0;
     return PIMDB_OK;
 }
 
-// what = 0: pair-force kernel launches, 1: whole steps
+// what = 0: pair-force kernel launches, 1: whole steps, 2: fused integrator launches
 extern "C" int pimdb_timing_get(pimdb_sim* sim, int what, double* ms_avg, unsigned long long* count) {
     Sim* s = reinterpret_cast<Sim*>(sim);
     if (!s || !ms_avg || !count) return PIMDB_ERR_INVALID_ARGUMENT;
     PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
     PIMDB_CUDA_TRY(s, cudaStreamSynchronize(s->stream));
-    auto& v = what == 0 ? s->ev_pair : s->ev_step;
+    auto& v = what == 0 ? s->ev_pair : (what == 2 ? s->ev_integ : s->ev_step);
     double tot = 0.0;
     for (auto& e : v) {
         float ms = 0.f;
@@ -917,6 +1140,14 @@ extern "C" int pimdb_timing_get(pimdb_sim* sim, int what, double* ms_avg, unsign
     }
     *count = v.size();
     *ms_avg = v.empty() ? 0.0 : tot / (double)v.size();
+    return PIMDB_OK;
+}
+
+// algorithmic bytes per launch of the fused integrator launches timed so far (what pimdb_timing_get(2) averages over)
+extern "C" int pimdb_timing_integrator_bytes(pimdb_sim* sim, double* bytes_per_launch) {
+    Sim* s = reinterpret_cast<Sim*>(sim);
+    if (!s || !bytes_per_launch) return PIMDB_ERR_INVALID_ARGUMENT;
+    *bytes_per_launch = s->ev_integ.empty() ? 0.0 : s->integ_bytes / (double)s->ev_integ.size();
     return PIMDB_OK;
 }
 

@@ -133,6 +133,71 @@ __device__ __forceinline__ void tl_end(unsigned long long* tl) {
     if (tl && threadIdx.x == 0) atomicMax(tl + 1, gtimer_ns());
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Peer-memory signalling (bead sharding, internal.cuh PeerMailbox): system-scope relaxed loads / stores of flag words
+// that another GPU (or another process on this GPU) writes or reads, and BOUNDED waits on them. A wait that runs out
+// raises `err_bit` in the host-mapped error word and returns false; once the bit is up every later wait returns at
+// once, so a dead peer costs one time-out, not one per kernel of the remaining graph replays.
+__device__ __forceinline__ unsigned ld_sys_u32(const unsigned* p) {
+    unsigned v;
+    asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_sys_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_sys_u32(unsigned* p, unsigned v) {
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// wait until the counter at p has reached `want` (wrap-safe)
+__device__ __forceinline__ bool wait_sys_u32_ge(const unsigned* p, unsigned want, unsigned long long timeout_ns, int* err,
+                                                int err_bit) {
+    if ((int)(ld_sys_u32(p) - want) >= 0) return true;
+    if (*(volatile int*)err & err_bit) return false;
+    const unsigned long long t0 = gtimer_ns();
+    unsigned spins = 0;
+    while ((int)(ld_sys_u32(p) - want) < 0) {
+        if ((++spins & 255u) == 0 && gtimer_ns() - t0 > timeout_ns) {
+            atomicOr(err, err_bit);
+            return false;
+        }
+    }
+    return true;
+}
+// wait until the high half of the self-validating word at p equals `seq`; returns its low half
+__device__ __forceinline__ unsigned wait_sys_word(const unsigned long long* p, unsigned seq, unsigned long long timeout_ns,
+                                                  int* err, int err_bit) {
+    unsigned long long w = ld_sys_u64(p);
+    if ((unsigned)(w >> 32) == seq) return (unsigned)w;
+    if (*(volatile int*)err & err_bit) return 0u;
+    const unsigned long long t0 = gtimer_ns();
+    unsigned spins = 0;
+    while ((unsigned)((w = ld_sys_u64(p)) >> 32) != seq) {
+        if ((++spins & 255u) == 0 && gtimer_ns() - t0 > timeout_ns) {
+            atomicOr(err, err_bit);
+            return 0u;
+        }
+    }
+    return (unsigned)w;
+}
+
+// Every block of a kernel that reads the halo slabs of a bead shard calls this first: the neighbours have raised the
+// flags to the number of slices this rank itself has sent (all ranks push in lock-step program order).
+__device__ __forceinline__ void peer_wait_halos(const unsigned int* halo_flag, const unsigned int* halo_seq,
+                                                unsigned long long timeout_ns, int* err) {
+    if (!halo_flag) return;
+    if (threadIdx.x < 2) {
+        wait_sys_u32_ge(&halo_flag[threadIdx.x], *halo_seq, timeout_ns, err, 8 /* kErrPeerTimeout */);
+        __threadfence_system();
+    }
+    __syncthreads();
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);

@@ -125,6 +125,9 @@ struct ExArgs {
     long long* dbg;            // optional profiling buffer (clock64 stamps per warp), nullptr in production
     int N, D, pbc, do_first, do_last;
     double k, beta, h, L, invL;   // h = beta*k/2
+    // bead shard over peer memory: the other exterior bead arrives in a halo slab written by a ring neighbour; the
+    // first kernels of the chain wait (bounded) for it (device_utils.cuh peer_wait_halos), nullptr otherwise
+    const unsigned int* halo_flag; const unsigned int* halo_seq; unsigned long long timeout_ns;
 };
 
 template <int D>
@@ -151,6 +154,7 @@ __global__ void __launch_bounds__(1024) k_exch_prefix(ExArgs a) {
     __shared__ double warp_tot[32];
     __shared__ double carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    peer_wait_halos(a.halo_flag, a.halo_seq, a.timeout_ns, a.err);
     if (tid < 32) warp_tot[tid] = 0.0;
     if (tid == 0) carry = 0.0;
     __syncthreads();
@@ -335,6 +339,7 @@ __global__ void __launch_bounds__(1024, 2) k_exch_coeff_tiles(ExArgs a) {
     __shared__ double sA[kExchFastMaxN + 1];       // the prefix sums A(w), recomputed by every tile (N <= 512: one chunk)
     __shared__ double warp_tot[32];
     tl_begin(a.tl0);
+    peer_wait_halos(a.halo_flag, a.halo_seq, a.timeout_ns, a.err);
     const int N = a.N, nb = (N + 31) >> 5;
     const int rb = blockIdx.x / nb, sb = blockIdx.x % nb;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -1983,6 +1988,9 @@ static ExArgs make_args(Sim* s) {
     a.do_first = s->has_first; a.do_last = s->has_last;
     a.k = s->kspring; a.beta = s->exch_beta; a.h = 0.5 * s->exch_beta * s->kspring;
     a.L = s->L; a.invL = 1.0 / s->L;
+    a.halo_flag = s->peer_on ? s->peer.mine->halo_flag : nullptr;
+    a.halo_seq = s->peer_on ? s->peer.seq + 1 : nullptr;
+    a.timeout_ns = s->peer.timeout_ns;
     return a;
 }
 

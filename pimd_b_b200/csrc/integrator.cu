@@ -26,11 +26,14 @@ struct AssembleArgs {
     int pbc, ext_pot, write_split;
     unsigned long long* tl;
     double ext_a, ext_b, mass;     // double_well: strength, location ; cosine: amplitude, phase
+    // bead shard over peer memory: the halo slabs are written by the ring neighbours; wait (bounded) for both slices
+    const unsigned int* halo_flag; const unsigned int* halo_seq; unsigned long long timeout_ns; int* err;
 };
 
 template <int D>
 __global__ void __launch_bounds__(256) k_assemble(AssembleArgs a) {
     tl_begin(a.tl);
+    peer_wait_halos(a.halo_flag, a.halo_seq, a.timeout_ns, a.err);
     const long long total = (long long)a.nb * a.N;
     for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
          idx += (long long)gridDim.x * blockDim.x) {
@@ -132,6 +135,10 @@ int launch_assemble_chunk(Sim* s, int bead_lo, int nb, bool with_pair) {
     a.pbc = s->cfg.pbc; a.ext_pot = s->cfg.ext_potential; a.write_split = 1;
     a.mass = s->cfg.mass;
     a.tl = tl_slot(s);
+    a.halo_flag = s->peer_on ? s->peer.mine->halo_flag : nullptr;   // (address arithmetic only: the mailbox is device memory)
+    a.halo_seq = s->peer_on ? s->peer.seq + 1 : nullptr;
+    a.timeout_ns = s->peer.timeout_ns; a.err = s->err_d;
+    if (bead_lo + nb >= s->Ploc) s->split_stale = false;
     if (s->cfg.ext_potential == PIMDB_POT_DOUBLE_WELL) { a.ext_a = s->cfg.ext_strength; a.ext_b = s->cfg.ext_location; }
     else { a.ext_a = s->cfg.ext_amplitude; a.ext_b = s->cfg.ext_phase; }
     const int grid = grid_for((size_t)nb * s->N, 256);
@@ -144,18 +151,32 @@ int launch_assemble_chunk(Sim* s, int bead_lo, int nb, bool with_pair) {
 }
 
 // ------------------------------------------------------------------------------------------------------
-// Fused integrator. One thread owns the particle pair (2q, 2q+1) of a row (owned bead b, axis c); the
-// stages run in the fixed order SUBCM -> O_PRE -> B -> O_POST -> A and are selected by `ops`:
-//   SUBCM  p -= com/(N P)                       zeroMomentum, second half (subtract)
-//   O_*    p  = c1 p + c2 xi                    LangevinThermostat::momentaUpdate (Cartesian coupling)
-//   B      p += dt/2 f   (B_PHYS: f_phys only)  Propagator::momentStep
-//   A      x += dt p / m                        Propagator::coordsStep
-//   SUM    block partials of sum p, finalised in fixed order by the last block -> com[c]   (zeroMomentum, first half)
-//   HALO   with A on a handle that owns all beads: also write the ring-wrap halo slabs
+// Fused integrator. One thread owns the particle pair (2q, 2q+1) of a row (owned bead b, axis c) -- one 16-byte
+// access per array when N is even (VEC) -- and the stages run in the fixed order
+// ASSEMBLE -> SUBCM -> O_PRE -> B -> O_POST -> A, selected by `ops`:
+//   ASSEMBLE  f = springs (or exterior exchange force) + external force + pair partials, the arithmetic of k_assemble
+//             in the same order (bit-identical); only f is written (f_spring / f_phys are rebuilt on request)
+//   SUBCM     p -= com/(N P)                       zeroMomentum, second half (subtract)
+//   O_*       p  = c1 p + c2 xi                    LangevinThermostat::momentaUpdate (Cartesian coupling)
+//   B         p += dt/2 f   (B_PHYS: f_phys only)  Propagator::momentStep
+//   A         x += dt p / m                        Propagator::coordsStep
+//   SUM       block partials of sum p, finalised in fixed order by the last block -> com[c]   (zeroMomentum, first half)
+//   HALO      with A: also write the halo slabs -- by ring wrap on a handle that owns all beads, into the ring
+//             neighbours' slabs over peer memory on a bead shard
 // The last block to finish also advances the noise draw counter when an O stage ran.
+//
+// Bead shards over peer memory (a.peer_on; internal.cuh PeerMailbox, DESIGN.md "Multi-GPU"):
+//   SUM   the last block publishes this rank's sums to EVERY rank's mailbox as self-validating 8-byte words
+//   SUBCM every block waits (bounded) for the words of all ranks and adds them in rank order: all ranks subtract the
+//         bit-identical shift, and no host call or collective sits between the two kernels
+//   HALO  every block first tells the neighbours "I am done reading the slices you sent" (reaching this kernel proves
+//         it: everything that read them precedes it in stream order) and waits for the same word from them; then the
+//         boundary beads are stored straight into the neighbours' halo slabs; the last block fences at system scope
+//         and raises the neighbours' halo flags.
 struct IntArgs {
     double *x, *p;
-    const double *f;
+    const double* f;
+    double* fw;            // ASSEMBLE: where the assembled forces go (= f)
     double* com_part; double* com; unsigned int* ticket; unsigned long long* draw;
     int N, D, Ploc, bead_begin;
     size_t S;
@@ -164,34 +185,153 @@ struct IntArgs {
     unsigned ops;
     const double* noise;   // reference-compatible stream: [Ploc][N][D] gaussians of this half-step, or nullptr (Philox)
     unsigned long long* tl;
+    // ASSEMBLE
+    const double* scratch; const double* exF;
+    int T, first_local, last_local, pbc, ext_pot;
+    double k, kext, L, invL, ext_a, ext_b, mass;
+    // peers
+    int peer_on;
+    PeerDev peer;
+    int* err;
 };
 
+template <bool VEC>
+__device__ __forceinline__ double2 ld_pair(const double* ptr, size_t o, bool two) {
+    if (VEC) return *reinterpret_cast<const double2*>(ptr + o);
+    double2 r;
+    r.x = ptr[o];
+    r.y = two ? ptr[o + 1] : 0.0;
+    return r;
+}
+template <bool VEC>
+__device__ __forceinline__ void st_pair(double* ptr, size_t o, double2 v, bool two) {
+    if (VEC) { *reinterpret_cast<double2*>(ptr + o) = v; return; }
+    ptr[o] = v.x;
+    if (two) ptr[o + 1] = v.y;
+}
+
+template <bool VEC>
 __global__ void __launch_bounds__(256) k_integrate(IntArgs a) {
     tl_begin(a.tl);
     __shared__ double sm[3 * 32];
+    __shared__ double sh_cm[4];
+    __shared__ unsigned long long sh_draw;
+    __shared__ unsigned sh_seq[2];
+    __shared__ unsigned sh_words[kMaxPeers * kComWords];
     __shared__ bool is_last;
+    const int tid = threadIdx.x;
     const int Q = (a.N + 1) >> 1;
     const long long rows = (long long)a.Ploc * a.D;
     const long long total = rows * Q;
     const bool do_o = (a.ops & (OP_O_PRE | OP_O_POST)) != 0;
-    const unsigned long long draw = do_o ? *a.draw : 0ull;
-    double cm[3] = {0.0, 0.0, 0.0};
-    if (a.ops & OP_SUBCM) {
-        for (int c = 0; c < a.D; ++c) cm[c] = a.com[c] * a.inv_np;
+    const bool peer = a.peer_on != 0;
+    // ---- prologue: counters (read by ONE thread, before the barrier: nothing below can overtake the last block's
+    // update of them), centre-of-mass shift, hand-shake with the ring neighbours
+    if (tid == 0) {
+        sh_draw = do_o ? *a.draw : 0ull;
+        if (peer) { sh_seq[0] = a.peer.seq[0]; sh_seq[1] = a.peer.seq[1]; }
     }
+    if (tid < 4) sh_cm[tid] = 0.0;
+    __syncthreads();
+    if (a.ops & OP_SUBCM) {
+        if (peer) {
+            const unsigned seq = sh_seq[0];
+            if (tid < a.peer.world * kComWords)
+                sh_words[tid] = wait_sys_word(&a.peer.mine->com_in[seq & 1u][tid / kComWords][tid % kComWords], seq,
+                                              a.peer.timeout_ns, a.err, kErrPeerTimeout);
+            __syncthreads();
+            if (tid < 3) {
+                double t = 0.0;
+                for (int r = 0; r < a.peer.world; ++r)   // rank order: every rank forms the bit-identical total
+                    t += __hiloint2double((int)sh_words[r * kComWords + 2 * tid + 1], (int)sh_words[r * kComWords + 2 * tid]);
+                sh_cm[tid] = t * a.inv_np;
+            }
+        } else if (tid < 3) {
+            sh_cm[tid] = tid < a.D ? a.com[tid] * a.inv_np : 0.0;
+        }
+    }
+    if (peer && (a.ops & OP_ASSEMBLE) && tid < 2) {   // the springs of the boundary beads read the neighbours' slices
+        wait_sys_u32_ge(&a.peer.mine->halo_flag[tid], sh_seq[1], a.peer.timeout_ns, a.err, kErrPeerTimeout);
+        __threadfence_system();
+    }
+    const bool push_halo = peer && (a.ops & OP_HALO);
+    if (push_halo && tid < 2) {
+        const unsigned k = sh_seq[1] + 1u;                         // index of the halo push this kernel makes
+        // I am the previous rank of `next` (its credit[0]) and the next rank of `prev` (its credit[1])
+        st_sys_u32(tid == 0 ? &a.peer.box[a.peer.next]->credit[0] : &a.peer.box[a.peer.prev]->credit[1], k);
+        wait_sys_u32_ge(&a.peer.mine->credit[tid], k, a.peer.timeout_ns, a.err, kErrPeerTimeout);
+    }
+    __syncthreads();
+    const unsigned long long draw = sh_draw;
+    const double cm[3] = {sh_cm[0], sh_cm[1], sh_cm[2]};
     double acc[3] = {0.0, 0.0, 0.0};
-    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
-         idx += (long long)gridDim.x * blockDim.x) {
+    bool stored_remote = false;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + tid; idx < total; idx += (long long)gridDim.x * blockDim.x) {
         const long long row = idx / Q;
         const int q = (int)(idx % Q);
         const int b = (int)(row / a.D), c = (int)(row % a.D);
         const int n0 = 2 * q;
-        const bool two = (n0 + 1) < a.N;
+        const bool two = VEC || (n0 + 1) < a.N;
         const size_t o = (size_t)row * a.N + n0;
-        double p0 = a.p[o], p1 = two ? a.p[o + 1] : 0.0;
+        const size_t ox = o + a.S;  // skip the leading halo slab
+        double2 pv = ld_pair<VEC>(a.p, o, two);
+        double2 fv = make_double2(0.0, 0.0);
+        if (a.ops & OP_ASSEMBLE) {
+            const double2 xv = ld_pair<VEC>(a.x, ox, two);
+            double2 phys = make_double2(0.0, 0.0), spring;
+            if (a.ext_pot == PIMDB_POT_HARMONIC) {
+                phys.x = -(a.kext * xv.x); phys.y = -(a.kext * xv.y);
+            } else if (a.ext_pot == PIMDB_POT_DOUBLE_WELL) {   // grad = 4 m lambda (|x|^2 - a^2) x  (double_well.cpp:22-40)
+                double r2x = 0.0, r2y = 0.0;
+                for (int cc = 0; cc < a.D; ++cc) {
+                    const double2 xo = ld_pair<VEC>(a.x, (size_t)(b + 1) * a.S + (size_t)cc * a.N + n0, two);
+                    r2x += xo.x * xo.x; r2y += xo.y * xo.y;
+                }
+                phys.x = -((4.0 * a.mass * a.ext_a * (r2x - a.ext_b * a.ext_b)) * xv.x);
+                phys.y = -((4.0 * a.mass * a.ext_a * (r2y - a.ext_b * a.ext_b)) * xv.y);
+            } else if (a.ext_pot == PIMDB_POT_COSINE) {        // F = A k sin(k x + phase), k = 2 pi / L  (cosine.cpp:9-35)
+                const double kk = 2.0 * M_PI / a.L;
+                phys.x = a.ext_a * kk * sin(kk * xv.x + a.ext_b);
+                phys.y = a.ext_a * kk * sin(kk * xv.y + a.ext_b);
+            }
+            if (a.scratch) {   // pair partials in the fixed order m = 0..T-1, eight loads in flight
+                const int K = n0 / kTile, lane = n0 % kTile;
+                const double* sp = a.scratch + (((size_t)b * a.T + K) * a.T * a.D + c) * kTile + lane;
+                const size_t stride = (size_t)a.D * kTile;
+                int m = 0;
+                for (; m + 8 <= a.T; m += 8) {
+                    double2 v[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) v[k] = ld_pair<VEC>(sp, (size_t)(m + k) * stride, two);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { phys.x += v[k].x; phys.y += v[k].y; }
+                }
+                for (; m < a.T; ++m) {
+                    const double2 v = ld_pair<VEC>(sp, (size_t)m * stride, two);
+                    phys.x += v.x; phys.y += v.y;
+                }
+            }
+            if (b == a.first_local || b == a.last_local) {
+                spring = ld_pair<VEC>(a.exF, (size_t)((b == a.first_local ? 0 : 1) * a.D + c) * a.N + n0, two);
+            } else {
+                const double2 xp = ld_pair<VEC>(a.x, ox - a.S, two), xn = ld_pair<VEC>(a.x, ox + a.S, two);
+                double dp0 = xp.x - xv.x, dn0 = xn.x - xv.x, dp1 = xp.y - xv.y, dn1 = xn.y - xv.y;
+                if (a.pbc) {
+                    dp0 = min_image(dp0, a.L, a.invL); dn0 = min_image(dn0, a.L, a.invL);
+                    dp1 = min_image(dp1, a.L, a.invL); dn1 = min_image(dn1, a.L, a.invL);
+                }
+                spring.x = a.k * (dp0 + dn0);
+                spring.y = a.k * (dp1 + dn1);
+            }
+            fv.x = spring.x + phys.x;
+            fv.y = spring.y + phys.y;
+            st_pair<VEC>(a.fw, o, fv, two);
+        } else if (a.ops & (OP_B | OP_B_PHYS)) {
+            fv = ld_pair<VEC>(a.f, o, two);
+        }
         if (a.ops & OP_SUBCM) {
             const double cmc = c == 0 ? cm[0] : (c == 1 ? cm[1] : cm[2]);
-            p0 -= cmc; p1 -= cmc;
+            pv.x -= cmc; pv.y -= cmc;
         }
         double z0 = 0.0, z1 = 0.0;
         if (do_o) {
@@ -202,68 +342,86 @@ __global__ void __launch_bounds__(256) k_integrate(IntArgs a) {
                 gaussian_pair((uint32_t)q, (uint32_t)((a.bead_begin + b) * a.D + c), draw, a.seed, z0, z1);
             }
         }
-        if (a.ops & OP_O_PRE) { p0 = a.c1 * p0 + a.c2 * z0; p1 = a.c1 * p1 + a.c2 * z1; }
+        if (a.ops & OP_O_PRE) { pv.x = a.c1 * pv.x + a.c2 * z0; pv.y = a.c1 * pv.y + a.c2 * z1; }
         if (a.ops & (OP_B | OP_B_PHYS)) {
-            p0 += a.hdt * a.f[o];
-            if (two) p1 += a.hdt * a.f[o + 1];
+            pv.x += a.hdt * fv.x;
+            if (two) pv.y += a.hdt * fv.y;
         }
-        if (a.ops & OP_O_POST) { p0 = a.c1 * p0 + a.c2 * z0; p1 = a.c1 * p1 + a.c2 * z1; }
-        a.p[o] = p0;
-        if (two) a.p[o + 1] = p1;
+        if (a.ops & OP_O_POST) { pv.x = a.c1 * pv.x + a.c2 * z0; pv.y = a.c1 * pv.y + a.c2 * z1; }
+        if (a.ops & (OP_SUBCM | OP_O_PRE | OP_O_POST | OP_B | OP_B_PHYS)) st_pair<VEC>(a.p, o, pv, two);
         if (a.ops & OP_A) {
-            const size_t ox = o + a.S;  // skip the leading halo slab
-            double x0 = a.x[ox] + a.dt_over_m * p0;
-            a.x[ox] = x0;
-            double x1 = 0.0;
-            if (two) { x1 = a.x[ox + 1] + a.dt_over_m * p1; a.x[ox + 1] = x1; }
+            double2 xv = ld_pair<VEC>(a.x, ox, two);
+            xv.x += a.dt_over_m * pv.x;
+            if (two) xv.y += a.dt_over_m * pv.y;
+            st_pair<VEC>(a.x, ox, xv, two);
             if (a.ops & OP_HALO) {
-                if (b == 0) {  // first owned bead -> halo after the last
-                    size_t oh = (size_t)(a.Ploc + 1) * a.S + (size_t)c * a.N + n0;
-                    a.x[oh] = x0;
-                    if (two) a.x[oh + 1] = x1;
+                const size_t within = (size_t)c * a.N + n0;
+                if (b == 0) {  // first owned bead -> the trailing halo slab of the previous rank (own slab on a full ring)
+                    if (peer) { st_pair<VEC>(a.peer.halo_to_prev, within, xv, two); stored_remote = true; }
+                    else st_pair<VEC>(a.x, (size_t)(a.Ploc + 1) * a.S + within, xv, two);
                 }
-                if (b == a.Ploc - 1) {  // last owned bead -> halo before the first
-                    size_t oh = (size_t)c * a.N + n0;
-                    a.x[oh] = x0;
-                    if (two) a.x[oh + 1] = x1;
+                if (b == a.Ploc - 1) {  // last owned bead -> the leading halo slab of the next rank
+                    if (peer) { st_pair<VEC>(a.peer.halo_to_next, within, xv, two); stored_remote = true; }
+                    else st_pair<VEC>(a.x, within, xv, two);
                 }
             }
         }
         if (a.ops & OP_SUM) {
             // (odd N: the second slot of the last pair is no particle, but SUBCM and the Langevin step have acted on it)
-            const double ps = p0 + (two ? p1 : 0.0);
+            const double ps = pv.x + (two ? pv.y : 0.0);
             acc[0] += c == 0 ? ps : 0.0;
             acc[1] += c == 1 ? ps : 0.0;
             acc[2] += c == 2 ? ps : 0.0;
         }
     }
-    if (a.ops & (OP_SUM | OP_O_PRE | OP_O_POST)) {
+    if ((a.ops & (OP_SUM | OP_O_PRE | OP_O_POST | OP_ZERO_SUM)) || push_halo) {
         if (a.ops & OP_SUM) {
             block_sum<3>(acc, sm);
-            if (threadIdx.x == 0) {
+            if (tid == 0) {
                 for (int c = 0; c < 3; ++c) a.com_part[blockIdx.x * 4 + c] = acc[c];
             }
         }
-        if (threadIdx.x == 0) {
+        if (stored_remote) __threadfence_system();   // my slices are on their way before this block takes its ticket
+        __syncthreads();
+        if (tid == 0) {
             __threadfence();
             unsigned int t = atomicAdd(a.ticket, 1u);
             is_last = (t == gridDim.x - 1);
         }
         __syncthreads();
         if (is_last) {
+            double tot[3] = {0.0, 0.0, 0.0};
             if (a.ops & OP_SUM) {
                 __threadfence();
-                double tot[3] = {0.0, 0.0, 0.0};
                 // fixed order: each thread takes a strided set of blocks, then a block reduction
-                for (int blk = threadIdx.x; blk < (int)gridDim.x; blk += blockDim.x) {
+                for (int blk = tid; blk < (int)gridDim.x; blk += blockDim.x) {
                     for (int c = 0; c < 3; ++c) tot[c] += __ldcg(&a.com_part[blk * 4 + c]);
                 }
                 block_sum<3>(tot, sm);
-                if (threadIdx.x == 0) {
-                    for (int c = 0; c < 3; ++c) a.com[c] = tot[c];
+                if (tid == 0) {
+                    for (int c = 0; c < 3; ++c) { a.com[c] = tot[c]; sh_cm[c] = tot[c]; }
                 }
+                __syncthreads();
             }
-            if (threadIdx.x == 0) {
+            if (peer && (a.ops & (OP_SUM | OP_ZERO_SUM))) {
+                // publish to every rank (myself included): word w carries half w&1 of sum w/2, tagged with the sequence number
+                const unsigned seq = sh_seq[0] + 1u;
+                if (tid < a.peer.world * kComWords) {
+                    const int r = tid / kComWords, w = tid % kComWords;
+                    const double v = (w < 6 && (a.ops & OP_SUM)) ? sh_cm[w >> 1] : 0.0;
+                    const unsigned half = (w & 1) ? (unsigned)__double2hiint(v) : (unsigned)__double2loint(v);
+                    st_sys_u64(&a.peer.box[r]->com_in[seq & 1u][a.peer.rank][w], ((unsigned long long)seq << 32) | half);
+                }
+                if (tid == 0) a.peer.seq[0] = seq;
+            }
+            if (push_halo && tid == 0) {
+                __threadfence_system();      // every block fenced its slices before its ticket; order the flags behind them
+                const unsigned k = sh_seq[1] + 1u;
+                st_sys_u32(&a.peer.box[a.peer.prev]->halo_flag[1], k);   // my first bead is prev's trailing halo
+                st_sys_u32(&a.peer.box[a.peer.next]->halo_flag[0], k);   // my last bead is next's leading halo
+                a.peer.seq[1] = k;
+            }
+            if (tid == 0) {
                 *a.ticket = 0u;
                 if (do_o) *a.draw = draw + 1ull;
             }
@@ -272,10 +430,53 @@ __global__ void __launch_bounds__(256) k_integrate(IntArgs a) {
     tl_end(a.tl);
 }
 
+// Simulation::updateNeighboringCoordinates on a bead shard (peer memory): the first / last owned bead slices go to the
+// ring neighbours' halo slabs, same hand-shake as the HALO stage of k_integrate. One launch per state upload.
+__global__ void __launch_bounds__(256) k_peer_push_halos(const double* x, size_t S, int Ploc, PeerDev peer, unsigned int* ticket, int* err) {
+    __shared__ bool is_last;
+    __shared__ unsigned sh_k;
+    const int tid = threadIdx.x;
+    if (tid == 0) sh_k = peer.seq[1] + 1u;
+    __syncthreads();
+    const unsigned k = sh_k;
+    if (tid < 2) {
+        st_sys_u32(tid == 0 ? &peer.box[peer.next]->credit[0] : &peer.box[peer.prev]->credit[1], k);
+        wait_sys_u32_ge(&peer.mine->credit[tid], k, peer.timeout_ns, err, kErrPeerTimeout);
+    }
+    __syncthreads();
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + tid; i < S; i += (size_t)gridDim.x * blockDim.x) {
+        peer.halo_to_prev[i] = x[S + i];
+        peer.halo_to_next[i] = x[(size_t)Ploc * S + i];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence();
+        is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (is_last && tid == 0) {
+        __threadfence_system();
+        st_sys_u32(&peer.box[peer.prev]->halo_flag[1], k);
+        st_sys_u32(&peer.box[peer.next]->halo_flag[0], k);
+        peer.seq[1] = k;
+        *ticket = 0u;
+    }
+}
+
+int launch_peer_push_halos(Sim* s) {
+    if (!s->peer_on) return PIMDB_OK;
+    k_peer_push_halos<<<grid_for(s->S, 256, kNumSM), 256, 0, s->stream>>>(s->x, s->S, s->Ploc, s->peer, s->tickets + 1, s->err_d);
+    s->launches += 1;
+    PIMDB_CUDA_TRY(s, cudaGetLastError());
+    return PIMDB_OK;
+}
+
 int launch_integrate(Sim* s, unsigned ops) {
     IntArgs a;
     a.x = s->x; a.p = s->p;
     a.f = (ops & OP_B_PHYS) ? s->fp : s->f;
+    a.fw = s->f;
     a.com_part = s->com_part; a.com = s->com; a.ticket = s->tickets; a.draw = s->draw;
     a.N = s->N; a.D = s->D; a.Ploc = s->Ploc; a.bead_begin = s->b0; a.S = s->S;
     a.c1 = s->c1; a.c2 = s->c2;
@@ -290,10 +491,42 @@ int launch_integrate(Sim* s, unsigned ops) {
         a.noise = s->rm_noise;
     }
     a.tl = tl_slot(s);
+    a.scratch = s->pair_on ? s->pair_scratch : nullptr; a.exF = s->exF;
+    a.T = s->T;
+    a.first_local = (s->bosonic && s->has_first) ? 0 : -1;
+    a.last_local = (s->bosonic && s->has_last) ? s->Ploc - 1 : -1;
+    a.pbc = s->cfg.pbc; a.ext_pot = s->cfg.ext_potential;
+    a.k = s->kspring; a.kext = s->kext; a.L = s->L; a.invL = 1.0 / s->L; a.mass = s->cfg.mass;
+    if (s->cfg.ext_potential == PIMDB_POT_DOUBLE_WELL) { a.ext_a = s->cfg.ext_strength; a.ext_b = s->cfg.ext_location; }
+    else { a.ext_a = s->cfg.ext_amplitude; a.ext_b = s->cfg.ext_phase; }
+    a.peer_on = s->peer_on ? 1 : 0;
+    a.peer = s->peer;
+    a.err = s->err_d;
+    if (ops & OP_ASSEMBLE) s->split_stale = true;
     const size_t items = (size_t)s->Ploc * s->D * ((s->N + 1) / 2);
     const int grid = grid_for(items, 256, kMaxPartials);
-    k_integrate<<<grid, 256, 0, s->stream>>>(a);
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (s->timing) {
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, s->stream);
+    }
+    if (s->N % 2 == 0) k_integrate<true><<<grid, 256, 0, s->stream>>>(a);
+    else k_integrate<false><<<grid, 256, 0, s->stream>>>(a);
     s->launches += 1;
+    if (e0) {
+        cudaEventRecord(e1, s->stream);
+        s->ev_integ.emplace_back(e0, e1);
+        // algorithmic bytes of this launch per degree of freedom: p read + written when a stage changes it, f read by a kick
+        // (written, with x and its two neighbours and the T pair partials read, when the forces are assembled here),
+        // x read + written by the drift
+        double per_dof = 0.0;
+        if (ops & (OP_SUBCM | OP_O_PRE | OP_O_POST | OP_B | OP_B_PHYS)) per_dof += 16.0;
+        else if (ops & (OP_SUM | OP_A)) per_dof += 8.0;
+        if (ops & OP_ASSEMBLE) per_dof += 8.0 + 24.0 + (s->pair_on ? 8.0 * s->T : 0.0);
+        else if (ops & (OP_B | OP_B_PHYS)) per_dof += 8.0;
+        if (ops & OP_A) per_dof += 16.0;
+        s->integ_bytes += per_dof * (double)s->Ploc * (double)s->S;
+    }
     PIMDB_CUDA_TRY(s, cudaGetLastError());
     return PIMDB_OK;
 }
@@ -316,34 +549,66 @@ int launch_fill_halos(Sim* s) {
 }
 
 // ------------------------------------------------------------------------------------------------------
-// Boundary transposes: host dVec layout [bead][particle][axis] <-> device [bead][axis][particle].
-__global__ void k_aos_to_soa(const double* __restrict__ aos, double* __restrict__ soa, int N, int D, long long total) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        long long b = i / ((long long)N * D);
-        int r = (int)(i % ((long long)N * D));
-        int c = r / N, n = r % N;                // i indexes the SoA side (coalesced writes)
-        soa[i] = aos[(b * N + n) * D + c];
+// Boundary transposes: host dVec layout [bead][particle][axis] <-> device [bead][axis][particle], up to three arrays
+// per launch (staging buffer: the arrays one after the other).
+struct TransposeArgs {
+    double* soa[3];        // device arrays (already offset past a leading halo slab)
+    double* aos;           // staging buffer
+    int n, N, D;
+    long long total;       // elements per array
+};
+__global__ void k_aos_to_soa(TransposeArgs a) {
+    const long long ND = (long long)a.N * a.D;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.total * a.n; i += (long long)gridDim.x * blockDim.x) {
+        const int arr = (int)(i / a.total);
+        const long long j = i - arr * a.total;
+        const long long b = j / ND;
+        const int r = (int)(j % ND);
+        const int c = r / a.N, n = r % a.N;       // j indexes the SoA side (coalesced writes)
+        double* dst = arr == 0 ? a.soa[0] : (arr == 1 ? a.soa[1] : a.soa[2]);
+        dst[j] = a.aos[arr * a.total + (b * a.N + n) * a.D + c];
     }
 }
-__global__ void k_soa_to_aos(const double* __restrict__ soa, double* __restrict__ aos, int N, int D, long long total) {
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        long long b = i / ((long long)N * D);
-        int r = (int)(i % ((long long)N * D));
-        int n = r / D, c = r % D;                // i indexes the AoS side
-        aos[i] = soa[(b * D + c) * N + n];
+__global__ void k_soa_to_aos(TransposeArgs a) {
+    const long long ND = (long long)a.N * a.D;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.total * a.n; i += (long long)gridDim.x * blockDim.x) {
+        const int arr = (int)(i / a.total);
+        const long long j = i - arr * a.total;
+        const long long b = j / ND;
+        const int r = (int)(j % ND);
+        const int n = r / a.D, c = r % a.D;       // j indexes the AoS side
+        const double* src = arr == 0 ? a.soa[0] : (arr == 1 ? a.soa[1] : a.soa[2]);
+        a.aos[i] = src[(b * a.D + c) * a.N + n];
     }
 }
 
-int launch_aos_to_soa(Sim* s, double* dst_soa, bool dst_has_halo) {
-    long long total = (long long)s->Ploc * s->S;
-    k_aos_to_soa<<<grid_for(total, 256), 256, 0, s->stream>>>(s->stage_d, dst_soa + (dst_has_halo ? s->S : 0), s->N, s->D, total);
+int launch_aos_to_soa(Sim* s, int n, double* const* dst_soa, const bool* has_halo) {
+    TransposeArgs a{};
+    for (int i = 0; i < n; ++i) a.soa[i] = dst_soa[i] + (has_halo[i] ? s->S : 0);
+    a.aos = s->stage_d; a.n = n; a.N = s->N; a.D = s->D; a.total = (long long)s->Ploc * s->S;
+    k_aos_to_soa<<<grid_for(a.total * n, 256), 256, 0, s->stream>>>(a);
     s->launches += 1;
     PIMDB_CUDA_TRY(s, cudaGetLastError());
     return PIMDB_OK;
 }
-int launch_soa_to_aos(Sim* s, const double* src_soa, bool src_has_halo) {
-    long long total = (long long)s->Ploc * s->S;
-    k_soa_to_aos<<<grid_for(total, 256), 256, 0, s->stream>>>(src_soa + (src_has_halo ? s->S : 0), s->stage_d, s->N, s->D, total);
+int launch_soa_to_aos(Sim* s, int n, const double* const* src_soa, const bool* has_halo) {
+    TransposeArgs a{};
+    for (int i = 0; i < n; ++i) a.soa[i] = const_cast<double*>(src_soa[i]) + (has_halo[i] ? s->S : 0);
+    a.aos = s->stage_d; a.n = n; a.N = s->N; a.D = s->D; a.total = (long long)s->Ploc * s->S;
+    k_soa_to_aos<<<grid_for(a.total * n, 256), 256, 0, s->stream>>>(a);
+    s->launches += 1;
+    PIMDB_CUDA_TRY(s, cudaGetLastError());
+    return PIMDB_OK;
+}
+
+// Bead shard: a one-block kernel that waits (bounded) for both halo slices; used ahead of kernels that read the halo
+// slabs but are not part of the force evaluation (estimators right after an upload).
+__global__ void k_peer_wait_halos(const unsigned int* halo_flag, const unsigned int* halo_seq, unsigned long long timeout_ns, int* err) {
+    peer_wait_halos(halo_flag, halo_seq, timeout_ns, err);
+}
+int launch_peer_wait_halos(Sim* s) {
+    if (!s->peer_on) return PIMDB_OK;
+    k_peer_wait_halos<<<1, 32, 0, s->stream>>>(s->peer.mine->halo_flag, s->peer.seq + 1, s->peer.timeout_ns, s->err_d);
     s->launches += 1;
     PIMDB_CUDA_TRY(s, cudaGetLastError());
     return PIMDB_OK;

@@ -20,7 +20,37 @@ constexpr double kAzRm = 5.60738, kAzA = 0.5448504e6, kAzEps = 3.42016E-5, kAzAl
                  kAzD = 1.241314, kAzC6 = 1.3732412, kAzC8 = 0.4253785, kAzC10 = 0.1781;
 
 // device-side error flags (host-mapped)
-enum : int { kErrOverflowFwd = 1, kErrOverflowBwd = 2, kErrSyncTimeout = 4 };
+enum : int { kErrOverflowFwd = 1, kErrOverflowBwd = 2, kErrSyncTimeout = 4, kErrPeerTimeout = 8 };
+
+// ---- bead sharding over peer memory (DESIGN.md "Multi-GPU") --------------------------------------------
+// Every handle owns a small MAILBOX in its own device memory that its peers write over NVLink (cudaIpc mapping, or
+// plain pointers inside one process) and that only the owner reads:
+//   com_in[slot][rank][word]  centre-of-mass momentum sums of every rank, as self-validating 8-byte words
+//                             {32 data bits, 32-bit sequence number} (an 8-byte store is single-copy atomic, so no
+//                             fence / flag round trip sits between the sum and its consumers); slot = sequence & 1
+//   halo_flag[2]              number of halo slices received so far from the previous / next rank (the slices land
+//                             directly in the halo slabs of x; flag written after a system-scope fence)
+//   credit[2]                 number of force evaluations the previous / next rank has completed, i.e. how many of
+//                             the slices this rank sent have been consumed (a slice is only overwritten after that)
+constexpr int kMaxPeers = 8;          // GPUs of one box
+constexpr int kComWords = 8;          // 4 doubles as 8 half-words
+struct PeerMailbox {
+    unsigned long long com_in[2][kMaxPeers][kComWords];
+    unsigned int halo_flag[2];
+    unsigned int credit[2];
+    unsigned int pad[60];
+};
+struct PeerDev {                      // passed by value to the kernels that talk to peers
+    int world, rank;
+    PeerMailbox* mine;                // local mailbox
+    PeerMailbox* box[kMaxPeers];      // every rank's mailbox (box[rank] == mine)
+    double* halo_to_prev;             // previous rank's trailing halo slab (receives this rank's first bead)
+    double* halo_to_next;             // next rank's leading halo slab (receives this rank's last bead)
+    unsigned int* seq;                // local counters: [0] COM pushes, [1] halo pushes, [2] force evaluations of sharded steps,
+                                      //                 [3] halo pushes made by sharded steps (what credits are compared with)
+    int prev, next;
+    unsigned long long timeout_ns;    // bound of every device-side wait
+};
 
 struct DevObs {  // partial sums produced on device; assembled into pimdb_observables on the host
     double spring_e[1];      // sum over owned classical links of 0.5 k |x_b - x_{b-1}|^2 (exterior link excluded for bosons)
@@ -60,12 +90,12 @@ struct Sim {
     int sm_count = 148;
     cudaStream_t stream = nullptr, stream_x = nullptr;  // main stream, exchange side stream
     bool own_stream = true;
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_copy = nullptr;
 
     // state (device). x has Ploc+2 slabs (halo, owned..., halo); the others Ploc slabs.
     double *x = nullptr, *p = nullptr, *f = nullptr, *fs = nullptr, *fp = nullptr;
-    double *stage_d = nullptr;         // AoS staging [Ploc][N][D]
-    double *stage_h = nullptr;         // pinned host staging
+    double *stage_d = nullptr;         // AoS staging [3][Ploc][N][D]
+    double *stage_h = nullptr;         // pinned host staging, same size
     // pair forces
     ushort2* tile_ij = nullptr;        // TP entries (I,J), I<=J
     double* pair_scratch = nullptr;    // [bead_chunk][T][T][D][32]
@@ -99,10 +129,20 @@ struct Sim {
     cudaGraph_t graph = nullptr; cudaGraphExec_t graph_exec = nullptr;
     unsigned long long graph_kernels = 0;
     bool p_shift_pending = false;      // fixcom: COM shift computed but not yet subtracted from p
+    // peer-memory bead sharding (pimdb_peer_attach)
+    bool peer_on = false;
+    PeerDev peer{};
+    PeerMailbox* mailbox = nullptr;    // own mailbox (exported)
+    unsigned int* peer_seq = nullptr;  // own counters
+    std::vector<void*> ipc_opened;     // mappings to close
+    bool z_owed = false;               // peer mode, Langevin / no thermostat: the closing zeroMomentum of the last iteration
+                                       // has not been carried out (it is subsumed by the first one of the next iteration)
+    bool split_stale = false;          // f is current but f_spring / f_phys are not (fused closing kernel)
     unsigned long long launches = 0;
     // timing
     bool timing = false;
-    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pair, ev_step;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev_pair, ev_step, ev_integ;
+    double integ_bytes = 0.0;          // algorithmic bytes moved by the k_integrate launches in ev_integ
     std::string err;
 };
 
@@ -132,8 +172,13 @@ int launch_exchange(Sim* s, cudaStream_t st);          // prep + forward/backwar
 int launch_exchange_tables(Sim* s, int table);
 int launch_exchange_estimators(Sim* s);
 int launch_fill_halos(Sim* s);
-enum : unsigned { OP_SUBCM = 1, OP_O_PRE = 2, OP_B = 4, OP_O_POST = 8, OP_A = 16, OP_SUM = 32, OP_HALO = 64, OP_B_PHYS = 128 };
+enum : unsigned { OP_SUBCM = 1, OP_O_PRE = 2, OP_B = 4, OP_O_POST = 8, OP_A = 16, OP_SUM = 32, OP_HALO = 64, OP_B_PHYS = 128,
+                  OP_ASSEMBLE = 256,   // form f = springs + external + pair partials in the same pass (before B)
+                  OP_CREDIT = 512,     // peer mode: tell the ring neighbours that their halo slices have been consumed
+                  OP_ZERO_SUM = 1024   // peer mode: publish zero momentum sums (uniform entry state of a captured step)
+};
 int launch_integrate(Sim* s, unsigned ops);
+int launch_peer_push_halos(Sim* s);
 int launch_nm_propagate(Sim* s);
 int launch_nm_thermostat(Sim* s);
 int launch_nm_momenta(Sim* s, bool forward);   // p <-> normal-mode momenta, in place
@@ -142,7 +187,8 @@ int ranmars_create(Sim* s);
 int launch_ranmars_fill(Sim* s);   // the next thermostat half-step's gaussians, all owned beads
 int launch_nose_hoover(Sim* s);
 int launch_nose_hoover_energy(Sim* s, double* out_dev);
-int launch_aos_to_soa(Sim* s, double* dst_soa, bool dst_has_halo);
-int launch_soa_to_aos(Sim* s, const double* src_soa, bool src_has_halo);
+int launch_aos_to_soa(Sim* s, int n, double* const* dst_soa, const bool* has_halo);          // up to 3 arrays per launch
+int launch_soa_to_aos(Sim* s, int n, const double* const* src_soa, const bool* has_halo);
+int launch_peer_wait_halos(Sim* s);
 
 }  // namespace pimdb

@@ -1,5 +1,16 @@
 """Bead sharding across the GPUs of one box: one process per GPU, torch.distributed for the plumbing.
 
+Two ways to couple the shards:
+
+* ``PeerShardedSimulation`` (the product path): the ranks exchange one 256-byte blob each at start-up
+  (``gather_blobs``: cudaIpc handles of the coordinate array and of a small mailbox), after which halo slices and
+  momentum sums are *stored into the peers' memory by the step's own kernels* over NVLink (csrc/integrator.cu,
+  include/pimdb200.h ``pimdb_peer_attach``). A step is one CUDA-graph replay per rank with no host call or collective
+  inside; torch.distributed is only used for the start-up gather and for the all-reduce of the observable partials on
+  logging steps.
+* ``ShardedSimulation`` (host-driven, kept as the portable cross-check): the host runs NCCL / gloo collectives between
+  the four phases of ``pimdb_step_phase``. This is the choreography described next, and what the gloo tests exercise.
+
 The reference runs one MPI rank per bead and moves, every step, one bead slice to each ring neighbour
 (MPI_Sendrecv, src/simulation.cpp:299-347), NDIM doubles for zeroMomentum (MPI_Allreduce, :595) and one double
 per observable column (src/observables/observable.cpp:105). Here rank r owns the contiguous bead range
@@ -194,6 +205,64 @@ class ShardedSimulation:
     def observables(self) -> dict:
         self.flush()
         part = self.shard.observables_partial()
+        if self.world > 1:
+            dist.all_reduce(part, op=dist.ReduceOp.SUM, group=self.group)
+        return {n: float(v) for n, v in zip(OBS_FIELDS, part.tolist())}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+def gather_blobs(blob: bytes, group=None) -> bytes:
+    """All-gather one fixed-size byte record per rank, in rank order (the start-up exchange of the peer-memory path).
+    Works on any backend: the staging tensor lives where the backend wants it (CUDA for nccl, host for gloo)."""
+    world = dist.get_world_size(group)
+    backend = dist.get_backend(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu")
+    mine = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
+    out = torch.empty(world * len(blob), dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(out, mine, group=group)
+    return bytes(out.cpu().numpy().tobytes())
+
+
+class PeerShardedSimulation:
+    """Simulation::run's loop body (src/simulation.cpp:246-259) over bead shards coupled through peer memory.
+
+    ``make_sim(lo, hi)`` builds this rank's handle (default: a DeviceSim on ``device``); the handle must offer
+    ``peer_export() -> bytes`` and ``peer_attach(world, rank, blobs)`` -- which is all this class needs from it at
+    start-up, so the choreography is testable on CPU with a stand-in (tests/test_sharding_gloo.py)."""
+
+    def __init__(self, cfg, rank: int = None, world: int = None, device: int = 0, group=None, make_sim=None):
+        self.cfg = cfg
+        self.group = group
+        self.rank = dist.get_rank(group) if rank is None else rank
+        self.world = dist.get_world_size(group) if world is None else world
+        self.lo, self.hi = bead_range(cfg.nbeads, self.world, self.rank)
+        if make_sim is None:
+            from .engine import DeviceSim
+            torch.cuda.set_device(device)
+            self.stream = torch.cuda.Stream(device=device)
+            self.sim = DeviceSim(cfg, self.lo, self.hi, device)
+            self.sim.set_stream(self.stream.cuda_stream)
+            self.device = torch.device("cuda", device)
+        else:
+            self.sim = make_sim(self.lo, self.hi)
+            self.stream = None
+            self.device = torch.device("cpu")
+        blobs = gather_blobs(self.sim.peer_export(), group)
+        self.sim.peer_attach(self.world, self.rank, blobs)
+        dist.barrier(group)     # every rank is attached (and has pushed its halo slices) before anyone steps
+
+    def set_state(self, x=None, p=None):
+        """Global arrays [P][N][D]; this rank uploads its own beads. Collective (the coordinates' halo slices move)."""
+        self.sim.upload(None if x is None else x[self.lo:self.hi], None if p is None else p[self.lo:self.hi])
+
+    def step(self, nsteps: int = 1):
+        self.sim.step(nsteps)
+
+    def observables(self) -> dict:
+        """Sum of the per-rank partial structs, what ObservablesLogger::log does with MPI_Allreduce
+        (src/observables/observable.cpp:92-116). Collective."""
+        o = self.sim.observables()
+        part = torch.tensor([o[n] for n in OBS_FIELDS], dtype=torch.float64, device=self.device)
         if self.world > 1:
             dist.all_reduce(part, op=dist.ReduceOp.SUM, group=self.group)
         return {n: float(v) for n, v in zip(OBS_FIELDS, part.tolist())}

@@ -78,6 +78,42 @@ class DeviceSim:
         self._ck(self.lib.pimdb_get_state(self.h, _cabi.ARRAY[which], out.ctypes.data_as(C.c_void_p)))
         return out
 
+    def _hostptr(self, a):
+        return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+    def _checked(self, a):
+        if a is None:
+            return None
+        if a.dtype != np.float64 or not a.flags.c_contiguous or a.shape != self.shape:
+            raise ValueError(f"expected a C-contiguous float64 array of shape {self.shape}")
+        return a
+
+    def upload(self, x=None, p=None):
+        """Several arrays per call: one PCIe copy each, one transpose kernel (pimdb_upload_state)."""
+        x = None if x is None else np.ascontiguousarray(x, dtype=np.float64)
+        p = None if p is None else np.ascontiguousarray(p, dtype=np.float64)
+        self._ck(self.lib.pimdb_upload_state(self.h, self._hostptr(self._checked(x)), self._hostptr(self._checked(p))))
+
+    def download(self, x=None, p=None, f=None):
+        """Fill the given arrays (coordinates / momenta / forces) with one synchronisation (pimdb_download_state)."""
+        self._ck(self.lib.pimdb_download_state(self.h, self._hostptr(self._checked(x)), self._hostptr(self._checked(p)),
+                                               self._hostptr(self._checked(f))))
+
+    # -- bead sharding over peer memory (include/pimdb200.h)
+    def peer_export(self) -> bytes:
+        buf = C.create_string_buffer(_cabi.PEER_BLOB_BYTES)
+        self._ck(self.lib.pimdb_peer_export(self.h, buf))
+        return buf.raw
+
+    def peer_attach(self, world: int, rank: int, blobs: bytes):
+        if len(blobs) != world * _cabi.PEER_BLOB_BYTES:
+            raise ValueError("blobs must hold one PEER_BLOB_BYTES record per rank, in rank order")
+        self._ck(self.lib.pimdb_peer_attach(self.h, int(world), int(rank), C.c_char_p(blobs)))
+
+    @property
+    def peer_attached(self) -> bool:
+        return bool(self.lib.pimdb_peer_attached(self.h))
+
     # -- the reference's calls
     def update_neighboring_coordinates(self):
         self._ck(self.lib.pimdb_update_neighbors(self.h))
@@ -148,6 +184,11 @@ class DeviceSim:
 
     def timing_enable(self, on: bool):
         self._ck(self.lib.pimdb_timing_enable(self.h, int(on)))
+
+    def timing_integrator_bytes(self) -> float:
+        b = C.c_double()
+        self._ck(self.lib.pimdb_timing_integrator_bytes(self.h, C.byref(b)))
+        return b.value
 
     def timing_get(self, what: int):
         ms = C.c_double()

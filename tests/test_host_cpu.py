@@ -113,7 +113,7 @@ def test_library_exports_every_declared_symbol():
     declared -= {"pimdb_config", "pimdb_observables", "pimdb_sim"}
     assert declared == set(_cabi.SYMBOLS), declared ^ set(_cabi.SYMBOLS)
     lib = _cabi.load()   # raises if a declared symbol is missing from libpimdb200.so
-    assert lib.pimdb_abi_version() == 1
+    assert lib.pimdb_abi_version() == _cabi.ABI_VERSION == 2
     assert C.sizeof(_cabi.PimdbConfig) == 12 * 4 + 13 * 8 + 8 + 3 * 4 + 4 * 4 + 4   # matches the C struct layout (+ tail padding)
 
 
