@@ -275,8 +275,8 @@ def measure(run: Runner, K: int, W: int, sfreq: int, flush, clocks_rank0: bool, 
             # the same step through the host-buffer API: upload x,p -> step -> download x,p,f, page-locked host buffers
             # (the library copies straight from / into them), one transpose kernel and one synchronisation per direction
             shape = run.x[run.lo:run.hi].shape
-            pin = [torch.empty(shape, dtype=torch.float64, pin_memory=True) for _ in range(3)]
-            hx, hp, hf = (t.numpy() for t in pin)
+            pin = torch.empty((3,) + tuple(shape), dtype=torch.float64, pin_memory=True)   # x | p | f back to back: one copy each way
+            hx, hp, hf = (pin[i].numpy() for i in range(3))
             sim.download(hx, hp, None)
             Ke = max(20, min(K, 300))
             for _ in range(3):

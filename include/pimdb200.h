@@ -160,7 +160,8 @@ int pimdb_get_state(pimdb_sim* sim, int which, double* host);
 
 /* Several arrays per call: one PCIe copy per array back to back and ONE transpose kernel (upload), one transpose kernel,
  * the copies and ONE synchronisation (download). NULL = skip that array. Same layout and buffer rules as above; the
- * caller's buffers may be reused as soon as the call returns. What a host loop that keeps its own copy of the state
+ * caller's buffers may be reused as soon as the call returns; page-locked arrays that sit back to back in host memory
+ * (x | p | f slices of one allocation) travel as a single copy. What a host loop that keeps its own copy of the state
  * pays per step (bench.py's e2e figure). */
 int pimdb_upload_state(pimdb_sim* sim, const double* x, const double* p);
 int pimdb_download_state(pimdb_sim* sim, double* x, double* p, double* f);
@@ -235,6 +236,11 @@ int pimdb_step_phase(pimdb_sim* sim, int phase);
 int pimdb_peer_export(pimdb_sim* sim, void* blob_out /* PIMDB_PEER_BLOB_BYTES */);
 int pimdb_peer_attach(pimdb_sim* sim, int world, int rank, const void* blobs /* world x PIMDB_PEER_BLOB_BYTES */);
 int pimdb_peer_attached(const pimdb_sim* sim);
+/* Enqueue, without waiting, whatever deferred work the next read of the momenta would trigger (the lazily closed
+ * zeroMomentum above). One host thread driving several shards calls it on EVERY handle before it reads any of them
+ * (pimdb_get_state(P), pimdb_observables_calc): those reads block, and the deferred work is collective. Harmless no-op
+ * otherwise. */
+int pimdb_settle(pimdb_sim* sim);
 
 /* Number of kernels this handle has launched (graph replays count their kernel nodes). */
 unsigned long long pimdb_launch_count(const pimdb_sim* sim);

@@ -897,3 +897,122 @@ int orc_exchange_get(const orc_sim* s, char which, double* dst) {
     if (dst) memcpy(dst, src, n * sizeof(double));
     return (int)n;
 }
+
+
+/* ------------------------------------------------------------------ extended-precision exchange (rounding-noise yardstick)
+ * The same Feldman-Hirshberg algorithm (quadratic_bosonic_exchange.cpp:34-215: cycle-energy recurrence, shifted
+ * log-sum-exp recursions for V and V_backwards, connection probabilities, exterior spring forces) with every
+ * intermediate in `long double` (x87, 64-bit mantissa). The double-precision algorithm loses digits where beta*V is
+ * large: the exponent -beta (V[u] + E + Vb[l+1] - V[N]) is a difference of numbers ~beta*|V| (6e4 at N = 8192), so the
+ * connection probabilities of the reference itself carry ~1e-11 .. 1e-9 of rounding noise at N >= 512 (rows of its
+ * probability matrix sum to 1 only to 1e-11). This version says which of two double-precision results is closer to
+ * the algorithm's exact answer. Host AoS slices [N][D]; x2 = bead after the first, xPm1 = bead before the last. */
+static long double ld_sep2(int D, int pbc, long double L, const double* xa, int ia, const double* xb, int ib, long double* d) {
+    long double r2 = 0.0L;
+    for (int a = 0; a < D; ++a) {
+        long double dx = (long double)xb[(size_t)ib * D + a] - (long double)xa[(size_t)ia * D + a];
+        if (pbc) dx -= L * floorl(dx / L + 0.5L);
+        if (d) d[a] = dx;
+        r2 += dx * dx;
+    }
+    return r2;
+}
+
+int orc_exchange_ld(int N, int D, int pbc, double size, double kspring, double beta_exch, const double* x1, const double* xP,
+                    const double* x2, const double* xPm1, double* V_out, double* Vb_out, double* f_first, double* f_last,
+                    double* prim_out, int l_stride) {
+    const long double L = size, k = kspring, beta = beta_exch;
+    const size_t ntri = (size_t)N * (N + 1) / 2;
+    long double* E = (long double*)malloc(sizeof(long double) * ntri);
+    long double* V = (long double*)malloc(sizeof(long double) * (N + 1));
+    long double* Vb = (long double*)malloc(sizeof(long double) * (N + 1));
+    long double* tmp = (long double*)malloc(sizeof(long double) * (N + 1));
+    if (!E || !V || !Vb || !tmp) { free(E); free(V); free(Vb); free(tmp); return -1; }
+#define ELD(m, kk) E[(size_t)(m) * ((m) + 1) / 2 - (kk)]
+    /* (OpenMP where the build has it -- rows, force particles and the terms of a sum are independent; in long double the
+     * order of a sum does not matter at the 1e-10 level this yardstick serves) */
+#pragma omp parallel for schedule(dynamic, 16)
+    for (int v = 0; v < N; ++v) {
+        ELD(v + 1, 1) = 0.5L * k * ld_sep2(D, pbc, L, x1, v, xP, v, NULL);
+        for (int u = v - 1; u >= 0; --u)
+            ELD(v + 1, v - u + 1) = ELD(v + 1, v - u) + 0.5L * k * (ld_sep2(D, pbc, L, xP, u, x1, u + 1, NULL) -
+                                                                   ld_sep2(D, pbc, L, x1, u + 1, xP, v, NULL) +
+                                                                   ld_sep2(D, pbc, L, x1, u, xP, v, NULL));
+    }
+    V[0] = 0.0L;
+    for (int m = 1; m <= N; ++m) {
+        long double shift = LDBL_MAX;
+        for (int kk = m; kk > 0; --kk) {
+            tmp[kk - 1] = ELD(m, kk) + V[m - kk];
+            if (tmp[kk - 1] < shift) shift = tmp[kk - 1];
+        }
+        long double denom = 0.0L;
+#pragma omp parallel for reduction(+ : denom) if (m > 512)
+        for (int kk = m; kk > 0; --kk) denom += expl(-beta * (tmp[kk - 1] - shift));
+        V[m] = shift - logl(denom / (long double)m) / beta;
+    }
+    Vb[N] = 0.0L;
+    for (int l = N - 1; l > 0; --l) {
+        long double shift = LDBL_MAX;
+        for (int p = l; p < N; ++p) {
+            tmp[p] = ELD(p + 1, p - l + 1) + Vb[p + 1];
+            if (tmp[p] < shift) shift = tmp[p];
+        }
+        long double denom = 0.0L;
+#pragma omp parallel for reduction(+ : denom) if (N - l > 512)
+        for (int p = l; p < N; ++p) denom += expl(-beta * (tmp[p] - shift)) / (long double)(p + 1);
+        Vb[l] = shift - logl(denom) / beta;
+    }
+    Vb[0] = V[N];
+    for (int i = 0; i <= N; ++i) { if (V_out) V_out[i] = (double)V[i]; if (Vb_out) Vb_out[i] = (double)Vb[i]; }
+    if (f_first) {   /* :188-215: sum over u >= l-1 of P(u -> l) (r^P_u - r^1_l) + (r^2_l - r^1_l) */
+#pragma omp parallel for schedule(dynamic, 16)
+        for (int l = 0; l < N; l += l_stride) {   /* (l_stride > 1: a sample of the particles, the others are left untouched) */
+            long double d[3];
+            long double acc[3] = {0, 0, 0};
+            for (int u = (l - 1 > 0 ? l - 1 : 0); u < N; ++u) {
+                long double pr;
+                if (l == u + 1) pr = 1.0L - expl(-beta * (V[u + 1] + Vb[u + 1] - V[N]));
+                else pr = expl(-beta * (V[l] + ELD(u + 1, u - l + 1) + Vb[u + 1] - V[N])) / (long double)(u + 1);
+                ld_sep2(D, pbc, L, x1, l, xP, u, d);
+                for (int a = 0; a < D; ++a) acc[a] += pr * d[a];
+            }
+            ld_sep2(D, pbc, L, x1, l, x2, l, d);
+            for (int a = 0; a < D; ++a) f_first[(size_t)l * D + a] = (double)((acc[a] + d[a]) * k);
+        }
+    }
+    if (f_last) {    /* :159-186: sum over u <= l+1 of P(l -> u) (r^1_u - r^P_l) + (r^{P-1}_l - r^P_l) */
+#pragma omp parallel for schedule(dynamic, 16)
+        for (int l = 0; l < N; l += l_stride) {
+            long double d[3];
+            long double acc[3] = {0, 0, 0};
+            for (int u = 0; u <= l + 1 && u < N; ++u) {
+                long double pr;
+                if (u == l + 1) pr = 1.0L - expl(-beta * (V[l + 1] + Vb[l + 1] - V[N]));
+                else pr = expl(-beta * (V[u] + ELD(l + 1, l - u + 1) + Vb[l + 1] - V[N])) / (long double)(l + 1);
+                ld_sep2(D, pbc, L, xP, l, x1, u, d);
+                for (int a = 0; a < D; ++a) acc[a] += pr * d[a];
+            }
+            ld_sep2(D, pbc, L, xP, l, xPm1, l, d);
+            for (int a = 0; a < D; ++a) f_last[(size_t)l * D + a] = (double)((acc[a] + d[a]) * k);
+        }
+    }
+    if (prim_out) {  /* :250-279, without the 1/P of the caller */
+        long double* e = tmp;
+        long double* prim = (long double*)malloc(sizeof(long double) * (N + 1));
+        prim[0] = 0.0L;
+        for (int m = 1; m <= N; ++m) {
+            long double shift = LDBL_MAX;
+            for (int kk = m; kk > 0; --kk) { long double val = ELD(m, kk) + V[m - kk]; if (val < shift) shift = val; }
+            long double sig = 0.0L;
+            for (int kk = m; kk > 0; --kk) sig += (prim[m - kk] - ELD(m, kk)) * expl(-beta * (ELD(m, kk) + V[m - kk] - shift));
+            prim[m] = sig / (m * expl(-beta * (V[m] - shift)));
+        }
+        *prim_out = (double)prim[N];
+        free(prim);
+        (void)e;
+    }
+#undef ELD
+    free(E); free(V); free(Vb); free(tmp);
+    return 0;
+}

@@ -98,6 +98,13 @@ void orc_ranmars_free(orc_ranmars* r);
  * returns V(r) and writes dV/dr divided by r (so that grad = out * r_vec) */
 double orc_pair_potential(int pot, double r, double omega_or_strength, double mass, double* dVdr_over_r);
 
+/* The exchange algorithm (cycle energies, V, V_backwards, connection probabilities, exterior forces, primitive
+ * estimator e[N]) with every intermediate in long double: the yardstick for the double-precision algorithm's own rounding
+ * noise at large N (see pimd_oracle.c). Slices are host AoS [N][D]; any output pointer may be NULL. Returns 0. */
+int orc_exchange_ld(int N, int D, int pbc, double size, double kspring, double beta_exch, const double* x1, const double* xP,
+                    const double* x2, const double* xPm1, double* V, double* Vb, double* f_first, double* f_last,
+                    double* prim, int l_stride /* forces for particles 0, l_stride, 2 l_stride, ... only */);
+
 #ifdef __cplusplus
 }
 #endif

@@ -86,6 +86,7 @@ SYMBOLS = {
     "pimdb_peer_export": (C.c_int, [_VP, _VP]),
     "pimdb_peer_attach": (C.c_int, [_VP, C.c_int, C.c_int, _VP]),
     "pimdb_peer_attached": (C.c_int, [_VP]),
+    "pimdb_settle": (C.c_int, [_VP]),
     "pimdb_launch_count": (C.c_ulonglong, [_VP]),
     "pimdb_timing_enable": (C.c_int, [_VP, C.c_int]),
     "pimdb_timing_get": (C.c_int, [_VP, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_ulonglong)]),

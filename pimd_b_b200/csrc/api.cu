@@ -363,9 +363,8 @@ static int check_deferred(Sim* s) {
         if (e & kErrPeerTimeout)
             return fail(s, PIMDB_ERR_RUNTIME, "bead shard timed out waiting for a peer GPU (halo slice / momentum sums); every rank must "
                                               "make the same sequence of calls");
-        if (e & kErrSyncTimeout)
-            return fail(s, PIMDB_ERR_RUNTIME, "exchange recurrence timed out waiting for its factor tiles (kernels serialised by a "
-                                              "profiler? set PIMDB_EXCH_SERIAL=1)");
+        if (e & kErrSyncTimeout)   // the bounded waits between the blocks of the cluster recurrence (never seen; an internal error)
+            return fail(s, PIMDB_ERR_RUNTIME, "exchange recurrence: a wait between the blocks of its thread-block cluster ran out");
         // same wording as the reference's std::overflow_error (quadratic_bosonic_exchange.cpp:92-97,119-124)
         return fail(s, PIMDB_ERR_OVERFLOW,
                     std::string("Invalid sig_denom / e_shift in bosonic exchange potential (non-finite ") +
@@ -425,10 +424,16 @@ static int upload_arrays(Sim* s, int n, const int* which, const double* const* h
         if (which[i] == PIMDB_P) { s->p_shift_pending = false; s->z_owed = false; }   // the caller replaces the momenta
     }
     if (!all_pinned) PIMDB_CUDA_TRY(s, cudaStreamSynchronize(s->stream));   // the pinned staging buffer is about to be rewritten
-    for (int i = 0; i < n; ++i) {
-        const double* src = host[i];
-        if (!all_pinned) { memcpy(s->stage_h + i * count, host[i], bytes); src = s->stage_h + i * count; }
-        PIMDB_CUDA_TRY(s, cudaMemcpyAsync(s->stage_d + i * count, src, bytes, cudaMemcpyHostToDevice, s->stream));
+    bool packed = true;                                                      // arrays adjacent in host memory: ONE copy
+    for (int i = 1; i < n; ++i) packed = packed && host[i] == host[i - 1] + count;
+    if (!all_pinned) {
+        for (int i = 0; i < n; ++i) memcpy(s->stage_h + i * count, host[i], bytes);
+        PIMDB_CUDA_TRY(s, cudaMemcpyAsync(s->stage_d, s->stage_h, n * bytes, cudaMemcpyHostToDevice, s->stream));
+    } else if (packed) {
+        PIMDB_CUDA_TRY(s, cudaMemcpyAsync(s->stage_d, host[0], n * bytes, cudaMemcpyHostToDevice, s->stream));
+    } else {
+        for (int i = 0; i < n; ++i)
+            PIMDB_CUDA_TRY(s, cudaMemcpyAsync(s->stage_d + i * count, host[i], bytes, cudaMemcpyHostToDevice, s->stream));
     }
     // The caller may reuse its buffers as soon as the call returns (pageable and page-locked alike): wait for the copies,
     // not for the transpose.
@@ -455,9 +460,14 @@ static int download_arrays(Sim* s, int n, const int* which, double* const* host)
         if (which[i] == PIMDB_F_SPRING || which[i] == PIMDB_F_PHYS) API_TRY(refresh_split_forces(s));
     }
     API_TRY(launch_soa_to_aos(s, n, src, halo));
-    for (int i = 0; i < n; ++i)
-        PIMDB_CUDA_TRY(s, cudaMemcpyAsync(all_pinned ? host[i] : s->stage_h + i * count, s->stage_d + i * count, bytes,
-                                          cudaMemcpyDeviceToHost, s->stream));
+    bool packed = true;
+    for (int i = 1; i < n; ++i) packed = packed && host[i] == host[i - 1] + count;
+    if (!all_pinned || packed) {
+        PIMDB_CUDA_TRY(s, cudaMemcpyAsync(all_pinned ? host[0] : s->stage_h, s->stage_d, n * bytes, cudaMemcpyDeviceToHost, s->stream));
+    } else {
+        for (int i = 0; i < n; ++i)
+            PIMDB_CUDA_TRY(s, cudaMemcpyAsync(host[i], s->stage_d + i * count, bytes, cudaMemcpyDeviceToHost, s->stream));
+    }
     PIMDB_CUDA_TRY(s, cudaStreamSynchronize(s->stream));
     if (!all_pinned)
         for (int i = 0; i < n; ++i) memcpy(host[i], s->stage_h + i * count, bytes);
@@ -505,46 +515,22 @@ extern "C" int pimdb_download_state(pimdb_sim* sim, double* x, double* p, double
 // and one launch fewer on the step's critical path.
 static int enqueue_forces(Sim* s, bool assemble_later = false) {
     const bool ex = s->bosonic && (s->has_first || s->has_last);
-    bool early = false;
     if (ex) {
-        // The exchange chain runs beside the pair tiles on two high-priority side streams. For N <= 512 (blocked
-        // recurrence) the two-block recurrence kernel is launched FIRST, on its own stream: its blocks need a whole SM
-        // each (512 threads x 126 registers), which they only get before the pair tiles flood the GPU; resident, they
-        // wait on a device-side counter for the factor tiles + block inverses (k_exch_coeff_tiles, launched second on the
-        // other side stream), so neither the tiles nor the inverses sit on the main stream ahead of the pair forces.
-        // Kernels serialised by a profiler would turn that wait into a time-out, so PIMDB_EXCH_SERIAL=1 (or a CUDA
-        // injection library in the environment: ncu, compute-sanitizer) selects the plain order: tiles on the main
-        // stream, then recurrences + exterior forces on the side stream.
-        static const bool serial = getenv("PIMDB_EXCH_SERIAL") || getenv("CUDA_INJECTION64_PATH") ||
-                                   getenv("NV_COMPUTE_PROFILER_PERFWORKS_DIR");
-        // Only inside a stream capture: in a graph every kernel is loaded when the graph is instantiated, whereas an
-        // eager first launch may have to load its kernel lazily, which waits for the device to go idle -- behind a
-        // recurrence kernel that is itself waiting for that very launch.
-        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-        cudaStreamIsCapturing(s->stream, &cap);
-        // N <= 512 only: beyond that the tiles follow a prefix-sum kernel on their stream and would be dispatched behind
-        // the (much larger) pair-tile grid, which delays the whole chain to the end of the pair forces (measured at C4)
-        early = !serial && cap == cudaStreamCaptureStatusActive && s->exK && s->N <= 512 && !getenv("PIMDB_EXCH_NOBLOCKED");
-        if (early) {
-            PIMDB_CUDA_TRY(s, cudaEventRecord(s->ev_fork, s->stream));
-            PIMDB_CUDA_TRY(s, cudaStreamWaitEvent(s->stream_r, s->ev_fork, 0));
-            PIMDB_CUDA_TRY(s, cudaStreamWaitEvent(s->stream_x, s->ev_fork, 0));
-            API_TRY(launch_exchange_part(s, s->stream_r, 1));      // recurrences (resident, waiting) + exterior forces
-            API_TRY(launch_exchange_part(s, s->stream_x, 0));      // factor tiles + block inverses
-            PIMDB_CUDA_TRY(s, cudaEventRecord(s->ev_join, s->stream_r));
-            PIMDB_CUDA_TRY(s, cudaEventRecord(s->ev_join2, s->stream_x));
-        } else {
-            API_TRY(launch_exchange_part(s, s->stream, 0));
-            PIMDB_CUDA_TRY(s, cudaEventRecord(s->ev_fork, s->stream));
-            PIMDB_CUDA_TRY(s, cudaStreamWaitEvent(s->stream_x, s->ev_fork, 0));
-            API_TRY(launch_exchange_part(s, s->stream_x, 1));
-            PIMDB_CUDA_TRY(s, cudaEventRecord(s->ev_join, s->stream_x));
-        }
+        // The exchange chain (factor tiles + block inverses -> recurrences -> exterior forces) runs beside the pair tiles on
+        // a high-priority side stream. The recurrence kernel depends on the tile kernel through a programmatic dependent
+        // launch (exchange.cu): its few, large blocks can take their SMs and set themselves up while the tiles are still
+        // being produced, and block in griddepcontrol.wait until that grid has completed -- a real dependency, with nothing
+        // to time out under a profiler, MPS or time slicing (round 1 launched the recurrence first and let it spin on a
+        // device counter).
+        PIMDB_CUDA_TRY(s, cudaEventRecord(s->ev_fork, s->stream));
+        PIMDB_CUDA_TRY(s, cudaStreamWaitEvent(s->stream_x, s->ev_fork, 0));
+        API_TRY(launch_exchange_part(s, s->stream_x, 0));
+        API_TRY(launch_exchange_part(s, s->stream_x, 1));
+        PIMDB_CUDA_TRY(s, cudaEventRecord(s->ev_join, s->stream_x));
     }
     bool joined = !ex;
     auto join = [&]() -> int {
         PIMDB_CUDA_TRY(s, cudaStreamWaitEvent(s->stream, s->ev_join, 0));
-        if (early) PIMDB_CUDA_TRY(s, cudaStreamWaitEvent(s->stream, s->ev_join2, 0));
         joined = true;
         return PIMDB_OK;
     };
@@ -962,6 +948,16 @@ extern "C" int pimdb_peer_attach(pimdb_sim* sim, int world, int rank, const void
     return launch_peer_push_halos(s);
 }
 
+// Enqueue (asynchronously) what the next read of the momenta would have to do first. A single host thread that drives
+// several shards calls this on every handle before it reads any of them: the closing zeroMomentum is collective, and a
+// blocking read of one handle would otherwise wait for sums that the other handles have not been asked to publish yet.
+extern "C" int pimdb_settle(pimdb_sim* sim) {
+    Sim* s = reinterpret_cast<Sim*>(sim);
+    if (!s) return PIMDB_ERR_INVALID_ARGUMENT;
+    PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
+    return settle_momenta(s);
+}
+
 extern "C" int pimdb_peer_attached(const pimdb_sim* sim) {
     const Sim* s = reinterpret_cast<const Sim*>(sim);
     return s && s->peer_on ? 1 : 0;
@@ -1015,6 +1011,7 @@ extern "C" int pimdb_observables_calc(pimdb_sim* sim, pimdb_observables* out) {
     PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
     API_TRY(settle_momenta(s));
     API_TRY(launch_peer_wait_halos(s));
+    if (s->pair_on) API_TRY(refresh_split_forces(s));   // the pair estimators reuse the scratch slab that holds the pair partials
     PIMDB_CUDA_TRY(s, cudaMemsetAsync(s->obs_d, 0, sizeof(DevObs), s->stream));
     API_TRY(launch_obs_elementwise(s));
     if (s->pair_on) {

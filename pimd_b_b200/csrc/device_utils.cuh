@@ -198,6 +198,13 @@ __device__ __forceinline__ void peer_wait_halos(const unsigned int* halo_flag, c
     __syncthreads();
 }
 
+// Programmatic dependent launch (PTX griddepcontrol): the producer lets its dependents be scheduled early, the consumer
+// blocks until the producer grid has completed and its writes are visible. A real dependency -- nothing to time out,
+// correct under any serialisation of kernels (profilers, MPS, time slicing) -- that still lets the consumer's blocks take
+// their SMs and run their prologue while the producer is running. No-ops without the launch attribute.
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(kFullMask, v, o);

@@ -339,6 +339,7 @@ __global__ void __launch_bounds__(1024, 2) k_exch_coeff_tiles(ExArgs a) {
     __shared__ double sA[kExchFastMaxN + 1];       // the prefix sums A(w), recomputed by every tile (N <= 512: one chunk)
     __shared__ double warp_tot[32];
     tl_begin(a.tl0);
+    grid_launch_dependents();    // the recurrence kernel may take its SMs now; it waits for this grid before it reads the tiles
     peer_wait_halos(a.halo_flag, a.halo_seq, a.timeout_ns, a.err);
     const int N = a.N, nb = (N + 31) >> 5;
     const int rb = blockIdx.x / nb, sb = blockIdx.x % nb;
@@ -428,17 +429,6 @@ __global__ void __launch_bounds__(1024, 2) k_exch_coeff_tiles(ExArgs a) {
         __syncthreads();                             // s_e2 is free now: it becomes the scratch of the inversion
         static_assert(sizeof(s_e2) >= 2 * 16 * 17 * sizeof(double), "scratch too small");
         diag_block_inverse(a, rb, kf, kb, maxf, maxb, reinterpret_cast<double (*)[16][17]>(&s_e2[0][0][0]));
-    }
-    // The recurrence kernel is already resident and polls sync[1] (it is launched first so that its two large blocks
-    // get their SMs before the pair tiles flood the GPU): the last tile to finish publishes this generation of tables.
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence();
-        if (atomicAdd(&a.sync[0], 1) == (int)gridDim.x - 1) {
-            a.sync[0] = 0;
-            __threadfence();
-            atomicAdd(&a.sync[1], 1);
-        }
     }
     tl_end(a.tl0);
 }
@@ -879,15 +869,11 @@ __device__ __forceinline__ void recur_blocked(const ExArgs& a, double* smem_d) {
     for (int i = tid; i < nb2; i += nt) sFlag[i] = 0;
     if (tid == 0) {
         sHandOm[0] = 1.0; sHandE[0] = 0;
-        // wait for this generation of factor tiles and block inverses (k_exch_coeff_tiles may still be running: this
-        // kernel is launched ahead of it on its own stream). Bounded: a missing producer becomes an error, not a hang.
-        const int used = a.sync[FWD ? 2 : 3];
-        int done, spins = 0;
-        do {
-            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(done) : "l"(a.sync + 1) : "memory");
-        } while (done - used <= 0 && ++spins < (1 << 22));
-        if (done - used <= 0) atomicOr(a.err, kErrSyncTimeout);
     }
+    // The factor tiles and block inverses come from k_exch_coeff_tiles, the previous kernel on this stream. This kernel is
+    // launched with programmatic stream serialisation: its blocks may become resident (and run the set-up above) while the
+    // tile kernel is still running; everything below reads its output.
+    grid_dependency_wait();
     __syncthreads();
     if (lane == 0) {
 #pragma unroll
@@ -1197,13 +1183,8 @@ __device__ __forceinline__ void recur_cluster(const ExArgs& a, double* smem_d) {
     __syncthreads();
     if (tid == 0) {
         sHandOm[0] = 1.0;
-        const int used = a.sync[FWD ? 2 : 3];
-        int done, spins = 0;
-        do {
-            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(done) : "l"(a.sync + 1) : "memory");
-        } while (done - used <= 0 && ++spins < (1 << 22));
-        if (done - used <= 0) atomicOr(a.err, kErrSyncTimeout);
     }
+    grid_dependency_wait();     // the tiles / block inverses of k_exch_coeff_tiles (programmatic stream serialisation, see above)
     __syncthreads();
     if (lane == 0 && has_block) {
 #pragma unroll
@@ -1501,13 +1482,8 @@ __device__ __forceinline__ void recur_cluster_multi(const ExArgs& a, double* sme
     __syncthreads();
     if (tid == 0) {
         sHandOm[0] = 1.0;
-        const int used = a.sync[FWD ? 2 : 3];
-        int done, spins = 0;
-        do {
-            asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(done) : "l"(a.sync + 1) : "memory");
-        } while (done - used <= 0 && ++spins < (1 << 22));
-        if (done - used <= 0) atomicOr(a.err, kErrSyncTimeout);
     }
+    grid_dependency_wait();     // the tiles / block inverses of k_exch_coeff_tiles (programmatic stream serialisation, see above)
     __syncthreads();
     cur_norm(prod);
     if (lane == 0) {
@@ -2021,6 +1997,7 @@ static int run_recursion(Sim* s, const ExArgs& a, cudaStream_t st) {
     const int R = rows_per_thread(s->N, nt);
     const int nblk = (s->N + 31) / 32;                       // 32-row blocks
     const bool blocked_ok = a.Kf && !getenv("PIMDB_EXCH_NOBLOCKED");
+    static const bool pdl = !getenv("PIMDB_EXCH_NOPDL");     // plain stream order instead (A/B timing)
     if (blocked_ok && nblk > 8 * kClusterSize) {
         // more than 64 row blocks (2048 < N <= 8192): the same cluster, up to 4 row blocks per warp
         const int nb = nblk, nb2 = (nb + 3) & ~1, wpc = kMultiWpc;
@@ -2032,11 +2009,13 @@ static int run_recursion(Sim* s, const ExArgs& a, cudaStream_t st) {
         lc.blockDim = dim3(32 * wpc);
         lc.dynamicSmemBytes = smem_cl;
         lc.stream = st;
-        cudaLaunchAttribute at[1];
+        cudaLaunchAttribute at[2];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = kClusterSize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // may start while k_exch_coeff_tiles is running
+        at[1].val.programmaticStreamSerializationAllowed = 1;
         lc.attrs = at;
-        lc.numAttrs = 1;
+        lc.numAttrs = pdl ? 2 : 1;
         cudaLaunchKernelEx(&lc, k_exch_recur_cluster_multi, a);
         return PIMDB_OK;
     }
@@ -2053,11 +2032,13 @@ static int run_recursion(Sim* s, const ExArgs& a, cudaStream_t st) {
             lc.blockDim = dim3(32 * wpc);
             lc.dynamicSmemBytes = smem_cl;
             lc.stream = st;
-            cudaLaunchAttribute at[1];
+            cudaLaunchAttribute at[2];
             at[0].id = cudaLaunchAttributeClusterDimension;
             at[0].val.clusterDim.x = kClusterSize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[1].val.programmaticStreamSerializationAllowed = 1;
             lc.attrs = at;
-            lc.numAttrs = 1;
+            lc.numAttrs = pdl ? 2 : 1;
             cudaLaunchKernelEx(&lc, k_exch_recur_cluster, a);
         }
         return PIMDB_OK;
@@ -2073,7 +2054,14 @@ static int run_recursion(Sim* s, const ExArgs& a, cudaStream_t st) {
                                     + sizeof(int) * ((size_t)32 * nb + 3 * nb2) + 16;
             if (smem_blk > 48 * 1024)
                 cudaFuncSetAttribute(k_exch_recur_blocked, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_blk);
-            k_exch_recur_blocked<<<2, nt, smem_blk, st>>>(a);
+            cudaLaunchConfig_t lc = {};
+            lc.gridDim = dim3(2); lc.blockDim = dim3(nt); lc.dynamicSmemBytes = smem_blk; lc.stream = st;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+            at[0].val.programmaticStreamSerializationAllowed = 1;
+            lc.attrs = at;
+            lc.numAttrs = pdl ? 1 : 0;
+            cudaLaunchKernelEx(&lc, k_exch_recur_blocked, a);
         } else if (ST == 16) {
             if (smem > 48 * 1024)
                 cudaFuncSetAttribute(k_exch_recur_dec<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

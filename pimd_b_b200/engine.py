@@ -110,6 +110,10 @@ class DeviceSim:
             raise ValueError("blobs must hold one PEER_BLOB_BYTES record per rank, in rank order")
         self._ck(self.lib.pimdb_peer_attach(self.h, int(world), int(rank), C.c_char_p(blobs)))
 
+    def settle(self):
+        """Enqueue the deferred (collective) momentum work without waiting; see pimdb_settle."""
+        self._ck(self.lib.pimdb_settle(self.h))
+
     @property
     def peer_attached(self) -> bool:
         return bool(self.lib.pimdb_peer_attached(self.h))

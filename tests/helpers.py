@@ -86,8 +86,28 @@ def oracle_lib():
     lib.orc_ranmars_free.argtypes = [C.c_void_p]
     lib.orc_pair_potential.restype = C.c_double
     lib.orc_pair_potential.argtypes = [C.c_int, C.c_double, C.c_double, C.c_double, C.POINTER(C.c_double)]
+    lib.orc_exchange_ld.restype = C.c_int
+    lib.orc_exchange_ld.argtypes = [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double] + [C.c_void_p] * 9 + [C.c_int]
     _lib = lib
     return lib
+
+
+def exchange_long_double(cfg: SimConfig, x, l_stride: int = 1, want_prim: bool = True) -> dict:
+    """The exchange algorithm in long double on the exterior beads of x [P][N][D] (oracle/pimd_oracle.c orc_exchange_ld):
+    V, Vb, the exterior-bead spring forces and the primitive-estimator recursion's e[N] -- the yardstick that tells the
+    double-precision algorithm's own rounding noise from a real difference."""
+    lib = oracle_lib()
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    P, N, D = x.shape
+    V, Vb = np.empty(N + 1), np.empty(N + 1)
+    ff, fl = np.full((N, D), np.nan), np.full((N, D), np.nan)   # l_stride > 1: only every l_stride-th particle is filled
+    prim = np.full(1, np.nan)
+    sl = [np.ascontiguousarray(x[b]) for b in (0, P - 1, 1 % P, (P - 2) % P)]
+    ptr = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = lib.orc_exchange_ld(N, D, int(cfg.pbc), cfg.size, cfg.spring_constant, cfg.beta / cfg.nbeads,
+                             ptr(sl[0]), ptr(sl[1]), ptr(sl[2]), ptr(sl[3]), ptr(V), ptr(Vb), ptr(ff), ptr(fl), ptr(prim) if want_prim else None, int(l_stride))
+    assert rc == 0
+    return dict(V=V, Vb=Vb, f_first=ff, f_last=fl, prim=float(prim[0]))
 
 
 def to_orc_config(cfg: SimConfig) -> OrcConfig:

@@ -53,6 +53,8 @@ def _in_process(cfg, x, p, nsteps, world, devices=None):
     f0 = np.concatenate([s.get("f") for s in sims])
     for s in sims:              # asynchronous: every handle enqueues all its graph replays, the devices sort out the rest
         s.step(nsteps)
+    for s in sims:              # reading the momenta is collective and blocking: enqueue its deferred part everywhere first
+        s.settle()
     obs = [s.observables() for s in sims]
     out = dict(x=np.concatenate([s.get("x") for s in sims]), p=np.concatenate([s.get("p") for s in sims]),
                f=np.concatenate([s.get("f") for s in sims]), f0=f0,
@@ -113,12 +115,18 @@ def test_peer_steps_split_over_calls_and_state_reads(gpu_required):
         lo, hi = bead_range(cfg.nbeads, 2, r)
         s.upload(x[lo:hi], p[lo:hi])
     for s in sims:
+        s.update_forces()       # (as _in_process does: the first kick then uses f(x0) in both runs)
+    for s in sims:
         s.step(5)
     # reading the momenta is collective (it carries out the closing zeroMomentum): enqueue on both, then read
+    for s in sims:
+        s.settle()
     mid = [s.observables() for s in sims]
     assert all(np.isfinite(m["cl_kinetic"]) for m in mid)
     for s in sims:
         s.step(7)
+    for s in sims:
+        s.settle()
     got_x = np.concatenate([s.get("x") for s in sims])
     got_p = np.concatenate([s.get("p") for s in sims])
     for s in sims:
