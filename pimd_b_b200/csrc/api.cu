@@ -9,7 +9,7 @@
 #include "internal.cuh"
 
 namespace pimdb {
-int launch_pair_chunk(Sim* s, int bead_lo, int nb, bool with_obs);
+int launch_pair_chunk(Sim* s, int bead_lo, int nb, bool with_obs, bool early = false);
 int launch_assemble_chunk(Sim* s, int bead_lo, int nb, bool with_pair);
 int launch_exchange_part(Sim* s, cudaStream_t st, int part);
 }  // namespace pimdb
@@ -515,17 +515,40 @@ extern "C" int pimdb_download_state(pimdb_sim* sim, double* x, double* p, double
 // and one launch fewer on the step's critical path.
 static int enqueue_forces(Sim* s, bool assemble_later = false) {
     const bool ex = s->bosonic && (s->has_first || s->has_last);
+    bool pair_early = false;
     if (ex) {
-        // The exchange chain (factor tiles + block inverses -> recurrences -> exterior forces) runs beside the pair tiles on
-        // a high-priority side stream. The recurrence kernel depends on the tile kernel through a programmatic dependent
-        // launch (exchange.cu): its few, large blocks can take their SMs and set themselves up while the tiles are still
-        // being produced, and block in griddepcontrol.wait until that grid has completed -- a real dependency, with nothing
-        // to time out under a profiler, MPS or time slicing (round 1 launched the recurrence first and let it spin on a
-        // device counter).
-        PIMDB_CUDA_TRY(s, cudaEventRecord(s->ev_fork, s->stream));
-        PIMDB_CUDA_TRY(s, cudaStreamWaitEvent(s->stream_x, s->ev_fork, 0));
-        API_TRY(launch_exchange_part(s, s->stream_x, 0));
-        API_TRY(launch_exchange_part(s, s->stream_x, 1));
+        // The exchange chain is: factor tiles + block inverses -> recurrences (a few large blocks, latency-bound) -> exterior
+        // forces, beside the pair tiles. What matters is the ORDER in which the grids get their SMs: the recurrence blocks
+        // must be resident before the pair tiles flood the GPU, or they wait for pair-tile blocks to retire (one wave is
+        // ~19 us at C3). Round 1 launched the recurrence first and let it spin on a device counter for the tiles; now every
+        // dependency is real. In a captured step all three grids sit on the main stream, chained by programmatic dependent
+        // launches (PTX griddepcontrol):
+        //     tiles  ->  recurrences (scheduled once every tile block has started; block in griddepcontrol.wait until the
+        //                tile grid has completed)  ->  pair tiles (scheduled once every recurrence block has started; they
+        //                read nothing the exchange kernels write, so they never wait)
+        // and the exterior forces follow the recurrences on the high-priority side stream. Nothing can time out, and a
+        // profiler / MPS / time slicing that serialises the kernels only removes the overlap.
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(s->stream, &cap);
+        static const bool no_chain = getenv("PIMDB_EXCH_NOCHAIN") != nullptr;     // plain order (A/B timing)
+        const bool chain = cap == cudaStreamCaptureStatusActive && s->exK && !getenv("PIMDB_EXCH_NOBLOCKED") && !no_chain;
+        API_TRY(launch_exchange_part(s, s->stream, 0));
+        if (chain) {
+            s->pdl_recur = true;
+            const int rc2 = launch_exchange_part(s, s->stream, 2);
+            s->pdl_recur = false;
+            API_TRY(rc2);
+            PIMDB_CUDA_TRY(s, cudaEventRecord(s->ev_fork, s->stream));
+            PIMDB_CUDA_TRY(s, cudaStreamWaitEvent(s->stream_x, s->ev_fork, 0));
+            API_TRY(launch_exchange_part(s, s->stream_x, 3));
+            pair_early = true;
+        } else {
+            // eager launches (call-by-call entry points, the timing pass): tiles on the main stream, the rest of the chain on
+            // the side stream in plain stream order
+            PIMDB_CUDA_TRY(s, cudaEventRecord(s->ev_fork, s->stream));
+            PIMDB_CUDA_TRY(s, cudaStreamWaitEvent(s->stream_x, s->ev_fork, 0));
+            API_TRY(launch_exchange_part(s, s->stream_x, 1));
+        }
         PIMDB_CUDA_TRY(s, cudaEventRecord(s->ev_join, s->stream_x));
     }
     bool joined = !ex;
@@ -537,7 +560,7 @@ static int enqueue_forces(Sim* s, bool assemble_later = false) {
     if (s->pair_on) {
         for (int lo = 0; lo < s->Ploc; lo += s->bead_chunk) {
             const int nb = std::min(s->bead_chunk, s->Ploc - lo);
-            API_TRY(launch_pair_chunk(s, lo, nb, false));
+            API_TRY(launch_pair_chunk(s, lo, nb, false, pair_early && lo == 0));
             if (!joined) API_TRY(join());
             if (!assemble_later) API_TRY(launch_assemble_chunk(s, lo, nb, true));
         }

@@ -1701,6 +1701,8 @@ __device__ __forceinline__ void recur_cluster_multi(const ExArgs& a, double* sme
 __global__ void __launch_bounds__(256, 1) k_exch_recur_cluster(ExArgs a) {
     extern __shared__ __align__(16) double smem_d[];
     tl_begin(a.tl1);
+    grid_launch_dependents();   // whatever follows on this stream with the programmatic attribute (the pair tiles of a captured
+                                // step) may be scheduled now: these few blocks hold their SMs before that grid floods the GPU
     if (blockIdx.x < kClusterSize) recur_cluster<true>(a, smem_d);
     else recur_cluster<false>(a, smem_d);
     tl_end(a.tl1);
@@ -1709,6 +1711,7 @@ __global__ void __launch_bounds__(256, 1) k_exch_recur_cluster(ExArgs a) {
 __global__ void __launch_bounds__(256, 1) k_exch_recur_cluster_multi(ExArgs a) {
     extern __shared__ __align__(16) double smem_d[];
     tl_begin(a.tl1);
+    grid_launch_dependents();
     if (blockIdx.x < kClusterSize) recur_cluster_multi<true>(a, smem_d);
     else recur_cluster_multi<false>(a, smem_d);
     tl_end(a.tl1);
@@ -1997,7 +2000,7 @@ static int run_recursion(Sim* s, const ExArgs& a, cudaStream_t st) {
     const int R = rows_per_thread(s->N, nt);
     const int nblk = (s->N + 31) / 32;                       // 32-row blocks
     const bool blocked_ok = a.Kf && !getenv("PIMDB_EXCH_NOBLOCKED");
-    static const bool pdl = !getenv("PIMDB_EXCH_NOPDL");     // plain stream order instead (A/B timing)
+    const bool pdl = s->pdl_recur;     // launched right behind k_exch_coeff_tiles on the same stream (api.cu enqueue_forces)
     if (blocked_ok && nblk > 8 * kClusterSize) {
         // more than 64 row blocks (2048 < N <= 8192): the same cluster, up to 4 row blocks per warp
         const int nb = nblk, nb2 = (nb + 3) & ~1, wpc = kMultiWpc;
@@ -2084,14 +2087,15 @@ static int run_recursion(Sim* s, const ExArgs& a, cudaStream_t st) {
     }
 }
 
-// part 0: prefix sums + Boltzmann factors (fully parallel, a few microseconds);
-// part 1: the two recurrences (2 thread blocks, latency-bound) + the exterior forces.
-// They are separate so the caller can start part 1 on a side stream *before* it floods the GPU with pair tiles.
+// part 0: prefix sums + Boltzmann factors / factor tiles + block inverses (fully parallel);
+// part 1: the two recurrences (latency-bound) + the exterior forces; part 2: the recurrences only; part 3: the forces only.
+// They are separate so that the caller can place them on different streams around the pair tiles (api.cu enqueue_forces).
 template <int D>
 static int exchange_impl(Sim* s, cudaStream_t st, int part) {
     ExArgs a = make_args(s);
     if (part == 0) a.tl0 = tl_slot(s);
-    else { a.tl1 = tl_slot(s); a.tl2 = tl_slot(s); }
+    if (part == 1 || part == 2) a.tl1 = tl_slot(s);
+    if (part == 1 || part == 3) a.tl2 = tl_slot(s);
     if (part == 0) {
         if (a.Kf) {      // N <= 2048: factor tiles + diagonal-block inverses; up to N = 512 the tiles recompute the prefix sums
             const int nb = (s->N + 31) / 32;
@@ -2107,9 +2111,12 @@ static int exchange_impl(Sim* s, cudaStream_t st, int part) {
             s->launches += 2;
         }
     } else {
-        int rc = run_recursion(s, a, st);
-        if (rc != PIMDB_OK) return rc;
-        {
+        if (part != 3) {
+            int rc = run_recursion(s, a, st);
+            if (rc != PIMDB_OK) return rc;
+            s->launches += 1;
+        }
+        if (part != 2) {
             const int per_kind = std::max(1, std::min((s->N + 2 * kFW - 1) / (2 * kFW), 4 * kNumSM));   // 2 tasks per warp
             const size_t smem_w = sizeof(double) * ((size_t)s->N + 1 + ((s->N + 2) >> 1));            // weights + exponents
             const size_t smem_full = smem_w + sizeof(double) * (size_t)D * s->N;                         // + the bead slice
@@ -2124,8 +2131,8 @@ static int exchange_impl(Sim* s, cudaStream_t st, int part) {
             } else {
                 k_exch_forces<D, 0><<<2 * per_kind, 32 * kFW, 0, st>>>(a);
             }
+            s->launches += 1;
         }
-        s->launches += 2;
     }
     PIMDB_CUDA_TRY(s, cudaGetLastError());
     return PIMDB_OK;

@@ -137,6 +137,7 @@ struct Sim {
     std::vector<void*> ipc_opened;     // mappings to close
     bool z_owed = false;               // peer mode, Langevin / no thermostat: the closing zeroMomentum of the last iteration
                                        // has not been carried out (it is subsumed by the first one of the next iteration)
+    bool pdl_recur = false;            // the next recurrence launch may use programmatic stream serialisation
     bool split_stale = false;          // f is current but f_spring / f_phys are not (fused closing kernel)
     unsigned long long launches = 0;
     // timing

@@ -262,27 +262,42 @@ __global__ void __launch_bounds__(1024) k_pair_obs_reduce(const double* part, lo
     }
 }
 
+// `early`: launch with programmatic stream serialisation. The kernel never waits for the grid in front of it (it reads
+// nothing that grid writes), so it is scheduled as soon as every block of that grid has started -- used in a captured step
+// to put the pair tiles right behind the resident blocks of the exchange recurrence (api.cu enqueue_forces).
+template <typename K>
+static void launch_tiles(K kernel, Sim* s, const PairArgs& a, int grid, bool early) {
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(grid); lc.blockDim = dim3(32 * kPairWarps); lc.dynamicSmemBytes = 0; lc.stream = s->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    lc.attrs = at;
+    lc.numAttrs = early ? 1 : 0;
+    cudaLaunchKernelEx(&lc, kernel, a);
+}
+
 template <int D, int POT, bool OBS>
-static void dispatch2(Sim* s, const PairArgs& a, int grid) {
+static void dispatch2(Sim* s, const PairArgs& a, int grid, bool early) {
     const bool pbc = s->cfg.pbc != 0, cut = s->rc > 0.0;
-    if (pbc && cut) k_pair_tiles<D, POT, true, true, OBS><<<grid, 32 * kPairWarps, 0, s->stream>>>(a);
-    else if (pbc) k_pair_tiles<D, POT, true, false, OBS><<<grid, 32 * kPairWarps, 0, s->stream>>>(a);
-    else if (cut) k_pair_tiles<D, POT, false, true, OBS><<<grid, 32 * kPairWarps, 0, s->stream>>>(a);
-    else k_pair_tiles<D, POT, false, false, OBS><<<grid, 32 * kPairWarps, 0, s->stream>>>(a);
+    if (pbc && cut) launch_tiles(k_pair_tiles<D, POT, true, true, OBS>, s, a, grid, early);
+    else if (pbc) launch_tiles(k_pair_tiles<D, POT, true, false, OBS>, s, a, grid, early);
+    else if (cut) launch_tiles(k_pair_tiles<D, POT, false, true, OBS>, s, a, grid, early);
+    else launch_tiles(k_pair_tiles<D, POT, false, false, OBS>, s, a, grid, early);
 }
 
 template <int D, bool OBS>
-static void dispatch1(Sim* s, const PairArgs& a, int grid) {
+static void dispatch1(Sim* s, const PairArgs& a, int grid, bool early) {
     switch (s->cfg.int_potential) {
-        case PIMDB_POT_AZIZ: dispatch2<D, PIMDB_POT_AZIZ, OBS>(s, a, grid); break;
-        case PIMDB_POT_HARMONIC: dispatch2<D, PIMDB_POT_HARMONIC, OBS>(s, a, grid); break;
-        case PIMDB_POT_DIPOLE: dispatch2<D, PIMDB_POT_DIPOLE, OBS>(s, a, grid); break;
+        case PIMDB_POT_AZIZ: dispatch2<D, PIMDB_POT_AZIZ, OBS>(s, a, grid, early); break;
+        case PIMDB_POT_HARMONIC: dispatch2<D, PIMDB_POT_HARMONIC, OBS>(s, a, grid, early); break;
+        case PIMDB_POT_DIPOLE: dispatch2<D, PIMDB_POT_DIPOLE, OBS>(s, a, grid, early); break;
         default: break;
     }
 }
 
 // Enqueue the tile kernel for owned beads [bead_lo, bead_lo+nb) (nb <= bead_chunk).
-static int launch_chunk(Sim* s, int bead_lo, int nb, bool with_obs) {
+static int launch_chunk(Sim* s, int bead_lo, int nb, bool with_obs, bool early) {
     PairArgs a;
     a.x = s->x + (size_t)(bead_lo + 1) * s->S;
     a.scratch = s->pair_scratch;
@@ -316,15 +331,15 @@ static int launch_chunk(Sim* s, int bead_lo, int nb, bool with_obs) {
         cudaEventRecord(e0, s->stream);
     }
     if (with_obs) {
-        if (s->D == 1) dispatch1<1, true>(s, a, grid);
-        else if (s->D == 2) dispatch1<2, true>(s, a, grid);
-        else dispatch1<3, true>(s, a, grid);
+        if (s->D == 1) dispatch1<1, true>(s, a, grid, false);
+        else if (s->D == 2) dispatch1<2, true>(s, a, grid, false);
+        else dispatch1<3, true>(s, a, grid, false);
         k_pair_obs_reduce<<<1, 1024, 0, s->stream>>>(s->pair_scratch, (long long)grid * kPairWarps, &s->obs_d->pair_v, &s->obs_d->pair_vir);
         s->launches += 2;
     } else {
-        if (s->D == 1) dispatch1<1, false>(s, a, grid);
-        else if (s->D == 2) dispatch1<2, false>(s, a, grid);
-        else dispatch1<3, false>(s, a, grid);
+        if (s->D == 1) dispatch1<1, false>(s, a, grid, early);
+        else if (s->D == 2) dispatch1<2, false>(s, a, grid, early);
+        else dispatch1<3, false>(s, a, grid, early);
         s->launches += 1;
     }
     if (e0) {
@@ -335,6 +350,6 @@ static int launch_chunk(Sim* s, int bead_lo, int nb, bool with_obs) {
     return PIMDB_OK;
 }
 
-int launch_pair_chunk(Sim* s, int bead_lo, int nb, bool with_obs) { return launch_chunk(s, bead_lo, nb, with_obs); }
+int launch_pair_chunk(Sim* s, int bead_lo, int nb, bool with_obs, bool early) { return launch_chunk(s, bead_lo, nb, with_obs, early); }
 
 }  // namespace pimdb

@@ -1,5 +1,7 @@
 // pimdb_gpu: the reference's `pimdb` entry point (src/pimdb.cpp:31-68) on top of the B200 hot path.
-//   pimdb_gpu [-in config.ini] [--dim D] [--device K] [--rng philox|ranmars] [--bosonic_alg]
+//   pimdb_gpu [-in config.ini] [--dim D] [--device K] [--gpus G] [--rng philox|ranmars] [--bosonic_alg]
+// --gpus G shards the beads over G GPUs (devices K .. K+G-1) coupled through peer memory: the counterpart of the
+// reference's `mpirun -np P pimdb` (README.md:200-203), in one process.
 // --rng ranmars (or PIMDB_RNG=ranmars) draws the Langevin noise from the reference's own generator, one sequential
 // RANMAR stream per bead (libs/random_mars.cpp): thermostatted runs then follow the reference's trajectories.
 // Same INI schema, same output/ files (simulation.out, position_b.xyz, velocity_b.dat, force_b.dat, report.txt),
@@ -14,7 +16,7 @@
 
 int main(int argc, char** argv) {
     std::string config = "config.ini";
-    int ndim = 3, device = 0;
+    int ndim = 3, device = 0, ngpus = 1;
     std::string rng = std::getenv("PIMDB_RNG") ? std::getenv("PIMDB_RNG") : "philox";
     bool info = false;
     try {
@@ -27,6 +29,8 @@ int main(int argc, char** argv) {
                 info = true;
             } else if (!std::strcmp(argv[i], "--device")) {
                 if (i + 1 < argc) device = std::atoi(argv[++i]);
+            } else if (!std::strcmp(argv[i], "--gpus")) {
+                if (i + 1 < argc) ngpus = std::atoi(argv[++i]);
             } else if (!std::strcmp(argv[i], "--rng")) {
                 if (i + 1 < argc) rng = argv[++i];
             } else if (!std::strcmp(argv[i], "-in")) {
@@ -39,7 +43,7 @@ int main(int argc, char** argv) {
             pimdb_host::Params params(config, ndim);
             if (rng == "ranmars") params.cfg.rng = PIMDB_RNG_RANMARS;
             else if (rng != "philox") throw std::invalid_argument("--rng takes philox or ranmars");
-            pimdb_host::Simulation sim(params, device);
+            pimdb_host::Simulation sim(params, device, ngpus);
             sim.run();
         }
     } catch (const std::invalid_argument& ex) {

@@ -270,12 +270,15 @@ Params::Params(const std::string& filename, int ndim) {
 }
 
 // ====================================================================================== plugins -> C ABI
-void BosonicExchange::prepare() { sim_.check(pimdb_exchange_prepare(sim_.handle)); }
+void BosonicExchange::prepare() {
+    sim_.check(pimdb_exchange_prepare(sim_.handles.front()), sim_.handles.front());
+    if (sim_.handles.size() > 1) sim_.check(pimdb_exchange_prepare(sim_.handles.back()), sim_.handles.back());
+}
 
 void BosonicExchange::exteriorSpringForce(std::vector<double>& f, int bead) {
     std::vector<double> all((size_t)sim_.nbeads * sim_.natoms * sim_.ndim);
-    sim_.check(pimdb_update_forces(sim_.handle));
-    sim_.check(pimdb_get_state(sim_.handle, PIMDB_F_SPRING, all.data()));
+    sim_.updateForces();
+    sim_.pullArray(PIMDB_F_SPRING, all);
     const size_t slab = (size_t)sim_.natoms * sim_.ndim;
     f.assign(all.begin() + bead * slab, all.begin() + (bead + 1) * slab);
 }
@@ -295,10 +298,10 @@ double BosonicExchange::primEstimator() {
 double BosonicExchange::getDistinctProbability() { return sim_.deviceObservables().prob_dist; }
 double BosonicExchange::getLongestProbability() { return sim_.deviceObservables().prob_all; }
 
-void Propagator::step() { sim.check(pimdb_propagator_step(sim.handle)); }
-void Propagator::momentStep() { sim.check(pimdb_moment_step(sim.handle)); }
-void Propagator::coordsStep() { sim.check(pimdb_coords_step(sim.handle)); }
-void Thermostat::step() { sim.check(pimdb_thermostat_step(sim.handle)); }
+void Propagator::step() { sim.forEach(pimdb_propagator_step); }
+void Propagator::momentStep() { sim.forEach(pimdb_moment_step); }
+void Propagator::coordsStep() { sim.forEach(pimdb_coords_step); }
+void Thermostat::step() { sim.forEach(pimdb_thermostat_step); }
 
 // ====================================================================================== observables
 void Observable::initialize(const std::vector<std::string>& labels) {
@@ -413,16 +416,16 @@ void State::output(long step) {
 }
 
 // ====================================================================================== Simulation
-void Simulation::check(int rc) const {
+void Simulation::check(int rc, pimdb_sim* h) const {
     if (rc == PIMDB_OK) return;
-    const char* m = pimdb_last_error(handle);
+    const char* m = pimdb_last_error(h ? h : handle);
     std::string msg = m ? m : "pimdb error";
     if (rc == PIMDB_ERR_INVALID_ARGUMENT) throw std::invalid_argument(msg);
     if (rc == PIMDB_ERR_OVERFLOW) throw std::overflow_error(msg);
     throw std::runtime_error(msg);
 }
 
-Simulation::Simulation(Params& p, int device) : params(p) {
+Simulation::Simulation(Params& p, int device, int ngpus) : params(p) {
     pimdb_config& c = p.cfg;
     c.device = device;
     natoms = c.natoms; nbeads = c.nbeads; ndim = c.ndim;
@@ -434,11 +437,31 @@ Simulation::Simulation(Params& p, int device) : params(p) {
     interaction_potential_name = p.interaction_name;
     thermostat_type = p.thermostat_type;
     propagator_type = p.propagator_type;
-    int rc = pimdb_create(&c, &handle);
-    if (rc != PIMDB_OK) {
-        std::string msg = pimdb_last_error(nullptr);
-        if (rc == PIMDB_ERR_INVALID_ARGUMENT) throw std::invalid_argument(msg);
-        throw std::runtime_error(msg);
+    if (ngpus < 1 || ngpus > nbeads) throw std::invalid_argument("--gpus must be between 1 and the number of beads");
+    // contiguous, balanced bead ranges: the first nbeads % ngpus shards own one bead more
+    for (int g = 0; g <= ngpus; ++g) bead_begin.push_back(g * (nbeads / ngpus) + std::min(g, nbeads % ngpus));
+    for (int g = 0; g < ngpus; ++g) {
+        pimdb_config cg = c;
+        // PIMDB_SHARD_SAME_DEVICE=1: every shard on `device` (tests on a one-GPU box; the shards still talk through their mailboxes)
+        cg.device = std::getenv("PIMDB_SHARD_SAME_DEVICE") ? device : device + g;
+        cg.bead_begin = bead_begin[g];
+        cg.bead_end = bead_begin[g + 1];
+        pimdb_sim* h = nullptr;
+        const int rc = pimdb_create(&cg, &h);
+        if (rc != PIMDB_OK) {
+            std::string msg = pimdb_last_error(nullptr);
+            for (pimdb_sim* made : handles) pimdb_destroy(made);
+            handles.clear();
+            if (rc == PIMDB_ERR_INVALID_ARGUMENT) throw std::invalid_argument(msg);
+            throw std::runtime_error(msg);
+        }
+        handles.push_back(h);
+    }
+    handle = handles.front();
+    if (ngpus > 1) {   // one process drives every shard: the blobs are simply concatenated
+        std::vector<char> blobs((size_t)ngpus * PIMDB_PEER_BLOB_BYTES);
+        for (int g = 0; g < ngpus; ++g) check(pimdb_peer_export(handles[g], blobs.data() + (size_t)g * PIMDB_PEER_BLOB_BYTES), handles[g]);
+        for (int g = 0; g < ngpus; ++g) check(pimdb_peer_attach(handles[g], ngpus, g, blobs.data()), handles[g]);
     }
     ext_potential = std::make_unique<Potential>(external_potential_name, c.ext_potential);
     int_potential = std::make_unique<Potential>(interaction_potential_name, c.int_potential);
@@ -474,21 +497,49 @@ Simulation::Simulation(Params& p, int device) : params(p) {
 }
 
 Simulation::~Simulation() {
-    if (handle) pimdb_destroy(handle);
+    for (pimdb_sim* h : handles) pimdb_destroy(h);
 }
 
-void Simulation::pushCoord() { check(pimdb_set_state(handle, PIMDB_X, coord.data())); }
-void Simulation::pushMomenta() { check(pimdb_set_state(handle, PIMDB_P, momenta.data())); }
-void Simulation::pullCoord() { check(pimdb_get_state(handle, PIMDB_X, coord.data())); }
-void Simulation::pullMomenta() { check(pimdb_get_state(handle, PIMDB_P, momenta.data())); }
-void Simulation::pullForces() { check(pimdb_get_state(handle, PIMDB_F, forces.data())); }
-void Simulation::updateForces() { check(pimdb_update_forces(handle)); }
-void Simulation::updateNeighboringCoordinates() { check(pimdb_update_neighbors(handle)); }
-void Simulation::zeroMomentum() { check(pimdb_zero_momentum(handle)); }
+// Every entry point but the reads only enqueues work, so one host thread keeps all shards busy: the call goes to every
+// handle in turn and the devices sort out the hand-shakes among themselves.
+void Simulation::forEach(int (*fn)(pimdb_sim*)) {
+    for (pimdb_sim* h : handles) check(fn(h), h);
+}
+void Simulation::pushArray(int which, const std::vector<double>& host) {
+    const size_t slab = (size_t)natoms * ndim;
+    for (size_t g = 0; g < handles.size(); ++g) check(pimdb_set_state(handles[g], which, host.data() + bead_begin[g] * slab), handles[g]);
+}
+void Simulation::pullArray(int which, std::vector<double>& host) {
+    const size_t slab = (size_t)natoms * ndim;
+    forEach(pimdb_settle);   // the reads block and their deferred part is collective: enqueue it everywhere first
+    for (size_t g = 0; g < handles.size(); ++g) check(pimdb_get_state(handles[g], which, host.data() + bead_begin[g] * slab), handles[g]);
+}
+void Simulation::pushCoord() { pushArray(PIMDB_X, coord); }
+void Simulation::pushMomenta() { pushArray(PIMDB_P, momenta); }
+void Simulation::pullCoord() { pullArray(PIMDB_X, coord); }
+void Simulation::pullMomenta() { pullArray(PIMDB_P, momenta); }
+void Simulation::pullForces() { pullArray(PIMDB_F, forces); }
+void Simulation::updateForces() { forEach(pimdb_update_forces); }
+void Simulation::updateNeighboringCoordinates() { forEach(pimdb_update_neighbors); }
+void Simulation::zeroMomentum() {
+    if (handles.size() == 1) { check(pimdb_zero_momentum(handle)); return; }
+    throw std::runtime_error("zeroMomentum as a separate call needs all beads on one GPU (sharded runs fold it into the step)");
+}
 
+// ObservablesLogger::log sums the per-rank values with MPI_Allreduce (src/observables/observable.cpp:92-116): here the
+// per-shard partial structs are added field by field.
 const pimdb_observables& Simulation::deviceObservables() {
     if (obs_step != md_step) {
-        check(pimdb_observables_calc(handle, &obs_cache));
+        forEach(pimdb_settle);
+        pimdb_observables total{};
+        static_assert(sizeof(pimdb_observables) % sizeof(double) == 0, "a struct of doubles");
+        for (pimdb_sim* h : handles) {
+            pimdb_observables part{};
+            check(pimdb_observables_calc(h, &part), h);
+            for (size_t i = 0; i < sizeof(pimdb_observables) / sizeof(double); ++i)
+                reinterpret_cast<double*>(&total)[i] += reinterpret_cast<const double*>(&part)[i];
+        }
+        obs_cache = total;
         obs_step = md_step;
     }
     return obs_cache;
@@ -634,7 +685,7 @@ void Simulation::run() {
         if (event) {
             for (auto& o : observables) o->resetValues();
             for (auto& s : states) s->output(step);
-            check(pimdb_step(handle, 1));
+            for (pimdb_sim* h : handles) check(pimdb_step(h, 1), h);
             md_step = step + 1;   // observables follow the update of this iteration (App. A-3)
             if (!(step < threshold)) {
                 for (auto& o : observables) o->calculate();
@@ -643,11 +694,11 @@ void Simulation::run() {
             ++step;
         } else {
             const long next_event = std::min(steps + 1, (step / sfreq + 1) * sfreq);
-            check(pimdb_step(handle, (int)(next_event - step)));
+            for (pimdb_sim* h : handles) check(pimdb_step(h, (int)(next_event - step)), h);
             step = next_event;
         }
     }
-    check(pimdb_synchronize(handle));
+    forEach(pimdb_synchronize);
     const double wall = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     std::cout << std::format("[*] Simulation finished running successfully (Runtime = {:.3} sec)\n", wall);
     printReport(wall);
@@ -677,6 +728,7 @@ void Simulation::printReport(double wall_time) const {
     line("Wrapping of coordinates", true);
     line("Using i-Pi convention", true);
     line("Device path", "libpimdb200 (sm_100a)");
+    line("GPUs (bead shards)", handles.size());
     rep << "---------\n";
     line("Wall time (sec)", std::format("{:.3f}", wall_time));
     line("Wall time per step (sec)", std::format("{:.5e}", wall_time / steps));

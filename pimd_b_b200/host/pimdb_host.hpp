@@ -187,7 +187,9 @@ private:
 // ------------------------------------------------------------------ Simulation (include/simulation.h:20-131)
 class Simulation {
 public:
-    Simulation(Params& params, int device = 0);
+    // ngpus > 1: the beads are sharded over that many GPUs (devices device, device+1, ...), one handle each, coupled through
+    // peer memory (pimdb_peer_export / pimdb_peer_attach) -- what `mpirun -np P pimdb` is to the reference (README.md:200-203)
+    Simulation(Params& params, int device = 0, int ngpus = 1);
     ~Simulation();
     Simulation(const Simulation&) = delete;
 
@@ -218,8 +220,13 @@ public:
     std::vector<std::unique_ptr<Observable>> observables;
     std::vector<std::unique_ptr<State>> states;
 
-    pimdb_sim* handle = nullptr;
-    void check(int rc) const;                     // status code -> the reference's exception type
+    pimdb_sim* handle = nullptr;                  // the shard that owns bead 0 (the only one on a single GPU)
+    std::vector<pimdb_sim*> handles;              // all shards, in bead order
+    std::vector<int> bead_begin;                  // first bead of every shard (+ nbeads at the end)
+    void check(int rc, pimdb_sim* h = nullptr) const;   // status code -> the reference's exception type
+    void forEach(int (*fn)(pimdb_sim*));          // the same (asynchronous) call on every shard
+    void pushArray(int which, const std::vector<double>& host);
+    void pullArray(int which, std::vector<double>& host);
     long getStep() const { return md_step; }
 
 private:

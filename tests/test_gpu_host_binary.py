@@ -118,3 +118,37 @@ def test_pimdb_gpu_reports_config_errors_like_the_reference(gpu_required, tmp_pa
     r = subprocess.run([str(BIN), "-in", "config.ini"], cwd=tmp_path, capture_output=True, text=True, timeout=120)
     assert r.returncode == 0       # the reference prints the error and returns 0 (src/pimdb.cpp:57-67)
     assert "[X] Invalid argument error: Normal modes propogation is currently not available for bosons!" in r.stdout
+
+
+@pytest.mark.parametrize("case,gpus", [("nve_aziz_grid_pbc", 2), ("nve_trap_bosonic", 2), ("nve_trap_bosonic", 4)])
+def test_pimdb_gpu_sharded_over_several_handles_reproduces_reference_run(gpu_required, case, gpus, tmp_path):
+    """`pimdb_gpu --gpus G`: the beads sharded over G handles coupled through peer memory, driven by one host thread -- the
+    counterpart of `mpirun -np P pimdb` (README.md:200-203). On a one-GPU box the shards share the device
+    (PIMDB_SHARD_SAME_DEVICE=1); the output files must match the unmodified reference's complete run."""
+    import os
+    import torch
+    ndim = int(E2E[f"{case}/ndim"])
+    (tmp_path / "config.ini").write_text(str(E2E[f"{case}/ini"]))
+    env = dict(os.environ)
+    if torch.cuda.device_count() < gpus:
+        env["PIMDB_SHARD_SAME_DEVICE"] = "1"
+    r = subprocess.run([str(BIN), "-in", "config.ini", "--dim", str(ndim), "--gpus", str(gpus)], cwd=tmp_path, capture_output=True,
+                       text=True, timeout=300, env=env)
+    assert "[X]" not in r.stdout, r.stdout
+    assert "finished running successfully" in r.stdout, r.stdout + r.stderr
+    got = pio.read_simulation_out(str(tmp_path / "output" / "simulation.out"))
+    cols = [str(c) for c in E2E[f"{case}/simout_columns"]]
+    ref = E2E[f"{case}/simout"]
+    assert list(got.keys()) == cols
+    for i, c in enumerate(cols):
+        assert np.allclose(got[c], ref[:, i], rtol=1e-5), c
+        scale = np.max(np.abs(ref[:, i])) + 1e-300
+        assert np.max(np.abs(got[c] - ref[:, i])) <= 2e-7 * max(scale, 1.0), (c, got[c], ref[:, i])
+    nb = E2E[f"{case}/x"].shape[0]
+    for kind, pat in (("x", "position_{}.xyz"), ("v", "velocity_{}.dat"), ("f", "force_{}.dat")):
+        key = f"{case}/{kind}"
+        if key not in E2E.files:
+            continue
+        for b in range(nb):
+            frames = np.asarray(pio.read_dump_frames(str(tmp_path / "output" / pat.format(b)), ndim))
+            assert np.max(np.abs(frames - E2E[key][b])) <= 1e-8 * np.max(np.abs(E2E[key])), (kind, b)
