@@ -359,7 +359,7 @@ extern "C" void pimdb_destroy(pimdb_sim* sim) {
 static int check_deferred(Sim* s) {
     if (*s->err_h != 0) {
         const int e = *s->err_h;
-        *s->err_h = 0;
+        *s->err_h = e & kErrPeerTimeout;   // a lost peer is permanent: every later synchronising call reports it again
         if (e & kErrPeerTimeout)
             return fail(s, PIMDB_ERR_RUNTIME, "bead shard timed out waiting for a peer GPU (halo slice / momentum sums); every rank must "
                                               "make the same sequence of calls");
@@ -672,7 +672,26 @@ static int settle_momenta(Sim* s) {
 }
 
 // body of Simulation::run, src/simulation.cpp:246-259
+// Bead shard, fixcom, Cartesian Langevin (or no) thermostat: the boundary slices leave one kernel early (OP_HALO_EARLY).
+static bool early_halo_push(const Sim* s) {
+    static const bool off = getenv("PIMDB_PEER_LATE_HALO") != nullptr;   // A/B timing
+    return !off && lazy_closing_com(s) && s->cfg.propagator == PIMDB_PROP_CARTESIAN;
+}
+
 static int enqueue_step(Sim* s, bool defer_last_com) {
+    if (early_halo_push(s)) {
+        //   [O | SUM -> peers | boundary slices -> neighbours]  [wait sums | SUBCM | B | A | fix received slices]  forces  [assemble | B | O]
+        const unsigned o_pre = s->cfg.thermostat == PIMDB_THERMO_LANGEVIN ? OP_O_PRE : 0u;
+        const unsigned o_post = s->cfg.thermostat == PIMDB_THERMO_LANGEVIN ? OP_O_POST : 0u;
+        s->p_shift_pending = false; s->z_owed = false;
+        API_TRY(launch_integrate(s, o_pre | OP_SUM | OP_HALO_EARLY));
+        API_TRY(launch_integrate(s, OP_SUBCM | OP_B | OP_A | OP_HALO_FIX));
+        const bool fuse = fuse_assembly(s);
+        API_TRY(enqueue_forces(s, fuse));
+        API_TRY(launch_integrate(s, (fuse ? OP_ASSEMBLE : 0u) | OP_B | o_post));
+        s->z_owed = true;
+        return PIMDB_OK;
+    }
     Fuser fz(s);
     const bool lazy = lazy_closing_com(s);
     if (lazy) { s->p_shift_pending = false; s->z_owed = false; }   // whatever Z is outstanding is subsumed by this iteration's first

@@ -136,8 +136,11 @@ __device__ __forceinline__ void tl_end(unsigned long long* tl) {
 // ---------------------------------------------------------------------------------------------------
 // Peer-memory signalling (bead sharding, internal.cuh PeerMailbox): system-scope relaxed loads / stores of flag words
 // that another GPU (or another process on this GPU) writes or reads, and BOUNDED waits on them. A wait that runs out
-// raises `err_bit` in the host-mapped error word and returns false; once the bit is up every later wait returns at
-// once, so a dead peer costs one time-out, not one per kernel of the remaining graph replays.
+// raises `err_bit` in the host-mapped error word and a flag in device memory (`dead`), and returns false; once the flag
+// is up every later wait returns at once, so a dead peer costs one time-out, not one per kernel of the remaining graph
+// replays. (The flag that the waits consult lives in DEVICE memory: the error word is zero-copy host memory, and a read
+// of it from every waiting thread of every block costs a PCIe round trip each -- 250 us per step at C3 when it was
+// the one consulted.)
 __device__ __forceinline__ unsigned ld_sys_u32(const unsigned* p) {
     unsigned v;
     asm volatile("ld.relaxed.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -156,13 +159,14 @@ __device__ __forceinline__ void st_sys_u64(unsigned long long* p, unsigned long 
 }
 // wait until the counter at p has reached `want` (wrap-safe)
 __device__ __forceinline__ bool wait_sys_u32_ge(const unsigned* p, unsigned want, unsigned long long timeout_ns, int* err,
-                                                int err_bit) {
+                                                int err_bit, unsigned* dead) {
     if ((int)(ld_sys_u32(p) - want) >= 0) return true;
-    if (*(volatile int*)err & err_bit) return false;
+    if (*(volatile unsigned*)dead) return false;
     const unsigned long long t0 = gtimer_ns();
     unsigned spins = 0;
     while ((int)(ld_sys_u32(p) - want) < 0) {
         if ((++spins & 255u) == 0 && gtimer_ns() - t0 > timeout_ns) {
+            *(volatile unsigned*)dead = 1u;
             atomicOr(err, err_bit);
             return false;
         }
@@ -171,14 +175,15 @@ __device__ __forceinline__ bool wait_sys_u32_ge(const unsigned* p, unsigned want
 }
 // wait until the high half of the self-validating word at p equals `seq`; returns its low half
 __device__ __forceinline__ unsigned wait_sys_word(const unsigned long long* p, unsigned seq, unsigned long long timeout_ns,
-                                                  int* err, int err_bit) {
+                                                  int* err, int err_bit, unsigned* dead) {
     unsigned long long w = ld_sys_u64(p);
     if ((unsigned)(w >> 32) == seq) return (unsigned)w;
-    if (*(volatile int*)err & err_bit) return 0u;
+    if (*(volatile unsigned*)dead) return 0u;
     const unsigned long long t0 = gtimer_ns();
     unsigned spins = 0;
     while ((unsigned)((w = ld_sys_u64(p)) >> 32) != seq) {
         if ((++spins & 255u) == 0 && gtimer_ns() - t0 > timeout_ns) {
+            *(volatile unsigned*)dead = 1u;
             atomicOr(err, err_bit);
             return 0u;
         }
@@ -192,7 +197,8 @@ __device__ __forceinline__ void peer_wait_halos(const unsigned int* halo_flag, c
                                                 unsigned long long timeout_ns, int* err) {
     if (!halo_flag) return;
     if (threadIdx.x < 2) {
-        wait_sys_u32_ge(&halo_flag[threadIdx.x], *halo_seq, timeout_ns, err, 8 /* kErrPeerTimeout */);
+        wait_sys_u32_ge(&halo_flag[threadIdx.x], *halo_seq, timeout_ns, err, 8 /* kErrPeerTimeout */,
+                        const_cast<unsigned*>(halo_seq) + 2 /* the handle's "peer is dead" flag, PeerDev::seq[3] */);
         __threadfence_system();
     }
     __syncthreads();

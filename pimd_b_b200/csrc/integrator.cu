@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(256) k_integrate(IntArgs a) {
             const unsigned seq = sh_seq[0];
             if (tid < a.peer.world * kComWords)
                 sh_words[tid] = wait_sys_word(&a.peer.mine->com_in[seq & 1u][tid / kComWords][tid % kComWords], seq,
-                                              a.peer.timeout_ns, a.err, kErrPeerTimeout);
+                                              a.peer.timeout_ns, a.err, kErrPeerTimeout, a.peer.seq + 3);
             __syncthreads();
             if (tid < 3) {
                 double t = 0.0;
@@ -251,15 +251,19 @@ __global__ void __launch_bounds__(256) k_integrate(IntArgs a) {
         }
     }
     if (peer && (a.ops & OP_ASSEMBLE) && tid < 2) {   // the springs of the boundary beads read the neighbours' slices
-        wait_sys_u32_ge(&a.peer.mine->halo_flag[tid], sh_seq[1], a.peer.timeout_ns, a.err, kErrPeerTimeout);
+        wait_sys_u32_ge(&a.peer.mine->halo_flag[tid], sh_seq[1], a.peer.timeout_ns, a.err, kErrPeerTimeout, a.peer.seq + 3);
         __threadfence_system();
     }
-    const bool push_halo = peer && (a.ops & OP_HALO);
+    if (peer && (a.ops & OP_HALO_FIX) && tid < 2) {   // the slices the neighbours sent one kernel ago (OP_HALO_EARLY)
+        wait_sys_u32_ge(&a.peer.mine->halo_flag[tid], sh_seq[1], a.peer.timeout_ns, a.err, kErrPeerTimeout, a.peer.seq + 3);
+        __threadfence_system();
+    }
+    const bool push_halo = peer && (a.ops & (OP_HALO | OP_HALO_EARLY));
     if (push_halo && tid < 2) {
         const unsigned k = sh_seq[1] + 1u;                         // index of the halo push this kernel makes
         // I am the previous rank of `next` (its credit[0]) and the next rank of `prev` (its credit[1])
         st_sys_u32(tid == 0 ? &a.peer.box[a.peer.next]->credit[0] : &a.peer.box[a.peer.prev]->credit[1], k);
-        wait_sys_u32_ge(&a.peer.mine->credit[tid], k, a.peer.timeout_ns, a.err, kErrPeerTimeout);
+        wait_sys_u32_ge(&a.peer.mine->credit[tid], k, a.peer.timeout_ns, a.err, kErrPeerTimeout, a.peer.seq + 3);
     }
     __syncthreads();
     const unsigned long long draw = sh_draw;
@@ -349,6 +353,31 @@ __global__ void __launch_bounds__(256) k_integrate(IntArgs a) {
         }
         if (a.ops & OP_O_POST) { pv.x = a.c1 * pv.x + a.c2 * z0; pv.y = a.c1 * pv.y + a.c2 * z1; }
         if (a.ops & (OP_SUBCM | OP_O_PRE | OP_O_POST | OP_B | OP_B_PHYS)) st_pair<VEC>(a.p, o, pv, two);
+        if ((a.ops & OP_HALO_EARLY) && (b == 0 || b == a.Ploc - 1)) {
+            // x~ = x + dt/m (p + dt/2 f): where this bead will be after the coming kick and drift, up to the uniform shift
+            const double2 fb = ld_pair<VEC>(a.f, o, two);
+            double2 xt = ld_pair<VEC>(a.x, ox, two);
+            xt.x += a.dt_over_m * (pv.x + a.hdt * fb.x);
+            xt.y += a.dt_over_m * (pv.y + a.hdt * fb.y);
+            const size_t within = (size_t)c * a.N + n0;
+            if (b == 0) st_pair<VEC>(a.peer.halo_to_prev, within, xt, two);
+            if (b == a.Ploc - 1) st_pair<VEC>(a.peer.halo_to_next, within, xt, two);
+            stored_remote = true;
+        }
+        if ((a.ops & OP_HALO_FIX) && (b == 0 || b == a.Ploc - 1)) {
+            const double shift = a.dt_over_m * (c == 0 ? cm[0] : (c == 1 ? cm[1] : cm[2]));
+            const size_t within = (size_t)c * a.N + n0;
+            if (b == a.Ploc - 1) {   // trailing halo slab: the next rank's first bead
+                double2 h = ld_pair<VEC>(a.x, (size_t)(a.Ploc + 1) * a.S + within, two);
+                h.x -= shift; h.y -= shift;
+                st_pair<VEC>(a.x, (size_t)(a.Ploc + 1) * a.S + within, h, two);
+            }
+            if (b == 0) {            // leading halo slab: the previous rank's last bead
+                double2 h = ld_pair<VEC>(a.x, within, two);
+                h.x -= shift; h.y -= shift;
+                st_pair<VEC>(a.x, within, h, two);
+            }
+        }
         if (a.ops & OP_A) {
             double2 xv = ld_pair<VEC>(a.x, ox, two);
             xv.x += a.dt_over_m * pv.x;
@@ -381,10 +410,12 @@ __global__ void __launch_bounds__(256) k_integrate(IntArgs a) {
                 for (int c = 0; c < 3; ++c) a.com_part[blockIdx.x * 4 + c] = acc[c];
             }
         }
-        if (stored_remote) __threadfence_system();   // my slices are on their way before this block takes its ticket
-        __syncthreads();
+        // (remote stores of this block's threads -> barrier -> ONE system-scope fence by thread 0 -> ticket: fences are
+        // cumulative, so the slices are ordered before whatever the last block publishes after it has seen every ticket)
+        const bool any_remote = __syncthreads_or(stored_remote);
         if (tid == 0) {
-            __threadfence();
+            if (any_remote) __threadfence_system();
+            else __threadfence();
             unsigned int t = atomicAdd(a.ticket, 1u);
             is_last = (t == gridDim.x - 1);
         }
@@ -421,6 +452,11 @@ __global__ void __launch_bounds__(256) k_integrate(IntArgs a) {
                 st_sys_u32(&a.peer.box[a.peer.next]->halo_flag[0], k);   // my last bead is next's leading halo
                 a.peer.seq[1] = k;
             }
+            if (peer && (a.ops & OP_ASSEMBLE) && tid < 2) {
+                // every block has read the halo slabs for the last time before the next push: tell the neighbours now, so
+                // that the hand-shake of their next push finds the word already there
+                st_sys_u32(tid == 0 ? &a.peer.box[a.peer.next]->credit[0] : &a.peer.box[a.peer.prev]->credit[1], sh_seq[1] + 1u);
+            }
             if (tid == 0) {
                 *a.ticket = 0u;
                 if (do_o) *a.draw = draw + 1ull;
@@ -441,7 +477,7 @@ __global__ void __launch_bounds__(256) k_peer_push_halos(const double* x, size_t
     const unsigned k = sh_k;
     if (tid < 2) {
         st_sys_u32(tid == 0 ? &peer.box[peer.next]->credit[0] : &peer.box[peer.prev]->credit[1], k);
-        wait_sys_u32_ge(&peer.mine->credit[tid], k, peer.timeout_ns, err, kErrPeerTimeout);
+        wait_sys_u32_ge(&peer.mine->credit[tid], k, peer.timeout_ns, err, kErrPeerTimeout, peer.seq + 3);
     }
     __syncthreads();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + tid; i < S; i += (size_t)gridDim.x * blockDim.x) {

@@ -46,8 +46,8 @@ struct PeerDev {                      // passed by value to the kernels that tal
     PeerMailbox* box[kMaxPeers];      // every rank's mailbox (box[rank] == mine)
     double* halo_to_prev;             // previous rank's trailing halo slab (receives this rank's first bead)
     double* halo_to_next;             // next rank's leading halo slab (receives this rank's last bead)
-    unsigned int* seq;                // local counters: [0] COM pushes, [1] halo pushes, [2] force evaluations of sharded steps,
-                                      //                 [3] halo pushes made by sharded steps (what credits are compared with)
+    unsigned int* seq;                // local counters: [0] momentum-sum pushes made, [1] halo pushes made (= slices expected from each
+                                      // neighbour), [2] unused, [3] "a peer timed out" (sticky; later waits return at once)
     int prev, next;
     unsigned long long timeout_ns;    // bound of every device-side wait
 };
@@ -176,7 +176,14 @@ int launch_fill_halos(Sim* s);
 enum : unsigned { OP_SUBCM = 1, OP_O_PRE = 2, OP_B = 4, OP_O_POST = 8, OP_A = 16, OP_SUM = 32, OP_HALO = 64, OP_B_PHYS = 128,
                   OP_ASSEMBLE = 256,   // form f = springs + external + pair partials in the same pass (before B)
                   OP_CREDIT = 512,     // peer mode: tell the ring neighbours that their halo slices have been consumed
-                  OP_ZERO_SUM = 1024   // peer mode: publish zero momentum sums (uniform entry state of a captured step)
+                  OP_ZERO_SUM = 1024,  // peer mode: publish zero momentum sums (uniform entry state of a captured step)
+                  // peer mode, fixcom: the boundary beads' NEW coordinates are sent to the ring neighbours one kernel early, by the
+                  // kernel that takes the momentum sums, without the (not yet known) centre-of-mass shift
+                  //     x~ = x + dt/m (p + dt/2 f),    x_new = x~ - dt/m com/(N P);
+                  // the next kernel (SUBCM|B|A), which waits for the sums anyway, subtracts the uniform shift from the two halo
+                  // slabs it received (OP_HALO_FIX). Halo slices then travel while the sums do, and neither the hand-shake nor
+                  // the remote stores sit on the kernel that the force evaluation waits for.
+                  OP_HALO_EARLY = 2048, OP_HALO_FIX = 4096
 };
 int launch_integrate(Sim* s, unsigned ops);
 int launch_peer_push_halos(Sim* s);

@@ -203,7 +203,10 @@ class PeerNumpySim:
             assert time.time() - t0 < 30.0, "peer wait timed out"
             time.sleep(0.0005)
 
-    def _push_halos(self):
+    def _push_halos(self, first=None, last=None):
+        """first / last: what to send instead of the current first / last owned bead (the early push of a step)."""
+        first = self.x[1] if first is None else first
+        last = self.x[self.n] if last is None else last
         k = self.seq_halo + 1
         _, _, _, credit_next = self._views(self.box[self.next])
         _, _, _, credit_prev = self._views(self.box[self.prev])
@@ -215,8 +218,8 @@ class PeerNumpySim:
         xprev = self.box[self.prev][self.words:].reshape(nprev + 2, self.cfg.ndim, self.cfg.natoms)
         nnext = self.ranges[self.next][1] - self.ranges[self.next][0]
         xnext = self.box[self.next][self.words:].reshape(nnext + 2, self.cfg.ndim, self.cfg.natoms)
-        xprev[nprev + 1] = self.x[1]          # my first bead -> prev's trailing halo
-        xnext[0] = self.x[self.n]             # my last bead  -> next's leading halo
+        xprev[nprev + 1] = first              # my first bead -> prev's trailing halo
+        xnext[0] = last                       # my last bead  -> next's leading halo
         self._views(self.box[self.prev])[2][1] = k
         self._views(self.box[self.next])[2][0] = k
         self.seq_halo = k
@@ -241,7 +244,9 @@ class PeerNumpySim:
         tot = np.zeros(self.cfg.ndim)
         for r in range(self.world):
             tot += com[s & 1, r, :self.cfg.ndim]
-        self.p -= (tot / (self.cfg.natoms * self.cfg.nbeads)).reshape(1, -1, 1)
+        shift = (tot / (self.cfg.natoms * self.cfg.nbeads)).reshape(1, -1, 1)
+        self.p -= shift
+        return shift
 
     def upload(self, x, p):
         self.x[1:self.n + 1] = np.transpose(x, (0, 2, 1))
@@ -253,12 +258,18 @@ class PeerNumpySim:
         c = self.cfg
         for _ in range(nsteps):
             self.z_owed = False                  # subsumed by this iteration's first zeroMomentum
+            # kernel 1: momentum sums -> every rank; the boundary beads' coming positions, without the (unknown) shift,
+            # -> the ring neighbours:  x~ = x + dt/m (p + dt/2 f)
             self._sum_push()
-            self._subcm_wait()
+            xt = lambda b: self.x[1 + b] + c.dt / c.mass * (self.p[b] + 0.5 * c.dt * self.f[b])
+            self._push_halos(first=xt(0), last=xt(self.n - 1))
+            # kernel 2: wait for the sums, COM removal, B, A, and the uniform shift taken off the two received slices
+            shift = self._subcm_wait()
             self.p += 0.5 * c.dt * self.f
             self.x[1:self.n + 1] += c.dt * self.p / c.mass
-            self._push_halos()
             self._wait_halos()
+            self.x[0] -= c.dt / c.mass * shift[0]
+            self.x[self.n + 1] -= c.dt / c.mass * shift[0]
             xc = self.x[1:self.n + 1]
             self.f = self.k * (self.x[0:self.n] + self.x[2:self.n + 2] - 2 * xc) - self.kext * xc
             self.p += 0.5 * c.dt * self.f
