@@ -147,7 +147,7 @@ static void free_all(Sim* s) {
     cudaFreeHost(s->err_h);
     cudaFree(s->nmC); cudaFree(s->nmFreq); cudaFree(s->nh_state);
     for (void* m : s->ipc_opened) cudaIpcCloseMemHandle(m);
-    cudaFree(s->mailbox); cudaFree(s->peer_seq);
+    cudaFree(s->mailbox); cudaFree(s->peer_seq); cudaFree(s->stamps);
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     if (s->ev_join) cudaEventDestroy(s->ev_join);
     if (s->ev_copy) cudaEventDestroy(s->ev_copy);
@@ -306,10 +306,15 @@ extern "C" int pimdb_create(const pimdb_config* cfg, pimdb_sim** out) {
         if (rc != PIMDB_OK) { g_create_error = s->err; free_all(s); return rc; }
     }
     if (!s->all_local) {   // mailbox + counters of the peer-memory sharding protocol (pimdb_peer_export / _attach)
-        CREATE_TRY(cudaMalloc(&s->mailbox, sizeof(PeerMailbox)));
-        CREATE_TRY(cudaMemset(s->mailbox, 0, sizeof(PeerMailbox)));
+        const size_t mb_bytes = sizeof(PeerMailbox) + sizeof(unsigned long long) * 2 * 2 * 2 * s->S;   // + the self-validating halo inbox
+        CREATE_TRY(cudaMalloc(&s->mailbox, mb_bytes));
+        CREATE_TRY(cudaMemset(s->mailbox, 0, mb_bytes));
         CREATE_TRY(cudaMalloc(&s->peer_seq, sizeof(unsigned int) * 4));
         CREATE_TRY(cudaMemset(s->peer_seq, 0, sizeof(unsigned int) * 4));
+    }
+    if (getenv("PIMDB_TIMELINE")) {
+        CREATE_TRY(cudaMalloc(&s->stamps, sizeof(unsigned long long) * 64));
+        CREATE_TRY(cudaMemset(s->stamps, 0, sizeof(unsigned long long) * 64));
     }
     CREATE_TRY(cudaMalloc(&s->com_part, sizeof(double) * 4 * kMaxPartials));
     CREATE_TRY(cudaMalloc(&s->com, sizeof(double) * 4));
@@ -822,6 +827,7 @@ extern "C" int pimdb_step(pimdb_sim* sim, int nsteps) {
         const bool pending0 = s->p_shift_pending, owed0 = s->z_owed, stale0 = s->split_stale;
         PIMDB_CUDA_TRY(s, cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
         s->tl_next = 0;
+        s->stamp_next = 0;
         int rc = enqueue_step(s, true);
         cudaGraph_t g = nullptr;
         cudaError_t ce = cudaStreamEndCapture(s->stream, &g);
@@ -970,6 +976,7 @@ extern "C" int pimdb_peer_attach(pimdb_sim* sim, int world, int rank, const void
     pd.world = world; pd.rank = rank;
     pd.prev = (rank + world - 1) % world; pd.next = (rank + 1) % world;
     pd.mine = s->mailbox; pd.seq = s->peer_seq;
+    pd.ll_mine = reinterpret_cast<unsigned long long*>(s->mailbox + 1);
     unsigned long long ms = 20000;
     if (const char* e = getenv("PIMDB_PEER_TIMEOUT_MS")) ms = (unsigned long long)std::max(1, atoi(e));
     pd.timeout_ns = ms * 1000000ull;
@@ -981,6 +988,8 @@ extern "C" int pimdb_peer_attach(pimdb_sim* sim, int world, int rank, const void
         const size_t ploc_r = (size_t)(tab[r].bead_end - tab[r].bead_begin);
         if (r == pd.prev) pd.halo_to_prev = reinterpret_cast<double*>(x) + (ploc_r + 1) * s->S;   // its trailing halo slab
         if (r == pd.next) pd.halo_to_next = reinterpret_cast<double*>(x);                          // its leading halo slab
+        if (r == pd.prev) pd.ll_to_prev = reinterpret_cast<unsigned long long*>(pd.box[r] + 1);
+        if (r == pd.next) pd.ll_to_next = reinterpret_cast<unsigned long long*>(pd.box[r] + 1);
     }
     s->peer = pd;
     s->peer_on = true;
@@ -1240,6 +1249,17 @@ extern "C" int pimdb_debug_timeline(pimdb_sim* sim, unsigned long long* out) {
     for (int i = 0; i < 32; ++i) { init[2 * i] = ~0ull; init[2 * i + 1] = 0ull; }
     cudaMemcpy(s->tl, init.data(), sizeof(unsigned long long) * 64, cudaMemcpyHostToDevice);
     return s->tl_next;
+}
+
+// Profiling aid (PIMDB_TIMELINE=1): the %globaltimer stamps of the phases of the k_integrate launches of the captured step
+// (block 0: 0 start, 1 counters read, 2 sums in, 3 halo / credit waits done, 4 main loop done, 5 ticket taken; last block: 6, 7 end).
+extern "C" int pimdb_debug_integrate_stamps(pimdb_sim* sim, unsigned long long* out) {
+    Sim* s = reinterpret_cast<Sim*>(sim);
+    if (!s || !out || !s->stamps) return 0;
+    cudaSetDevice(s->device);
+    cudaDeviceSynchronize();
+    cudaMemcpy(out, s->stamps, sizeof(unsigned long long) * 64, cudaMemcpyDeviceToHost);
+    return s->stamp_next;
 }
 
 // ----------------------------------------------------------------------------------------------------

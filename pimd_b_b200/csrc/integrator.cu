@@ -193,7 +193,9 @@ struct IntArgs {
     int peer_on;
     PeerDev peer;
     int* err;
+    unsigned long long* stamps;   // profiling aid (PIMDB_TIMELINE): %globaltimer at the phases of this launch, or nullptr
 };
+#define PIMDB_STAMP(i) do { if (a.stamps && tid == 0 && (blockIdx.x == 0 || (i) >= 6)) a.stamps[i] = gtimer_ns(); } while (0)
 
 template <bool VEC>
 __device__ __forceinline__ double2 ld_pair(const double* ptr, size_t o, bool two) {
@@ -216,7 +218,7 @@ __global__ void __launch_bounds__(256) k_integrate(IntArgs a) {
     __shared__ double sm[3 * 32];
     __shared__ double sh_cm[4];
     __shared__ unsigned long long sh_draw;
-    __shared__ unsigned sh_seq[2];
+    __shared__ unsigned sh_seq[3];
     __shared__ unsigned sh_words[kMaxPeers * kComWords];
     __shared__ bool is_last;
     const int tid = threadIdx.x;
@@ -227,12 +229,14 @@ __global__ void __launch_bounds__(256) k_integrate(IntArgs a) {
     const bool peer = a.peer_on != 0;
     // ---- prologue: counters (read by ONE thread, before the barrier: nothing below can overtake the last block's
     // update of them), centre-of-mass shift, hand-shake with the ring neighbours
+    PIMDB_STAMP(0);
     if (tid == 0) {
         sh_draw = do_o ? *a.draw : 0ull;
-        if (peer) { sh_seq[0] = a.peer.seq[0]; sh_seq[1] = a.peer.seq[1]; }
+        if (peer) { sh_seq[0] = a.peer.seq[0]; sh_seq[1] = a.peer.seq[1]; sh_seq[2] = a.peer.seq[2]; }
     }
     if (tid < 4) sh_cm[tid] = 0.0;
     __syncthreads();
+    PIMDB_STAMP(1);
     if (a.ops & OP_SUBCM) {
         if (peer) {
             const unsigned seq = sh_seq[0];
@@ -250,15 +254,10 @@ __global__ void __launch_bounds__(256) k_integrate(IntArgs a) {
             sh_cm[tid] = tid < a.D ? a.com[tid] * a.inv_np : 0.0;
         }
     }
-    if (peer && (a.ops & OP_ASSEMBLE) && tid < 2) {   // the springs of the boundary beads read the neighbours' slices
+    PIMDB_STAMP(2);
+    if (peer && (a.ops & OP_ASSEMBLE) && tid < 2)     // the springs of the boundary beads read the neighbours' slices
         wait_sys_u32_ge(&a.peer.mine->halo_flag[tid], sh_seq[1], a.peer.timeout_ns, a.err, kErrPeerTimeout, a.peer.seq + 3);
-        __threadfence_system();
-    }
-    if (peer && (a.ops & OP_HALO_FIX) && tid < 2) {   // the slices the neighbours sent one kernel ago (OP_HALO_EARLY)
-        wait_sys_u32_ge(&a.peer.mine->halo_flag[tid], sh_seq[1], a.peer.timeout_ns, a.err, kErrPeerTimeout, a.peer.seq + 3);
-        __threadfence_system();
-    }
-    const bool push_halo = peer && (a.ops & (OP_HALO | OP_HALO_EARLY));
+    const bool push_halo = peer && (a.ops & OP_HALO);
     if (push_halo && tid < 2) {
         const unsigned k = sh_seq[1] + 1u;                         // index of the halo push this kernel makes
         // I am the previous rank of `next` (its credit[0]) and the next rank of `prev` (its credit[1])
@@ -266,6 +265,7 @@ __global__ void __launch_bounds__(256) k_integrate(IntArgs a) {
         wait_sys_u32_ge(&a.peer.mine->credit[tid], k, a.peer.timeout_ns, a.err, kErrPeerTimeout, a.peer.seq + 3);
     }
     __syncthreads();
+    PIMDB_STAMP(3);
     const unsigned long long draw = sh_draw;
     const double cm[3] = {sh_cm[0], sh_cm[1], sh_cm[2]};
     double acc[3] = {0.0, 0.0, 0.0};
@@ -360,21 +360,42 @@ __global__ void __launch_bounds__(256) k_integrate(IntArgs a) {
             xt.x += a.dt_over_m * (pv.x + a.hdt * fb.x);
             xt.y += a.dt_over_m * (pv.y + a.hdt * fb.y);
             const size_t within = (size_t)c * a.N + n0;
-            if (b == 0) st_pair<VEC>(a.peer.halo_to_prev, within, xt, two);
-            if (b == a.Ploc - 1) st_pair<VEC>(a.peer.halo_to_next, within, xt, two);
-            stored_remote = true;
+            const unsigned k = sh_seq[2] + 1u;                      // number of this self-validating push
+            const unsigned long long tag = (unsigned long long)k << 32;
+            const size_t slot = (size_t)(k & 1u) * 2;
+            if (b == 0) {                  // my first bead is the previous rank's trailing halo: its inbox, side 1
+                unsigned long long* d = a.peer.ll_to_prev + ((slot + 1) * a.S + within) * 2;
+                st_sys_u64(d, tag | (unsigned)__double2loint(xt.x)); st_sys_u64(d + 1, tag | (unsigned)__double2hiint(xt.x));
+                if (two) { st_sys_u64(d + 2, tag | (unsigned)__double2loint(xt.y)); st_sys_u64(d + 3, tag | (unsigned)__double2hiint(xt.y)); }
+            }
+            if (b == a.Ploc - 1) {         // my last bead is the next rank's leading halo: its inbox, side 0
+                unsigned long long* d = a.peer.ll_to_next + (slot * a.S + within) * 2;
+                st_sys_u64(d, tag | (unsigned)__double2loint(xt.x)); st_sys_u64(d + 1, tag | (unsigned)__double2hiint(xt.x));
+                if (two) { st_sys_u64(d + 2, tag | (unsigned)__double2loint(xt.y)); st_sys_u64(d + 3, tag | (unsigned)__double2hiint(xt.y)); }
+            }
         }
         if ((a.ops & OP_HALO_FIX) && (b == 0 || b == a.Ploc - 1)) {
+            // unpack what the neighbours sent one kernel ago (each word carries the push number: poll the words
+            // themselves), take the now-known uniform shift off, and store the slice where every reader expects it
             const double shift = a.dt_over_m * (c == 0 ? cm[0] : (c == 1 ? cm[1] : cm[2]));
             const size_t within = (size_t)c * a.N + n0;
-            if (b == a.Ploc - 1) {   // trailing halo slab: the next rank's first bead
-                double2 h = ld_pair<VEC>(a.x, (size_t)(a.Ploc + 1) * a.S + within, two);
-                h.x -= shift; h.y -= shift;
+            const unsigned k = sh_seq[2];
+            const size_t slot = (size_t)(k & 1u) * 2;
+            auto recv = [&](const unsigned long long* w) {
+                const unsigned lo = wait_sys_word(w, k, a.peer.timeout_ns, a.err, kErrPeerTimeout, a.peer.seq + 3);
+                const unsigned hi = wait_sys_word(w + 1, k, a.peer.timeout_ns, a.err, kErrPeerTimeout, a.peer.seq + 3);
+                return __hiloint2double((int)hi, (int)lo) - shift;
+            };
+            if (b == a.Ploc - 1) {   // trailing halo slab: the next rank's first bead (inbox side 1)
+                const unsigned long long* w = a.peer.ll_mine + ((slot + 1) * a.S + within) * 2;
+                double2 h;
+                h.x = recv(w); h.y = two ? recv(w + 2) : 0.0;
                 st_pair<VEC>(a.x, (size_t)(a.Ploc + 1) * a.S + within, h, two);
             }
-            if (b == 0) {            // leading halo slab: the previous rank's last bead
-                double2 h = ld_pair<VEC>(a.x, within, two);
-                h.x -= shift; h.y -= shift;
+            if (b == 0) {            // leading halo slab: the previous rank's last bead (inbox side 0)
+                const unsigned long long* w = a.peer.ll_mine + (slot * a.S + within) * 2;
+                double2 h;
+                h.x = recv(w); h.y = two ? recv(w + 2) : 0.0;
                 st_pair<VEC>(a.x, within, h, two);
             }
         }
@@ -403,6 +424,7 @@ __global__ void __launch_bounds__(256) k_integrate(IntArgs a) {
             acc[2] += c == 2 ? ps : 0.0;
         }
     }
+    PIMDB_STAMP(4);
     if ((a.ops & (OP_SUM | OP_O_PRE | OP_O_POST | OP_ZERO_SUM)) || push_halo) {
         if (a.ops & OP_SUM) {
             block_sum<3>(acc, sm);
@@ -420,7 +442,9 @@ __global__ void __launch_bounds__(256) k_integrate(IntArgs a) {
             is_last = (t == gridDim.x - 1);
         }
         __syncthreads();
+        PIMDB_STAMP(5);
         if (is_last) {
+            PIMDB_STAMP(6);
             double tot[3] = {0.0, 0.0, 0.0};
             if (a.ops & OP_SUM) {
                 __threadfence();
@@ -445,6 +469,7 @@ __global__ void __launch_bounds__(256) k_integrate(IntArgs a) {
                 }
                 if (tid == 0) a.peer.seq[0] = seq;
             }
+            if (peer && (a.ops & OP_HALO_EARLY) && tid == 0) a.peer.seq[2] = sh_seq[2] + 1u;
             if (push_halo && tid == 0) {
                 __threadfence_system();      // every block fenced its slices before its ticket; order the flags behind them
                 const unsigned k = sh_seq[1] + 1u;
@@ -461,6 +486,7 @@ __global__ void __launch_bounds__(256) k_integrate(IntArgs a) {
                 *a.ticket = 0u;
                 if (do_o) *a.draw = draw + 1ull;
             }
+            PIMDB_STAMP(7);
         }
     }
     tl_end(a.tl);
@@ -538,6 +564,7 @@ int launch_integrate(Sim* s, unsigned ops) {
     a.peer_on = s->peer_on ? 1 : 0;
     a.peer = s->peer;
     a.err = s->err_d;
+    a.stamps = s->stamps ? s->stamps + 8 * (s->stamp_next++ % 8) : nullptr;
     if (ops & OP_ASSEMBLE) s->split_stale = true;
     const size_t items = (size_t)s->Ploc * s->D * ((s->N + 1) / 2);
     const int grid = grid_for(items, 256, kMaxPartials);

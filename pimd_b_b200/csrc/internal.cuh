@@ -46,8 +46,16 @@ struct PeerDev {                      // passed by value to the kernels that tal
     PeerMailbox* box[kMaxPeers];      // every rank's mailbox (box[rank] == mine)
     double* halo_to_prev;             // previous rank's trailing halo slab (receives this rank's first bead)
     double* halo_to_next;             // next rank's leading halo slab (receives this rank's last bead)
-    unsigned int* seq;                // local counters: [0] momentum-sum pushes made, [1] halo pushes made (= slices expected from each
-                                      // neighbour), [2] unused, [3] "a peer timed out" (sticky; later waits return at once)
+    // Self-validating halo slices (the step's own halo traffic, OP_HALO_EARLY / OP_HALO_FIX): every double travels as two
+    // 8-byte words {32 data bits, 32-bit push number}, so the receiver polls the words themselves and neither side needs a
+    // system-scope fence (3.5 us each on this platform) or a flag round trip. Inbox layout, behind the PeerMailbox in the
+    // same allocation: [slot = push number & 1][side: 0 from the previous rank, 1 from the next][S doubles][2 words].
+    unsigned long long* ll_mine;      // local inbox
+    unsigned long long* ll_to_prev;   // previous rank's inbox (my first bead goes to its side 1)
+    unsigned long long* ll_to_next;   // next rank's inbox (my last bead goes to its side 0)
+    unsigned int* seq;                // local counters: [0] momentum-sum pushes made, [1] flag-protocol halo pushes made (= slices
+                                      // expected from each neighbour), [2] self-validating halo pushes made, [3] "a peer timed
+                                      // out" (sticky; later waits return at once)
     int prev, next;
     unsigned long long timeout_ns;    // bound of every device-side wait
 };
@@ -124,6 +132,7 @@ struct Sim {
     // Nose-Hoover chains: eta | eta_dot | eta_dot_dot, each [bead][group][nchains]
     double *nh_state = nullptr; size_t nh_len = 0;
     RanMarsState* rm_state = nullptr; double* rm_noise = nullptr;   // reference-compatible noise mode (ranmars.cu): [Ploc], [Ploc][N][D]
+    unsigned long long* stamps = nullptr; int stamp_next = 0;   // phase stamps of the k_integrate launches [8][8] (PIMDB_TIMELINE=1)
     unsigned long long* tl = nullptr; int tl_next = 0;   // in-kernel timeline slots [32][2] (PIMDB_TIMELINE=1), next slot
     // graph
     cudaGraph_t graph = nullptr; cudaGraphExec_t graph_exec = nullptr;

@@ -38,6 +38,13 @@ with torch.cuda.stream(ps.stream):
                 print(f"rank {rank} step {rep}: kernels in launch order [start us, end us, duration us]")
                 for i, (a, b) in enumerate(t):
                     print(f"   #{i}: {(a - t0) / 1e3:8.2f} {(b - t0) / 1e3:8.2f} {(b - a) / 1e3:8.2f}", flush=True)
+                fs = sim.lib.pimdb_debug_integrate_stamps; fs.restype = C.c_int; fs.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong)]
+                sb = (C.c_ulonglong * 64)()
+                k = fs(sim.h, sb)
+                st = np.array(sb[:], dtype=np.uint64).reshape(8, 8).astype(np.int64)
+                for i in range(min(k, 8)):
+                    print(f"   k_integrate launch {i}: phase stamps (us after the step's first kernel)",
+                          " ".join(f"{(v - t0) / 1e3:7.2f}" if v else "      -" for v in st[i]), flush=True)
             dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     dist.barrier(); torch.cuda.synchronize()
