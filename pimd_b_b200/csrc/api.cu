@@ -9,7 +9,7 @@
 #include "internal.cuh"
 
 namespace pimdb {
-int launch_pair_chunk(Sim* s, int bead_lo, int nb, bool with_obs, bool early = false);
+int launch_pair_chunk(Sim* s, int bead_lo, int nb, bool with_obs, bool early = false, int scratch_lo = 0);
 int launch_assemble_chunk(Sim* s, int bead_lo, int nb, bool with_pair);
 int launch_exchange_part(Sim* s, cudaStream_t st, int part);
 }  // namespace pimdb
@@ -18,6 +18,7 @@ using namespace pimdb;
 
 static thread_local std::string g_create_error;
 static int settle_momenta(Sim* s);
+static void allow_early_launch(Sim* s);
 
 #define API_TRY(expr)                      \
     do {                                   \
@@ -151,6 +152,7 @@ static void free_all(Sim* s) {
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     if (s->ev_join) cudaEventDestroy(s->ev_join);
     if (s->ev_copy) cudaEventDestroy(s->ev_copy);
+    for (cudaEvent_t e : s->ev_slice) cudaEventDestroy(e);
     if (s->stream_x) cudaStreamDestroy(s->stream_x);
     if (s->stream_r) cudaStreamDestroy(s->stream_r);
     if (s->ev_join2) cudaEventDestroy(s->ev_join2);
@@ -229,6 +231,7 @@ extern "C" int pimdb_create(const pimdb_config* cfg, pimdb_sim** out) {
     CREATE_TRY(cudaSetDevice(s->device));
     int lo = 0, hi = 0;
     CREATE_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    s->prio_hi = hi; s->prio_lo = lo;
     CREATE_TRY(cudaStreamCreateWithPriority(&s->stream, cudaStreamNonBlocking, lo));
     CREATE_TRY(cudaStreamCreateWithPriority(&s->stream_x, cudaStreamNonBlocking, hi));
     CREATE_TRY(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
@@ -518,7 +521,9 @@ extern "C" int pimdb_download_state(pimdb_sim* sim, double* x, double* p, double
 // force evaluation: exchange on the high-priority side stream, pair tiles + assembly on the main stream
 // `assemble_later`: the caller's next k_integrate launch forms f itself (OP_ASSEMBLE) -- one pass over the pair partials
 // and one launch fewer on the step's critical path.
-static int enqueue_forces(Sim* s, bool assemble_later = false) {
+// `after_integrate`: the previous launch on the main stream was one of our integrator kernels (a captured step): the first
+// kernel of the exchange chain may be launched early behind it.
+static int enqueue_forces(Sim* s, bool assemble_later = false, bool after_integrate = false) {
     const bool ex = s->bosonic && (s->has_first || s->has_last);
     bool pair_early = false;
     if (ex) {
@@ -536,9 +541,24 @@ static int enqueue_forces(Sim* s, bool assemble_later = false) {
         cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
         cudaStreamIsCapturing(s->stream, &cap);
         static const bool no_chain = getenv("PIMDB_EXCH_NOCHAIN") != nullptr;     // plain order (A/B timing)
-        const bool chain = cap == cudaStreamCaptureStatusActive && s->exK && !getenv("PIMDB_EXCH_NOBLOCKED") && !no_chain;
-        API_TRY(launch_exchange_part(s, s->stream, 0));
-        if (chain) {
+        // (only while the tile grid is a single wave, N <= 512: the pair tiles are scheduled once every tile block and then every
+        // recurrence block has STARTED, and a tile grid of many waves would hold them back for most of its run time)
+        const bool chain = cap == cudaStreamCaptureStatusActive && s->exK && s->N <= 512 && !getenv("PIMDB_EXCH_NOBLOCKED") && !no_chain;
+        if (!chain) {
+            // Tile grids of many waves (N > 512), or eager launches: factor tiles on the main stream AHEAD of the pair tiles, the
+            // rest of the chain on the side stream. (A 1024-thread tile block needs more registers than one retiring pair-tile
+            // block frees, so behind a running pair-tile grid it is never placed, whatever its priority: launched after the
+            // pair tiles, the tile grid of C4 started when the pair tiles had finished -- measured.)
+            API_TRY(launch_exchange_part(s, s->stream, 0));
+            PIMDB_CUDA_TRY(s, cudaEventRecord(s->ev_fork, s->stream));
+            PIMDB_CUDA_TRY(s, cudaStreamWaitEvent(s->stream_x, s->ev_fork, 0));
+            API_TRY(launch_exchange_part(s, s->stream_x, 1));
+        } else {
+        if (after_integrate) allow_early_launch(s);
+        const int rc0 = launch_exchange_part(s, s->stream, 0);
+        s->pdl_next = false;
+        API_TRY(rc0);
+        {
             s->pdl_recur = true;
             const int rc2 = launch_exchange_part(s, s->stream, 2);
             s->pdl_recur = false;
@@ -547,12 +567,7 @@ static int enqueue_forces(Sim* s, bool assemble_later = false) {
             PIMDB_CUDA_TRY(s, cudaStreamWaitEvent(s->stream_x, s->ev_fork, 0));
             API_TRY(launch_exchange_part(s, s->stream_x, 3));
             pair_early = true;
-        } else {
-            // eager launches (call-by-call entry points, the timing pass): tiles on the main stream, the rest of the chain on
-            // the side stream in plain stream order
-            PIMDB_CUDA_TRY(s, cudaEventRecord(s->ev_fork, s->stream));
-            PIMDB_CUDA_TRY(s, cudaStreamWaitEvent(s->stream_x, s->ev_fork, 0));
-            API_TRY(launch_exchange_part(s, s->stream_x, 1));
+        }
         }
         PIMDB_CUDA_TRY(s, cudaEventRecord(s->ev_join, s->stream_x));
     }
@@ -563,9 +578,44 @@ static int enqueue_forces(Sim* s, bool assemble_later = false) {
         return PIMDB_OK;
     };
     if (s->pair_on) {
+        // A captured step cuts a LARGE pair-tile grid into several launches of >= ~4 waves each, chained by programmatic
+        // launches without a wait (they are independent): the next launch is scheduled as soon as every block of the
+        // previous one has started, so the SMs never drain in between -- but each boundary is a point where the hardware
+        // picks among the pending grids again, and the exterior-force kernel of the exchange chain (higher priority, ready
+        // long before the pair tiles are through) gets its blocks placed there instead of behind the whole pair-tile
+        // queue (measured at C4: it started when the last pair-tile block had been dispatched, 880 us after it was ready).
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        cudaStreamIsCapturing(s->stream, &cap);
+        const bool capturing = cap == cudaStreamCaptureStatusActive;
+        // (slices of ~6 waves -- cutting costs ~4 % of the pair tiles through the joints -- but at least two once the grid is
+        // 4 waves long, so that a bead shard of C4 on 8 GPUs has a joint as well; C3, 2.5 waves, stays one launch)
+        const double waves = (double)s->Ploc * std::max(1, s->TP / 8) / (3.0 * s->sm_count);
+        int disp = s->bead_chunk;
+        if (capturing && ex && waves >= 4.0 && !getenv("PIMDB_PAIR_ONE_LAUNCH")) {
+            const int nslices = std::max(2, std::min(16, (int)(waves / 6.0)));
+            disp = std::max(1, (s->Ploc + nslices - 1) / nslices);
+        }
         for (int lo = 0; lo < s->Ploc; lo += s->bead_chunk) {
             const int nb = std::min(s->bead_chunk, s->Ploc - lo);
-            API_TRY(launch_pair_chunk(s, lo, nb, false, pair_early && lo == 0));
+            int nslice = 0;
+            for (int d0 = 0; d0 < nb;) {
+                int nd = std::min(disp, nb - d0);
+                if (nb - (d0 + nd) < (disp + 1) / 2) nd = nb - d0;          // no small last slice: it joins the one before
+                const bool early = (lo == 0 && d0 == 0) ? pair_early : (capturing && d0 > 0);
+                API_TRY(launch_pair_chunk(s, lo + d0, nd, false, early, d0));
+                d0 += nd;
+                if (d0 < nb) {
+                    // a programmatic edge orders the next slice behind the START of this one only: what comes after the last
+                    // slice gets a full dependency on every slice
+                    if ((int)s->ev_slice.size() <= nslice) {
+                        cudaEvent_t e;
+                        PIMDB_CUDA_TRY(s, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                        s->ev_slice.push_back(e);
+                    }
+                    PIMDB_CUDA_TRY(s, cudaEventRecord(s->ev_slice[nslice++], s->stream));
+                }
+            }
+            for (int k = 0; k < nslice; ++k) PIMDB_CUDA_TRY(s, cudaStreamWaitEvent(s->stream, s->ev_slice[k], 0));
             if (!joined) API_TRY(join());
             if (!assemble_later) API_TRY(launch_assemble_chunk(s, lo, nb, true));
         }
@@ -601,8 +651,13 @@ struct Fuser {
     int stage = -1;
     int rc = PIMDB_OK;
     explicit Fuser(Sim* sim) : s(sim) {}
+    bool chained = false;      // the previous launch on the main stream was made by this Fuser (nothing in between)
     void flush() {
-        if (ops && rc == PIMDB_OK) rc = launch_integrate(s, ops);
+        if (ops && rc == PIMDB_OK) {
+            if (chained) allow_early_launch(s);
+            rc = launch_integrate(s, ops);
+            chained = true;
+        }
         ops = 0;
         stage = -1;
     }
@@ -633,12 +688,14 @@ static void thermostat_into(Sim* s, Fuser& fz) {
         if (s->cfg.nmthermostat && fz.rc == PIMDB_OK) fz.rc = launch_nm_momenta(s, true);
         if (fz.rc == PIMDB_OK) fz.rc = launch_nose_hoover(s);
         if (s->cfg.nmthermostat && fz.rc == PIMDB_OK) fz.rc = launch_nm_momenta(s, false);
+        fz.chained = false;
         return;
     }
     if (s->cfg.thermostat != PIMDB_THERMO_LANGEVIN) return;
     if (s->cfg.nmthermostat) {
         fz.flush();
         if (fz.rc == PIMDB_OK) fz.rc = launch_nm_thermostat(s);
+        fz.chained = false;
     } else {
         fz.langevin();
     }
@@ -651,10 +708,12 @@ static void propagator_into(Sim* s, Fuser& fz) {
         fz.flush();
         if (!s->all_local && !s->peer_on) return;   // host-driven sharding: the host exchanges halos, then calls phase 2
         const bool fuse = fuse_assembly(s);
-        if (fz.rc == PIMDB_OK) fz.rc = enqueue_forces(s, fuse);
+        if (fz.rc == PIMDB_OK) fz.rc = enqueue_forces(s, fuse, fz.chained);
+        fz.chained = false;
         fz.kick(false, fuse);
     } else {
         fz.flush();
+        fz.chained = false;
         if (fz.rc == PIMDB_OK) fz.rc = launch_nm_propagate(s);   // half kick (physical forces) + exact ring rotation
         if (fz.rc == PIMDB_OK) fz.rc = launch_fill_halos(s);
         if (fz.rc == PIMDB_OK) fz.rc = enqueue_forces(s);
@@ -677,6 +736,16 @@ static int settle_momenta(Sim* s) {
 }
 
 // body of Simulation::run, src/simulation.cpp:246-259
+// Inside a captured step, a kernel that directly follows another kernel of ours on the main stream can be launched with
+// programmatic stream serialisation (it calls griddepcontrol.wait first thing): its launch latency, ~1 us per kernel
+// boundary, overlaps the tail of its predecessor. Eager launches keep the plain order.
+static void allow_early_launch(Sim* s) {
+    static const bool off = getenv("PIMDB_NO_PDL") != nullptr;   // A/B timing
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(s->stream, &cap);
+    s->pdl_next = !off && cap == cudaStreamCaptureStatusActive;
+}
+
 // Bead shard, fixcom, Cartesian Langevin (or no) thermostat: the boundary slices leave one kernel early (OP_HALO_EARLY).
 static bool early_halo_push(const Sim* s) {
     static const bool off = getenv("PIMDB_PEER_LATE_HALO") != nullptr;   // A/B timing
@@ -690,9 +759,10 @@ static int enqueue_step(Sim* s, bool defer_last_com) {
         const unsigned o_post = s->cfg.thermostat == PIMDB_THERMO_LANGEVIN ? OP_O_POST : 0u;
         s->p_shift_pending = false; s->z_owed = false;
         API_TRY(launch_integrate(s, o_pre | OP_SUM | OP_HALO_EARLY));
+        allow_early_launch(s);
         API_TRY(launch_integrate(s, OP_SUBCM | OP_B | OP_A | OP_HALO_FIX));
         const bool fuse = fuse_assembly(s);
-        API_TRY(enqueue_forces(s, fuse));
+        API_TRY(enqueue_forces(s, fuse, true));
         API_TRY(launch_integrate(s, (fuse ? OP_ASSEMBLE : 0u) | OP_B | o_post));
         s->z_owed = true;
         return PIMDB_OK;

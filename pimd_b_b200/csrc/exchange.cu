@@ -338,6 +338,7 @@ __global__ void __launch_bounds__(1024, 2) k_exch_coeff_tiles(ExArgs a) {
     __shared__ int s_mf[32], s_mb[32];
     __shared__ double sA[kExchFastMaxN + 1];       // the prefix sums A(w), recomputed by every tile (N <= 512: one chunk)
     __shared__ double warp_tot[32];
+    grid_dependency_wait();      // (a captured step launches this grid early behind the integrator kernel that moves the beads)
     tl_begin(a.tl0);
     grid_launch_dependents();    // the recurrence kernel may take its SMs now; it waits for this grid before it reads the tiles
     peer_wait_halos(a.halo_flag, a.halo_seq, a.timeout_ns, a.err);
@@ -1728,8 +1729,11 @@ constexpr int kFW = 4;                       // warps per block (127 registers x
 constexpr int kFU = 16;                      // terms per lane held in flight (covers N <= 512)
 // STAGE: 1 = weights, exponents and the bead slice in shared memory (N <= ~5000), 2 = weights and exponents only (the
 // slice is read from global memory; N <= 8192), 0 = nothing staged and no chunk skipping (larger N)
+// (At most 160 registers: 160 x 128 = 20480 is exactly what ONE retiring pair-tile block (80 registers x 256 threads) frees,
+// so a block of this kernel can take the first SM slot that opens up while the pair tiles are still being dispatched; at 165
+// it had to wait for two neighbouring slots, i.e. for the tail of the pair-tile grid.)
 template <int D, int STAGE>
-__global__ void __launch_bounds__(32 * kFW) k_exch_forces(ExArgs a) {
+__global__ void __maxnreg__(160) k_exch_forces(ExArgs a) {   // (blocks of 32 * kFW threads; __maxnreg__ excludes __launch_bounds__)
     extern __shared__ __align__(16) double fsm[];
     tl_begin(a.tl2);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -1973,6 +1977,30 @@ static ExArgs make_args(Sim* s) {
     return a;
 }
 
+// One launch helper for the kernels of the exchange chain. Every launch carries an explicit PRIORITY attribute (the side
+// stream's priority is not what decides which pending thread block gets a freed SM slot once the launch is a node of a
+// captured graph: measured, the exterior-force kernel sat behind the whole queue of pair-tile blocks), optionally a cluster
+// dimension and programmatic stream serialisation.
+template <typename K>
+static void launch_chain(Sim* s, K kernel, const ExArgs& a, int grid, int block, size_t smem, cudaStream_t st, int cluster, bool pdl) {
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(grid); lc.blockDim = dim3(block); lc.dynamicSmemBytes = smem; lc.stream = st;
+    cudaLaunchAttribute at[3];
+    int n = 0;
+    at[n].id = cudaLaunchAttributePriority; at[n].val.priority = s->prio_hi; ++n;
+    if (cluster > 1) {
+        at[n].id = cudaLaunchAttributeClusterDimension;
+        at[n].val.clusterDim.x = cluster; at[n].val.clusterDim.y = 1; at[n].val.clusterDim.z = 1; ++n;
+    }
+    if (pdl) {
+        at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[n].val.programmaticStreamSerializationAllowed = 1; ++n;
+    }
+    lc.attrs = at;
+    lc.numAttrs = n;
+    cudaLaunchKernelEx(&lc, kernel, a);
+}
+
 static int rows_per_thread(int N, int& nt) {
     nt = ((N + 31) / 32) * 32;
     if (nt > 1024) nt = 1024;
@@ -1991,7 +2019,7 @@ static int launch_recur(Sim* s, const ExArgs& a, cudaStream_t st, int nt) {
     }
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(k_exch_recur<R, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    k_exch_recur<R, ST><<<2, nt, smem, st>>>(a);
+    launch_chain(s, k_exch_recur<R, ST>, a, 2, nt, smem, st, 1, false);
     return PIMDB_OK;
 }
 
@@ -2007,19 +2035,7 @@ static int run_recursion(Sim* s, const ExArgs& a, cudaStream_t st) {
         const size_t smem_cl = sizeof(double) * ((size_t)wpc * 3 * 512 + 32 * nb + 32 * wpc + nb2) + 8 * ((size_t)nb2 + wpc * 3 + (wpc & 1))
                                + sizeof(int) * ((size_t)32 * nb + nb2) + 16;
         cudaFuncSetAttribute(k_exch_recur_cluster_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cl);
-        cudaLaunchConfig_t lc = {};
-        lc.gridDim = dim3(2 * kClusterSize);
-        lc.blockDim = dim3(32 * wpc);
-        lc.dynamicSmemBytes = smem_cl;
-        lc.stream = st;
-        cudaLaunchAttribute at[2];
-        at[0].id = cudaLaunchAttributeClusterDimension;
-        at[0].val.clusterDim.x = kClusterSize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // may start while k_exch_coeff_tiles is running
-        at[1].val.programmaticStreamSerializationAllowed = 1;
-        lc.attrs = at;
-        lc.numAttrs = pdl ? 2 : 1;
-        cudaLaunchKernelEx(&lc, k_exch_recur_cluster_multi, a);
+        launch_chain(s, k_exch_recur_cluster_multi, a, 2 * kClusterSize, 32 * wpc, smem_cl, st, kClusterSize, pdl);
         return PIMDB_OK;
     }
     if (blocked_ok && (nblk > 16 || !getenv("PIMDB_EXCH_NOCLUSTER"))) {
@@ -2030,19 +2046,7 @@ static int run_recursion(Sim* s, const ExArgs& a, cudaStream_t st) {
                                    + sizeof(int) * ((size_t)32 * nb + nb2) + 16;
             if (smem_cl > 48 * 1024)
                 cudaFuncSetAttribute(k_exch_recur_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cl);
-            cudaLaunchConfig_t lc = {};
-            lc.gridDim = dim3(2 * kClusterSize);
-            lc.blockDim = dim3(32 * wpc);
-            lc.dynamicSmemBytes = smem_cl;
-            lc.stream = st;
-            cudaLaunchAttribute at[2];
-            at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = kClusterSize; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            at[1].val.programmaticStreamSerializationAllowed = 1;
-            lc.attrs = at;
-            lc.numAttrs = pdl ? 2 : 1;
-            cudaLaunchKernelEx(&lc, k_exch_recur_cluster, a);
+            launch_chain(s, k_exch_recur_cluster, a, 2 * kClusterSize, 32 * wpc, smem_cl, st, kClusterSize, pdl);
         }
         return PIMDB_OK;
     }
@@ -2057,21 +2061,14 @@ static int run_recursion(Sim* s, const ExArgs& a, cudaStream_t st) {
                                     + sizeof(int) * ((size_t)32 * nb + 3 * nb2) + 16;
             if (smem_blk > 48 * 1024)
                 cudaFuncSetAttribute(k_exch_recur_blocked, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_blk);
-            cudaLaunchConfig_t lc = {};
-            lc.gridDim = dim3(2); lc.blockDim = dim3(nt); lc.dynamicSmemBytes = smem_blk; lc.stream = st;
-            cudaLaunchAttribute at[1];
-            at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-            at[0].val.programmaticStreamSerializationAllowed = 1;
-            lc.attrs = at;
-            lc.numAttrs = pdl ? 1 : 0;
-            cudaLaunchKernelEx(&lc, k_exch_recur_blocked, a);
+            launch_chain(s, k_exch_recur_blocked, a, 2, nt, smem_blk, st, 1, pdl);
         } else if (ST == 16) {
             if (smem > 48 * 1024)
                 cudaFuncSetAttribute(k_exch_recur_dec<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            k_exch_recur_dec<16><<<2, nt, smem, st>>>(a);
+            launch_chain(s, k_exch_recur_dec<16>, a, 2, nt, smem, st, 1, false);
         } else {
             cudaFuncSetAttribute(k_exch_recur_dec<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            k_exch_recur_dec<8><<<2, nt, smem, st>>>(a);
+            launch_chain(s, k_exch_recur_dec<8>, a, 2, nt, smem, st, 1, false);
         }
         return PIMDB_OK;
     }
@@ -2100,14 +2097,18 @@ static int exchange_impl(Sim* s, cudaStream_t st, int part) {
         if (a.Kf) {      // N <= 2048: factor tiles + diagonal-block inverses; up to N = 512 the tiles recompute the prefix sums
             const int nb = (s->N + 31) / 32;
             if (s->N > kExchFastMaxN) {
-                k_exch_prefix<D><<<1, 1024, 0, st>>>(a);
+                launch_chain(s, k_exch_prefix<D>, a, 1, 1024, 0, st, 1, false);
                 s->launches += 1;
             }
-            k_exch_coeff_tiles<D><<<nb * nb, 1024, 0, st>>>(a);
+            {
+                const bool early = s->pdl_next && s->N <= kExchFastMaxN;   // (beyond that the prefix kernel sits in front)
+                s->pdl_next = false;
+                launch_chain(s, k_exch_coeff_tiles<D>, a, nb * nb, 1024, 0, st, 1, early);
+            }
             s->launches += 1;
         } else {
-            k_exch_prefix<D><<<1, 1024, 0, st>>>(a);
-            k_exch_coeff<D><<<grid_for((size_t)s->N * s->N, 256, 16 * kNumSM), 256, 0, st>>>(a);
+            launch_chain(s, k_exch_prefix<D>, a, 1, 1024, 0, st, 1, false);
+            launch_chain(s, k_exch_coeff<D>, a, grid_for((size_t)s->N * s->N, 256, 16 * kNumSM), 256, 0, st, 1, false);
             s->launches += 2;
         }
     } else {
@@ -2117,19 +2118,22 @@ static int exchange_impl(Sim* s, cudaStream_t st, int part) {
             s->launches += 1;
         }
         if (part != 2) {
-            const int per_kind = std::max(1, std::min((s->N + 2 * kFW - 1) / (2 * kFW), 4 * kNumSM));   // 2 tasks per warp
+            // tasks (particles) per warp: a task is a chain of ~4 dependent L2 round trips, so one per warp while the grid
+            // still fits the machine a few times over (PIMDB_EXCH_FTASKS overrides, for timing)
+            static const int ftasks = getenv("PIMDB_EXCH_FTASKS") ? std::max(1, atoi(getenv("PIMDB_EXCH_FTASKS"))) : 1;
+            const int per_kind = std::max(1, std::min((s->N + ftasks * kFW - 1) / (ftasks * kFW), 4 * kNumSM));
             const size_t smem_w = sizeof(double) * ((size_t)s->N + 1 + ((s->N + 2) >> 1));            // weights + exponents
             const size_t smem_full = smem_w + sizeof(double) * (size_t)D * s->N;                         // + the bead slice
             if (a.Kf && smem_full <= 200 * 1024) {
                 if (smem_full > 48 * 1024)
                     cudaFuncSetAttribute(k_exch_forces<D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_full);
-                k_exch_forces<D, 1><<<2 * per_kind, 32 * kFW, smem_full, st>>>(a);
+                launch_chain(s, k_exch_forces<D, 1>, a, 2 * per_kind, 32 * kFW, smem_full, st, 1, false);
             } else if (a.Kf && smem_w <= 200 * 1024) {
                 if (smem_w > 48 * 1024)
                     cudaFuncSetAttribute(k_exch_forces<D, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w);
-                k_exch_forces<D, 2><<<2 * per_kind, 32 * kFW, smem_w, st>>>(a);
+                launch_chain(s, k_exch_forces<D, 2>, a, 2 * per_kind, 32 * kFW, smem_w, st, 1, false);
             } else {
-                k_exch_forces<D, 0><<<2 * per_kind, 32 * kFW, 0, st>>>(a);
+                launch_chain(s, k_exch_forces<D, 0>, a, 2 * per_kind, 32 * kFW, 0, st, 1, false);
             }
             s->launches += 1;
         }

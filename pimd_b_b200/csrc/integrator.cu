@@ -214,6 +214,8 @@ __device__ __forceinline__ void st_pair(double* ptr, size_t o, double2 v, bool t
 
 template <bool VEC>
 __global__ void __launch_bounds__(256) k_integrate(IntArgs a) {
+    grid_dependency_wait();      // (launched early behind the previous kernel of a captured step: wait for it, then let the next in)
+    grid_launch_dependents();
     tl_begin(a.tl);
     __shared__ double sm[3 * 32];
     __shared__ double sh_cm[4];
@@ -573,8 +575,18 @@ int launch_integrate(Sim* s, unsigned ops) {
         cudaEventCreate(&e0); cudaEventCreate(&e1);
         cudaEventRecord(e0, s->stream);
     }
-    if (s->N % 2 == 0) k_integrate<true><<<grid, 256, 0, s->stream>>>(a);
-    else k_integrate<false><<<grid, 256, 0, s->stream>>>(a);
+    {
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3(grid); lc.blockDim = dim3(256); lc.dynamicSmemBytes = 0; lc.stream = s->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = at;
+        lc.numAttrs = s->pdl_next ? 1 : 0;
+        s->pdl_next = false;
+        if (s->N % 2 == 0) cudaLaunchKernelEx(&lc, k_integrate<true>, a);
+        else cudaLaunchKernelEx(&lc, k_integrate<false>, a);
+    }
     s->launches += 1;
     if (e0) {
         cudaEventRecord(e1, s->stream);

@@ -96,9 +96,11 @@ struct Sim {
 
     int device = 0;
     int sm_count = 148;
+    int prio_hi = 0, prio_lo = 0;      // stream / launch priorities (numerically lower = more urgent)
     cudaStream_t stream = nullptr, stream_x = nullptr;  // main stream, exchange side stream
     bool own_stream = true;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_copy = nullptr;
+    std::vector<cudaEvent_t> ev_slice;  // completion of the slices of a pair-tile grid cut into chained launches
 
     // state (device). x has Ploc+2 slabs (halo, owned..., halo); the others Ploc slabs.
     double *x = nullptr, *p = nullptr, *f = nullptr, *fs = nullptr, *fp = nullptr;
@@ -147,6 +149,9 @@ struct Sim {
     bool z_owed = false;               // peer mode, Langevin / no thermostat: the closing zeroMomentum of the last iteration
                                        // has not been carried out (it is subsumed by the first one of the next iteration)
     bool pdl_recur = false;            // the next recurrence launch may use programmatic stream serialisation
+    bool pdl_next = false;             // the next k_integrate / factor-tile launch follows a kernel of ours on the same stream in
+                                       // a captured step: launch it with programmatic stream serialisation (it waits for that
+                                       // grid first thing; what is hidden is its launch latency)
     bool split_stale = false;          // f is current but f_spring / f_phys are not (fused closing kernel)
     unsigned long long launches = 0;
     // timing

@@ -161,6 +161,8 @@ __device__ __forceinline__ void pair_rotation(const PairArgs& a, int t, int lane
 template <int D, int POT, bool PBC, bool CUT, bool OBS>
 __global__ void __launch_bounds__(32 * kPairWarps, PIMDB_PAIR_MINBLOCKS) k_pair_tiles(PairArgs a) {
     __shared__ double s_x[kPairWarps][D * 32], s_f[kPairWarps][D * 32];
+    grid_launch_dependents();   // a launch chained behind this one (the next slice of the pair tiles) may be scheduled as soon as
+                                // every block of this grid has started
     tl_begin(a.tl);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int sp = a.split;
@@ -297,10 +299,11 @@ static void dispatch1(Sim* s, const PairArgs& a, int grid, bool early) {
 }
 
 // Enqueue the tile kernel for owned beads [bead_lo, bead_lo+nb) (nb <= bead_chunk).
-static int launch_chunk(Sim* s, int bead_lo, int nb, bool with_obs, bool early) {
+// `scratch_lo`: the slot of the scratch slab that bead `bead_lo` writes to (several launches can fill one slab)
+static int launch_chunk(Sim* s, int bead_lo, int nb, bool with_obs, bool early, int scratch_lo) {
     PairArgs a;
     a.x = s->x + (size_t)(bead_lo + 1) * s->S;
-    a.scratch = s->pair_scratch;
+    a.scratch = s->pair_scratch + (size_t)scratch_lo * s->T * s->T * s->D * kTile;
     a.obs_part = s->pair_scratch;  // the scratch slab doubles as the (V, virial) partial buffer
     a.tile_ij = s->tile_ij;
     a.N = s->N; a.T = s->T; a.TP = s->TP; a.nb = nb; a.S = s->S;
@@ -350,6 +353,8 @@ static int launch_chunk(Sim* s, int bead_lo, int nb, bool with_obs, bool early) 
     return PIMDB_OK;
 }
 
-int launch_pair_chunk(Sim* s, int bead_lo, int nb, bool with_obs, bool early) { return launch_chunk(s, bead_lo, nb, with_obs, early); }
+int launch_pair_chunk(Sim* s, int bead_lo, int nb, bool with_obs, bool early, int scratch_lo) {
+    return launch_chunk(s, bead_lo, nb, with_obs, early, scratch_lo);
+}
 
 }  // namespace pimdb
