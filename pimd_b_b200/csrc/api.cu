@@ -89,8 +89,10 @@ static int validate(const pimdb_config* c, std::string& msg) {
         return PIMDB_ERR_INVALID_ARGUMENT;
     }
     const bool all_local = (c->bead_begin == 0 && c->bead_end == c->nbeads);
-    if (!all_local && (c->propagator == PIMDB_PROP_NORMAL_MODES || c->nmthermostat)) {
-        msg = "normal-mode propagator / thermostat need all beads on one handle in this build";
+    if (!all_local && c->nmthermostat && (c->thermostat >= PIMDB_THERMO_NOSE_HOOVER || c->rng == PIMDB_RNG_RANMARS)) {
+        // (on a bead shard every rank transforms all modes from gathered slabs; the chains / the sequential generators of the
+        // modes would have to be replicated as well)
+        msg = "on a bead shard the normal-mode thermostat coupling supports the Langevin thermostat with the default noise stream";
         return PIMDB_ERR_INVALID_ARGUMENT;
     }
     if (c->natoms > 65535 * kTile) { msg = "natoms too large"; return PIMDB_ERR_INVALID_ARGUMENT; }
@@ -309,11 +311,13 @@ extern "C" int pimdb_create(const pimdb_config* cfg, pimdb_sim** out) {
         if (rc != PIMDB_OK) { g_create_error = s->err; free_all(s); return rc; }
     }
     if (!s->all_local) {   // mailbox + counters of the peer-memory sharding protocol (pimdb_peer_export / _attach)
-        const size_t mb_bytes = sizeof(PeerMailbox) + sizeof(unsigned long long) * 2 * 2 * 2 * s->S;   // + the self-validating halo inbox
+        size_t mb_bytes = sizeof(PeerMailbox) + sizeof(unsigned long long) * 2 * 2 * 2 * s->S;   // + the self-validating halo inbox
+        if (cfg->propagator == PIMDB_PROP_NORMAL_MODES || cfg->nmthermostat)
+            mb_bytes += sizeof(double) * 2 * 2 * (size_t)s->P * s->S;                            // + the all-gather buffer
         CREATE_TRY(cudaMalloc(&s->mailbox, mb_bytes));
         CREATE_TRY(cudaMemset(s->mailbox, 0, mb_bytes));
-        CREATE_TRY(cudaMalloc(&s->peer_seq, sizeof(unsigned int) * 4));
-        CREATE_TRY(cudaMemset(s->peer_seq, 0, sizeof(unsigned int) * 4));
+        CREATE_TRY(cudaMalloc(&s->peer_seq, sizeof(unsigned int) * 8));
+        CREATE_TRY(cudaMemset(s->peer_seq, 0, sizeof(unsigned int) * 8));
     }
     if (getenv("PIMDB_TIMELINE")) {
         CREATE_TRY(cudaMalloc(&s->stamps, sizeof(unsigned long long) * 64));
@@ -715,7 +719,7 @@ static void propagator_into(Sim* s, Fuser& fz) {
         fz.flush();
         fz.chained = false;
         if (fz.rc == PIMDB_OK) fz.rc = launch_nm_propagate(s);   // half kick (physical forces) + exact ring rotation
-        if (fz.rc == PIMDB_OK) fz.rc = launch_fill_halos(s);
+        if (fz.rc == PIMDB_OK) fz.rc = s->peer_on ? launch_peer_push_halos(s) : launch_fill_halos(s);
         if (fz.rc == PIMDB_OK) fz.rc = enqueue_forces(s);
         fz.kick(true);
     }
@@ -1027,8 +1031,6 @@ extern "C" int pimdb_peer_attach(pimdb_sim* sim, int world, int rank, const void
     if (s->peer_on) return fail(s, PIMDB_ERR_INVALID_ARGUMENT, "handle is already attached to its peers");
     if (world < 2 || world > kMaxPeers || rank < 0 || rank >= world)
         return fail(s, PIMDB_ERR_INVALID_ARGUMENT, "peer sharding supports 2.." + std::to_string(kMaxPeers) + " ranks");
-    if (s->cfg.propagator != PIMDB_PROP_CARTESIAN || s->cfg.nmthermostat)
-        return fail(s, PIMDB_ERR_INVALID_ARGUMENT, "bead shards support the cartesian propagator / thermostat coupling only");
     PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
     std::vector<PeerBlob> tab(world);
     int expect = 0;
@@ -1047,6 +1049,8 @@ extern "C" int pimdb_peer_attach(pimdb_sim* sim, int world, int rank, const void
     pd.prev = (rank + world - 1) % world; pd.next = (rank + 1) % world;
     pd.mine = s->mailbox; pd.seq = s->peer_seq;
     pd.ll_mine = reinterpret_cast<unsigned long long*>(s->mailbox + 1);
+    const bool nm = s->cfg.propagator == PIMDB_PROP_NORMAL_MODES || s->cfg.nmthermostat;
+    if (nm) pd.gather_mine = pd.gather_to[rank] = reinterpret_cast<double*>(pd.ll_mine + 2 * 2 * 2 * s->S);
     unsigned long long ms = 20000;
     if (const char* e = getenv("PIMDB_PEER_TIMEOUT_MS")) ms = (unsigned long long)std::max(1, atoi(e));
     pd.timeout_ns = ms * 1000000ull;
@@ -1060,6 +1064,7 @@ extern "C" int pimdb_peer_attach(pimdb_sim* sim, int world, int rank, const void
         if (r == pd.next) pd.halo_to_next = reinterpret_cast<double*>(x);                          // its leading halo slab
         if (r == pd.prev) pd.ll_to_prev = reinterpret_cast<unsigned long long*>(pd.box[r] + 1);
         if (r == pd.next) pd.ll_to_next = reinterpret_cast<unsigned long long*>(pd.box[r] + 1);
+        if (nm) pd.gather_to[r] = reinterpret_cast<double*>(reinterpret_cast<unsigned long long*>(pd.box[r] + 1) + 2 * 2 * 2 * s->S);
     }
     s->peer = pd;
     s->peer_on = true;

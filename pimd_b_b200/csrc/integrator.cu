@@ -528,6 +528,53 @@ __global__ void __launch_bounds__(256) k_peer_push_halos(const double* x, size_t
     }
 }
 
+// All-gather of the owned bead slabs for the normal-mode transforms (NormalModes::shareData, src/normal_modes.cpp:13-46:
+// the reference copies every rank's row into a shared window). `kick`: the momenta leave with the propagator's first half
+// kick applied, p + dt/2 f_phys (normal_modes_propagator.cpp:73-103), so that the transform kernel needs no forces of beads
+// it does not own.
+__global__ void __launch_bounds__(256) k_peer_allgather(const double* x, const double* p, const double* fphys, size_t S, int P,
+                                                        int Ploc, int b0, double hdt, int with_x, PeerDev peer,
+                                                        unsigned int* ticket, int* err) {
+    __shared__ bool is_last;
+    __shared__ unsigned sh_g;
+    const int tid = threadIdx.x;
+    if (tid == 0) sh_g = peer.seq[4] + 1u;
+    __syncthreads();
+    const unsigned g = sh_g;
+    const size_t slot = (size_t)(g & 1u) * 2 * P * S;
+    const size_t own = (size_t)Ploc * S;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + tid; i < own; i += (size_t)gridDim.x * blockDim.x) {
+        const double pv = p[i] + (fphys ? hdt * fphys[i] : 0.0);
+        const double xv = with_x ? x[S + i] : 0.0;          // (x carries a leading halo slab)
+        const size_t at = (size_t)b0 * S + i;
+        for (int r = 0; r < peer.world; ++r) {
+            double* dst = peer.gather_to[r] + slot;
+            if (with_x) dst[at] = xv;
+            dst[(size_t)P * S + at] = pv;
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        __threadfence_system();
+        is_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (is_last && tid < peer.world) {
+        if (tid == 0) __threadfence_system();
+        __syncwarp();
+        st_sys_u32(&peer.box[tid]->gather_flag[peer.rank], g);
+        if (tid == 0) { peer.seq[4] = g; *ticket = 0u; }
+    }
+}
+
+int launch_peer_allgather(Sim* s, bool with_x, bool kick) {
+    k_peer_allgather<<<grid_for((size_t)s->Ploc * s->S, 256, 2 * kNumSM), 256, 0, s->stream>>>(
+        s->x, s->p, kick ? s->fp : nullptr, s->S, s->P, s->Ploc, s->b0, 0.5 * s->cfg.dt, with_x ? 1 : 0, s->peer, s->tickets + 1, s->err_d);
+    s->launches += 1;
+    PIMDB_CUDA_TRY(s, cudaGetLastError());
+    return PIMDB_OK;
+}
+
 int launch_peer_push_halos(Sim* s) {
     if (!s->peer_on) return PIMDB_OK;
     k_peer_push_halos<<<grid_for(s->S, 256, kNumSM), 256, 0, s->stream>>>(s->x, s->S, s->Ploc, s->peer, s->tickets + 1, s->err_d);

@@ -38,7 +38,8 @@ struct PeerMailbox {
     unsigned long long com_in[2][kMaxPeers][kComWords];
     unsigned int halo_flag[2];
     unsigned int credit[2];
-    unsigned int pad[60];
+    unsigned int gather_flag[kMaxPeers];   // all-gather of bead slabs (normal-mode paths): number of gathers rank r has delivered
+    unsigned int pad[52];
 };
 struct PeerDev {                      // passed by value to the kernels that talk to peers
     int world, rank;
@@ -50,12 +51,17 @@ struct PeerDev {                      // passed by value to the kernels that tal
     // 8-byte words {32 data bits, 32-bit push number}, so the receiver polls the words themselves and neither side needs a
     // system-scope fence (3.5 us each on this platform) or a flag round trip. Inbox layout, behind the PeerMailbox in the
     // same allocation: [slot = push number & 1][side: 0 from the previous rank, 1 from the next][S doubles][2 words].
+    // All-gather of whole bead slabs for the normal-mode transforms (every rank needs every bead of a column): each rank
+    // stores its owned beads of x and p into EVERY rank's gather buffer [slot = gather number & 1][x | p][P][S], fences at
+    // system scope and raises gather_flag[its rank] there. Behind the self-validating inbox in the mailbox allocation.
+    double* gather_mine;              // local gather buffer (nullptr unless a normal-mode path is configured)
+    double* gather_to[kMaxPeers];     // every rank's gather buffer (gather_to[rank] == gather_mine)
     unsigned long long* ll_mine;      // local inbox
     unsigned long long* ll_to_prev;   // previous rank's inbox (my first bead goes to its side 1)
     unsigned long long* ll_to_next;   // next rank's inbox (my last bead goes to its side 0)
     unsigned int* seq;                // local counters: [0] momentum-sum pushes made, [1] flag-protocol halo pushes made (= slices
                                       // expected from each neighbour), [2] self-validating halo pushes made, [3] "a peer timed
-                                      // out" (sticky; later waits return at once)
+                                      // out" (sticky; later waits return at once), [4] all-gathers made
     int prev, next;
     unsigned long long timeout_ns;    // bound of every device-side wait
 };
@@ -201,6 +207,7 @@ enum : unsigned { OP_SUBCM = 1, OP_O_PRE = 2, OP_B = 4, OP_O_POST = 8, OP_A = 16
 };
 int launch_integrate(Sim* s, unsigned ops);
 int launch_peer_push_halos(Sim* s);
+int launch_peer_allgather(Sim* s, bool with_x, bool kick);   // owned beads of (x and) p -> every rank's gather buffer
 int launch_nm_propagate(Sim* s);
 int launch_nm_thermostat(Sim* s);
 int launch_nm_momenta(Sim* s, bool forward);   // p <-> normal-mode momenta, in place

@@ -27,6 +27,11 @@ struct NmArgs {
     double hdt, dt_over_m, c1, c2;
     unsigned long long seed;
     const double* noise;       // reference-compatible stream: [mode][N][D] gaussians of this half-step, or nullptr (Philox)
+    // bead shard: the tile is staged from the gathered slabs of ALL beads (gx / gp, [P][M]; the propagator's half kick is
+    // already in gp) and only the owned beads [b0, b1) are written back, to x / p of this handle. nullptr on a full ring.
+    const double *gx, *gp;
+    int b0, b1;
+    const unsigned int* gather_flag; const unsigned int* gather_seq; int world; unsigned long long timeout_ns; int* err; unsigned* dead;
 };
 
 // mode 0: propagator (x and p), mode 1: Langevin thermostat on the mode momenta (p only),
@@ -42,6 +47,15 @@ __global__ void __launch_bounds__(256) k_nm_fused(NmArgs a) {
     const int tid = threadIdx.x;
     const int tc = tid % TC, kg = tid / TC, KG = blockDim.x / TC;
     const unsigned long long draw = (MODE == 1) ? *a.draw : 0ull;
+    const bool shard = a.gp != nullptr;
+    const double *gx = a.gx, *gp = a.gp;
+    if (shard) {   // every rank has delivered its beads of this gather (bounded wait, acquire)
+        const unsigned g = *a.gather_seq;
+        if (tid < a.world) wait_sys_u32_ge(&a.gather_flag[tid], g, a.timeout_ns, a.err, kErrPeerTimeout, a.dead);
+        __syncthreads();
+        const size_t slot = (size_t)(g & 1u) * 2 * (size_t)P * a.M;     // gathers alternate between two buffers
+        gx += slot; gp += slot;
+    }
 
     for (int col0 = blockIdx.x * TC; col0 < a.M; col0 += gridDim.x * TC) {
         const int col = col0 + tc;
@@ -49,7 +63,10 @@ __global__ void __launch_bounds__(256) k_nm_fused(NmArgs a) {
         // 1. stage (propagator: with the half kick p += dt/2 f_phys, normal_modes_propagator.cpp:73-103)
         for (int j = kg; j < P; j += KG) {
             double pv = 0.0, xv = 0.0;
-            if (ok) {
+            if (ok && shard) {
+                pv = gp[(size_t)j * a.M + col];
+                if (MODE == 0) xv = gx[(size_t)j * a.M + col];
+            } else if (ok) {
                 pv = a.p[(size_t)j * a.M + col];
                 if (MODE == 0) {
                     pv += a.hdt * a.fphys[(size_t)j * a.M + col];
@@ -124,9 +141,9 @@ __global__ void __launch_bounds__(256) k_nm_fused(NmArgs a) {
                     if (MODE == 0) xc += ck * sx[k * TC + tc];
                 }
             }
-            if (ok) {
-                a.p[(size_t)j * a.M + col] = pc;
-                if (MODE == 0) a.x[(size_t)j * a.M + col] = xc;
+            if (ok && j >= a.b0 && j < a.b1) {
+                a.p[(size_t)(j - a.b0) * a.M + col] = pc;
+                if (MODE == 0) a.x[(size_t)(j - a.b0) * a.M + col] = xc;
             }
         }
         __syncthreads();
@@ -148,6 +165,24 @@ __global__ void __launch_bounds__(256) k_nm_fused(NmArgs a) {
 static int launch_nm(Sim* s, int mode) {
     NmArgs a;
     a.x = s->x + s->S; a.p = s->p; a.fphys = s->fp;
+    a.gx = a.gp = nullptr; a.b0 = 0; a.b1 = s->P;
+    a.gather_flag = nullptr; a.gather_seq = nullptr; a.world = 1; a.timeout_ns = 0; a.err = s->err_d; a.dead = nullptr;
+    if (!s->all_local) {
+        if (!s->peer_on || !s->peer.gather_mine) {
+            s->err = "normal-mode transforms on a bead shard need the handle attached to its peers (pimdb_peer_attach)";
+            return PIMDB_ERR_INVALID_ARGUMENT;
+        }
+        if (mode >= 2) { s->err = "Nose-Hoover chains on the normal modes need all beads on one handle"; return PIMDB_ERR_INVALID_ARGUMENT; }
+        // every rank sends its beads to every rank (momenta with the propagator's half kick applied), then transforms all modes
+        int rc = launch_peer_allgather(s, mode == 0, mode == 0);
+        if (rc != PIMDB_OK) return rc;
+        const size_t PS = (size_t)s->P * s->S;
+        // (the slot of the gather just launched: the kernel reads seq[4] after that launch has advanced it)
+        a.gx = s->peer.gather_mine; a.gp = s->peer.gather_mine + PS;
+        a.b0 = s->b0; a.b1 = s->b1;
+        a.gather_flag = s->peer.mine->gather_flag; a.gather_seq = s->peer.seq + 4; a.world = s->peer.world;
+        a.timeout_ns = s->peer.timeout_ns; a.dead = s->peer.seq + 3;
+    }
     a.C = s->nmC; a.Cinv = s->nmC + (size_t)s->P * s->P; a.tab = s->nmFreq;
     a.draw = s->draw; a.ticket = s->tickets;
     a.P = s->P; a.M = (int)s->S; a.N = s->N; a.D = s->D;

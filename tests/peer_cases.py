@@ -27,6 +27,17 @@ def make_case(name: str):
                         mass=1.0, size=200.0, interaction="dipole", int_strength=1.0, external="harmonic",
                         ext_omega=3 * wl.MEV, thermostat="nose_hoover", nchains=3, seed=9, dt=wl.FEMTOSECOND)
         kind = "c2"
+    elif name == "nm_langevin":    # C2 in small: 2-D dipoles, normal-mode propagator + normal-mode Langevin thermostat (Philox)
+        cfg = SimConfig(nbeads=8, natoms=12, ndim=2, bosonic=False, fixcom=False, pbc=False, temperature=5 * wl.KELVIN,
+                        mass=1.0, size=200.0, interaction="dipole", int_strength=1.0, external="harmonic",
+                        ext_omega=3 * wl.MEV, thermostat="langevin", nmthermostat=True, propagator="normal_modes", seed=777,
+                        dt=wl.FEMTOSECOND)
+        kind = "c2"
+    elif name == "nm_nve_fixcom":  # normal-mode propagator alone, with the centre-of-mass exchange, uneven bead split
+        cfg = SimConfig(nbeads=6, natoms=9, ndim=3, bosonic=False, fixcom=True, pbc=False, temperature=5 * wl.KELVIN,
+                        mass=1.0, size=200.0, interaction="harmonic", int_omega=1 * wl.MEV, external="harmonic",
+                        ext_omega=3 * wl.MEV, thermostat="none", propagator="normal_modes", seed=3, dt=wl.FEMTOSECOND)
+        kind = "c1"
     else:
         raise ValueError(name)
     x, p = wl.initial_state(cfg, kind, seed=cfg.seed)

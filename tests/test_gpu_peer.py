@@ -72,7 +72,8 @@ def _compare(got, ref, tol_x=1e-10, tol_p=1e-9, tol_f=1e-9):
 
 
 @pytest.mark.parametrize("case,world", [("he_langevin", 2), ("he_langevin", 4), ("he_nve_odd", 2), ("he_nve_odd", 3),
-                                        ("trap_nofixcom", 2), ("trap_nofixcom", 3), ("dist_nh", 2), ("dist_nh", 4)])
+                                        ("trap_nofixcom", 2), ("trap_nofixcom", 3), ("dist_nh", 2), ("dist_nh", 4),
+                                        ("nm_langevin", 2), ("nm_langevin", 4), ("nm_nve_fixcom", 2), ("nm_nve_fixcom", 4)])
 def test_peer_shards_in_one_process_match_a_single_handle(gpu_required, case, world):
     cfg, x, p = make_case(case)
     nsteps = 12
@@ -172,7 +173,7 @@ def _gpu_count():
     return torch.cuda.device_count()
 
 
-@pytest.mark.parametrize("case", ["he_langevin", "trap_nofixcom"])
+@pytest.mark.parametrize("case", ["he_langevin", "trap_nofixcom", "nm_langevin"])
 def test_peer_shards_in_separate_processes_one_gpu(gpu_required, tmp_path, case):
     """Two processes on cuda:0, coupled through cudaIpc mappings (the multi-process path on a one-GPU box; the two
     contexts are time-sliced, so every hand-shake costs a context switch -- correctness only)."""
