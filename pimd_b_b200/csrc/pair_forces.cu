@@ -32,6 +32,7 @@ struct PairArgs {
     double* scratch;      // [nb][T][T][D][32]
     double* obs_part;     // [items * split][2] (V, virial) when OBS
     const ushort2* tile_ij;
+    const ushort4* dual_ijj;   // work items of the two-rows-per-warp kernel: tiles (I, I+1) against tile J >= I + 2, all three full
     int N, T, TP, nb;
     int split;            // warps per tile pair: 1, 2 or 4
     size_t S;
@@ -249,6 +250,90 @@ __global__ void __launch_bounds__(32 * kPairWarps, PIMDB_PAIR_MINBLOCKS) k_pair_
     tl_end(a.tl);
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Two i-particles per lane. The single-row kernel above issues one instruction per warp every ~8 cycles: two thirds of
+// its stall cycles are fixed-latency dependencies of the FP64 chain of ONE pair (ncu: "wait" 3.5 of 8.1 cycles per
+// instruction), and the registers do not allow more warps. Here a warp owns the tile pairs (I, J) and (I+1, J) at once:
+// lane l keeps particle l of BOTH row tiles in registers and meets the same j particle in a rotation, so two independent
+// pair evaluations interleave in every lane, the j coordinates are loaded once for two pairs, and the two reaction forces
+// reach the j particle in one shared-memory read-modify-write. Only full, off-diagonal tiles (no masking); everything
+// else -- diagonal tiles, the tile next to the diagonal, ragged last tiles, cutoffs -- goes through the kernel above.
+// The reaction of both rows is accumulated together and written to the (J, I) slot of the scratch slab; the (J, I+1) slot
+// gets zeros, so the fixed-order sum of the assembly is unchanged.
+template <int D, int POT, bool PBC>
+__global__ void __launch_bounds__(32 * kPairWarps, 2) k_pair_tiles_dual(PairArgs a, int ndual) {
+    __shared__ double s_x[kPairWarps][D * 32], s_f[kPairWarps][D * 32];
+    grid_launch_dependents();
+    tl_begin(a.tl);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long gw = (long long)blockIdx.x * kPairWarps + warp;
+    if (gw >= (long long)a.nb * ndual) { tl_end(a.tl); return; }     // (no block-wide barrier in this kernel)
+    const int bl = (int)(gw / ndual);
+    const ushort4 it = a.dual_ijj[gw % ndual];
+    const int I1 = it.x, I2 = it.y, J = it.z;
+    const double* xb = a.x + (size_t)bl * a.S;
+    double* sx = s_x[warp];
+    double* sf = s_f[warp];
+    double x1[D], x2[D], f1[D], f2[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        x1[c] = xb[(size_t)c * a.N + I1 * kTile + lane];
+        x2[c] = xb[(size_t)c * a.N + I2 * kTile + lane];
+        sx[c * 32 + lane] = xb[(size_t)c * a.N + J * kTile + lane];
+        sf[c * 32 + lane] = 0.0;
+        f1[c] = 0.0; f2[c] = 0.0;
+    }
+    __syncwarp();
+#pragma unroll 1
+    for (int t = 0; t < 32; ++t) {
+        const int src = (lane + t) & 31;
+        double d1[D], d2[D];
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            const double xo = sx[c * 32 + src];
+            d1[c] = x1[c] - xo;
+            d2[c] = x2[c] - xo;
+        }
+        if (PBC) {   // (I < J in both pairs: the separation is x_lower - x_higher as in the reference, no sign to fix at a tie)
+            min_image_vec<D>(d1, a.L, a.invL, a.tie_hi, false);
+            min_image_vec<D>(d2, a.L, a.invL, a.tie_hi, false);
+        }
+        double r1 = d1[0] * d1[0], r2 = d2[0] * d2[0];
+#pragma unroll
+        for (int c = 1; c < D; ++c) { r1 = fma(d1[c], d1[c], r1); r2 = fma(d2[c], d2[c], r2); }
+        double g1, g2, v;
+        if (POT == PIMDB_POT_AZIZ && __all_sync(kFullMask, r1 > a.az_far2 && r2 > a.az_far2)) {   // see pair_rotation
+            double y1, y2;
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y1) : "d"(r1));
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y2) : "d"(r2));
+            y1 = fma(y1, fma(-r1, y1, 1.0), y1); y2 = fma(y2, fma(-r2, y2, 1.0), y2);
+            const double u1 = fma(y1, fma(-r1, y1, 1.0), y1), u2 = fma(y2, fma(-r2, y2, 1.0), y2);
+            const double q1 = u1 * u1, q2 = u2 * u2;
+            g1 = (q1 * q1) * fma(fma(a.az_h2, u1, a.az_h1), u1, a.az_h0);
+            g2 = (q2 * q2) * fma(fma(a.az_h2, u2, a.az_h1), u2, a.az_h0);
+        } else {
+            g1 = pair_eval<POT, false>(r1, a, v);
+            g2 = pair_eval<POT, false>(r2, a, v);
+        }
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            f1[c] = fma(-g1, d1[c], f1[c]);
+            f2[c] = fma(-g2, d2[c], f2[c]);
+            sf[c * 32 + src] = fma(g2, d2[c], fma(g1, d1[c], sf[c * 32 + src]));
+        }
+        __syncwarp();
+    }
+    double* sc = a.scratch + (size_t)bl * a.T * a.T * D * kTile;
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        sc[(((size_t)I1 * a.T + J) * D + c) * kTile + lane] = f1[c];
+        sc[(((size_t)I2 * a.T + J) * D + c) * kTile + lane] = f2[c];
+        sc[(((size_t)J * a.T + I1) * D + c) * kTile + lane] = sf[c * 32 + lane];
+        sc[(((size_t)J * a.T + I2) * D + c) * kTile + lane] = 0.0;
+    }
+    tl_end(a.tl);
+}
+
 // Deterministic final reduction of the per-warp (V, virial) partials: one block, fixed order.
 __global__ void __launch_bounds__(1024) k_pair_obs_reduce(const double* part, long long n, double* out_v, double* out_vir) {
     __shared__ double sm[64];
@@ -299,6 +384,32 @@ static void dispatch1(Sim* s, const PairArgs& a, int grid, bool early) {
 }
 
 // Enqueue the tile kernel for owned beads [bead_lo, bead_lo+nb) (nb <= bead_chunk).
+template <int D>
+static void dispatch_dual_d(Sim* s, const PairArgs& a, int grid, int ndual, bool early) {
+    auto go = [&](auto kernel) {
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3(grid); lc.blockDim = dim3(32 * kPairWarps); lc.dynamicSmemBytes = 0; lc.stream = s->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        lc.attrs = at;
+        lc.numAttrs = early ? 1 : 0;
+        cudaLaunchKernelEx(&lc, kernel, a, ndual);
+    };
+    const bool pbc = s->cfg.pbc != 0;
+    switch (s->cfg.int_potential) {
+        case PIMDB_POT_AZIZ: pbc ? go(k_pair_tiles_dual<D, PIMDB_POT_AZIZ, true>) : go(k_pair_tiles_dual<D, PIMDB_POT_AZIZ, false>); break;
+        case PIMDB_POT_HARMONIC: pbc ? go(k_pair_tiles_dual<D, PIMDB_POT_HARMONIC, true>) : go(k_pair_tiles_dual<D, PIMDB_POT_HARMONIC, false>); break;
+        case PIMDB_POT_DIPOLE: pbc ? go(k_pair_tiles_dual<D, PIMDB_POT_DIPOLE, true>) : go(k_pair_tiles_dual<D, PIMDB_POT_DIPOLE, false>); break;
+        default: break;
+    }
+}
+static void dispatch_dual(Sim* s, const PairArgs& a, int grid, int ndual, bool early) {
+    if (s->D == 1) dispatch_dual_d<1>(s, a, grid, ndual, early);
+    else if (s->D == 2) dispatch_dual_d<2>(s, a, grid, ndual, early);
+    else dispatch_dual_d<3>(s, a, grid, ndual, early);
+}
+
 // `scratch_lo`: the slot of the scratch slab that bead `bead_lo` writes to (several launches can fill one slab)
 static int launch_chunk(Sim* s, int bead_lo, int nb, bool with_obs, bool early, int scratch_lo) {
     PairArgs a;
@@ -306,6 +417,7 @@ static int launch_chunk(Sim* s, int bead_lo, int nb, bool with_obs, bool early, 
     a.scratch = s->pair_scratch + (size_t)scratch_lo * s->T * s->T * s->D * kTile;
     a.obs_part = s->pair_scratch;  // the scratch slab doubles as the (V, virial) partial buffer
     a.tile_ij = s->tile_ij;
+    a.dual_ijj = s->dual_ijj;
     a.N = s->N; a.T = s->T; a.TP = s->TP; a.nb = nb; a.S = s->S;
     a.L = s->L; a.invL = 1.0 / s->L; a.rc = s->rc; a.par = s->pair_par;
     a.tie_hi = min_image_tie_threshold(s->L);
@@ -320,7 +432,18 @@ static int launch_chunk(Sim* s, int bead_lo, int nb, bool with_obs, bool early, 
         a.az_h1 = (double)(g0 * rm7 * rm2 * 8.0L * kAzC8);
         a.az_h2 = (double)(g0 * rm7 * rm2 * rm2 * 10.0L * kAzC10);
     }
-    const long long items = (long long)nb * s->TP;
+    // forces without a cutoff: the full off-diagonal tiles two rows at a time (k_pair_tiles_dual), the rest singly, as two
+    // launches chained by a programmatic launch (no wait: they are independent) so that the short single items fill the tail
+    // Measured on B200: the two-row kernel runs 8 independent pair chains per scheduler instead of 6 (98 registers, two
+    // blocks per SM) and is ~1.3x faster per SM, but its blocks live twice as long: at C3 (1.5 waves of them) the tail eats
+    // the gain (pair tiles 42 -> 46 us), at C4 (50 waves) it is worth 2 %. So: only for grids of at least four waves
+    // (PIMDB_PAIR_DUAL=0/1 forces it off / on).
+    static const char* dual_env = getenv("PIMDB_PAIR_DUAL");
+    const double dual_waves = (double)nb * s->n_dual / kPairWarps / (2.0 * s->sm_count);
+    const bool dual_wanted = dual_env ? atoi(dual_env) != 0 : dual_waves >= 4.0;
+    const bool dual = !with_obs && dual_wanted && s->n_dual > 0 && !(s->rc > 0.0);
+    if (dual) { a.tile_ij = s->rest_ij; a.TP = s->n_rest; }
+    const long long items = (long long)nb * a.TP;
     // `split` > 1 cuts a tile pair's rotations over 2 or 4 warps. Measured on B200 at C3 (2.45 waves of tile pairs):
     // 52.0 / 52.2 / 58.3 us for split 1 / 2 / 4 -- the tail is not what limits the kernel, so the default stays 1.
     a.split = 1;
@@ -340,6 +463,16 @@ static int launch_chunk(Sim* s, int bead_lo, int nb, bool with_obs, bool early, 
         k_pair_obs_reduce<<<1, 1024, 0, s->stream>>>(s->pair_scratch, (long long)grid * kPairWarps, &s->obs_d->pair_v, &s->obs_d->pair_vir);
         s->launches += 2;
     } else {
+        if (dual) {
+            PairArgs ad = a;
+            ad.tl = a.tl; a.tl = tl_slot(s);
+            const int gd = (int)(((long long)nb * s->n_dual + kPairWarps - 1) / kPairWarps);
+            dispatch_dual(s, ad, gd, s->n_dual, early);
+            s->launches += 1;
+            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+            cudaStreamIsCapturing(s->stream, &cap);
+            early = cap == cudaStreamCaptureStatusActive;     // the single items ride behind the dual ones
+        }
         if (s->D == 1) dispatch1<1, false>(s, a, grid, early);
         else if (s->D == 2) dispatch1<2, false>(s, a, grid, early);
         else dispatch1<3, false>(s, a, grid, early);
