@@ -296,8 +296,12 @@ extern "C" int pimdb_create(const pimdb_config* cfg, pimdb_sim** out) {
     if (s->bosonic) {
         const size_t NN = (size_t)s->N * s->N;
         CREATE_TRY(cudaMalloc(&s->exA, sizeof(double) * (2 * s->N + 2)));   // A[N] | Inv[N+1]
-        CREATE_TRY(cudaMalloc(&s->exC, sizeof(int4) * 2 * NN));
-        if (s->N <= 8192) {  // block-scaled factor tiles + diagonal-block inverses of the blocked recurrence (exchange.cu)
+        // Up to N = 8192 the Boltzmann factors exist only as block-scaled tiles (8 bytes per entry) + diagonal-block inverses; the
+        // 16-byte extended-range tables (2 N^2 entries, 2.1 GB at N = 8192) are allocated for larger N and for the scalar
+        // cross-check recurrences (PIMDB_EXCH_NOBLOCKED=1) only
+        const bool scalar_path = s->N > 8192 || getenv("PIMDB_EXCH_NOBLOCKED");
+        if (scalar_path) CREATE_TRY(cudaMalloc(&s->exC, sizeof(int4) * 2 * NN));
+        if (!scalar_path) {  // block-scaled factor tiles + diagonal-block inverses of the blocked recurrence (exchange.cu)
             const size_t nbk = (size_t)((s->N + 31) / 32);
             CREATE_TRY(cudaMalloc(&s->exK, sizeof(double) * 2 * nbk * nbk * 1024));      // 32 x 32 tiles, forward | backward
             CREATE_TRY(cudaMemset(s->exK, 0, sizeof(double) * 2 * nbk * nbk * 1024));
@@ -567,7 +571,7 @@ static int enqueue_forces(Sim* s, bool assemble_later = false, bool after_integr
         static const bool no_chain = getenv("PIMDB_EXCH_NOCHAIN") != nullptr;     // plain order (A/B timing)
         // (only while the tile grid is a single wave, N <= 512: the pair tiles are scheduled once every tile block and then every
         // recurrence block has STARTED, and a tile grid of many waves would hold them back for most of its run time)
-        const bool chain = cap == cudaStreamCaptureStatusActive && s->exK && s->N <= 512 && !getenv("PIMDB_EXCH_NOBLOCKED") && !no_chain;
+        const bool chain = cap == cudaStreamCaptureStatusActive && s->exK && s->N <= 512 && !no_chain;
         if (!chain) {
             // Tile grids of many waves (N > 512), or eager launches: factor tiles on the main stream AHEAD of the pair tiles, the
             // rest of the chain on the side stream. (A 1024-thread tile block needs more registers than one retiring pair-tile

@@ -128,6 +128,7 @@ struct ExArgs {
     // bead shard over peer memory: the other exterior bead arrives in a halo slab written by a ring neighbour; the
     // first kernels of the chain wait (bounded) for it (device_utils.cuh peer_wait_halos), nullptr otherwise
     const unsigned int* halo_flag; const unsigned int* halo_seq; unsigned long long timeout_ns;
+    int tiles_diag_only;          // k_exch_coeff_tiles: one block per DIAGONAL tile (the others come from k_exch_offdiag_tiles)
 };
 
 template <int D>
@@ -147,6 +148,13 @@ template <int D>
 __device__ __forceinline__ double cycle_energy(const ExArgs& a, int u, int v) {
     return 0.5 * a.k * (a.A[v] - a.A[u] + dist2<D>(a, a.x1, u, a.xP, v));
 }
+
+// The Boltzmann factor the 16-byte tables of round 1 held at [r][v], recomputed from the positions (only the rarely taken
+// exact paths of the blocked recurrences need extended-range factors; everything on the fast paths reads the block-scaled
+// tiles): forward c(r, v), v >= r; backward c(v, r) / (r + 1), v <= r -- the same operations in the same order as the
+// tile kernel, so the value is bit-identical to what that kernel scaled into its tile.
+template <bool FWD>
+__device__ __forceinline__ int4 factor_exact(const ExArgs& a, int r, int v);
 
 // ---------------------------------------------------------------- 1. prefix sums A(w), one block
 template <int D>
@@ -187,6 +195,33 @@ __global__ void __launch_bounds__(1024) k_exch_prefix(ExArgs a) {
     }
     if (tid == 0) a.A[0] = 0.0;
     for (int i = tid; i <= a.N; i += blockDim.x) a.Inv[i] = i > 0 ? 1.0 / (double)i : 0.0;
+}
+
+template <bool FWD>
+__device__ __forceinline__ int4 factor_exact(const ExArgs& a, int r, int v) {
+    const int u = FWD ? r : v, w = FWD ? v : r;        // u <= w
+    double d2 = 0.0;
+    for (int c = 0; c < a.D; ++c) {                    // dist2<D>(a, x1, u, xP, w) with the dimension at run time
+        double dx = a.xP[(size_t)c * a.N + w] - a.x1[(size_t)c * a.N + u];
+        if (a.pbc) dx = min_image(dx, a.L, a.invL);
+        d2 = fma(dx, dx, d2);
+    }
+    const double y = a.h * (a.A[w] - a.A[u] + d2);
+    Ext c = ext_exp_neg(y < 0.0 ? 0.0 : y);
+    if (!FWD) c = ext_normalize(c.m * (1.0 / (double)(r + 1)), c.e);
+    return ext_pack(c.m, c.e);
+}
+
+// A block-scaled tile entry is the factor divided by 2^B, flushed to 0 when it lies more than 2^1022 below the largest factor
+// of its 32 rows in that column. Next to FAST blocks that loses nothing (their W stay within 2^+-400 of each other); once a
+// recurrence had to solve a block exactly the weights may span more, and whoever forms products W c Wb afterwards (exterior
+// forces, estimators, the probability table) recomputes the factors instead of reading the tiles. Called by every thread
+// of a block.
+__device__ __forceinline__ bool any_exact_block(const ExArgs& a) {
+    const int nb = (a.N + 31) >> 5;
+    bool e = false;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) e = e || (a.statf[i] & 15) == 2 || (a.statb[i] & 15) == 2;
+    return __syncthreads_or(e);
 }
 
 // ---------------------------------------------------------------- 2. Boltzmann factors, fully parallel
@@ -343,7 +378,7 @@ __global__ void __launch_bounds__(1024, 2) k_exch_coeff_tiles(ExArgs a) {
     grid_launch_dependents();    // the recurrence kernel may take its SMs now; it waits for this grid before it reads the tiles
     peer_wait_halos(a.halo_flag, a.halo_seq, a.timeout_ns, a.err);
     const int N = a.N, nb = (N + 31) >> 5;
-    const int rb = blockIdx.x / nb, sb = blockIdx.x % nb;
+    const int rb = a.tiles_diag_only ? blockIdx.x : blockIdx.x / nb, sb = a.tiles_diag_only ? blockIdx.x : blockIdx.x % nb;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const bool own_prefix = N <= kExchFastMaxN;      // beyond that k_exch_prefix has run before this kernel
     if (own_prefix) {
@@ -381,19 +416,16 @@ __global__ void __launch_bounds__(1024, 2) k_exch_coeff_tiles(ExArgs a) {
     const int r = rb * 32 + ty, sc = sb * 32 + tx;   // one element per thread: 4x the parallelism of a 256-thread tile
     double mf = 0.0, mb = 0.0;
     int ef = kExtZeroExp, eb = kExtZeroExp;
-    const long long i = (long long)r * N + sc;
     if (r < N && sc < N) {
         const int u = min(r, sc), v = max(r, sc);
         const double Av = own_prefix ? sA[v] : a.A[v], Au = own_prefix ? sA[u] : a.A[u];
         const double y = a.h * (Av - Au + dist2<D>(a, a.x1, u, a.xP, v));
         const Ext c = ext_exp_neg(y < 0.0 ? 0.0 : y);   // (a NaN position stays NaN and is reported, like the reference)
-        if (sc >= r) {
-            a.Cf[i] = ext_pack(c.m, c.e);
-            mf = c.m; ef = c.e;
-        }
-        if (sc <= r) {   // backward table: the 1/(p+1) weight of the sum (p = r) is folded in here, off the chain
+        // (the factors live on only as block-scaled tiles + block exponents: 8 bytes instead of 24 per entry, which is what
+        // bounds this kernel from N ~ 2000 on; the exact paths of the recurrences recompute what they need, factor_exact)
+        if (sc >= r) { mf = c.m; ef = c.e; }
+        if (sc <= r) {   // backward: the 1/(p+1) weight of the sum (p = r) is folded in here, off the chain
             const Ext cb = ext_normalize(c.m * (1.0 / (double)(r + 1)), c.e);
-            a.Cb[i] = ext_pack(cb.m, cb.e);
             mb = cb.m; eb = cb.e;
         }
     }
@@ -432,6 +464,45 @@ __global__ void __launch_bounds__(1024, 2) k_exch_coeff_tiles(ExArgs a) {
         diag_block_inverse(a, rb, kf, kb, maxf, maxb, reinterpret_cast<double (*)[16][17]>(&s_e2[0][0][0]));
     }
     tl_end(a.tl0);
+}
+
+// Off-diagonal factor tiles for N > 512, where the tile grid is many waves long and what bounds it is the latency of one
+// tile times the tiles in flight per SM (measured at N = 8192: 65536 blocks of 1024 threads, two per SM, 3.3 us each =
+// 730 us for 0.55 GB of output). Here a tile is a block of 256 threads, four rows per thread -- four independent exp()
+// chains per thread and up to eight tiles in flight per SM. A tile above the diagonal only feeds the forward recurrence,
+// one below it only the backward one; the diagonal tiles, which also invert their block, stay with k_exch_coeff_tiles.
+template <int D>
+__global__ void __launch_bounds__(256) k_exch_offdiag_tiles(ExArgs a) {
+    __shared__ int s_max[8][32];
+    const int N = a.N, nb = (N + 31) >> 5;
+    const int rb = blockIdx.x / nb, sb = blockIdx.x % nb;
+    if (rb == sb) return;
+    const bool fwd = sb > rb;
+    const int tx = threadIdx.x & 31, tq = threadIdx.x >> 5;
+    const int sc = sb * 32 + tx;
+    double m[4];
+    int e[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int r = rb * 32 + tq * 4 + k;
+        m[k] = 0.0; e[k] = kExtZeroExp;
+        if (r < N && sc < N) {
+            const int u = min(r, sc), v = max(r, sc);
+            const double y = a.h * (a.A[v] - a.A[u] + dist2<D>(a, a.x1, u, a.xP, v));
+            Ext c = ext_exp_neg(y < 0.0 ? 0.0 : y);
+            if (!fwd) c = ext_normalize(c.m * (1.0 / (double)(r + 1)), c.e);
+            m[k] = c.m; e[k] = c.e;
+        }
+    }
+    s_max[tq][tx] = max(max(e[0], e[1]), max(e[2], e[3]));
+    __syncthreads();
+    int mx = s_max[0][tx];
+#pragma unroll
+    for (int q = 1; q < 8; ++q) mx = max(mx, s_max[q][tx]);
+    double* K = (fwd ? a.Kf : a.Kb) + ((size_t)rb * nb + sb) * 1024;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) K[(tq * 4 + k) * 32 + tx] = m[k] * pow2i(max(e[k] - mx, -1100));
+    if (tq == 0 && sc < N) (fwd ? a.Bf : a.Bb)[rb * N + sc] = mx;
 }
 
 // ---------------------------------------------------------------- 3. the two recurrences
@@ -853,7 +924,6 @@ __device__ __forceinline__ void recur_blocked(const ExArgs& a, double* smem_d) {
     const int last_need = row_ok ? (FWD ? v : N - 1 - v) : -1;
     auto need = [&](int s) { return s <= last_need; };
     const int* Bg = FWD ? a.Bf : a.Bb;
-    const int4* Cg = FWD ? a.Cf : a.Cb;
     // my warp's factor tiles, one per earlier block in step order: K[q][warp], q = pos (forward) / nb-1-pos (backward)
     const double* Ktile = (FWD ? a.Kf : a.Kb) + (size_t)warp * 1024;
     const size_t tile_stride = (size_t)nb * 1024;
@@ -944,7 +1014,7 @@ __device__ __forceinline__ void recur_blocked(const ExArgs& a, double* smem_d) {
             for (int s = s0; s <= s1; ++s) {
                 if (need(s)) {
                     const int r = row_of(s);
-                    const int4 c = __ldg(&Cg[(long long)r * N + v]);
+                    const int4 c = factor_exact<FWD>(a, r, v);
                     ext_fma(am, ae, ext_m(c), c.z, sOm[r], sEx[r]);
                 }
             }
@@ -1020,7 +1090,7 @@ __device__ __forceinline__ void recur_blocked(const ExArgs& a, double* smem_d) {
 #pragma unroll 1
             for (int st = own_lo; st <= own_hi; ++st) {
                 if (need(st)) {
-                    const int4 c = __ldg(&Cg[(long long)row_of(st) * N + v]);
+                    const int4 c = factor_exact<FWD>(a, row_of(st), v);
                     ext_fma(am, ae, ext_m(c), c.z, wm, we);
                 }
                 const int lane_o = row_of(st) & 31;
@@ -1165,7 +1235,6 @@ __device__ __forceinline__ void recur_cluster(const ExArgs& a, double* smem_d) {
     const int last_need = row_ok ? (FWD ? v : N - 1 - v) : -1;
     auto need = [&](int s) { return s <= last_need; };
     const int* Bg = FWD ? a.Bf : a.Bb;
-    const int4* Cg = FWD ? a.Cf : a.Cb;
     const double* Ktile = (FWD ? a.Kf : a.Kb) + (size_t)warp * 1024;
     const size_t tile_stride = (size_t)nb * 1024;
     const int ntile_half = has_block ? 2 * min(mypos, npos) : 0;
@@ -1261,7 +1330,7 @@ __device__ __forceinline__ void recur_cluster(const ExArgs& a, double* smem_d) {
             for (int s = s0; s <= s1; ++s) {
                 if (need(s)) {
                     const int r = row_of(s);
-                    const int4 c = __ldg(&Cg[(long long)r * N + v]);
+                    const int4 c = factor_exact<FWD>(a, r, v);
                     ext_fma(am, ae, ext_m(c), c.z, sOm[r], sEx[r]);
                 }
             }
@@ -1369,7 +1438,7 @@ __device__ __forceinline__ void recur_cluster(const ExArgs& a, double* smem_d) {
 #pragma unroll 1
             for (int st = own_lo; st <= own_hi; ++st) {
                 if (need(st)) {
-                    const int4 c = __ldg(&Cg[(long long)row_of(st) * N + v]);
+                    const int4 c = factor_exact<FWD>(a, row_of(st), v);
                     ext_fma(am, ae, ext_m(c), c.z, wm, we);
                 }
                 const int lane_o = row_of(st) & 31;
@@ -1438,7 +1507,6 @@ __device__ __forceinline__ void recur_cluster_multi(const ExArgs& a, double* sme
     auto pos_of = [&](int q) { return FWD ? q : nb - 1 - q; };
     auto blk_at = [&](int pos) { return FWD ? pos : nb - 1 - pos; };
     const int* Bg = FWD ? a.Bf : a.Bb;
-    const int4* Cg = FWD ? a.Cf : a.Cb;
     const double* Kall = FWD ? a.Kf : a.Kb;
 
     // my row blocks q_j = gwarp + j NW and my row in each of them
@@ -1571,7 +1639,7 @@ __device__ __forceinline__ void recur_cluster_multi(const ExArgs& a, double* sme
                 for (int s_ = s0; s_ <= s1; ++s_) {
                     if (s_ <= last_need_c) {
                         const int r = row_of(s_);
-                        const int4 c = __ldg(&Cg[(long long)r * N + v]);
+                        const int4 c = factor_exact<FWD>(a, r, v);
                         ext_fma(am, ae, ext_m(c), c.z, sOm[r], sEx[r]);
                     }
                 }
@@ -1675,7 +1743,7 @@ __device__ __forceinline__ void recur_cluster_multi(const ExArgs& a, double* sme
 #pragma unroll 1
                 for (int st = own_lo; st <= own_hi; ++st) {
                     if (st <= last_need) {
-                        const int4 c = __ldg(&Cg[(long long)row_of(st) * N + v]);
+                        const int4 c = factor_exact<FWD>(a, row_of(st), v);
                         ext_fma(amo, aeo, ext_m(c), c.z, wm, we);
                     }
                     const int lane_o = row_of(st) & 31;
@@ -1767,7 +1835,10 @@ __global__ void __maxnreg__(160) k_exch_forces(ExArgs a) {   // (blocks of 32 * 
     const bool active = which == 0 ? a.do_first : a.do_last;
     const double iWN = 1.0 / a.Wm[N];
     const int eWN = a.We[N];
-    const int4* Ctab = which == 0 ? a.Cf : a.Cb;
+    const int4* Ctab = which == 0 ? a.Cf : a.Cb;             // (STAGE == 0 only: N beyond the block-scaled tiles)
+    const double* Ktab = which == 0 ? a.Kf : a.Kb;           // block-scaled factor tiles, 32 x 32, [row block][column block]
+    const int nbk = (N + 31) >> 5;
+    const bool exact = STAGE ? any_exact_block(a) : false;   // (block-uniform) recompute the factors instead of reading tiles
     for (int l = blk * kFW + warp; active && l < N; l += nblk * kFW) {
         // first bead: f_l = k [ sum_{u=max(0,l-1)}^{N-1} P(u->l) mi(r^P_u - r^1_l) + mi(r^2_l - r^1_l) ]
         //             P(u->l) = W[l] c(l,u) Wb[u+1] / ((u+1) W[N]),  P(l-1->l) = 1 - W[l] Wb[l] / W[N]
@@ -1781,7 +1852,10 @@ __global__ void __maxnreg__(160) k_exch_forces(ExArgs a) {   // (blocks of 32 * 
         double xl[D], acc[D];
 #pragma unroll
         for (int c = 0; c < D; ++c) { xl[c] = xs[(size_t)c * N + l]; acc[c] = 0.0; }
-        const int4* Crow = Ctab + (size_t)l * N;
+        const int4* Crow = STAGE ? nullptr : Ctab + (size_t)l * N;
+        // row l of the factor matrix inside its row block of tiles: element u sits at Krow[(u >> 5) * 1024 + (u & 31)], and
+        // equals the factor divided by 2^B[l / 32][u] (exactly: a power-of-two scaling)
+        const double* Krow = STAGE ? Ktab + (size_t)(l >> 5) * nbk * 1024 + (l & 31) * 32 : nullptr;
         // Upper bound of a term's binary exponent from the block-scaled tables: B[l/32][u] >= exponent of the factor
         // (l, u), so  e(term) <= el + B + e(g_u) + 3.  Below -1080 the connection probability is exactly 0 (the same
         // cut ext_to_double applies); a 32-wide chunk whose lanes are all below it is skipped before its factors are
@@ -1789,10 +1863,11 @@ __global__ void __maxnreg__(160) k_exch_forces(ExArgs a) {   // (blocks of 32 * 
         const int* Brow = STAGE ? (which == 0 ? a.Bf : a.Bb) + (size_t)(l >> 5) * N : nullptr;
         for (int ub = ulo; ub <= uhi; ub += 32 * kFU) {     // warp-uniform trip count (votes inside)
             const int u0 = ub + lane;
-            int4 cv[kFU];
+            int4 cv[STAGE ? 1 : kFU];
+            double kv[STAGE ? kFU : 1];
+            int bexp[STAGE ? kFU : 1];
             unsigned live = ~0u;                  // bit k: chunk k of this batch may hold a non-zero probability
             if (STAGE) {
-                int bexp[kFU];
 #pragma unroll
                 for (int k = 0; k < kFU; ++k) {
                     const int u = u0 + 32 * k;
@@ -1806,10 +1881,26 @@ __global__ void __maxnreg__(160) k_exch_forces(ExArgs a) {   // (blocks of 32 * 
                     if (__any_sync(kFullMask, maybe)) live |= 1u << k;
                 }
             }
+            // (all loads of the batch are issued before the first is used; the rarely taken recompute path sits outside that loop)
+            if (!STAGE || !exact) {
 #pragma unroll
-            for (int k = 0; k < kFU; ++k) {
-                const int u = u0 + 32 * k;
-                cv[k] = ((live >> k) & 1u) && (u <= uhi && u != special) ? __ldg(Crow + u) : make_int4(0, 0, 0, kExtZeroExp);
+                for (int k = 0; k < kFU; ++k) {
+                    const int u = u0 + 32 * k;
+                    const bool want = ((live >> k) & 1u) && (u <= uhi && u != special);
+                    if (STAGE) kv[k] = want ? __ldg(Krow + (size_t)(u >> 5) * 1024 + (u & 31)) : 0.0;
+                    else cv[k] = want ? __ldg(Crow + u) : make_int4(0, 0, 0, kExtZeroExp);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < kFU; ++k) {
+                    const int u = u0 + 32 * k;
+                    const bool want = ((live >> k) & 1u) && (u <= uhi && u != special);
+                    kv[k] = 0.0;
+                    if (want) {
+                        const int4 c = which == 0 ? factor_exact<true>(a, l, u) : factor_exact<false>(a, l, u);
+                        kv[k] = ext_m(c); bexp[k] = c.z;         // the factor itself: mantissa and its own exponent
+                    }
+                }
             }
 #pragma unroll
             for (int k = 0; k < kFU; ++k) {
@@ -1822,7 +1913,8 @@ __global__ void __maxnreg__(160) k_exch_forces(ExArgs a) {   // (blocks of 32 * 
                     } else {
                         int e;
                         const double g = g_of(u, e);
-                        pr = ext_to_double(wl * ext_m(cv[k]) * g, el + cv[k].z + e);
+                        if (STAGE) pr = ext_to_double(wl * kv[k] * g, el + bexp[k] + e);
+                        else pr = ext_to_double(wl * ext_m(cv[k]) * g, el + cv[k].z + e);
                     }
                     if (pr != 0.0) {   // most connection probabilities underflow to exactly 0: skip their separations
 #pragma unroll
@@ -1859,6 +1951,7 @@ __global__ void __launch_bounds__(1024) k_exch_estimators(ExArgs a) {
     extern __shared__ double se[];   // e[0..N]
     __shared__ double red[32];
     const int tid = threadIdx.x, nt = blockDim.x, N = a.N;
+    const bool exact = a.Kf ? any_exact_block(a) : false;
     double acc[R], iwm[R];
     int iwe[R];
 #pragma unroll
@@ -1877,9 +1970,19 @@ __global__ void __launch_bounds__(1024) k_exch_estimators(ExArgs a) {
         for (int r = 0; r < R; ++r) {
             const int v = tid + r * nt;
             if (v >= j && v < N) {
-                const size_t ci = (size_t)j * N + v;
-                const int4 c = __ldg(&a.Cf[ci]);
-                const double wgt = ext_to_double(ext_m(c) * wjm * iwm[r], c.z + wje + iwe[r]);
+                double cm;
+                int ce;
+                if (exact) {
+                    const int4 c = factor_exact<true>(a, j, v);
+                    cm = ext_m(c); ce = c.z;
+                } else if (a.Kf) {   // block-scaled tile entry (j, v) and its block exponent
+                    cm = __ldg(&a.Kf[((size_t)(j >> 5) * ((N + 31) >> 5) + (v >> 5)) * 1024 + (j & 31) * 32 + (v & 31)]);
+                    ce = __ldg(&a.Bf[(size_t)(j >> 5) * N + v]);
+                } else {
+                    const int4 c = __ldg(&a.Cf[(size_t)j * N + v]);
+                    cm = ext_m(c); ce = c.z;
+                }
+                const double wgt = ext_to_double(cm * wjm * iwm[r], ce + wje + iwe[r]);
                 acc[r] = fma(wgt, ej - cycle_energy<D>(a, j, v), acc[r]);
             }
         }
@@ -1924,12 +2027,25 @@ __global__ void k_exch_table_prob(ExArgs a, double* out) {
     const long long tot = (long long)N * N;
     const double iWN = 1.0 / a.Wm[N];
     const int eWN = a.We[N];
+    const bool exact = a.Kb ? any_exact_block(a) : false;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (long long)gridDim.x * blockDim.x) {
         const int l = (int)(i / N), u = (int)(i % N);
         double pr = 0.0;
         if (u == l + 1) pr = 1.0 - ext_to_double(a.Wm[l + 1] * a.Wbm[l + 1] * iWN, a.We[l + 1] + a.Wbe[l + 1] - eWN);
-        else if (u <= l)
-            pr = ext_to_double(a.Wm[u] * ext_m(a.Cb[i]) * a.Wbm[l + 1] * iWN, a.We[u] + a.Cb[i].z + a.Wbe[l + 1] - eWN);
+        else if (u <= l) {
+            double cm;
+            int ce;
+            if (exact) {
+                const int4 c = factor_exact<false>(a, l, u);
+                cm = ext_m(c); ce = c.z;
+            } else if (a.Kb) {
+                cm = a.Kb[((size_t)(l >> 5) * ((N + 31) >> 5) + (u >> 5)) * 1024 + (l & 31) * 32 + (u & 31)];
+                ce = a.Bb[(size_t)(l >> 5) * N + u];
+            } else {
+                cm = ext_m(a.Cb[i]); ce = a.Cb[i].z;
+            }
+            pr = ext_to_double(a.Wm[u] * cm * a.Wbm[l + 1] * iWN, a.We[u] + ce + a.Wbe[l + 1] - eWN);
+        }
         out[i] = pr;
     }
 }
@@ -1954,6 +2070,7 @@ static ExArgs make_args(Sim* s) {
     a.Inv = s->exA + s->N;
     a.Cf = s->exC; a.Cb = s->exC + NN;
     const size_t nbk = (size_t)((s->N + 31) / 32);
+    // (PIMDB_EXCH_NOBLOCKED=1, read when the handle is created: the scalar recurrences on the 16-byte tables as a cross-check)
     a.Kf = s->exK; a.Kb = s->exK ? s->exK + nbk * nbk * 1024 : nullptr;
     a.Bf = s->exB; a.Bb = s->exB ? s->exB + (size_t)((s->N + 31) / 32) * s->N : nullptr;
     a.Gf = s->exG; a.Gb = s->exG ? s->exG + nbk * 1024 : nullptr;
@@ -1974,6 +2091,7 @@ static ExArgs make_args(Sim* s) {
     a.halo_flag = s->peer_on ? s->peer.mine->halo_flag : nullptr;
     a.halo_seq = s->peer_on ? s->peer.seq + 1 : nullptr;
     a.timeout_ns = s->peer.timeout_ns;
+    a.tiles_diag_only = 0;
     return a;
 }
 
@@ -2027,7 +2145,7 @@ static int run_recursion(Sim* s, const ExArgs& a, cudaStream_t st) {
     int nt;
     const int R = rows_per_thread(s->N, nt);
     const int nblk = (s->N + 31) / 32;                       // 32-row blocks
-    const bool blocked_ok = a.Kf && !getenv("PIMDB_EXCH_NOBLOCKED");
+    const bool blocked_ok = a.Kf != nullptr;   // (the scalar cross-check path is chosen when the handle is created: no tiles then)
     const bool pdl = s->pdl_recur;     // launched right behind k_exch_coeff_tiles on the same stream (api.cu enqueue_forces)
     if (blocked_ok && nblk > 8 * kClusterSize) {
         // more than 64 row blocks (2048 < N <= 8192): the same cluster, up to 4 row blocks per warp
@@ -2094,13 +2212,21 @@ static int exchange_impl(Sim* s, cudaStream_t st, int part) {
     if (part == 1 || part == 2) a.tl1 = tl_slot(s);
     if (part == 1 || part == 3) a.tl2 = tl_slot(s);
     if (part == 0) {
-        if (a.Kf) {      // N <= 2048: factor tiles + diagonal-block inverses; up to N = 512 the tiles recompute the prefix sums
+        if (a.Kf) {      // N <= 8192: factor tiles + diagonal-block inverses; up to N = 512 the tiles recompute the prefix sums
             const int nb = (s->N + 31) / 32;
             if (s->N > kExchFastMaxN) {
                 launch_chain(s, k_exch_prefix<D>, a, 1, 1024, 0, st, 1, false);
                 s->launches += 1;
             }
-            {
+            if (s->N > kExchFastMaxN && !getenv("PIMDB_EXCH_TILES1024")) {
+                // many waves of tiles: the off-diagonal ones four rows per thread, then one block per diagonal tile (+ inverse)
+                launch_chain(s, k_exch_offdiag_tiles<D>, a, nb * nb, 256, 0, st, 1, false);
+                s->launches += 1;
+                a.tiles_diag_only = 1;
+                s->pdl_next = false;
+                launch_chain(s, k_exch_coeff_tiles<D>, a, nb, 1024, 0, st, 1, false);
+                a.tiles_diag_only = 0;
+            } else {
                 const bool early = s->pdl_next && s->N <= kExchFastMaxN;   // (beyond that the prefix kernel sits in front)
                 s->pdl_next = false;
                 launch_chain(s, k_exch_coeff_tiles<D>, a, nb * nb, 1024, 0, st, 1, early);
