@@ -70,6 +70,12 @@ enum pimdb_rng {
     PIMDB_RNG_RANMARS = 1   /* the reference's own stream, sequential per bead: trajectory-level agreement, slow     */
 };
 
+/* bosonic exchange class (src/simulation.cpp:689-700) */
+enum pimdb_exchange_alg {
+    PIMDB_EXCH_QUADRATIC = 0,  /* Feldman-Hirshberg, O(N^2 + PN): src/bosonic_exchange/quadratic_bosonic_exchange.cpp           */
+    PIMDB_EXCH_FACTORIAL = 1   /* sum over all N! permutations, natoms <= 10: src/bosonic_exchange/factorial_bosonic_exchange.cpp */
+};
+
 /* which state array (include/simulation.h:59-60; the split forces are the two locals of
  * Simulation::updateForces, src/simulation.cpp:357-361) */
 enum pimdb_array {
@@ -119,7 +125,9 @@ typedef struct pimdb_config {
     int bead_begin, bead_end;
     int device;              /* CUDA device ordinal */
     int rng;                 /* enum pimdb_rng: noise stream of the Langevin thermostat (0 = default)                  */
-    int reserved[3];
+    int exchange_alg;        /* enum pimdb_exchange_alg: the reference picks its exchange class at compile time
+                                (CMakeLists.txt:50-54, -DFACTORIAL_BOSONIC_ALGORITHM)                                  */
+    int reserved[2];
 } pimdb_config;
 
 /* Columns of output/simulation.out (src/observables/energy.cpp, classical.cpp, bosonic.cpp), summed over the

@@ -442,17 +442,122 @@ static double exchange_prim_estimator(orc_sim* s) {
     return s->prim[N] / s->P; /* IPI convention */
 }
 
+
+/* ------------------------------------------------------------------ factorial exchange (-DFACTORIAL_BOSONIC_ALGORITHM) */
+/* src/bosonic_exchange/factorial_bosonic_exchange.cpp: every quantity is a sum over all N! permutations, enumerated with
+ * next_permutation from the identity; labels[l] is the particle whose first bead follows the last bead of particle l. */
+static int next_permutation_int(int* a, int n) { /* std::next_permutation */
+    int i = n - 1;
+    while (i > 0 && a[i - 1] >= a[i]) --i;
+    if (i <= 0) { for (int l = 0, r = n - 1; l < r; ++l, --r) { int t = a[l]; a[l] = a[r]; a[r] = t; } return 0; }
+    int j = n - 1;
+    while (a[j] <= a[i - 1]) --j;
+    { int t = a[i - 1]; a[i - 1] = a[j]; a[j] = t; }
+    for (int l = i, r = n - 1; l < r; ++l, --r) { int t = a[l]; a[l] = a[r]; a[r] = t; }
+    return 1;
+}
+/* getMinExteriorSpringEnergy :57-81 */
+static double factorial_e_shift(const orc_sim* s) {
+    const int N = s->N;
+    const double* first = s->x;
+    const double* last = s->x + (size_t)(s->P - 1) * slab(s);
+    int labels[16];
+    for (int i = 0; i < N; ++i) labels[i] = i;
+    double min_delta = DBL_MAX;
+    do {
+        double diff2 = 0.0;
+        for (int l = 0; l < N; ++l) diff2 += bead_sep2(s, first, l, last, labels[l]);   /* (as written in the reference) */
+        double e = 0.5 * s->k_spring * diff2;
+        if (e < min_delta) min_delta = e;
+    } while (next_permutation_int(labels, N));
+    return min_delta;
+}
+/* effectivePotential :90-113 */
+static double factorial_effective_potential(const orc_sim* s) {
+    const int N = s->N;
+    const double* first = s->x;
+    const double* last = s->x + (size_t)(s->P - 1) * slab(s);
+    const double beta = exch_beta(s), beta_half_k = beta * 0.5 * s->k_spring;
+    int labels[16];
+    for (int i = 0; i < N; ++i) labels[i] = i;
+    long count = 0;
+    double sum = 0.0;
+    do {
+        ++count;
+        double diff2 = 0.0;
+        for (int l = 0; l < N; ++l) diff2 += bead_sep2(s, first, l, last, labels[l]);
+        sum += exp(-beta_half_k * diff2);
+    } while (next_permutation_int(labels, N));
+    return (-1.0 / beta) * log(sum / count);
+}
+/* springForceLastBead :121-170 (which = 1) / springForceFirstBead :177-227 (which = 0) */
+static void factorial_force(const orc_sim* s, int which, double e_shift, double* out) {
+    const int N = s->N, D = s->D, P = s->P;
+    const double beta = exch_beta(s), k = s->k_spring;
+    const double* x = which ? s->x + (size_t)(P - 1) * slab(s) : s->x;
+    const double* other = which ? s->x : s->x + (size_t)(P - 1) * slab(s);           /* x_next of the last / x_prev of the first */
+    const double* inner = which ? s->x + (size_t)((P - 2 + P) % P) * slab(s) : s->x + (size_t)(1 % P) * slab(s);
+    int labels[16];
+    for (int i = 0; i < N; ++i) labels[i] = i;
+    double temp[16][3], denom = 0.0, d[3], din[3];
+    for (size_t q = 0; q < slab(s); ++q) out[q] = 0.0;
+    do {
+        double weight = 0.0;
+        for (int l = 0; l < N; ++l) {
+            int nb;
+            if (which) nb = labels[l];                                                /* lastBeadNeighbor  */
+            else { nb = 0; while (labels[nb] != l) ++nb; }                            /* firstBeadNeighbor */
+            bead_sep(s, x, l, other, nb, d);
+            for (int a = 0; a < D; ++a) weight += d[a] * d[a];
+            bead_sep(s, x, l, inner, l, din);
+            for (int a = 0; a < D; ++a) temp[l][a] = (din[a] + d[a]) * k;
+        }
+        weight = exp(-beta * (0.5 * k * weight - e_shift));
+        for (int l = 0; l < N; ++l)
+            for (int a = 0; a < D; ++a) out[(size_t)l * D + a] += weight * temp[l][a];
+        denom += weight;
+    } while (next_permutation_int(labels, N));
+    for (size_t q = 0; q < slab(s); ++q) out[q] /= denom;
+}
+/* primEstimator :258-291 */
+static double factorial_prim_estimator(const orc_sim* s, double e_shift) {
+    const int N = s->N;
+    const double beta = exch_beta(s);
+    const double* first = s->x;
+    const double* last = s->x + (size_t)(s->P - 1) * slab(s);
+    int labels[16];
+    for (int i = 0; i < N; ++i) labels[i] = i;
+    double num = 0.0, denom = 0.0;
+    do {
+        double w2 = 0.0;
+        for (int l = 0; l < N; ++l) {
+            int nb = 0;
+            while (labels[nb] != l) ++nb;                                             /* firstBeadNeighbor(l) */
+            w2 += bead_sep2(s, first, l, last, nb);
+        }
+        double de = 0.5 * s->k_spring * w2, w = exp(-beta * (de - e_shift));
+        num += de * w;
+        denom += w;
+    } while (next_permutation_int(labels, N));
+    return (-1.0) * (num / denom) / s->P;   /* IPI convention */
+}
+
 /* ------------------------------------------------------------------ force assembly */
 static int bosonic_active(const orc_sim* s) { return s->c.bosonic && s->P > 1; } /* src/simulation.cpp:690 */
 
 /* src/simulation.cpp:353-374, 394-420 for all beads */
 void orc_update_forces(orc_sim* s) {
     const int P = s->P;
-    if (bosonic_active(s)) exchange_prepare(s);
+    const int fact = bosonic_active(s) && s->c.factorial;
+    double e_shift = 0.0;
+    if (fact) e_shift = factorial_e_shift(s);                 /* FactorialBosonicExchange::prepare :18-20 */
+    else if (bosonic_active(s)) exchange_prepare(s);
     for (int b = 0; b < P; ++b) {
         double* fs = s->f_spring + (size_t)b * slab(s);
         double* fp = s->f_phys + (size_t)b * slab(s);
-        if (bosonic_active(s) && b == 0)
+        if (fact && (b == 0 || b == P - 1))
+            factorial_force(s, b == P - 1, e_shift, fs);
+        else if (bosonic_active(s) && b == 0)
             exchange_force_first(s, fs);
         else if (bosonic_active(s) && b == P - 1)
             exchange_force_last(s, fs);
@@ -721,13 +826,15 @@ void orc_observables_calc(orc_sim* s, orc_observables* o) {
     const int P = s->P, N = s->N, D = s->D;
     const int bos = bosonic_active(s);
     memset(o, 0, sizeof *o);
-    if (bos) exchange_prepare(s);
+    const int fact = bos && s->c.factorial;
+    const double fact_shift = fact ? factorial_e_shift(s) : 0.0;
+    if (bos && !fact) exchange_prepare(s);
     for (int b = 0; b < P; ++b) {
         const double* xb = s->x + (size_t)b * slab(s);
         /* kinetic (primitive estimator) */
         double kin = 0.5 * D * N / s->beta;
         if (b == 0 && bos)
-            kin += exchange_prim_estimator(s);
+            kin += fact ? factorial_prim_estimator(s, fact_shift) : exchange_prim_estimator(s);
         else
             kin -= ring_spring_energy(s, b) / P;
         o->kinetic += kin;
@@ -791,10 +898,10 @@ void orc_observables_calc(orc_sim* s, orc_observables* o) {
         o->cl_kinetic += ke;
         double dof = (double)D * N * P;
         o->temperature += 2.0 * ke / dof / P;
-        o->cl_spring += (b == 0 && bos) ? s->V[N] : ring_spring_energy(s, b);
+        o->cl_spring += (b == 0 && bos) ? (fact ? factorial_effective_potential(s) : s->V[N]) : ring_spring_energy(s, b);
     }
     if (s->c.thermostat >= ORC_THERMO_NOSE_HOOVER) o->nh_energy = nose_hoover_energy(s); /* classical.cpp:24-26 */
-    if (bos) {
+    if (bos && !fact) {   /* (the factorial class returns 0 for both, factorial_bosonic_exchange.cpp:234-251) */
         /* quadratic_bosonic_exchange.cpp:222-240 */
         double beta = exch_beta(s), sum = 0;
         for (int m = 1; m <= N; ++m) sum += *Eat(s, m, 1);

@@ -45,6 +45,8 @@ typedef struct {
     int nchains;                 /* Nose-Hoover chain length ([simulation] nchains, default 4) */
     double ext_strength, ext_location;   /* double_well: strength (energy), location (length), src/params.cpp:238-242 */
     double ext_amplitude, ext_phase;     /* cosine: amplitude (energy), phase; wavelength = box size (src/simulation.cpp:634-638) */
+    int factorial;               /* the reference built with -DFACTORIAL_BOSONIC_ALGORITHM: the sum over all N! permutations
+                                    (src/bosonic_exchange/factorial_bosonic_exchange.cpp) instead of Feldman-Hirshberg */
 } orc_config;
 
 typedef struct orc_sim orc_sim;

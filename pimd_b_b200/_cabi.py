@@ -21,6 +21,7 @@ PEER_BLOB_BYTES = 256
 POTENTIAL = {"free": 0, "aziz": 1, "harmonic": 2, "dipole": 3, "double_well": 4, "cosine": 5}
 PROPAGATOR = {"cartesian": 0, "normal_modes": 1}
 RNG = {"philox": 0, "ranmars": 1}
+EXCHANGE_ALG = {"quadratic": 0, "factorial": 1}
 THERMOSTAT = {"none": 0, "langevin": 1, "nose_hoover": 2, "nose_hoover_np": 3, "nose_hoover_np_dim": 4}
 ARRAY = {"x": 0, "p": 1, "f": 2, "f_spring": 3, "f_phys": 4}
 EXCH_TABLE = {"V": 0, "Vb": 1, "E": 2, "prob": 3}
@@ -42,7 +43,8 @@ class PimdbConfig(C.Structure):
         ("bead_begin", C.c_int), ("bead_end", C.c_int),
         ("device", C.c_int),
         ("rng", C.c_int),
-        ("reserved", C.c_int * 3),
+        ("exchange_alg", C.c_int),
+        ("reserved", C.c_int * 2),
     ]
 
 

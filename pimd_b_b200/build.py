@@ -18,7 +18,7 @@ PKG = Path(__file__).resolve().parent
 CSRC = PKG / "csrc"
 OBJ = PKG / "_build"
 LIB = PKG / "libpimdb200.so"
-SOURCES = ["api.cu", "pair_forces.cu", "exchange.cu", "integrator.cu", "normal_modes.cu", "nose_hoover.cu", "ranmars.cu"]
+SOURCES = ["api.cu", "pair_forces.cu", "exchange.cu", "integrator.cu", "normal_modes.cu", "nose_hoover.cu", "ranmars.cu", "factorial.cu"]
 HEADERS = [CSRC / "internal.cuh", CSRC / "device_utils.cuh", PKG.parent / "include" / "pimdb200.h"]
 
 NVCC_FLAGS = [

@@ -133,6 +133,9 @@ class SimConfig:
     # not an INI key: noise stream of the Langevin thermostat on the GPU, "philox" (parallel, default) or "ranmars"
     # (the reference's own generator, one sequential stream per bead: trajectory-level parity, slow)
     rng: str = "philox"
+    # not an INI key either: the reference chooses its exchange class at compile time (CMakeLists.txt:50-54,
+    # -DFACTORIAL_BOSONIC_ALGORITHM): "quadratic" (Feldman-Hirshberg, default) or "factorial" (all N! permutations, N <= 10)
+    exchange_alg: str = "quadratic"
 
     def __post_init__(self):
         if self.gamma < 0:

@@ -96,6 +96,12 @@ static int validate(const pimdb_config* c, std::string& msg) {
         return PIMDB_ERR_INVALID_ARGUMENT;
     }
     if (c->natoms > 65535 * kTile) { msg = "natoms too large"; return PIMDB_ERR_INVALID_ARGUMENT; }
+    if (c->exchange_alg != PIMDB_EXCH_QUADRATIC && c->exchange_alg != PIMDB_EXCH_FACTORIAL) {
+        msg = "unknown bosonic exchange algorithm"; return PIMDB_ERR_INVALID_ARGUMENT;
+    }
+    if (c->exchange_alg == PIMDB_EXCH_FACTORIAL && c->bosonic && c->nbeads > 1 && c->natoms > 10) {
+        msg = "the factorial exchange algorithm sums over all N! permutations: natoms <= 10"; return PIMDB_ERR_INVALID_ARGUMENT;
+    }
     return PIMDB_OK;
 }
 
@@ -150,7 +156,7 @@ static void free_all(Sim* s) {
     cudaFreeHost(s->err_h);
     cudaFree(s->nmC); cudaFree(s->nmFreq); cudaFree(s->nh_state);
     for (void* m : s->ipc_opened) cudaIpcCloseMemHandle(m);
-    cudaFree(s->mailbox); cudaFree(s->peer_seq); cudaFree(s->stamps);
+    cudaFree(s->mailbox); cudaFree(s->peer_seq); cudaFree(s->stamps); cudaFree(s->fact_work);
     if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     if (s->ev_join) cudaEventDestroy(s->ev_join);
     if (s->ev_copy) cudaEventDestroy(s->ev_copy);
@@ -209,6 +215,7 @@ extern "C" int pimdb_create(const pimdb_config* cfg, pimdb_sim** out) {
     s->has_first = (s->b0 == 0);
     s->has_last = (s->b1 == s->P);
     s->bosonic = cfg->bosonic && s->P > 1;                       // src/simulation.cpp:690
+    s->factorial = s->bosonic && cfg->exchange_alg == PIMDB_EXCH_FACTORIAL;
     s->S = (size_t)s->D * s->N;
     // src/simulation.cpp:37-52 (i-PI convention)
     s->beta = 1.0 / cfg->temperature;
@@ -299,9 +306,10 @@ extern "C" int pimdb_create(const pimdb_config* cfg, pimdb_sim** out) {
         // Up to N = 8192 the Boltzmann factors exist only as block-scaled tiles (8 bytes per entry) + diagonal-block inverses; the
         // 16-byte extended-range tables (2 N^2 entries, 2.1 GB at N = 8192) are allocated for larger N and for the scalar
         // cross-check recurrences (PIMDB_EXCH_NOBLOCKED=1) only
-        const bool scalar_path = s->N > 8192 || getenv("PIMDB_EXCH_NOBLOCKED");
+        const bool scalar_path = !s->factorial && (s->N > 8192 || getenv("PIMDB_EXCH_NOBLOCKED"));
+        if (s->factorial) CREATE_TRY(cudaMalloc(&s->fact_work, sizeof(double) * (5 * NN + s->N)));
         if (scalar_path) CREATE_TRY(cudaMalloc(&s->exC, sizeof(int4) * 2 * NN));
-        if (!scalar_path) {  // block-scaled factor tiles + diagonal-block inverses of the blocked recurrence (exchange.cu)
+        if (!scalar_path && !s->factorial) {  // block-scaled factor tiles + diagonal-block inverses of the blocked recurrence (exchange.cu)
             const size_t nbk = (size_t)((s->N + 31) / 32);
             CREATE_TRY(cudaMalloc(&s->exK, sizeof(double) * 2 * nbk * nbk * 1024));      // 32 x 32 tiles, forward | backward
             CREATE_TRY(cudaMemset(s->exK, 0, sizeof(double) * 2 * nbk * nbk * 1024));
@@ -1139,6 +1147,8 @@ extern "C" int pimdb_exchange_get(pimdb_sim* sim, int table, double* out, size_t
         default: return fail(s, PIMDB_ERR_INVALID_ARGUMENT, "unknown exchange table");
     }
     if (n < need) return fail(s, PIMDB_ERR_INVALID_ARGUMENT, "output buffer too small");
+    if (s->factorial && table != PIMDB_EXCH_V)
+        return fail(s, PIMDB_ERR_INVALID_ARGUMENT, "the factorial exchange class has no recursion tables (only V[N], its effective potential)");
     if (!src) {
         if (s->exTabCap < need) {
             cudaFree(s->exTab);
@@ -1170,7 +1180,7 @@ extern "C" int pimdb_observables_calc(pimdb_sim* sim, pimdb_observables* out) {
     }
     if (s->bosonic && s->has_first) {
         API_TRY(launch_exchange(s, s->stream));   // tables for the current positions
-        API_TRY(launch_exchange_estimators(s));
+        if (!s->factorial) API_TRY(launch_exchange_estimators(s));   // (the factorial class leaves its estimators with the forces)
     }
     if (s->cfg.thermostat >= PIMDB_THERMO_NOSE_HOOVER) API_TRY(launch_nose_hoover_energy(s, &s->obs_d->nh_energy));
     PIMDB_CUDA_TRY(s, cudaMemcpyAsync(s->obs_h, s->obs_d, sizeof(DevObs), cudaMemcpyDeviceToHost, s->stream));
@@ -1211,7 +1221,7 @@ extern "C" int pimdb_observables_calc(pimdb_sim* sim, pimdb_observables* out) {
         out->w_gsf = out->pot_gsf = std::nan("");
     }
     // bosonic.cpp:17-22, quadratic_bosonic_exchange.cpp:222-240
-    if (s->bosonic && s->has_first) {
+    if (s->bosonic && s->has_first && !s->factorial) {   // (factorial_bosonic_exchange.cpp:234-251: both "not implemented", 0)
         out->prob_dist = std::exp(-s->exch_beta * (o.e_diag_sum - o.v_n) - std::lgamma(N + 1.0));
         out->prob_all = std::exp(-s->exch_beta * (o.e_full - o.v_n));
     }

@@ -2269,6 +2269,7 @@ static int exchange_impl(Sim* s, cudaStream_t st, int part) {
 }
 
 int launch_exchange_part(Sim* s, cudaStream_t st, int part) {
+    if (s->factorial) return part == 0 ? launch_factorial_exchange(s, st) : PIMDB_OK;   // (one short chain of four small kernels)
     if (s->D == 1) return exchange_impl<1>(s, st, part);
     if (s->D == 2) return exchange_impl<2>(s, st, part);
     return exchange_impl<3>(s, st, part);

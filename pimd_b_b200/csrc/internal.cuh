@@ -95,6 +95,8 @@ struct Sim {
     int T = 0, TP = 0;                 // tiles per bead, upper-triangular tile pairs
     bool all_local = false, has_first = false, has_last = false, bosonic = false;
     bool pair_on = false;
+    bool factorial = false;            // the reference's N!-permutation exchange class instead of Feldman-Hirshberg (factorial.cu)
+    double* fact_work = nullptr;
     size_t S = 0;                      // slab stride = D*N
     double beta = 0, thermo_beta = 0, exch_beta = 0, omega_p = 0, kspring = 0, rc = 0, L = 0, kext = 0;
     double c1 = 1, c2 = 0;             // Langevin friction / noise coefficients
@@ -194,6 +196,7 @@ int launch_pair_forces(Sim* s, bool with_obs);
 int launch_assemble(Sim* s);
 int launch_exchange(Sim* s, cudaStream_t st);          // prep + forward/backward + exterior forces
 int launch_exchange_tables(Sim* s, int table);
+int launch_factorial_exchange(Sim* s, cudaStream_t st);
 int launch_exchange_estimators(Sim* s);
 int launch_fill_halos(Sim* s);
 enum : unsigned { OP_SUBCM = 1, OP_O_PRE = 2, OP_B = 4, OP_O_POST = 8, OP_A = 16, OP_SUM = 32, OP_HALO = 64, OP_B_PHYS = 128,

@@ -29,7 +29,8 @@ def make_c_config(cfg: SimConfig, bead_begin: int = 0, bead_end: Optional[int] =
         cutoff=cfg.cutoff, mass=cfg.mass, temperature=cfg.temperature, dt=cfg.dt, gamma=cfg.gamma,
         size=cfg.size, seed=cfg.seed,
         bead_begin=bead_begin, bead_end=cfg.nbeads if bead_end is None else bead_end, device=device,
-        rng=_cabi.RNG[getattr(cfg, "rng", "philox")])
+        rng=_cabi.RNG[getattr(cfg, "rng", "philox")],
+        exchange_alg=_cabi.EXCHANGE_ALG[getattr(cfg, "exchange_alg", "quadratic")])
 
 
 class DeviceSim:

@@ -1,5 +1,5 @@
 // pimdb_gpu: the reference's `pimdb` entry point (src/pimdb.cpp:31-68) on top of the B200 hot path.
-//   pimdb_gpu [-in config.ini] [--dim D] [--device K] [--gpus G] [--rng philox|ranmars] [--bosonic_alg]
+//   pimdb_gpu [-in config.ini] [--dim D] [--device K] [--gpus G] [--rng philox|ranmars] [--factorial] [--bosonic_alg]
 // --gpus G shards the beads over G GPUs (devices K .. K+G-1) coupled through peer memory: the counterpart of the
 // reference's `mpirun -np P pimdb` (README.md:200-203), in one process.
 // --rng ranmars (or PIMDB_RNG=ranmars) draws the Langevin noise from the reference's own generator, one sequential
@@ -18,15 +18,17 @@ int main(int argc, char** argv) {
     std::string config = "config.ini";
     int ndim = 3, device = 0, ngpus = 1;
     std::string rng = std::getenv("PIMDB_RNG") ? std::getenv("PIMDB_RNG") : "philox";
-    bool info = false;
+    bool info = false, factorial = false;
     try {
         for (int i = 1; i < argc; ++i) {
             if (!std::strcmp(argv[i], "--dim")) {
                 if (i + 1 < argc && std::isdigit((unsigned char)argv[i + 1][0])) ndim = std::atoi(argv[++i]);
                 else { std::cout << "Program runs 1-, 2- and 3-dimensional systems (select with --dim D)\n"; info = true; }
             } else if (!std::strcmp(argv[i], "--bosonic_alg")) {
-                std::cout << "Program was compiled with quadratic bosonic algorithm.\n";
+                std::cout << "Program runs the quadratic bosonic algorithm (--factorial selects the factorial one, natoms <= 10).\n";
                 info = true;
+            } else if (!std::strcmp(argv[i], "--factorial")) {
+                factorial = true;
             } else if (!std::strcmp(argv[i], "--device")) {
                 if (i + 1 < argc) device = std::atoi(argv[++i]);
             } else if (!std::strcmp(argv[i], "--gpus")) {
@@ -43,6 +45,7 @@ int main(int argc, char** argv) {
             pimdb_host::Params params(config, ndim);
             if (rng == "ranmars") params.cfg.rng = PIMDB_RNG_RANMARS;
             else if (rng != "philox") throw std::invalid_argument("--rng takes philox or ranmars");
+            if (factorial) params.cfg.exchange_alg = PIMDB_EXCH_FACTORIAL;   // the reference: -DFACTORIAL_BOSONIC_ALGORITHM at build time
             pimdb_host::Simulation sim(params, device, ngpus);
             sim.run();
         }

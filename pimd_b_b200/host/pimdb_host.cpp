@@ -708,7 +708,7 @@ void Simulation::printReport(double wall_time) const {
     std::ofstream rep("output/report.txt", std::ios::out | std::ios::app);
     auto line = [&](const std::string& k, const auto& v) { rep << std::format("{:<40}\t:\t{}\n", k, v); };
     rep << "---------\nParameters\n---------\n";
-    if (bosonic) { line("Statistics", "Bosonic"); line("Bosonic algorithm", "Feldman-Hirshberg"); }
+    if (bosonic) { line("Statistics", "Bosonic"); line("Bosonic algorithm", params.cfg.exchange_alg == PIMDB_EXCH_FACTORIAL ? "Naive" : "Feldman-Hirshberg"); }
     else line("Statistics", "Boltzmannonic");
     line("Time propagation algorithm", propagator_type);
     line("Periodic boundary conditions", pbc);

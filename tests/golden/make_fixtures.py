@@ -156,6 +156,65 @@ def make_refprobe():
     print("wrote refprobe.npz", sum(v.nbytes for v in out.values()) // 1024, "KiB raw")
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# The reference's compile-time alternative exchange class (-DFACTORIAL_BOSONIC_ALGORITHM, the sum over all N! permutations):
+# its two golden regression cases, and raw outputs of the unmodified reference BUILT WITH THAT FLAG
+# (oracle/_ref/ref_probe_ndim3_factorial, oracle/Makefile) on seeded inputs.
+FACTORIAL_CASES = ["bosonic_factorial_harmonic", "bosonic_factorial_harmonic_dynamics"]
+
+
+def factorial_probe_configs():
+    rng = np.random.default_rng(20261018)
+    items = {}
+    base = dict(ndim=3, bosonic=True, fixcom=False, temperature=5.802 * KELVIN, mass=1.0, interaction="free",
+                external="harmonic", ext_omega=3 * MEV, thermostat="langevin", dt=FEMTOSECOND, exchange_alg="factorial",
+                obs_classical="kelvin", obs_bosonic="true")
+    c = SimConfig(**base, nbeads=4, natoms=3, pbc=False, size=300.0, seed=7)
+    items["factorial_trap_n3"] = (c, rng.uniform(-20, 20, size=(4, 3, 3)), maxwell_momenta(c, rng))
+    c = SimConfig(**base, nbeads=3, natoms=5, pbc=True, size=60.0, seed=8)
+    items["factorial_trap_n5_pbc"] = (c, rng.uniform(-40, 40, size=(3, 5, 3)), maxwell_momenta(c, rng))
+    c = SimConfig(**{**base, "fixcom": True, "thermostat": "none"}, nbeads=8, natoms=7, pbc=False, size=300.0, seed=9)
+    items["factorial_trap_n7_nve_fixcom"] = (c, rng.uniform(-20, 20, size=(8, 7, 3)), maxwell_momenta(c, rng))
+    c = SimConfig(**{**base, "interaction": "harmonic", "int_omega": 1 * MEV}, nbeads=2, natoms=4, pbc=False, size=300.0, seed=10)
+    items["factorial_pair_n4_two_beads"] = (c, rng.uniform(-20, 20, size=(2, 4, 3)), maxwell_momenta(c, rng))
+    return items
+
+
+def make_reffactorial():
+    out = {}
+    for case in FACTORIAL_CASES:
+        d = REF_CASES / case
+        out[f"{case}/ini"] = np.array(next(d.glob("*.ini")).read_text())
+        so = pio.read_simulation_out(str(d / "simulation.out"))
+        out[f"{case}/simout_columns"] = np.array(list(so.keys()))
+        out[f"{case}/simout"] = np.stack(list(so.values()), axis=1)
+        if (d / "position_0.xyz").exists():
+            nb = len(list(d.glob("position_*.xyz")))
+            xs, fs = [], []
+            for b in range(nb):
+                xf = pio.read_dump_frames(str(d / f"position_{b}.xyz"), 3)
+                ff = pio.read_dump_frames(str(d / f"force_{b}.dat"), 3)
+                sel = [1, min(50, len(xf) - 2), len(xf) - 1]
+                xs.append([xf[i] for i in sel])
+                fs.append([ff[i] for i in sel])
+            out[f"{case}/x"] = np.transpose(np.asarray(xs), (1, 0, 2, 3))
+            out[f"{case}/f"] = np.transpose(np.asarray(fs), (1, 0, 2, 3))
+    for name, (cfg, x, p) in factorial_probe_configs().items():
+        out[f"{name}/cfg"] = np.array(repr(cfg.as_dict()))
+        out[f"{name}/x"] = x
+        out[f"{name}/p"] = p
+        r = run_ref_probe(cfg, x, p, "forces")
+        for k in ("f", "f_spring", "f_phys"):
+            out[f"{name}/{k}"] = r[k]
+        out[f"{name}/obs_names"] = np.array(list(r["obs"].keys()))
+        out[f"{name}/obs_values"] = np.array(list(r["obs"].values()))
+        t = run_ref_probe(cfg, x, p, "traj", k=12, every=12)
+        for k in ("x", "p", "f"):
+            out[f"{name}/traj12_{k}"] = t[f"{k}_12"]
+    np.savez_compressed(OUT / "reffactorial.npz", **out)
+    print("wrote reffactorial.npz", sum(v.nbytes for v in out.values()) // 1024, "KiB raw")
+
+
 E2E_INIS = {
     # the reference's own initial conditions (mt19937(seed+bead): uniform positions, Maxwell-Boltzmann momenta) and
     # no noise -> the whole run is deterministic and comparable file by file
@@ -286,6 +345,12 @@ def make_e2e():
 
 
 if __name__ == "__main__":
-    make_refcases()
-    make_refprobe()
-    make_e2e()
+    which = sys.argv[1:] or ["refcases", "refprobe", "e2e", "factorial"]
+    if "refcases" in which:
+        make_refcases()
+    if "refprobe" in which:
+        make_refprobe()
+    if "e2e" in which:
+        make_e2e()
+    if "factorial" in which:
+        make_reffactorial()

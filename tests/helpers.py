@@ -40,6 +40,7 @@ class OrcConfig(C.Structure):
         ("nchains", C.c_int),
         ("ext_strength", C.c_double), ("ext_location", C.c_double),
         ("ext_amplitude", C.c_double), ("ext_phase", C.c_double),
+        ("factorial", C.c_int),
     ]
 
 
@@ -123,7 +124,8 @@ def to_orc_config(cfg: SimConfig) -> OrcConfig:
         cutoff=cfg.cutoff, mass=cfg.mass, temperature=cfg.temperature, dt=cfg.dt, gamma=cfg.gamma,
         size=cfg.size, seed=cfg.seed, nchains=cfg.nchains,
         ext_strength=cfg.ext_strength, ext_location=cfg.ext_location,
-        ext_amplitude=cfg.ext_amplitude, ext_phase=cfg.ext_phase)
+        ext_amplitude=cfg.ext_amplitude, ext_phase=cfg.ext_phase,
+        factorial=int(getattr(cfg, "exchange_alg", "quadratic") == "factorial"))
 
 
 class Oracle:
@@ -194,6 +196,8 @@ def run_ref_probe(cfg: SimConfig, x, p=None, mode="forces", k=1, every=None, tim
     Returns {name: ndarray} for every *.bin written plus 'obs' / 'exch_scalars' dicts.
     """
     exe = REF_DIR / f"ref_probe_ndim{cfg.ndim}"
+    if getattr(cfg, "exchange_alg", "quadratic") == "factorial":      # the reference's compile-time alternative (NDIM = 3 build)
+        exe = REF_DIR / "ref_probe_ndim3_factorial"
     P, N, D = cfg.nbeads, cfg.natoms, cfg.ndim
     tmp = Path(tempfile.mkdtemp(prefix="refprobe_"))
     try:

@@ -399,3 +399,63 @@ def test_fixcom_with_odd_particle_count_in_the_fused_step(gpu_required, rng):
     for w in ("x", "p", "f"):
         assert relerr(a.get(w), b.get(w)) < 1e-12, w
     a.close(); b.close()
+
+
+# ----------------------------------------------------------------------------- factorial exchange (the reference's other class)
+REFFACT = np.load(GOLDEN_DIR / "reffactorial.npz")
+FACT_PROBES = sorted({k.split("/")[0] for k in REFFACT.files if k.startswith("factorial_")})
+
+
+@pytest.mark.parametrize("case", FACT_PROBES)
+def test_factorial_exchange_matches_reference_factorial_build(gpu_required, case):
+    """exchange_alg = "factorial" (csrc/factorial.cu) against raw outputs of the unmodified reference built with
+    -DFACTORIAL_BOSONIC_ALGORITHM (tests/golden/reffactorial.npz): forces, estimators, NVE trajectory."""
+    cfg = SimConfig(**ast.literal_eval(str(REFFACT[f"{case}/cfg"])))
+    x, p = REFFACT[f"{case}/x"], REFFACT[f"{case}/p"]
+    sim = DeviceSim(cfg)
+    sim.upload(x, p)
+    sim.update_forces()
+    for w, k in (("f", "f"), ("f_spring", "f_spring"), ("f_phys", "f_phys")):
+        assert relerr(sim.get(w), REFFACT[f"{case}/{k}"]) < 1e-10, k
+    obs = sim.observables()
+    kelvin = wl.KELVIN
+    for name, val in zip(REFFACT[f"{case}/obs_names"], REFFACT[f"{case}/obs_values"]):
+        mine = obs[str(name)] / kelvin if name == "temperature" else obs[str(name)]
+        assert abs(mine - val) <= 1e-10 * max(abs(val), abs(obs["cl_spring"]), 1e-300), (name, mine, val)
+    if cfg.thermostat == "none":
+        fresh = DeviceSim(cfg)
+        fresh.upload(x, p)
+        fresh.step(12)
+        for w in ("x", "p", "f"):
+            assert relerr(fresh.get(w), REFFACT[f"{case}/traj12_{w}"]) < 1e-9, w
+        fresh.close()
+    else:   # the reference's own noise: the Langevin trajectory itself
+        import dataclasses
+        fresh = DeviceSim(dataclasses.replace(cfg, rng="ranmars"))
+        fresh.upload(x, p)
+        fresh.step(12)
+        for w in ("x", "p", "f"):
+            assert relerr(fresh.get(w), REFFACT[f"{case}/traj12_{w}"]) < 1e-9, w
+        fresh.close()
+    sim.close()
+
+
+def test_factorial_exchange_matches_oracle_on_random_inputs_and_rejects_large_n(gpu_required):
+    from tests.helpers import Oracle
+    rng = np.random.default_rng(42)
+    for N, P, pbc in ((1, 3, False), (2, 2, False), (4, 5, True), (8, 4, False)):
+        cfg = SimConfig(nbeads=P, natoms=N, ndim=3, bosonic=True, fixcom=False, pbc=pbc, temperature=5.802 * wl.KELVIN, mass=1.0,
+                        size=60.0 if pbc else 300.0, interaction="free", external="harmonic", ext_omega=3 * wl.MEV,
+                        thermostat="none", seed=1, dt=wl.FEMTOSECOND, exchange_alg="factorial")
+        x = rng.uniform(-25, 25, size=(P, N, 3))
+        sim, orc = DeviceSim(cfg), Oracle(cfg)
+        sim.upload(x, np.zeros_like(x))
+        orc.set("x", x)
+        sim.update_forces(); orc.update_forces()
+        assert relerr(sim.get("f"), orc.get("f")) < 1e-10, N
+        o, r = sim.observables(), orc.observables()
+        for k in ("kinetic", "cl_spring"):
+            assert abs(o[k] - r[k]) <= 1e-10 * abs(r[k]), (N, k)
+        sim.close(); orc.close()
+    with pytest.raises(ValueError, match="natoms <= 10"):
+        DeviceSim(SimConfig(nbeads=4, natoms=11, bosonic=True, exchange_alg="factorial"))

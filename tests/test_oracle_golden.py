@@ -107,3 +107,53 @@ def test_oracle_live_against_reference_binary():
         orc.run_iteration()
     for w in ("x", "p", "f"):
         assert np.array_equal(orc.get(w), ref[f"{w}_8"])
+
+
+# ----------------------------------------------------------------------------- factorial exchange (the reference's other class)
+REFFACT = np.load(GOLDEN_DIR / "reffactorial.npz")
+FACT_PROBES = sorted({k.split("/")[0] for k in REFFACT.files if k.startswith("factorial_")})
+
+
+@pytest.mark.parametrize("case", FACT_PROBES)
+def test_oracle_factorial_exchange_bit_identical_to_reference_factorial_build(case):
+    """oracle (cfg.exchange_alg = "factorial", restating src/bosonic_exchange/factorial_bosonic_exchange.cpp) against raw
+    outputs of the unmodified reference built with -DFACTORIAL_BOSONIC_ALGORITHM (tests/golden/make_fixtures.py factorial)."""
+    cfg = SimConfig(**ast.literal_eval(str(REFFACT[f"{case}/cfg"])))
+    assert cfg.exchange_alg == "factorial"
+    x, p = REFFACT[f"{case}/x"], REFFACT[f"{case}/p"]
+    orc = Oracle(cfg)
+    orc.set("x", x)
+    orc.set("p", p)
+    orc.update_forces()
+    for w, k in (("f", "f"), ("s", "f_spring"), ("e", "f_phys")):
+        assert np.array_equal(orc.get(w), REFFACT[f"{case}/{k}"]), k
+    obs = orc.observables()
+    kelvin = convert_to_internal("temperature", "kelvin", 1.0)
+    for name, val in zip(REFFACT[f"{case}/obs_names"], REFFACT[f"{case}/obs_values"]):
+        mine = obs[str(name)] / kelvin if name == "temperature" else obs[str(name)]
+        assert abs(mine - val) <= 4e-16 * max(abs(val), abs(obs["cl_spring"]), 1e-300), (name, mine, val)
+    orc2 = Oracle(cfg)
+    orc2.set("x", x)
+    orc2.set("p", p)
+    for _ in range(12):
+        orc2.run_iteration()
+    for w in ("x", "p", "f"):
+        assert np.array_equal(orc2.get(w), REFFACT[f"{case}/traj12_{w}"]), (case, w)
+    orc.close(); orc2.close()
+
+
+def test_oracle_factorial_exchange_reproduces_reference_golden_force_frames(tmp_path):
+    """The reference's own golden case of its factorial build (tests/cases/bosonic_factorial_harmonic_dynamics): every
+    dumped position frame -> the dumped force frame."""
+    import dataclasses
+    case = "bosonic_factorial_harmonic_dynamics"
+    cfg = dataclasses.replace(_cfg_from_ini_text(str(REFFACT[f"{case}/ini"]), tmp_path), exchange_alg="factorial")
+    ang = convert_to_internal("length", "angstrom", 1.0)
+    evang = convert_to_internal("force", "ev/ang", 1.0)
+    X, F = REFFACT[f"{case}/x"], REFFACT[f"{case}/f"]
+    orc = Oracle(cfg)
+    for frame in range(X.shape[0]):
+        orc.set("x", X[frame] * ang)
+        orc.update_forces()
+        assert relerr(orc.get("f"), F[frame] * evang) < 5e-12, frame
+    orc.close()
