@@ -308,7 +308,7 @@ extern "C" int pimdb_create(const pimdb_config* cfg, pimdb_sim** out) {
         // cross-check recurrences (PIMDB_EXCH_NOBLOCKED=1) only
         const bool scalar_path = !s->factorial && (s->N > 8192 || getenv("PIMDB_EXCH_NOBLOCKED"));
         if (s->factorial) CREATE_TRY(cudaMalloc(&s->fact_work, sizeof(double) * (5 * NN + s->N)));
-        if (scalar_path) CREATE_TRY(cudaMalloc(&s->exC, sizeof(int4) * 2 * NN));
+        if (scalar_path || (!s->factorial && s->N <= 512)) CREATE_TRY(cudaMalloc(&s->exC, sizeof(int4) * 2 * NN));   // (N <= 512: kept beside the tiles)
         if (!scalar_path && !s->factorial) {  // block-scaled factor tiles + diagonal-block inverses of the blocked recurrence (exchange.cu)
             const size_t nbk = (size_t)((s->N + 31) / 32);
             CREATE_TRY(cudaMalloc(&s->exK, sizeof(double) * 2 * nbk * nbk * 1024));      // 32 x 32 tiles, forward | backward

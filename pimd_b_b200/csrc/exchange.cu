@@ -154,7 +154,7 @@ __device__ __forceinline__ double cycle_energy(const ExArgs& a, int u, int v) {
 // tiles): forward c(r, v), v >= r; backward c(v, r) / (r + 1), v <= r -- the same operations in the same order as the
 // tile kernel, so the value is bit-identical to what that kernel scaled into its tile.
 template <bool FWD>
-__device__ __forceinline__ int4 factor_exact(const ExArgs& a, int r, int v);
+__device__ __noinline__ int4 factor_exact(const ExArgs& a, int r, int v);
 
 // ---------------------------------------------------------------- 1. prefix sums A(w), one block
 template <int D>
@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(1024) k_exch_prefix(ExArgs a) {
 }
 
 template <bool FWD>
-__device__ __forceinline__ int4 factor_exact(const ExArgs& a, int r, int v) {
+__device__ __noinline__ int4 factor_exact(const ExArgs& a, int r, int v) {
     const int u = FWD ? r : v, w = FWD ? v : r;        // u <= w
     double d2 = 0.0;
     for (int c = 0; c < a.D; ++c) {                    // dist2<D>(a, x1, u, xP, w) with the dimension at run time
@@ -218,10 +218,7 @@ __device__ __forceinline__ int4 factor_exact(const ExArgs& a, int r, int v) {
 // forces, estimators, the probability table) recomputes the factors instead of reading the tiles. Called by every thread
 // of a block.
 __device__ __forceinline__ bool any_exact_block(const ExArgs& a) {
-    const int nb = (a.N + 31) >> 5;
-    bool e = false;
-    for (int i = threadIdx.x; i < nb; i += blockDim.x) e = e || (a.statf[i] & 15) == 2 || (a.statb[i] & 15) == 2;
-    return __syncthreads_or(e);
+    return *(volatile const int*)&a.sync[0] != 0;      // raised by the recurrence kernels, reset by the next tile kernel
 }
 
 // ---------------------------------------------------------------- 2. Boltzmann factors, fully parallel
@@ -376,6 +373,7 @@ __global__ void __launch_bounds__(1024, 2) k_exch_coeff_tiles(ExArgs a) {
     grid_dependency_wait();      // (a captured step launches this grid early behind the integrator kernel that moves the beads)
     tl_begin(a.tl0);
     grid_launch_dependents();    // the recurrence kernel may take its SMs now; it waits for this grid before it reads the tiles
+    if (blockIdx.x == 0 && threadIdx.x == 0) a.sync[0] = 0;   // "a block of these tables was solved exactly": raised by the recurrences
     peer_wait_halos(a.halo_flag, a.halo_seq, a.timeout_ns, a.err);
     const int N = a.N, nb = (N + 31) >> 5;
     const int rb = a.tiles_diag_only ? blockIdx.x : blockIdx.x / nb, sb = a.tiles_diag_only ? blockIdx.x : blockIdx.x % nb;
@@ -423,10 +421,16 @@ __global__ void __launch_bounds__(1024, 2) k_exch_coeff_tiles(ExArgs a) {
         const Ext c = ext_exp_neg(y < 0.0 ? 0.0 : y);   // (a NaN position stays NaN and is reported, like the reference)
         // (the factors live on only as block-scaled tiles + block exponents: 8 bytes instead of 24 per entry, which is what
         // bounds this kernel from N ~ 2000 on; the exact paths of the recurrences recompute what they need, factor_exact)
-        if (sc >= r) { mf = c.m; ef = c.e; }
+        // (a.Cf: up to N = 512 the 16-byte entries are kept as well -- 8 MB, L2 resident -- because the exterior forces read a
+        // contiguous row of them 1.7 us faster than the same row spread over 16 tiles)
+        if (sc >= r) {
+            mf = c.m; ef = c.e;
+            if (a.Cf) a.Cf[(long long)r * N + sc] = ext_pack(c.m, c.e);
+        }
         if (sc <= r) {   // backward: the 1/(p+1) weight of the sum (p = r) is folded in here, off the chain
             const Ext cb = ext_normalize(c.m * (1.0 / (double)(r + 1)), c.e);
             mb = cb.m; eb = cb.e;
+            if (a.Cb) a.Cb[(long long)r * N + sc] = ext_pack(cb.m, cb.e);
         }
     }
     s_ef[ty][tx] = ef;
@@ -1121,7 +1125,10 @@ __device__ __forceinline__ void recur_blocked(const ExArgs& a, double* smem_d) {
         a.dbg[192 + 2048 + (FWD ? 0 : 16) + warp] = t_own0;
     }
     __syncthreads();
-    if (tid < nb) (FWD ? a.statf : a.statb)[tid] = tid < npos ? sFlag[tid] + 16 * sReason[tid] : 0;
+    if (tid < nb) {
+        (FWD ? a.statf : a.statb)[tid] = tid < npos ? sFlag[tid] + 16 * sReason[tid] : 0;
+        if (tid < npos && sFlag[tid] == 2) atomicOr(&a.sync[0], 1);
+    }
     if (tid == 0) a.sync[FWD ? 2 : 3] += 1;          // this generation is consumed
 
     // V = -(ln W)/beta in parallel; publish W (normalised) for the force kernel
@@ -1457,7 +1464,7 @@ __device__ __forceinline__ void recur_cluster(const ExArgs& a, double* smem_d) {
                 publish_word(2, 0);
             }
         }
-        if (lane == 0) (FWD ? a.statf : a.statb)[mypos] = mode;
+        if (lane == 0) { (FWD ? a.statf : a.statb)[mypos] = mode; if (mode == 2) atomicOr(&a.sync[0], 1); }
     }
     if (has_block && n_own <= 0 && lane == 0) {
         (FWD ? a.statf : a.statb)[mypos] = 0;
@@ -1759,7 +1766,7 @@ __device__ __forceinline__ void recur_cluster_multi(const ExArgs& a, double* sme
                     for (int k = 0; k < kClusterSize; ++k) st_cluster_b64(map_to_cta(&sWord[pos], dest(k)), wb);
                 }
             }
-            if (lane == 0) (FWD ? a.statf : a.statb)[pos] = mode;
+            if (lane == 0) { (FWD ? a.statf : a.statb)[pos] = mode; if (mode == 2) atomicOr(&a.sync[0], 1); }
         }
         (void)Eq;
     }
@@ -1800,10 +1807,9 @@ constexpr int kFU = 16;                      // terms per lane held in flight (c
 // (At most 160 registers: 160 x 128 = 20480 is exactly what ONE retiring pair-tile block (80 registers x 256 threads) frees,
 // so a block of this kernel can take the first SM slot that opens up while the pair tiles are still being dispatched; at 165
 // it had to wait for two neighbouring slots, i.e. for the tail of the pair-tile grid.)
-template <int D, int STAGE>
-__global__ void __maxnreg__(160) k_exch_forces(ExArgs a) {   // (blocks of 32 * kFW threads; __maxnreg__ excludes __launch_bounds__)
-    extern __shared__ __align__(16) double fsm[];
-    tl_begin(a.tl2);
+// KSRC: the factors come from the block-scaled tiles (N > 512) instead of the 16-byte tables
+template <int D, int STAGE, bool KSRC, bool EXACT>
+__device__ __forceinline__ void exch_forces_body(const ExArgs& a, double* fsm) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int N = a.N;
     const int which = blockIdx.x & 1;         // 0: first bead, 1: last bead
@@ -1838,7 +1844,7 @@ __global__ void __maxnreg__(160) k_exch_forces(ExArgs a) {   // (blocks of 32 * 
     const int4* Ctab = which == 0 ? a.Cf : a.Cb;             // (STAGE == 0 only: N beyond the block-scaled tiles)
     const double* Ktab = which == 0 ? a.Kf : a.Kb;           // block-scaled factor tiles, 32 x 32, [row block][column block]
     const int nbk = (N + 31) >> 5;
-    const bool exact = STAGE ? any_exact_block(a) : false;   // (block-uniform) recompute the factors instead of reading tiles
+    constexpr bool exact = EXACT;   // recompute the factors instead of reading tiles (see any_exact_block)
     for (int l = blk * kFW + warp; active && l < N; l += nblk * kFW) {
         // first bead: f_l = k [ sum_{u=max(0,l-1)}^{N-1} P(u->l) mi(r^P_u - r^1_l) + mi(r^2_l - r^1_l) ]
         //             P(u->l) = W[l] c(l,u) Wb[u+1] / ((u+1) W[N]),  P(l-1->l) = 1 - W[l] Wb[l] / W[N]
@@ -1852,10 +1858,10 @@ __global__ void __maxnreg__(160) k_exch_forces(ExArgs a) {   // (blocks of 32 * 
         double xl[D], acc[D];
 #pragma unroll
         for (int c = 0; c < D; ++c) { xl[c] = xs[(size_t)c * N + l]; acc[c] = 0.0; }
-        const int4* Crow = STAGE ? nullptr : Ctab + (size_t)l * N;
+        const int4* Crow = KSRC ? nullptr : Ctab + (size_t)l * N;
         // row l of the factor matrix inside its row block of tiles: element u sits at Krow[(u >> 5) * 1024 + (u & 31)], and
         // equals the factor divided by 2^B[l / 32][u] (exactly: a power-of-two scaling)
-        const double* Krow = STAGE ? Ktab + (size_t)(l >> 5) * nbk * 1024 + (l & 31) * 32 : nullptr;
+        const double* Krow = KSRC ? Ktab + (size_t)(l >> 5) * nbk * 1024 + (l & 31) * 32 : nullptr;
         // Upper bound of a term's binary exponent from the block-scaled tables: B[l/32][u] >= exponent of the factor
         // (l, u), so  e(term) <= el + B + e(g_u) + 3.  Below -1080 the connection probability is exactly 0 (the same
         // cut ext_to_double applies); a 32-wide chunk whose lanes are all below it is skipped before its factors are
@@ -1863,8 +1869,8 @@ __global__ void __maxnreg__(160) k_exch_forces(ExArgs a) {   // (blocks of 32 * 
         const int* Brow = STAGE ? (which == 0 ? a.Bf : a.Bb) + (size_t)(l >> 5) * N : nullptr;
         for (int ub = ulo; ub <= uhi; ub += 32 * kFU) {     // warp-uniform trip count (votes inside)
             const int u0 = ub + lane;
-            int4 cv[STAGE ? 1 : kFU];
-            double kv[STAGE ? kFU : 1];
+            int4 cv[KSRC ? 1 : kFU];
+            double kv[KSRC ? kFU : 1];
             int bexp[STAGE ? kFU : 1];
             unsigned live = ~0u;                  // bit k: chunk k of this batch may hold a non-zero probability
             if (STAGE) {
@@ -1882,12 +1888,12 @@ __global__ void __maxnreg__(160) k_exch_forces(ExArgs a) {   // (blocks of 32 * 
                 }
             }
             // (all loads of the batch are issued before the first is used; the rarely taken recompute path sits outside that loop)
-            if (!STAGE || !exact) {
+            if (!KSRC || !exact) {
 #pragma unroll
                 for (int k = 0; k < kFU; ++k) {
                     const int u = u0 + 32 * k;
                     const bool want = ((live >> k) & 1u) && (u <= uhi && u != special);
-                    if (STAGE) kv[k] = want ? __ldg(Krow + (size_t)(u >> 5) * 1024 + (u & 31)) : 0.0;
+                    if (KSRC) kv[k] = want ? __ldg(Krow + (size_t)(u >> 5) * 1024 + (u & 31)) : 0.0;
                     else cv[k] = want ? __ldg(Crow + u) : make_int4(0, 0, 0, kExtZeroExp);
                 }
             } else {
@@ -1913,7 +1919,7 @@ __global__ void __maxnreg__(160) k_exch_forces(ExArgs a) {   // (blocks of 32 * 
                     } else {
                         int e;
                         const double g = g_of(u, e);
-                        if (STAGE) pr = ext_to_double(wl * kv[k] * g, el + bexp[k] + e);
+                        if (KSRC) pr = ext_to_double(wl * kv[k] * g, el + bexp[k] + e);
                         else pr = ext_to_double(wl * ext_m(cv[k]) * g, el + cv[k].z + e);
                     }
                     if (pr != 0.0) {   // most connection probabilities underflow to exactly 0: skip their separations
@@ -1940,6 +1946,21 @@ __global__ void __maxnreg__(160) k_exch_forces(ExArgs a) {   // (blocks of 32 * 
         }
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) a.Vb[0] = a.V[N];   // V_backwards[0] = V[N] (quadratic_bosonic_exchange.cpp:127)
+}
+
+// Two kernels, launched one behind the other: the common one reads the factor tiles and returns at once when a block of the
+// current tables was solved exactly; the other recomputes every factor and returns at once when none was. (One kernel with
+// both paths -- inlined or behind a call -- slowed the common path from 11 to 14-18 us at C3.)
+template <int D, int STAGE, bool KSRC, bool EXACT>
+__global__ void __maxnreg__(160) k_exch_forces(ExArgs a) {   // (blocks of 32 * kFW threads; __maxnreg__ excludes __launch_bounds__)
+    extern __shared__ __align__(16) double fsm[];
+    if (KSRC) {
+        if (EXACT) grid_dependency_wait();                   // (launched early behind the common kernel)
+        else grid_launch_dependents();
+        if (any_exact_block(a) != EXACT) return;
+    }
+    tl_begin(a.tl2);
+    exch_forces_body<D, STAGE, KSRC, EXACT>(a, fsm);
     tl_end(a.tl2);
 }
 
@@ -1951,7 +1972,7 @@ __global__ void __launch_bounds__(1024) k_exch_estimators(ExArgs a) {
     extern __shared__ double se[];   // e[0..N]
     __shared__ double red[32];
     const int tid = threadIdx.x, nt = blockDim.x, N = a.N;
-    const bool exact = a.Kf ? any_exact_block(a) : false;
+    const bool exact = (a.Kf && !a.Cf) ? any_exact_block(a) : false;
     double acc[R], iwm[R];
     int iwe[R];
 #pragma unroll
@@ -1975,7 +1996,7 @@ __global__ void __launch_bounds__(1024) k_exch_estimators(ExArgs a) {
                 if (exact) {
                     const int4 c = factor_exact<true>(a, j, v);
                     cm = ext_m(c); ce = c.z;
-                } else if (a.Kf) {   // block-scaled tile entry (j, v) and its block exponent
+                } else if (a.Kf && !a.Cf) {   // block-scaled tile entry (j, v) and its block exponent
                     cm = __ldg(&a.Kf[((size_t)(j >> 5) * ((N + 31) >> 5) + (v >> 5)) * 1024 + (j & 31) * 32 + (v & 31)]);
                     ce = __ldg(&a.Bf[(size_t)(j >> 5) * N + v]);
                 } else {
@@ -2027,7 +2048,7 @@ __global__ void k_exch_table_prob(ExArgs a, double* out) {
     const long long tot = (long long)N * N;
     const double iWN = 1.0 / a.Wm[N];
     const int eWN = a.We[N];
-    const bool exact = a.Kb ? any_exact_block(a) : false;
+    const bool exact = (a.Kb && !a.Cb) ? any_exact_block(a) : false;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += (long long)gridDim.x * blockDim.x) {
         const int l = (int)(i / N), u = (int)(i % N);
         double pr = 0.0;
@@ -2038,7 +2059,7 @@ __global__ void k_exch_table_prob(ExArgs a, double* out) {
             if (exact) {
                 const int4 c = factor_exact<false>(a, l, u);
                 cm = ext_m(c); ce = c.z;
-            } else if (a.Kb) {
+            } else if (a.Kb && !a.Cb) {
                 cm = a.Kb[((size_t)(l >> 5) * ((N + 31) >> 5) + (u >> 5)) * 1024 + (l & 31) * 32 + (u & 31)];
                 ce = a.Bb[(size_t)(l >> 5) * N + u];
             } else {
@@ -2068,7 +2089,7 @@ static ExArgs make_args(Sim* s) {
     const size_t NN = (size_t)s->N * s->N;
     a.A = s->exA;
     a.Inv = s->exA + s->N;
-    a.Cf = s->exC; a.Cb = s->exC + NN;
+    a.Cf = s->exC; a.Cb = s->exC ? s->exC + NN : nullptr;
     const size_t nbk = (size_t)((s->N + 31) / 32);
     // (PIMDB_EXCH_NOBLOCKED=1, read when the handle is created: the scalar recurrences on the 16-byte tables as a cross-check)
     a.Kf = s->exK; a.Kb = s->exK ? s->exK + nbk * nbk * 1024 : nullptr;
@@ -2250,17 +2271,23 @@ static int exchange_impl(Sim* s, cudaStream_t st, int part) {
             const int per_kind = std::max(1, std::min((s->N + ftasks * kFW - 1) / (ftasks * kFW), 4 * kNumSM));
             const size_t smem_w = sizeof(double) * ((size_t)s->N + 1 + ((s->N + 2) >> 1));            // weights + exponents
             const size_t smem_full = smem_w + sizeof(double) * (size_t)D * s->N;                         // + the bead slice
-            if (a.Kf && smem_full <= 200 * 1024) {
-                if (smem_full > 48 * 1024)
-                    cudaFuncSetAttribute(k_exch_forces<D, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_full);
-                launch_chain(s, k_exch_forces<D, 1>, a, 2 * per_kind, 32 * kFW, smem_full, st, 1, false);
-            } else if (a.Kf && smem_w <= 200 * 1024) {
-                if (smem_w > 48 * 1024)
-                    cudaFuncSetAttribute(k_exch_forces<D, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w);
-                launch_chain(s, k_exch_forces<D, 2>, a, 2 * per_kind, 32 * kFW, smem_w, st, 1, false);
-            } else {
-                launch_chain(s, k_exch_forces<D, 0>, a, 2 * per_kind, 32 * kFW, 0, st, 1, false);
-            }
+            auto forces = [&](auto common, auto recompute, size_t smem, bool two) {
+                if (smem > 48 * 1024) cudaFuncSetAttribute(common, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                launch_chain(s, common, a, 2 * per_kind, 32 * kFW, smem, st, 1, false);
+                if (two) {   // tile-sourced factors: the recompute twin rides behind and returns at once unless a block went exact
+                    if (smem > 48 * 1024) cudaFuncSetAttribute(recompute, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    launch_chain(s, recompute, a, 2 * per_kind, 32 * kFW, smem, st, 1, true);
+                    s->launches += 1;
+                }
+            };
+            if (a.Kf && a.Cf && smem_full <= 200 * 1024)          // N <= 512: staged operands, factors from the 16-byte tables
+                forces(k_exch_forces<D, 1, false, false>, k_exch_forces<D, 1, false, false>, smem_full, false);
+            else if (a.Kf && smem_full <= 200 * 1024)
+                forces(k_exch_forces<D, 1, true, false>, k_exch_forces<D, 1, true, true>, smem_full, true);
+            else if (a.Kf && smem_w <= 200 * 1024)
+                forces(k_exch_forces<D, 2, true, false>, k_exch_forces<D, 2, true, true>, smem_w, true);
+            else
+                forces(k_exch_forces<D, 0, false, false>, k_exch_forces<D, 0, false, false>, 0, false);
             s->launches += 1;
         }
     }

@@ -1,10 +1,10 @@
 #!/bin/bash
 # ncu launch list of the bench command (cold-cache, serialised: compare SHARES, not absolutes)
 # usage: profiles/run_launches.sh <tag>
-TAG=${1:-r01}
+TAG=${1:-r02}
 mkdir -p gpurun_out
 ncu --metrics gpu__time_duration.sum --clock-control none -s 200 -c 120 --csv \
-    --log-file gpurun_out/launches_${TAG}.csv env PIMDB_EXCH_SERIAL=1 python bench.py --steps 40 --warmup 5 --no-cpu-baseline > gpurun_out/bench_under_ncu_${TAG}.log 2>&1
+    --log-file gpurun_out/launches_${TAG}.csv python bench.py --steps 40 --warmup 5 --no-cpu-baseline --no-c4 > gpurun_out/bench_under_ncu_${TAG}.log 2>&1
 python - <<PY
 import csv, collections
 rows = [r for r in csv.reader(open("gpurun_out/launches_${TAG}.csv")) if len(r) > 5]

@@ -6,10 +6,10 @@ import json
 import sys
 from pathlib import Path
 
-tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
 ROOT = Path(__file__).resolve().parent.parent
 OUT = ROOT / "gpurun_out"
-KERNELS = ["k_pair_tiles", "k_exch_recur_cluster", "k_exch_coeff_tiles", "k_exch_forces", "k_integrate", "k_assemble"]
+KERNELS = ["k_pair_tiles", "k_exch_recur_cluster", "k_exch_coeff_tiles", "k_exch_forces", "k_integrate", "k_assemble"]   # (k_assemble: round 1 only)
 METRICS = {
     "gpu__time_duration.sum": "duration_us",
     "dram__bytes_read.sum": "dram_read_bytes",
@@ -77,5 +77,19 @@ for k, d in summary["kernels"].items():
 if "launch_list" in summary:
     lines += ["", "## launch list (gpu__time_duration.sum, 120 launches of the timed region; shares, not absolutes)", "", "```"]
     lines += summary["launch_list"] + ["```"]
+c5 = OUT / f"prof_{tag}_c5_exchange_raw.csv"
+if c5.exists():
+    rows = parse(c5)
+    summary["c5_exchange_chain"] = rows
+    lines += ["", "## C5 (N = 8192, P = 256): the kernels of one exchange chain, ncu --set full", "",
+              "| kernel | duration us | grid x block | regs | DRAM read | DRAM write | FP64 pipe % |", "|---|---|---|---|---|---|---|"]
+    tot = 0.0
+    for d in rows:
+        tot += d.get("dram_read_bytes", 0) + d.get("dram_write_bytes", 0)
+        lines.append(f"| {d['kernel']} | {d.get('duration_us', 0):.1f} | {int(d.get('grid', 0))} x {int(d.get('block', 0))} | {int(d.get('registers', 0))} | "
+                     f"{d.get('dram_read_bytes', 0) / 1e6:.1f} MB | {d.get('dram_write_bytes', 0) / 1e6:.1f} MB | {d.get('fp64_pipe_pct', 0):.1f} |")
+    lines.append(f"")
+    lines.append(f"DRAM traffic of the captured kernels: {tot / 1e6:.0f} MB")
+    (ROOT / "profiles" / f"{tag}_ncu_summary.json").write_text(json.dumps(summary, indent=1))
 (ROOT / "profiles" / f"{tag}_ncu_summary.md").write_text("\n".join(lines) + "\n")
 print("\n".join(lines))
