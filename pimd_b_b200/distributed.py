@@ -150,8 +150,15 @@ class ShardedSimulation:
             return False
         self.halo = "allgather"                       # point-to-point NCCL calls inside a capture hung on this stack
         try:
-            self._step_eager(2)                       # warm-up: NCCL communicators, lazy allocations
+            # warm-up (NCCL communicators, lazy allocations) must not advance the trajectory: put the state back afterwards
+            sim = getattr(self.shard, "sim", None)
+            saved = None if sim is None else (sim.get("x"), sim.get("p"), sim.get("f"))
+            self._step_eager(2)
             torch.cuda.synchronize()
+            if saved is not None:
+                sim.set("x", saved[0]); sim.set("p", saved[1]); sim.set("f", saved[2])
+                self.exchange_halos()
+                torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g, stream=self.shard.stream, capture_error_mode="thread_local"):
                 self._step_eager(1)
