@@ -197,6 +197,11 @@ int pimdb_zero_momentum(pimdb_sim* sim);
  * Requires all beads on the handle (bead sharding drives the phases below). */
 int pimdb_step(pimdb_sim* sim, int nsteps);
 
+/* pimdb_step(nsteps) followed by pimdb_download_state(x, p, f), with the copy of the coordinates overlapping the force
+ * evaluation of the last iteration (they are final once the drift has run). What a host loop that wants the state back
+ * after every step calls; page-locked `x` (otherwise the plain sequence is used). NULL p / f: not downloaded. */
+int pimdb_step_download(pimdb_sim* sim, int nsteps, double* x, double* p, double* f);
+
 /* Wait for the stream; reports deferred device-side errors (PIMDB_ERR_OVERFLOW). */
 int pimdb_synchronize(pimdb_sim* sim);
 

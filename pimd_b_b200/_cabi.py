@@ -76,6 +76,7 @@ SYMBOLS = {
     "pimdb_thermostat_step": (C.c_int, [_VP]),
     "pimdb_zero_momentum": (C.c_int, [_VP]),
     "pimdb_step": (C.c_int, [_VP, C.c_int]),
+    "pimdb_step_download": (C.c_int, [_VP, C.c_int, _VP, _VP, _VP]),
     "pimdb_synchronize": (C.c_int, [_VP]),
     "pimdb_exchange_prepare": (C.c_int, [_VP]),
     "pimdb_exchange_get": (C.c_int, [_VP, C.c_int, _VP, C.c_size_t]),

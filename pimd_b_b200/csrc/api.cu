@@ -19,6 +19,8 @@ using namespace pimdb;
 static thread_local std::string g_create_error;
 static int settle_momenta(Sim* s);
 static void allow_early_launch(Sim* s);
+static int maybe_download_x(Sim* s);
+static int join_download_x(Sim* s);
 
 #define API_TRY(expr)                      \
     do {                                   \
@@ -144,6 +146,11 @@ static void free_all(Sim* s) {
     cudaSetDevice(s->device);
     if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
     if (s->graph) cudaGraphDestroy(s->graph);
+    if (s->graph_dl_exec) cudaGraphExecDestroy(s->graph_dl_exec);
+    if (s->graph_dl) cudaGraphDestroy(s->graph_dl);
+    if (s->stream_c) cudaStreamDestroy(s->stream_c);
+    if (s->ev_dl_fork) cudaEventDestroy(s->ev_dl_fork);
+    if (s->ev_dl_join) cudaEventDestroy(s->ev_dl_join);
     for (auto* v : {&s->ev_pair, &s->ev_step, &s->ev_integ})
         for (auto& e : *v) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     cudaFree(s->x); cudaFree(s->p); cudaFree(s->f); cudaFree(s->fs); cudaFree(s->fp);
@@ -246,6 +253,9 @@ extern "C" int pimdb_create(const pimdb_config* cfg, pimdb_sim** out) {
     CREATE_TRY(cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
     CREATE_TRY(cudaEventCreateWithFlags(&s->ev_join, cudaEventDisableTiming));
     CREATE_TRY(cudaStreamCreateWithPriority(&s->stream_r, cudaStreamNonBlocking, hi));
+    CREATE_TRY(cudaStreamCreateWithPriority(&s->stream_c, cudaStreamNonBlocking, hi));
+    CREATE_TRY(cudaEventCreateWithFlags(&s->ev_dl_fork, cudaEventDisableTiming));
+    CREATE_TRY(cudaEventCreateWithFlags(&s->ev_dl_join, cudaEventDisableTiming));
     CREATE_TRY(cudaEventCreateWithFlags(&s->ev_join2, cudaEventDisableTiming));
 
     const size_t slab_bytes = s->S * sizeof(double);
@@ -743,6 +753,8 @@ static void propagator_into(Sim* s, Fuser& fz) {
         fz.drift();
         fz.flush();
         if (!s->all_local && !s->peer_on) return;   // host-driven sharding: the host exchanges halos, then calls phase 2
+        if (fz.rc == PIMDB_OK) fz.rc = maybe_download_x(s);
+        if (s->dl_forked) fz.chained = false;       // (an event record sits between the integrator kernel and the tile kernel)
         const bool fuse = fuse_assembly(s);
         if (fz.rc == PIMDB_OK) fz.rc = enqueue_forces(s, fuse, fz.chained);
         fz.chained = false;
@@ -752,6 +764,7 @@ static void propagator_into(Sim* s, Fuser& fz) {
         fz.chained = false;
         if (fz.rc == PIMDB_OK) fz.rc = launch_nm_propagate(s);   // half kick (physical forces) + exact ring rotation
         if (fz.rc == PIMDB_OK) fz.rc = s->peer_on ? launch_peer_push_halos(s) : launch_fill_halos(s);
+        if (fz.rc == PIMDB_OK) fz.rc = maybe_download_x(s);
         if (fz.rc == PIMDB_OK) fz.rc = enqueue_forces(s);
         fz.kick(true);
     }
@@ -782,6 +795,27 @@ static void allow_early_launch(Sim* s) {
     s->pdl_next = !off && cap == cudaStreamCaptureStatusActive;
 }
 
+// pimdb_step_download: the coordinates are final once the drift has run, long before the forces are; their transpose and
+// their PCIe copy go to a side stream here and overlap the force evaluation. Joined at the end of the iteration.
+static int maybe_download_x(Sim* s) {
+    if (!s->dl_hook || s->dl_forked) return PIMDB_OK;
+    PIMDB_CUDA_TRY(s, cudaEventRecord(s->ev_dl_fork, s->stream));
+    PIMDB_CUDA_TRY(s, cudaStreamWaitEvent(s->stream_c, s->ev_dl_fork, 0));
+    const double* src[1] = {s->x};
+    const bool halo[1] = {true};
+    API_TRY(launch_soa_to_aos(s, 1, src, halo, s->stream_c));
+    PIMDB_CUDA_TRY(s, cudaMemcpyAsync(s->dl_hook, s->stage_d, s->S * s->Ploc * sizeof(double), cudaMemcpyDeviceToHost, s->stream_c));
+    PIMDB_CUDA_TRY(s, cudaEventRecord(s->ev_dl_join, s->stream_c));
+    s->dl_forked = true;
+    return PIMDB_OK;
+}
+static int join_download_x(Sim* s) {
+    if (!s->dl_forked) return PIMDB_OK;
+    s->dl_forked = false;
+    PIMDB_CUDA_TRY(s, cudaStreamWaitEvent(s->stream, s->ev_dl_join, 0));
+    return PIMDB_OK;
+}
+
 // Bead shard, fixcom, Cartesian Langevin (or no) thermostat: the boundary slices leave one kernel early (OP_HALO_EARLY).
 static bool early_halo_push(const Sim* s) {
     static const bool off = getenv("PIMDB_PEER_LATE_HALO") != nullptr;   // A/B timing
@@ -797,9 +831,11 @@ static int enqueue_step(Sim* s, bool defer_last_com) {
         API_TRY(launch_integrate(s, o_pre | OP_SUM | OP_HALO_EARLY));
         allow_early_launch(s);
         API_TRY(launch_integrate(s, OP_SUBCM | OP_B | OP_A | OP_HALO_FIX));
+        API_TRY(maybe_download_x(s));
         const bool fuse = fuse_assembly(s);
-        API_TRY(enqueue_forces(s, fuse, true));
+        API_TRY(enqueue_forces(s, fuse, !s->dl_forked));
         API_TRY(launch_integrate(s, (fuse ? OP_ASSEMBLE : 0u) | OP_B | o_post));
+        API_TRY(join_download_x(s));
         s->z_owed = true;
         return PIMDB_OK;
     }
@@ -820,6 +856,7 @@ static int enqueue_step(Sim* s, bool defer_last_com) {
         }
     }
     fz.flush();
+    if (fz.rc == PIMDB_OK) fz.rc = join_download_x(s);
     return fz.rc;
 }
 
@@ -958,6 +995,55 @@ extern "C" int pimdb_step(pimdb_sim* sim, int nsteps) {
     }
     if (s->cfg.propagator == PIMDB_PROP_CARTESIAN && fuse_assembly(s)) s->split_stale = true;
     return PIMDB_OK;
+}
+
+// nsteps iterations, then the state on the host. The last iteration is a second captured graph in which the coordinates
+// leave for `x` as soon as the drift has produced them (their PCIe copy overlaps the force evaluation); momenta and forces
+// follow when the iteration is done. Page-locked destinations only get the overlap; otherwise step + download.
+extern "C" int pimdb_step_download(pimdb_sim* sim, int nsteps, double* x, double* p, double* f) {
+    Sim* s = reinterpret_cast<Sim*>(sim);
+    if (!s || nsteps < 1) return PIMDB_ERR_INVALID_ARGUMENT;
+    API_TRY(require_all_local(s, "pimdb_step_download"));
+    PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
+    if (!x || s->timing || !host_is_pinned(x)) {
+        API_TRY(pimdb_step(sim, nsteps));
+        return pimdb_download_state(sim, x, p, f);
+    }
+    if (nsteps > 1) API_TRY(pimdb_step(sim, nsteps - 1));
+    API_TRY(make_entry_state_uniform(s));
+    if (!s->graph_dl_exec || s->dl_x_host != x) {
+        if (s->graph_dl_exec) { cudaGraphExecDestroy(s->graph_dl_exec); s->graph_dl_exec = nullptr; }
+        if (s->graph_dl) { cudaGraphDestroy(s->graph_dl); s->graph_dl = nullptr; }
+        const unsigned long long before = s->launches;
+        const bool pending0 = s->p_shift_pending, owed0 = s->z_owed, stale0 = s->split_stale;
+        PIMDB_CUDA_TRY(s, cudaStreamBeginCapture(s->stream, cudaStreamCaptureModeThreadLocal));
+        s->dl_hook = x;
+        s->dl_forked = false;
+        int rc = enqueue_step(s, true);
+        s->dl_hook = nullptr;
+        cudaGraph_t g = nullptr;
+        cudaError_t ce = cudaStreamEndCapture(s->stream, &g);
+        s->p_shift_pending = pending0; s->z_owed = owed0; s->split_stale = stale0;
+        s->graph_dl_kernels = s->launches - before;
+        s->launches = before;
+        if (rc != PIMDB_OK) { if (g) cudaGraphDestroy(g); return rc; }
+        PIMDB_CUDA_TRY(s, ce);
+        s->graph_dl = g;
+        s->dl_x_host = x;
+        PIMDB_CUDA_TRY(s, cudaGraphInstantiate(&s->graph_dl_exec, s->graph_dl, 0));
+    }
+    PIMDB_CUDA_TRY(s, cudaGraphLaunch(s->graph_dl_exec, s->stream));
+    s->launches += s->graph_dl_kernels;
+    if (s->cfg.fixcom) {
+        if (lazy_closing_com(s)) { s->z_owed = true; s->p_shift_pending = false; }
+        else s->p_shift_pending = true;
+    }
+    if (s->cfg.propagator == PIMDB_PROP_CARTESIAN && fuse_assembly(s)) s->split_stale = true;
+    if (!p && !f) {
+        PIMDB_CUDA_TRY(s, cudaStreamSynchronize(s->stream));
+        return check_deferred(s);
+    }
+    return pimdb_download_state(sim, nullptr, p, f);
 }
 
 // phases for bead sharding; the host runs the collectives in between (include/pimdb200.h)

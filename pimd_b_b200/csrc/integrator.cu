@@ -713,11 +713,11 @@ int launch_aos_to_soa(Sim* s, int n, double* const* dst_soa, const bool* has_hal
     PIMDB_CUDA_TRY(s, cudaGetLastError());
     return PIMDB_OK;
 }
-int launch_soa_to_aos(Sim* s, int n, const double* const* src_soa, const bool* has_halo) {
+int launch_soa_to_aos(Sim* s, int n, const double* const* src_soa, const bool* has_halo, cudaStream_t st) {
     TransposeArgs a{};
     for (int i = 0; i < n; ++i) a.soa[i] = const_cast<double*>(src_soa[i]) + (has_halo[i] ? s->S : 0);
     a.aos = s->stage_d; a.n = n; a.N = s->N; a.D = s->D; a.total = (long long)s->Ploc * s->S;
-    k_soa_to_aos<<<grid_for(a.total * n, 256), 256, 0, s->stream>>>(a);
+    k_soa_to_aos<<<grid_for(a.total * n, 256), 256, 0, st ? st : s->stream>>>(a);
     s->launches += 1;
     PIMDB_CUDA_TRY(s, cudaGetLastError());
     return PIMDB_OK;

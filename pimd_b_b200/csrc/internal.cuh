@@ -150,6 +150,12 @@ struct Sim {
     // graph
     cudaGraph_t graph = nullptr; cudaGraphExec_t graph_exec = nullptr;
     unsigned long long graph_kernels = 0;
+    // pimdb_step_download: the same iteration with the coordinates leaving for the host as soon as they are final
+    cudaGraph_t graph_dl = nullptr; cudaGraphExec_t graph_dl_exec = nullptr;
+    unsigned long long graph_dl_kernels = 0;
+    double* dl_x_host = nullptr;       // page-locked destination baked into graph_dl
+    double* dl_hook = nullptr;         // set while an iteration is being enqueued with that hook
+    cudaStream_t stream_c = nullptr; cudaEvent_t ev_dl_fork = nullptr, ev_dl_join = nullptr; bool dl_forked = false;
     bool p_shift_pending = false;      // fixcom: COM shift computed but not yet subtracted from p
     // peer-memory bead sharding (pimdb_peer_attach)
     bool peer_on = false;
@@ -223,7 +229,7 @@ int launch_ranmars_fill(Sim* s);   // the next thermostat half-step's gaussians,
 int launch_nose_hoover(Sim* s);
 int launch_nose_hoover_energy(Sim* s, double* out_dev);
 int launch_aos_to_soa(Sim* s, int n, double* const* dst_soa, const bool* has_halo);          // up to 3 arrays per launch
-int launch_soa_to_aos(Sim* s, int n, const double* const* src_soa, const bool* has_halo);
+int launch_soa_to_aos(Sim* s, int n, const double* const* src_soa, const bool* has_halo, cudaStream_t st = nullptr);
 int launch_peer_wait_halos(Sim* s);
 
 }  // namespace pimdb

@@ -144,6 +144,11 @@ class DeviceSim:
     def step(self, nsteps: int = 1):
         self._ck(self.lib.pimdb_step(self.h, int(nsteps)))
 
+    def step_download(self, nsteps: int, x=None, p=None, f=None):
+        """``step(nsteps)`` + ``download(x, p, f)`` with the copy of x overlapping the last force evaluation."""
+        self._ck(self.lib.pimdb_step_download(self.h, int(nsteps), self._hostptr(self._checked(x)),
+                                              self._hostptr(self._checked(p)), self._hostptr(self._checked(f))))
+
     def step_phase(self, phase: int):
         self._ck(self.lib.pimdb_step_phase(self.h, int(phase)))
 

@@ -459,3 +459,31 @@ def test_factorial_exchange_matches_oracle_on_random_inputs_and_rejects_large_n(
         sim.close(); orc.close()
     with pytest.raises(ValueError, match="natoms <= 10"):
         DeviceSim(SimConfig(nbeads=4, natoms=11, bosonic=True, exchange_alg="factorial"))
+
+
+def test_step_download_equals_step_then_download(gpu_required):
+    """pimdb_step_download (coordinates copied to the host while the forces of the last iteration are still being computed)
+    returns exactly what pimdb_step + pimdb_download_state return, for page-locked and pageable destinations, and leaves the
+    handle in the same state."""
+    import torch
+    cfg = SimConfig(nbeads=8, natoms=64, ndim=3, bosonic=True, fixcom=True, pbc=True, temperature=2 * wl.KELVIN,
+                    mass=4.0026 * wl.DALTON, size=wl.helium_box(64), interaction="aziz", cutoff=-1.0 * wl.ANGSTROM,
+                    external="free", thermostat="langevin", seed=12345, dt=wl.FEMTOSECOND)
+    x, p = wl.initial_state(cfg, "c3", seed=1)
+    a, b = DeviceSim(cfg), DeviceSim(cfg)
+    a.upload(x, p); b.upload(x, p)
+    pin = torch.empty((3,) + x.shape, dtype=torch.float64, pin_memory=True)
+    hx, hp, hf = (pin[i].numpy() for i in range(3))
+    for nsteps in (1, 3, 1):
+        a.step(nsteps)
+        ref = (a.get("x"), a.get("p"), a.get("f"))
+        b.step_download(nsteps, hx, hp, hf)
+        for got, want in zip((hx, hp, hf), ref):
+            assert np.array_equal(got, want)
+    px, pp, pf = np.empty_like(x), np.empty_like(x), np.empty_like(x)      # pageable: the plain sequence
+    a.step(2); b.step_download(2, px, pp, pf)
+    assert np.array_equal(px, a.get("x")) and np.array_equal(pp, a.get("p")) and np.array_equal(pf, a.get("f"))
+    b.step_download(1, hx, None, None)
+    a.step(1)
+    assert np.array_equal(hx, a.get("x")) and np.array_equal(b.get("p"), a.get("p"))
+    a.close(); b.close()
