@@ -167,9 +167,13 @@ int pimdb_set_state(pimdb_sim* sim, int which, const double* host);
 int pimdb_get_state(pimdb_sim* sim, int which, double* host);
 
 /* Several arrays per call: one PCIe copy per array back to back and ONE transpose kernel (upload), one transpose kernel,
- * the copies and ONE synchronisation (download). NULL = skip that array. Same layout and buffer rules as above; the
- * caller's buffers may be reused as soon as the call returns; page-locked arrays that sit back to back in host memory
- * (x | p | f slices of one allocation) travel as a single copy. What a host loop that keeps its own copy of the state
+ * the copies and ONE synchronisation (download). NULL = skip that array. Same layout as above; page-locked arrays that sit
+ * back to back in host memory (x | p | f slices of one allocation) travel as a single copy.
+ * BUFFER LIFETIME: pimdb_set_state returns when the caller's buffer may be reused, whatever its kind. pimdb_upload_state
+ * does the same for pageable buffers, but with PAGE-LOCKED buffers it only enqueues the copy (the contract of
+ * cudaMemcpyAsync): the buffers must stay untouched until the next synchronising call on the handle returns
+ * (pimdb_download_state, pimdb_step_download, pimdb_get_state, pimdb_synchronize). That lets the host enqueue the step
+ * right behind the upload instead of waiting for the PCIe copy first. What a host loop that keeps its own copy of the state
  * pays per step (bench.py's e2e figure). */
 int pimdb_upload_state(pimdb_sim* sim, const double* x, const double* p);
 int pimdb_download_state(pimdb_sim* sim, double* x, double* p, double* f);

@@ -466,7 +466,10 @@ static int refresh_split_forces(Sim* s) {
 
 // One upload = one asynchronous PCIe copy per array (straight from a page-locked caller buffer, through the pinned
 // staging buffer otherwise) + ONE transpose kernel for all of them.
-static int upload_arrays(Sim* s, int n, const int* which, const double* const* host) {
+// `wait_for_copy`: return only when the PCIe copies out of the caller's buffers are done (pimdb_set_state: the caller may
+// reuse its buffer at once). pimdb_upload_state does not wait for page-locked buffers -- the usual contract of an
+// asynchronous copy, stated in the header -- so that the host can enqueue the step behind the upload without a bubble.
+static int upload_arrays(Sim* s, int n, const int* which, const double* const* host, bool wait_for_copy = true) {
     const size_t count = s->S * s->Ploc, bytes = count * sizeof(double);
     double* dst[3]; bool halo[3];
     if (n < 1 || n > 3) return fail(s, PIMDB_ERR_INVALID_ARGUMENT, "1 to 3 arrays per transfer");
@@ -497,7 +500,7 @@ static int upload_arrays(Sim* s, int n, const int* which, const double* const* h
     for (int i = 0; i < n; ++i) x_changed = x_changed || which[i] == PIMDB_X;
     if (x_changed && s->all_local) API_TRY(launch_fill_halos(s));
     if (x_changed && s->peer_on) API_TRY(launch_peer_push_halos(s));
-    PIMDB_CUDA_TRY(s, cudaEventSynchronize(s->ev_copy));
+    if (wait_for_copy || !all_pinned) PIMDB_CUDA_TRY(s, cudaEventSynchronize(s->ev_copy));
     return PIMDB_OK;
 }
 
@@ -549,7 +552,7 @@ extern "C" int pimdb_upload_state(pimdb_sim* sim, const double* x, const double*
     int which[2]; const double* host[2]; int n = 0;
     if (x) { which[n] = PIMDB_X; host[n++] = x; }
     if (p) { which[n] = PIMDB_P; host[n++] = p; }
-    return upload_arrays(s, n, which, host);
+    return upload_arrays(s, n, which, host, false);
 }
 
 extern "C" int pimdb_download_state(pimdb_sim* sim, double* x, double* p, double* f) {

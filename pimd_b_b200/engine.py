@@ -90,7 +90,9 @@ class DeviceSim:
         return a
 
     def upload(self, x=None, p=None):
-        """Several arrays per call: one PCIe copy each, one transpose kernel (pimdb_upload_state)."""
+        """Several arrays per call: one PCIe copy each, one transpose kernel (pimdb_upload_state). With page-locked arrays the
+        copy is only enqueued: keep them untouched until the next synchronising call (download / step_download / get /
+        synchronize) has returned. ``set`` waits for the copy."""
         x = None if x is None else np.ascontiguousarray(x, dtype=np.float64)
         p = None if p is None else np.ascontiguousarray(p, dtype=np.float64)
         self._ck(self.lib.pimdb_upload_state(self.h, self._hostptr(self._checked(x)), self._hostptr(self._checked(p))))
