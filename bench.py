@@ -283,7 +283,7 @@ def measure(run: Runner, K: int, W: int, sfreq: int, flush, clocks_rank0: bool, 
                 # what a host loop that keeps its own copy of the state pays per step: two calls
                 sim.upload(hx, hp)
                 if run.mode == "nccl":
-                    run.step(1); sim.download(hx, hp, hf)
+                    run.step(1); run.finish(); sim.download(hx, hp, hf)    # flush the host-driven phases before reading back
                 else:
                     sim.step_download(1, hx, hp, hf)      # = step(1) + download(x, p, f), x leaving while the forces are computed
             for _ in range(3):

@@ -669,164 +669,6 @@ __global__ void __launch_bounds__(1024) k_exch_recur(ExArgs a) {
     else recur_body<false, R, ST>(a, smem_d);
 }
 
-// ---------------------------------------------------------------- 3b. warp-decoupled recurrence (N <= 1024)
-// Same arithmetic as recur_body<., 1, .>, different synchronisation. The barrier version forces all warps through
-// every step in lock-step, so a step costs the serial latency of a whole warp's instruction stream (~480 cycles
-// measured). Here only ONE warp is on the dependency chain at any time:
-//   * "value #s" in step order is W[s] (forward) or Wb[N-s] (backward); step s turns it into value #s+1, owned by
-//     the thread of row r(s) = s (forward) / N-1-s (backward). 32 consecutive steps are owned by one warp.
-//   * inside its 32 owner steps a warp hands the new value from lane to lane with shuffles (no shared-memory round
-//     trip, no barrier: ~100 cycles per step, DFMA latency 8.3 and shuffle ~25 cycles measured, profiles/microbench.cu);
-//   * every value is also published to shared memory as ONE 16-byte entry {mantissa, exponent, tag = s+1}; data and
-//     flag travel in the same 128-bit store, so no fence sits on the chain. Every other warp consumes published
-//     values at its own pace -- four columns per poll, so it is faster than the owner and never holds it up -- and
-//     takes over as owner when its rows come up (one ~160-cycle shared-memory hand-off per 32 steps).
-//   Dependencies are acyclic (a warp only ever waits for values owned by earlier warps), so there is no deadlock.
-// smem: entries int4[N+2] | coefficient ring int4[ST][nt] | sInv[N+2]
-__device__ __forceinline__ int4 lds_volatile_v4(const int4* p) {
-    int4 r;
-    unsigned a = (unsigned)__cvta_generic_to_shared(p);
-    asm volatile("ld.volatile.shared.v4.s32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(a));
-    return r;
-}
-__device__ __forceinline__ void sts_volatile_v4(int4* p, int4 v) {
-    unsigned a = (unsigned)__cvta_generic_to_shared(p);
-    asm volatile("st.volatile.shared.v4.s32 [%0], {%1,%2,%3,%4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
-}
-
-template <bool FWD, int ST>
-__device__ __forceinline__ void recur_decoupled(const ExArgs& a, double* smem_d) {
-    static_assert(ST >= 8 && (ST & (ST - 1)) == 0, "ring depth must be a power of two >= 8");
-    constexpr int NB = 4;                            // columns a consumer applies per poll (2 was measured: slower hand-offs)
-    int tid;   // read %tid.x once into a register (the compiler otherwise re-reads the special register inside the chain loop)
-    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
-    const int nt = blockDim.x, N = a.N, lane = tid & 31, warp = tid >> 5;
-    int4* sW = (int4*)smem_d;                        // {m.lo, m.hi, e, tag}
-    int4* ring = sW + (N + 2);
-    double* sInv = (double*)(ring + (size_t)ST * nt);
-    const int nsteps = FWD ? N : N - 1;
-    const int dstep = FWD ? N : -N;
-    const int v = tid;                                              // my row
-    const bool row_ok = FWD ? (v < N) : (v >= 1 && v < N);
-    // steps in which my warp owns the completing row
-    const int own_lo = FWD ? 32 * warp : max(0, N - 1 - (32 * warp + 31));
-    const int own_hi = min(nsteps - 1, FWD ? 32 * warp + 31 : N - 1 - 32 * warp);
-
-    // does my row take part in step s ?  forward: v >= s; backward: v <= N-1-s  -- both are "s <= last_need", one
-    // integer compare against a per-thread constant (nothing is re-derived from %tid inside the chain loops)
-    const int last_need = row_ok ? (FWD ? v : N - 1 - v) : -1;
-    auto need = [&](int s) { return s <= last_need; };
-    auto idx_of = [&](int s) { return FWD ? s : N - s; };           // where value #s lives
-    const int4* gc = (FWD ? a.Cf : a.Cb) + (FWD ? 0 : (long long)(N - 1) * N) + tid;
-    int s_issue = 0;
-    auto issue = [&]() {
-        if (s_issue < nsteps && need(s_issue))
-            cp_async16(&ring[(s_issue & (ST - 1)) * nt + tid], gc);
-        cp_async_commit();
-        ++s_issue;
-        gc += dstep;
-    };
-    auto wait_value = [&](int s) {                                  // spin until value #s is published
-        int4 w;
-        do { w = lds_volatile_v4(&sW[idx_of(s)]); } while (w.w != s + 1);
-        return w;
-    };
-    // (Backing far consumers off with __nanosleep between polls was measured and does not help: the owner's step
-    // time is not set by the pollers.)
-
-    for (int i = tid; i <= N + 1; i += nt) sW[i] = make_int4(0, 0, 0, 0);
-    for (int i = tid; i <= N; i += nt) sInv[i] = i > 0 ? 1.0 / (double)i : 0.0;
-#pragma unroll
-    for (int s = 0; s < ST - 1; ++s) issue();
-    __syncthreads();
-    if (tid == 0) sts_volatile_v4(&sW[idx_of(0)], make_int4(__double2loint(1.0), __double2hiint(1.0), 0, 1));
-
-    double am = 0.0;
-    int ae = kExtZeroExp;
-    int s = 0;
-    const long long t_begin = a.dbg ? clock64() : 0;
-    // ---- consumer phase: columns owned by earlier warps; every row of my warp takes part in all of them
-    while (s < own_lo) {
-        if (own_lo - s >= NB) {
-            wait_value(s + NB - 1);                                 // values are published in order
-            cp_async_wait<ST - 1 - NB>();
-            double cm[NB], wm[NB];
-            int ce[NB], we[NB];
-#pragma unroll
-            for (int k = 0; k < NB; ++k) {
-                const int4 w = sW[idx_of(s + k)];
-                wm[k] = __hiloint2double(w.y, w.x);
-                we[k] = w.z;
-                const int4 c = ring[((s + k) & (ST - 1)) * nt + tid];
-                cm[k] = ext_m(c);
-                ce[k] = c.z;
-            }
-            if (row_ok) {
-#pragma unroll
-                for (int k = 0; k < NB; ++k) ext_fma(am, ae, cm[k], ce[k], wm[k], we[k]);
-            }
-#pragma unroll
-            for (int k = 0; k < NB; ++k) issue();
-            s += NB;
-        } else {
-            const int4 w = wait_value(s);
-            cp_async_wait<ST - 1 - NB>();
-            const int4 c = ring[(s & (ST - 1)) * nt + tid];
-            if (row_ok) ext_fma(am, ae, ext_m(c), c.z, __hiloint2double(w.y, w.x), w.z);
-            issue();
-            ++s;
-        }
-    }
-    const long long t_own0 = a.dbg ? clock64() : 0;
-    // ---- owner phase: the completing rows are my warp's; the chain runs lane to lane through shuffles
-    if (s <= own_hi) {
-        auto row_of = [&](int st) { return FWD ? st : (N - 1 - st); };
-        const int4 w0 = wait_value(s);
-        double wm = __hiloint2double(w0.y, w0.x);
-        int we = w0.z;
-#pragma unroll 1
-        for (; s <= own_hi; ++s) {
-            cp_async_wait<ST - 1 - NB>();
-            if (need(s)) {
-                const int4 c = ring[(s & (ST - 1)) * nt + tid];
-                ext_fma(am, ae, ext_m(c), c.z, wm, we);
-            }
-            const int lane_o = row_of(s) & 31;
-            const Ext fin = ext_normalize(FWD ? am * sInv[s + 1] : am, ae);
-            wm = __shfl_sync(kFullMask, fin.m, lane_o);
-            we = __shfl_sync(kFullMask, fin.e, lane_o);
-            if (lane == lane_o)
-                sts_volatile_v4(&sW[idx_of(s + 1)], make_int4(__double2loint(fin.m), __double2hiint(fin.m), fin.e, s + 2));
-            issue();
-        }
-    }
-    if (a.dbg && lane == 0) {
-        long long* o = a.dbg + ((FWD ? 0 : 32) + warp) * 3;
-        o[0] = t_own0 - t_begin;            // cycles spent as a consumer (incl. waiting)
-        o[1] = clock64() - t_own0;          // cycles spent as the owner
-        o[2] = t_begin;
-    }
-    cp_async_wait<0>();
-    __syncthreads();
-
-    // V = -(ln W)/beta in parallel; publish W for the force kernel
-    const double LN2 = 0.6931471805599453;
-    double* Wm_g = FWD ? a.Wm : a.Wbm;
-    int* We_g = FWD ? a.We : a.Wbe;
-    double* V_g = FWD ? a.V : a.Vb;
-    for (int i = (FWD ? 0 : 1) + tid; i <= N; i += nt) {
-        const int4 w = sW[i];
-        const Ext wn = ext_normalize(__hiloint2double(w.y, w.x), w.z);   // fast-path entries are not normalised
-        const double m = wn.m;
-        const int e = wn.e;
-        Wm_g[i] = m;
-        We_g[i] = e;
-        const double val = -(log(m) + (double)e * LN2) / a.beta;
-        if (!isfinite(val)) atomicOr(a.err, FWD ? kErrOverflowFwd : kErrOverflowBwd);
-        V_g[i] = (i == (FWD ? 0 : N)) ? 0.0 : val;
-    }
-}
-
 // (am, ae) += acc * 2^e for a plain non-negative double acc; out of line: it runs once per 32 columns
 static __device__ __noinline__ void ext_fold(double& am, int& ae, double acc, int e) {
     if (acc > 0.0 || acc != acc) {
@@ -837,15 +679,8 @@ static __device__ __noinline__ void ext_fold(double& am, int& ae, double acc, in
     }
 }
 
-template <int ST>
-__global__ void __launch_bounds__(1024) k_exch_recur_dec(ExArgs a) {
-    extern __shared__ __align__(16) double smem_d[];
-    if (blockIdx.x == 0) recur_decoupled<true, ST>(a, smem_d);
-    else recur_decoupled<false, ST>(a, smem_d);
-}
-
-// ---------------------------------------------------------------- 3d. blocked recurrence (N <= 512)
-// The two recurrences are triangular linear systems. The scalar kernels walk them one unknown at a time: N dependent
+// ---------------------------------------------------------------- 3d. blocked recurrence: the scheme (kernels in 3e / 3f)
+// The two recurrences are triangular linear systems. The scalar kernel (recur_body) walks them one unknown at a time: N dependent
 // steps of ~100-200 cycles. Here the system is solved 32 unknowns at a time: k_exch_coeff_tiles has already inverted
 // every 32 x 32 diagonal block (G and h, positions only -- off the chain), so the owner warp of block q turns "what
 // the earlier values contribute to my 32 rows" (A, one plain double per lane) into its 32 new values with ONE 32 x 32
@@ -856,7 +691,7 @@ __global__ void __launch_bounds__(1024) k_exch_recur_dec(ExArgs a) {
 //     is stored under the factor row it multiplies (r = s forward, N-1-s backward), so block q's 32 entries are
 //     sOm[32q .. 32q+31] in either direction.
 //   * the owner publishes its block as plain doubles omega relative to ONE binary exponent E_q (sOm / sEx), hands its
-//     last value to the next owner (sHand), fences, and raises the block's flag; every later warp then applies the
+//     last value to the next owner, fences, and raises the block's flag; every later warp then applies the
 //     block's 32 columns to its own rows as a plain dot product with the block-scaled factor tile K[q][warp] and folds
 //     it into its extended-range accumulator once.
 //   * factor tiles are contiguous 8 KB pieces (k_exch_coeff_tiles), fetched by TMA bulk copies (cp.async.bulk +
@@ -867,20 +702,8 @@ __global__ void __launch_bounds__(1024) k_exch_recur_dec(ExArgs a) {
 //     [2^-700, 2^300] (flag from the tile kernel), the accumulators entering the block are <= 2^600 on the block's
 //     scale, every new omega is a normal double in [2^-700, 2^300]. All terms are non-negative, so whatever underflows
 //     on the way is at least 2^-322 below the result it was added to. If any check fails the block is redone exactly:
-//     sequential extended-range steps from the untouched accumulators (the recur_decoupled arithmetic), flag value 2,
+//     sequential extended-range steps from the untouched accumulators (the recur_body arithmetic), flag value 2,
 //     and the consumers apply such a block column by column from the extended-range table.
-// smem: ring double[nb][3][512] | sOm double[32 nb] | sRho double[nb][32] | sHandOm double[nb+2] | mbarriers u64[nb][3]
-//       | sEx int[32 nb] | sHandE int[nb+2] | sFlag int[nb+2]
-__device__ __forceinline__ int lds_volatile_s32(const int* p) {
-    int r;
-    unsigned a = (unsigned)__cvta_generic_to_shared(p);
-    asm volatile("ld.volatile.shared.s32 %0, [%1];" : "=r"(r) : "r"(a) : "memory");
-    return r;
-}
-__device__ __forceinline__ void sts_volatile_s32(int* p, int v) {
-    unsigned a = (unsigned)__cvta_generic_to_shared(p);
-    asm volatile("st.volatile.shared.s32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
-}
 __device__ __forceinline__ void mbar_init(unsigned mbar, unsigned count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(mbar), "r"(count) : "memory");
 }
@@ -898,275 +721,17 @@ __device__ __forceinline__ void bulk_load(unsigned dst, const void* src, unsigne
                  ::"r"(dst), "l"(src), "r"(bytes), "r"(mbar) : "memory");
 }
 
-template <bool FWD>
-__device__ __forceinline__ void recur_blocked(const ExArgs& a, double* smem_d) {
-    constexpr int SLOTS = 3, HALF = 512;             // ring: 3 half tiles (16 factor rows x 32 lanes) per warp
-    int tid;
-    asm volatile("mov.u32 %0, %%tid.x;" : "=r"(tid));
-    const int nt = blockDim.x, N = a.N, lane = tid & 31, warp = tid >> 5, nb = nt >> 5;
-    const int nsteps = FWD ? N : N - 1;
-    const int npos = nsteps > 0 ? nb : 0;            // blocks that own at least one step
-    const int nb2 = (nb + 3) & ~1;
-    double* ring = smem_d;
-    double* sOm = ring + (size_t)nb * SLOTS * HALF;
-    double* sRho = sOm + 32 * nb;
-    double* sHandOm = sRho + 32 * nb;
-    unsigned long long* sBar = reinterpret_cast<unsigned long long*>(sHandOm + nb2);
-    int* sEx = reinterpret_cast<int*>(sBar + nb * SLOTS + (nb & 1));
-    int* sHandE = sEx + 32 * nb;
-    int* sFlag = sHandE + nb2;
-    int* sReason = sFlag + nb2;                      // why a block left the fast path (test aid): 1 accumulator range,
-                                                     // 2 hand-off value, 4 block inverse out of window, 8 new values out of window
-
-    auto g_lo = [&](int q) { return FWD ? 32 * q : max(0, N - 32 * (q + 1)); };
-    auto g_hi = [&](int q) { return min(nsteps - 1, FWD ? 32 * q + 31 : N - 1 - 32 * q); };
-    auto row_of = [&](int st) { return FWD ? st : (N - 1 - st); };  // factor row used by step st = row it completes
-    const int v = tid;                                              // my row
-    const bool row_ok = FWD ? (v < N) : (v >= 1 && v < N);
-    const int own_lo = g_lo(warp), own_hi = g_hi(warp), n_own = own_hi - own_lo + 1;
-    const int mypos = FWD ? warp : nb - 1 - warp;                   // my block's position in step order
-    const int last_need = row_ok ? (FWD ? v : N - 1 - v) : -1;
-    auto need = [&](int s) { return s <= last_need; };
-    const int* Bg = FWD ? a.Bf : a.Bb;
-    // my warp's factor tiles, one per earlier block in step order: K[q][warp], q = pos (forward) / nb-1-pos (backward)
-    const double* Ktile = (FWD ? a.Kf : a.Kb) + (size_t)warp * 1024;
-    const size_t tile_stride = (size_t)nb * 1024;
-    const int ntile_half = 2 * min(mypos, npos);                    // half tiles this warp consumes
-    double* const ring_w = ring + (size_t)warp * SLOTS * HALF;
-    const unsigned ring_s = (unsigned)__cvta_generic_to_shared(ring_w);
-    const unsigned bar_s = (unsigned)__cvta_generic_to_shared(sBar + warp * SLOTS);
-    auto issue_half = [&](int i) {                                  // lane 0 only: half tile #i -> slot i % 3
-        const int pos = i >> 1, q = FWD ? pos : nb - 1 - pos, slot = i % SLOTS;
-        bulk_load(ring_s + slot * HALF * 8, Ktile + (size_t)q * tile_stride + (i & 1) * HALF, HALF * 8, bar_s + slot * 8);
-    };
-
-    for (int i = tid; i < 32 * nb; i += nt) { sOm[i] = 0.0; sEx[i] = 0; }
-    for (int i = tid; i < nb2; i += nt) sFlag[i] = 0;
-    if (tid == 0) {
-        sHandOm[0] = 1.0; sHandE[0] = 0;
-    }
-    // The factor tiles and block inverses come from k_exch_coeff_tiles, the previous kernel on this stream. This kernel is
-    // launched with programmatic stream serialisation: its blocks may become resident (and run the set-up above) while the
-    // tile kernel is still running; everything below reads its output.
-    grid_dependency_wait();
-    __syncthreads();
-    if (lane == 0) {
-#pragma unroll
-        for (int k = 0; k < SLOTS; ++k) mbar_init(bar_s + k * 8, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async;" ::: "memory");      // shared (barrier init) and global (tiles written by a running kernel)
-        for (int i = 0; i < SLOTS && i < ntile_half; ++i) issue_half(i);
-    }
-    // row `lane`'s row of G (zero beyond the diagonal and for lanes without a row), h, and the block's validity flag
-    double Grow[32];
-    {
-        const double* Gg = (FWD ? a.Gf : a.Gb) + (size_t)warp * 1024 + lane;
-#pragma unroll
-        for (int k = 0; k < 32; ++k) Grow[k] = Gg[k * 32];
-    }
-    const double hrow = (FWD ? a.Hf : a.Hb)[warp * 32 + lane];
-    const int Gok = (FWD ? a.Gokf : a.Gokb)[warp];
-    const int Bown = row_ok ? Bg[warp * N + v] : kExtZeroExp;
-    __syncthreads();
-
-    double am = 0.0;                                 // extended-range accumulator of my row (normalised)
-    int ae = kExtZeroExp;
-    const long long t_begin = a.dbg ? clock64() : 0;
-    // ---- consumer phases: the blocks before mine in step order, each applied as soon as its flag is up
-    int Bnext = (mypos > 0 && row_ok) ? Bg[(FWD ? 0 : nb - 1) * N + v] : 0;
-#pragma unroll 1
-    for (int pos = 0; pos < mypos && pos < npos; ++pos) {
-        const int q = FWD ? pos : nb - 1 - pos;
-        const int Bq = Bnext;
-        if (pos + 1 < mypos && row_ok) Bnext = Bg[(FWD ? pos + 1 : nb - 2 - pos) * N + v];
-        int fl;
-        do { fl = lds_volatile_s32(&sFlag[pos]); } while (fl == 0);
-        long long* stamp = (a.dbg && lane == 0) ? a.dbg + 192 + (((FWD ? 0 : 16) + warp) * 16 + pos) * 4 : nullptr;
-        if (stamp) stamp[0] = clock64();             // flag seen
-        const double* om = sOm + 32 * q;
-        double acc0 = 0.0, acc1 = 0.0;
-#pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-            const int i = 2 * pos + h, slot = i % SLOTS;
-            mbar_wait(bar_s + slot * 8, (unsigned)(i / SLOTS) & 1u);
-            if (stamp) stamp[1 + h] = clock64();     // half tile landed
-            if (fl == 1) {
-                const double* kp = ring_w + slot * HALF + lane;
-                const double* op = om + 16 * h;
-#pragma unroll
-                for (int c = 0; c < 16; c += 4) {
-                    const double2 w01 = *reinterpret_cast<const double2*>(op + c);
-                    const double2 w23 = *reinterpret_cast<const double2*>(op + c + 2);
-                    acc0 = fma(kp[(c + 0) * 32], w01.x, acc0);
-                    acc1 = fma(kp[(c + 1) * 32], w01.y, acc1);
-                    acc0 = fma(kp[(c + 2) * 32], w23.x, acc0);
-                    acc1 = fma(kp[(c + 3) * 32], w23.y, acc1);
-                }
-            }
-            __syncwarp();
-            if (lane == 0 && i + SLOTS < ntile_half) {
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                issue_half(i + SLOTS);
-            }
-        }
-        if (stamp) stamp[3] = clock64();             // both halves applied
-        if (fl == 1) {
-            ext_fold(am, ae, acc0 + acc1, Bq + sEx[32 * q]);
-        } else {                                     // the block was solved exactly: entries are {mantissa, exponent} per value
-            const int s0 = g_lo(q), s1 = g_hi(q);
-#pragma unroll 1
-            for (int s = s0; s <= s1; ++s) {
-                if (need(s)) {
-                    const int r = row_of(s);
-                    const int4 c = factor_exact<FWD>(a, r, v);
-                    ext_fma(am, ae, ext_m(c), c.z, sOm[r], sEx[r]);
-                }
-            }
-        }
-    }
-    if (!row_ok) { am = 0.0; ae = kExtZeroExp; }     // (the tiles also hold factors of rows that take no part: backward row 0)
-    const long long t_own0 = a.dbg ? clock64() : 0;
-    // ---- owner phase
-    if (n_own > 0) {
-        const double hm = sHandOm[mypos];
-        const int he = sHandE[mypos];
-        const Ext n0 = ext_normalize(hm, he);
-        const int E = n0.e;
-        const double om0 = n0.m;
-        const int d = ae - E - Bown;
-        const double A = (am == 0.0) ? 0.0 : ext_to_double(am, min(d, 600));
-        bool exact = __any_sync(kFullMask, (am != 0.0) && (d > 600)) || !(om0 > 0.0) || !Gok;
-        int reason = (__any_sync(kFullMask, (am != 0.0) && (d > 600)) ? 1 : 0) | (!(om0 > 0.0) ? 2 : 0) | (!Gok ? 4 : 0);
-        // step index of my row inside the block = slot of my A (lanes without a row fill the unused slots with 0)
-        const int tt = FWD ? 0 : row_of(own_lo) & 31;
-        const int kslot = FWD ? lane : (tt - lane) & 31;
-        if (!exact) {
-            double* rho_w = sRho + warp * 32;
-            rho_w[kslot] = A;
-            __syncwarp();
-            double u0 = om0 * hrow, u1 = 0.0, u2 = 0.0, u3 = 0.0;
-#pragma unroll
-            for (int k = 0; k < 32; k += 4) {
-                const double2 r01 = *reinterpret_cast<const double2*>(rho_w + k);
-                const double2 r23 = *reinterpret_cast<const double2*>(rho_w + k + 2);
-                u0 = fma(Grow[k], r01.x, u0);
-                u1 = fma(Grow[k + 1], r01.y, u1);
-                u2 = fma(Grow[k + 2], r23.x, u2);
-                u3 = fma(Grow[k + 3], r23.y, u3);
-            }
-            const double u = (u0 + u1) + (u2 + u3);
-            const bool mine = kslot < n_own;
-            const unsigned hi = (unsigned)__double2hiint(u);
-            const bool okall = __all_sync(kFullMask, !mine || (hi - (323u << 20) < (1000u << 20)));
-            if (okall) {
-                if (mine) {
-                    if (kslot < n_own - 1) {
-                        const int r = row_of(own_lo + kslot + 1);
-                        sOm[r] = u;
-                        sEx[r] = E;
-                    } else {
-                        sHandOm[mypos + 1] = u;
-                        sHandE[mypos + 1] = E;
-                    }
-                }
-                if (lane == 0) {
-                    const int r = row_of(own_lo);
-                    sOm[r] = om0;
-                    sEx[r] = E;
-                }
-                __syncwarp();
-                __threadfence_block();
-                if (lane == 0) sts_volatile_s32(&sFlag[mypos], 1);
-            } else {
-                exact = true;
-                reason |= 8;
-            }
-        }
-        if (lane == 0) sReason[mypos] = reason;
-        if (exact) {
-            double wm = n0.m;                                         // (normalised: ext_fma wants moderate mantissas)
-            int we = n0.e;
-            if (lane == 0) {
-                const int r = row_of(own_lo);
-                sOm[r] = wm;
-                sEx[r] = we;
-            }
-#pragma unroll 1
-            for (int st = own_lo; st <= own_hi; ++st) {
-                if (need(st)) {
-                    const int4 c = factor_exact<FWD>(a, row_of(st), v);
-                    ext_fma(am, ae, ext_m(c), c.z, wm, we);
-                }
-                const int lane_o = row_of(st) & 31;
-                const Ext fin = ext_normalize(FWD ? am * a.Inv[st + 1] : am, ae);
-                wm = __shfl_sync(kFullMask, fin.m, lane_o);
-                we = __shfl_sync(kFullMask, fin.e, lane_o);
-                if (lane == lane_o) {
-                    if (st < own_hi) {
-                        const int r = row_of(st + 1);
-                        sOm[r] = fin.m;
-                        sEx[r] = fin.e;
-                    } else {
-                        sHandOm[mypos + 1] = fin.m;
-                        sHandE[mypos + 1] = fin.e;
-                    }
-                }
-            }
-            __syncwarp();
-            __threadfence_block();
-            if (lane == 0) sts_volatile_s32(&sFlag[mypos], 2);
-        }
-    }
-    if (a.dbg && lane == 0) {
-        long long* o = a.dbg + ((FWD ? 0 : 32) + warp) * 3;
-        o[0] = t_own0 - t_begin;            // cycles spent as a consumer (incl. waiting)
-        o[1] = clock64() - t_own0;          // cycles spent as the owner
-        o[2] = t_begin;
-        a.dbg[192 + 2048 + (FWD ? 0 : 16) + warp] = t_own0;
-    }
-    __syncthreads();
-    if (tid < nb) {
-        (FWD ? a.statf : a.statb)[tid] = tid < npos ? sFlag[tid] + 16 * sReason[tid] : 0;
-        if (tid < npos && sFlag[tid] == 2) atomicOr(&a.sync[0], 1);
-    }
-    if (tid == 0) a.sync[FWD ? 2 : 3] += 1;          // this generation is consumed
-
-    // V = -(ln W)/beta in parallel; publish W (normalised) for the force kernel
-    const double LN2 = 0.6931471805599453;
-    double* Wm_g = FWD ? a.Wm : a.Wbm;
-    int* We_g = FWD ? a.We : a.Wbe;
-    double* V_g = FWD ? a.V : a.Vb;
-    for (int i = (FWD ? 0 : 1) + tid; i <= N; i += nt) {
-        const int sv = FWD ? i : N - i;                              // value number
-        const int r = row_of(sv);
-        const Ext wn = sv < nsteps ? ext_normalize(sOm[r], sEx[r]) : ext_normalize(sHandOm[npos], sHandE[npos]);
-        Wm_g[i] = wn.m;
-        We_g[i] = wn.e;
-        const double val = -(log(wn.m) + (double)wn.e * LN2) / a.beta;
-        if (!isfinite(val)) atomicOr(a.err, FWD ? kErrOverflowFwd : kErrOverflowBwd);
-        V_g[i] = (i == (FWD ? 0 : N)) ? 0.0 : val;
-    }
-}
-
-__global__ void __launch_bounds__(512, 1) k_exch_recur_blocked(ExArgs a) {
-    extern __shared__ __align__(16) double smem_d[];
-    tl_begin(a.tl1);
-    if (blockIdx.x == 0) recur_blocked<true>(a, smem_d);
-    else recur_blocked<false>(a, smem_d);
-    tl_end(a.tl1);
-}
-
 // ---------------------------------------------------------------- 3e. blocked recurrence on a thread-block cluster
-// recur_blocked keeps all 16 consumer warps of a direction on ONE SM: every factor crosses that SM's shared-memory
-// pipe twice (TMA write + LDS read, ~2200 cycles per block with 15 consumers; measured with clock64 stamps) and the
-// owner's own shared-memory traffic queues behind it, so a block step costs ~2700 cycles although the chain itself
-// needs ~900. Here one recurrence is a CLUSTER of 8 thread blocks (one or two warps each, 8 SMs): each block keeps
+// With all consumer warps of a direction on ONE SM (round 1's single-block kernel, since removed) every factor crosses
+// that SM's shared-memory pipe twice (TMA write + LDS read, ~2200 cycles per block with 15 consumers; measured with
+// clock64 stamps) and the owner's own shared-memory traffic queues behind it, so a block step costs ~2700 cycles although
+// the chain itself needs ~900. Here one recurrence is a CLUSTER of 8 thread blocks (one or two warps each, 8 SMs): each block keeps
 // the rings, accumulators and G rows of its own row blocks, and a full copy of the published values. The owner of
 // row block q writes its 32 new values straight into the shared memory of every block that still needs them
 // (st.shared::cluster over the SM-to-SM network, ~215 cycles), orders them with one cluster-scope fence and raises
 // the block's flag in each of those copies; consumers poll their LOCAL flag. Per SM the factor traffic drops 8-fold,
 // so the chain is what is left. Small blocks also fit wherever a pair-tile block retires.
-// Arithmetic, validity checks and the exact fallback are those of recur_blocked.
+// Arithmetic, validity checks and the exact fallback are those described in 3d.
 __device__ __forceinline__ unsigned cluster_ctarank() {
     unsigned r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -2177,42 +1742,19 @@ static int run_recursion(Sim* s, const ExArgs& a, cudaStream_t st) {
         launch_chain(s, k_exch_recur_cluster_multi, a, 2 * kClusterSize, 32 * wpc, smem_cl, st, kClusterSize, pdl);
         return PIMDB_OK;
     }
-    if (blocked_ok && (nblk > 16 || !getenv("PIMDB_EXCH_NOCLUSTER"))) {
-        {
-            // blocked recurrence on two clusters of 8 thread blocks (forward, backward), 1..8 warps each (N <= 2048)
-            const int nb = nblk, nb2 = (nb + 3) & ~1, wpc = (nb + kClusterSize - 1) / kClusterSize;
-            const size_t smem_cl = sizeof(double) * ((size_t)wpc * 3 * 512 + 32 * nb + 32 * wpc + nb2) + 8 * ((size_t)nb2 + wpc * 3 + (wpc & 1))
-                                   + sizeof(int) * ((size_t)32 * nb + nb2) + 16;
-            if (smem_cl > 48 * 1024)
-                cudaFuncSetAttribute(k_exch_recur_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cl);
-            launch_chain(s, k_exch_recur_cluster, a, 2 * kClusterSize, 32 * wpc, smem_cl, st, kClusterSize, pdl);
-        }
+    if (blocked_ok) {
+        // blocked recurrence on two clusters of 8 thread blocks (forward, backward), 1..8 warps each (N <= 2048)
+        const int nb = nblk, nb2 = (nb + 3) & ~1, wpc = (nb + kClusterSize - 1) / kClusterSize;
+        const size_t smem_cl = sizeof(double) * ((size_t)wpc * 3 * 512 + 32 * nb + 32 * wpc + nb2) + 8 * ((size_t)nb2 + wpc * 3 + (wpc & 1))
+                               + sizeof(int) * ((size_t)32 * nb + nb2) + 16;
+        if (smem_cl > 48 * 1024)
+            cudaFuncSetAttribute(k_exch_recur_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cl);
+        launch_chain(s, k_exch_recur_cluster, a, 2 * kClusterSize, 32 * wpc, smem_cl, st, kClusterSize, pdl);
         return PIMDB_OK;
     }
-    if (R == 1 && !getenv("PIMDB_EXCH_BARRIER")) {           // N <= 1024: single-block kernels
-        // coefficient ring: 16 rows in flight up to 512 rows per block, 8 beyond (shared-memory budget)
-        const int ST = nt <= 512 ? 16 : 8;
-        const size_t smem = (size_t)(s->N + 2) * (sizeof(int4) + sizeof(double)) + (size_t)ST * nt * sizeof(int4) + 16;
-        if (nt <= 512 && blocked_ok) {
-            // blocked kernel: 32 unknowns per chain step through the precomputed diagonal-block inverses
-            const int nb = nt / 32, nb2 = (nb + 3) & ~1;
-            const size_t smem_blk = sizeof(double) * ((size_t)nb * 3 * 512 + 64 * nb + nb2) + 8 * ((size_t)nb * 3 + (nb & 1))
-                                    + sizeof(int) * ((size_t)32 * nb + 3 * nb2) + 16;
-            if (smem_blk > 48 * 1024)
-                cudaFuncSetAttribute(k_exch_recur_blocked, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_blk);
-            launch_chain(s, k_exch_recur_blocked, a, 2, nt, smem_blk, st, 1, pdl);
-        } else if (ST == 16) {
-            if (smem > 48 * 1024)
-                cudaFuncSetAttribute(k_exch_recur_dec<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            launch_chain(s, k_exch_recur_dec<16>, a, 2, nt, smem, st, 1, false);
-        } else {
-            cudaFuncSetAttribute(k_exch_recur_dec<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            launch_chain(s, k_exch_recur_dec<8>, a, 2, nt, smem, st, 1, false);
-        }
-        return PIMDB_OK;
-    }
+    // scalar recurrence, one unknown per step: the cross-check path (PIMDB_EXCH_NOBLOCKED=1) and N > 8192
     switch (R) {
-        case 1: return launch_recur<1, 8>(s, a, st, nt);    // N <= 1024 (barrier variant, PIMDB_EXCH_BARRIER=1)
+        case 1: return launch_recur<1, 8>(s, a, st, nt);    // N <= 1024
         case 2: return launch_recur<2, 4>(s, a, st, nt);    // N <= 2048
         case 4: return launch_recur<4, 0>(s, a, st, nt);    // N <= 4096: direct global loads
         case 8: return launch_recur<8, 0>(s, a, st, nt);    // N <= 8192

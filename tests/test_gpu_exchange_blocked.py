@@ -1,4 +1,4 @@
-"""The blocked exchange recurrence (csrc/exchange.cu, k_exch_recur_blocked: 32 unknowns per chain step through the
+"""The blocked exchange recurrence (csrc/exchange.cu, k_exch_recur_cluster / k_exch_recur_cluster_multi: 32 unknowns per chain step through the
 precomputed inverses of the diagonal blocks) against the CPU oracle, through the C ABI: V, V_backwards, exterior
 spring forces and connection probabilities at block-boundary sizes, plus which path (matrix-vector product / exact
 sequential steps) every block actually took.
@@ -98,7 +98,7 @@ def test_blocked_recurrence_helium_c3_slice(gpu_required):
 
 
 def test_blocked_equals_scalar_recurrence(gpu_required, monkeypatch):
-    """Same positions through the blocked kernel and through the scalar warp-decoupled kernel (PIMDB_EXCH_NOBLOCKED):
+    """Same positions through the blocked kernel and through the scalar one-unknown-per-step kernel (PIMDB_EXCH_NOBLOCKED):
     V and the forces agree to rounding."""
     cfg = trap(300, 4, temperature=1.0 * KELVIN, size=2000.0)
     rng = np.random.default_rng(8)

@@ -236,12 +236,15 @@ def test_zero_momentum(gpu_required):
     sim.close()
 
 
+@pytest.mark.parametrize("scalar", [False, True], ids=["blocked", "scalar"])
 @pytest.mark.parametrize("natoms", [129, 300, 512, 700, 1000, 1100, 2100, 4200])
-def test_exchange_large_n_paths(gpu_required, natoms):
-    """Every recurrence kernel against the oracle on V, V_backwards and the exterior forces: N <= 512 the fast
-    block-scaled kernel (several owner warps, N not a multiple of 32 or 4), 512 < N <= 1024 the extended-range
-    warp-decoupled kernel, N > 1024 the multi-row kernels (2 rows per thread with cp.async staging, 4+ rows with
-    direct loads)."""
+def test_exchange_large_n_paths(gpu_required, natoms, scalar, monkeypatch):
+    """Every recurrence kernel against the oracle on V, V_backwards and the exterior forces. Default path: the blocked
+    recurrence on thread-block clusters (one row block per warp up to N = 2048, several beyond; N not a multiple of 32
+    or 4). Cross-check path (PIMDB_EXCH_NOBLOCKED=1, also what N > 8192 runs): the scalar extended-range kernel, one
+    row per thread up to N = 1024, then 2 rows per thread with cp.async staging, 4+ rows with direct loads."""
+    if scalar:
+        monkeypatch.setenv("PIMDB_EXCH_NOBLOCKED", "1")
     cfg = trap(natoms, 3, temperature=1.0 * KELVIN, size=2000.0)
     rng = np.random.default_rng(natoms)
     centroid = rng.normal(0.0, 60.0, size=(1, natoms, 3))
