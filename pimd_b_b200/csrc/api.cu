@@ -10,6 +10,7 @@
 
 namespace pimdb {
 int launch_pair_chunk(Sim* s, int bead_lo, int nb, bool with_obs, bool early = false, int scratch_lo = 0);
+int pair_resident_warps_per_sm();
 int launch_assemble_chunk(Sim* s, int bead_lo, int nb, bool with_pair);
 int launch_exchange_part(Sim* s, cudaStream_t st, int part);
 }  // namespace pimdb
@@ -155,7 +156,7 @@ static void free_all(Sim* s) {
         for (auto& e : *v) { cudaEventDestroy(e.first); cudaEventDestroy(e.second); }
     cudaFree(s->x); cudaFree(s->p); cudaFree(s->f); cudaFree(s->fs); cudaFree(s->fp);
     cudaFree(s->stage_d); cudaFreeHost(s->stage_h);
-    cudaFree(s->tile_ij); cudaFree(s->dual_ijj); cudaFree(s->rest_ij); cudaFree(s->pair_scratch);
+    cudaFree(s->tile_ij); cudaFree(s->pair_scratch);
     cudaFree(s->exA); cudaFree(s->exV); cudaFree(s->exVb); cudaFree(s->exF); cudaFree(s->exTab);
     cudaFree(s->exC); cudaFree(s->exK); cudaFree(s->exB); cudaFree(s->exG); cudaFree(s->exGok); cudaFree(s->exSync); cudaFree(s->tl); cudaFree(s->rm_state); cudaFree(s->rm_noise); cudaFree(s->exWm); cudaFree(s->exWe);
     cudaFree(s->com_part); cudaFree(s->com); cudaFree(s->tickets); cudaFree(s->draw);
@@ -277,30 +278,11 @@ extern "C" int pimdb_create(const pimdb_config* cfg, pimdb_sim** out) {
     if (s->pair_on) {
         std::vector<ushort2> tiles;
         tiles.reserve(s->TP);
-        for (int I = 0; I < s->T; ++I)
-            for (int J = I; J < s->T; ++J) tiles.push_back(make_ushort2((unsigned short)I, (unsigned short)J));
+        for (int I = 0; I < s->T; ++I)       // off-diagonal tile pairs first, the diagonal ones (half the work) last: see k_pair_tiles
+            for (int J = I + 1; J < s->T; ++J) tiles.push_back(make_ushort2((unsigned short)I, (unsigned short)J));
+        for (int I = 0; I < s->T; ++I) tiles.push_back(make_ushort2((unsigned short)I, (unsigned short)I));
         CREATE_TRY(cudaMalloc(&s->tile_ij, tiles.size() * sizeof(ushort2)));
         CREATE_TRY(cudaMemcpy(s->tile_ij, tiles.data(), tiles.size() * sizeof(ushort2), cudaMemcpyHostToDevice));
-        {   // work lists of the two-rows-per-warp kernel: rows (I, I+1), I even, against every FULL tile J >= I+2; the rest singly
-            const int Tf = s->N / kTile;          // full tiles
-            std::vector<ushort4> dual;
-            std::vector<ushort2> rest;
-            std::vector<char> covered((size_t)s->T * s->T, 0);
-            for (int I = 0; I + 1 < Tf; I += 2)
-                for (int J = I + 2; J < Tf; ++J) {
-                    dual.push_back(make_ushort4((unsigned short)I, (unsigned short)(I + 1), (unsigned short)J, 0));
-                    covered[(size_t)I * s->T + J] = covered[(size_t)(I + 1) * s->T + J] = 1;
-                }
-            for (const ushort2& t : tiles)
-                if (!covered[(size_t)t.x * s->T + t.y]) rest.push_back(t);
-            s->n_dual = (int)dual.size(); s->n_rest = (int)rest.size();
-            if (s->n_dual) {
-                CREATE_TRY(cudaMalloc(&s->dual_ijj, dual.size() * sizeof(ushort4)));
-                CREATE_TRY(cudaMemcpy(s->dual_ijj, dual.data(), dual.size() * sizeof(ushort4), cudaMemcpyHostToDevice));
-                CREATE_TRY(cudaMalloc(&s->rest_ij, rest.size() * sizeof(ushort2)));
-                CREATE_TRY(cudaMemcpy(s->rest_ij, rest.data(), rest.size() * sizeof(ushort2), cudaMemcpyHostToDevice));
-            }
-        }
         const size_t per_bead = (size_t)s->T * s->T * s->D * kTile * sizeof(double);
         size_t cap_mb = 4096;
         if (const char* e = getenv("PIMDB_PAIR_SCRATCH_MB")) cap_mb = (size_t)std::max(1, atoi(e));
@@ -638,7 +620,7 @@ static int enqueue_forces(Sim* s, bool assemble_later = false, bool after_integr
         const bool capturing = cap == cudaStreamCaptureStatusActive;
         // (slices of ~6 waves -- cutting costs ~4 % of the pair tiles through the joints -- but at least two once the grid is
         // 4 waves long, so that a bead shard of C4 on 8 GPUs has a joint as well; C3, 2.5 waves, stays one launch)
-        const double waves = (double)s->Ploc * std::max(1, s->TP / 8) / (3.0 * s->sm_count);
+        const double waves = (double)s->Ploc * s->TP / ((double)pair_resident_warps_per_sm() * s->sm_count);
         int disp = s->bead_chunk;
         if (capturing && ex && waves >= 4.0 && !getenv("PIMDB_PAIR_ONE_LAUNCH")) {
             const int nslices = std::max(2, std::min(16, (int)(waves / 6.0)));

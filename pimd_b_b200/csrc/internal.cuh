@@ -116,9 +116,6 @@ struct Sim {
     double *stage_h = nullptr;         // pinned host staging, same size
     // pair forces
     ushort2* tile_ij = nullptr;        // TP entries (I,J), I<=J
-    ushort4* dual_ijj = nullptr;       // two-rows-per-warp items (I, I+1, J): full tiles, J >= I+2 (pair_forces.cu)
-    ushort2* rest_ij = nullptr;        // the tile pairs those items do not cover
-    int n_dual = 0, n_rest = 0;
     double* pair_scratch = nullptr;    // [bead_chunk][T][T][D][32]
     int bead_chunk = 0;
     // exchange

@@ -22,17 +22,22 @@
 
 namespace pimdb {
 
-#ifndef PIMDB_PAIR_MINBLOCKS
-#define PIMDB_PAIR_MINBLOCKS 3
+#ifndef PIMDB_PAIR_WARPS
+#define PIMDB_PAIR_WARPS 4
 #endif
-constexpr int kPairWarps = 8;   // warps per block
+#ifndef PIMDB_PAIR_MINBLOCKS
+#define PIMDB_PAIR_MINBLOCKS 5
+#endif
+#ifndef PIMDB_PAIR_ROT2
+#define PIMDB_PAIR_ROT2 1       // force-only launches take two rotations per loop step (pair_rotation2)
+#endif
+constexpr int kPairWarps = PIMDB_PAIR_WARPS;   // warps per block
 
 struct PairArgs {
     const double* x;      // first bead of this launch, slab stride S
     double* scratch;      // [nb][T][T][D][32]
     double* obs_part;     // [items * split][2] (V, virial) when OBS
     const ushort2* tile_ij;
-    const ushort4* dual_ijj;   // work items of the two-rows-per-warp kernel: tiles (I, I+1) against tile J >= I + 2, all three full
     int N, T, TP, nb;
     int split;            // warps per tile pair: 1, 2 or 4
     size_t S;
@@ -142,11 +147,16 @@ __device__ __forceinline__ void pair_rotation(const PairArgs& a, int t, int lane
         if (!active) { g = 0.0; v = 0.0; }
     }
     // force on i: -g d;  reaction on j: +g d  (every lane owns a distinct j slot in this rotation)
+    double of[D];   // (loads first, stores after: see pair_rotation2)
+#pragma unroll
+    for (int c = 0; c < D; ++c) of[c] = sf[c * 32 + src];
 #pragma unroll
     for (int c = 0; c < D; ++c) {
         fi[c] = fma(-g, d[c], fi[c]);
-        sf[c * 32 + src] = fma(g, d[c], sf[c * 32 + src]);
+        of[c] = fma(g, d[c], of[c]);
     }
+#pragma unroll
+    for (int c = 0; c < D; ++c) sf[c * 32 + src] = of[c];
     if (OBS) {
         // energy.cpp:88-90: virial -= x_first . f_on_first, "first" = the lower particle index of the pair
         vsum += v;
@@ -159,9 +169,172 @@ __device__ __forceinline__ void pair_rotation(const PairArgs& a, int t, int lane
     __syncwarp();
 }
 
+// shared-memory accesses by 32-bit window address (volatile: kept in program order among themselves)
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f64(unsigned addr, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+
+// Aziz, damped branch (x < D) and hard core, from quantities the common branch has already formed: see pair_eval.
+__device__ __forceinline__ double aziz_damped(double r, double ir, double e1, const PairArgs& a) {
+    const double xs = r * (1.0 / kAzRm);
+    double w;
+    if (xs > kEps && xs < 0.01) {
+        w = -kAzA * kAzAlpha * e1;
+    } else {
+        const double ix = kAzRm * ir;
+        const double ix2 = ix * ix, ix6 = ix2 * ix2 * ix2;
+        const double q = kAzD * ix - 1.0;
+        const double fdamp = exp_neg_fast(-q * q, a.ek);
+        const double dfdamp = 2.0 * kAzD * ix2 * q * fdamp;
+        const double disp = ix6 * fma(fma(kAzC10, ix2, kAzC8), ix2, kAzC6);
+        const double ddisp = (ix6 * ix) * fma(fma(10.0 * kAzC10, ix2, 8.0 * kAzC8), ix2, 6.0 * kAzC6);
+        w = fma(-kAzA * kAzAlpha, e1, ddisp * fdamp - disp * dfdamp);
+    }
+    return w * (ir * (kAzEps / kAzRm));
+}
+
+// Two rotations (t, t+1) in one loop step, force only. One pair evaluation is a chain of dependent FP64 operations
+// (~230 cycles for ~75 issue slots), and the registers allow ~5 warps per scheduler: with one pair in flight per lane the
+// schedulers issue 58 % of the time (ncu, round 1). Here every lane carries TWO independent pairs -- the same i particle
+// against the j slots (l+t) and (l+t+1) -- through straight-line code, so the two chains interleave. The reaction forces
+// of the two rotations go to two separate shared-memory accumulators (sfa for even, sfb for odd rotations of the run):
+// within a step every lane then owns one slot of each array, the read-modify-writes stay conflict-free and one
+// __syncwarp per step orders them against the next step. The arithmetic of every single pair is that of pair_rotation.
+template <int D, int POT, bool PBC, bool CUT, bool MASKED>
+__device__ __forceinline__ void pair_rotation2(const PairArgs& a, int t, int lane, bool diag, bool vi, int jbase,
+                                               const double (&xi)[D], double (&fi)[D], unsigned wsh) {
+    // wsh: shared-window address of this warp's arrays x | f (even rotations) | g (odd rotations), D*32 doubles each.
+    // Explicit ld/st.shared with immediate offsets: two address registers per step instead of re-deriving six generic
+    // addresses (that was ~15 of the ~190 instructions of a step).
+    const int sa = (lane + t) & 31, sb = (lane + t + 1) & 31;
+    const unsigned aa = wsh + 8u * sa, ab = wsh + 8u * sb;
+    constexpr int OF = D * 256, OG = 2 * D * 256;      // byte offsets of f and g
+    double da[D], db[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        da[c] = xi[c] - lds_f64(aa + c * 256);
+        db[c] = xi[c] - lds_f64(ab + c * 256);
+    }
+    // Minimum image: min_image_vec's arithmetic for both vectors. A suspected tie (a component within 2^-19 of +-L/2)
+    // takes the exact, out-of-line evaluation of the reference's expression. For Aziz the decision rides on the far/near
+    // vote below (a tie sends the rotation down the general path, which first redoes the separations exactly), so the
+    // common path has no branch of its own for it.
+    constexpr bool DEFER_TIE = PBC && POT == PIMDB_POT_AZIZ;
+    bool tie = false;
+    if (PBC) {
+        double wa[D], wb[D];
+        int worst = 0;
+#pragma unroll
+        for (int c = 0; c < D; ++c) {
+            wa[c] = fma(-a.L, rint(da[c] * a.invL), da[c]);
+            wb[c] = fma(-a.L, rint(db[c] * a.invL), db[c]);
+            worst = max(worst, max(__double2hiint(wa[c]) & 0x7fffffff, __double2hiint(wb[c]) & 0x7fffffff));
+        }
+        tie = worst >= a.tie_hi;
+        if (!DEFER_TIE && tie) {
+#pragma unroll
+            for (int c = 0; c < D; ++c) {
+                da[c] = min_image_exact(da[c], a.L, MASKED && diag && (sa < lane));
+                db[c] = min_image_exact(db[c], a.L, MASKED && diag && (sb < lane));
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < D; ++c) { da[c] = wa[c]; db[c] = wb[c]; }
+        }
+    }
+    double ra, rb;
+    bool acta, actb;
+    auto norms_and_masks = [&]() {
+        ra = da[0] * da[0]; rb = db[0] * db[0];
+#pragma unroll
+        for (int c = 1; c < D; ++c) { ra = fma(da[c], da[c], ra); rb = fma(db[c], db[c], rb); }
+        acta = true; actb = true;
+        if (MASKED) {
+            acta = vi && (jbase + sa < a.N) && !(diag && t == 16 && lane >= 16);
+            actb = vi && (jbase + sb < a.N) && !(diag && t + 1 == 16 && lane >= 16);
+        }
+        if (CUT) {
+            acta = acta && (sqrt(ra) < a.rc);
+            actb = actb && (sqrt(rb) < a.rc);
+        }
+        if (MASKED || CUT) {
+            if (!acta) ra = 1.0;
+            if (!actb) rb = 1.0;
+        }
+    };
+    norms_and_masks();
+    double ga, gb;
+    if (POT == PIMDB_POT_AZIZ) {
+        if (__all_sync(kFullMask, ra > a.az_far2 && rb > a.az_far2 && !tie)) {       // see pair_rotation
+            double ya, yb;
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(ya) : "d"(ra));
+            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(yb) : "d"(rb));
+            ya = fma(ya, fma(-ra, ya, 1.0), ya); yb = fma(yb, fma(-rb, yb, 1.0), yb);
+            const double ua = fma(ya, fma(-ra, ya, 1.0), ya), ub = fma(yb, fma(-rb, yb, 1.0), yb);
+            const double qa = ua * ua, qb = ub * ub;
+            ga = (qa * qa) * fma(fma(a.az_h2, ua, a.az_h1), ua, a.az_h0);
+            gb = (qb * qb) * fma(fma(a.az_h2, ub, a.az_h1), ub, a.az_h0);
+        } else {
+            if (DEFER_TIE && __any_sync(kFullMask, tie)) {      // rare: the reference's expression, literally, for the whole rotation
+#pragma unroll
+                for (int c = 0; c < D; ++c) {
+                    da[c] = min_image_exact(xi[c] - lds_f64(aa + c * 256), a.L, MASKED && diag && (sa < lane));
+                    db[c] = min_image_exact(xi[c] - lds_f64(ab + c * 256), a.L, MASKED && diag && (sb < lane));
+                }
+                norms_and_masks();
+            }
+            // the undamped branch of pair_eval for both pairs, unconditionally; lanes inside x < D redo theirs
+            const double ira = rsqrt_fast(ra), irb = rsqrt_fast(rb);
+            const double sra = ra * ira, srb = rb * irb;
+            const double ea = exp2_lin_fast(sra, a.az_k2, a.ek), eb = exp2_lin_fast(srb, a.az_k2, a.ek);
+            const double ua = ira * ira, ub = irb * irb, ua2 = ua * ua, ub2 = ub * ub;
+            const double Pa = (ua2 * ua2) * fma(fma(a.az_h2, ua, a.az_h1), ua, a.az_h0);
+            const double Pb = (ub2 * ub2) * fma(fma(a.az_h2, ub, a.az_h1), ub, a.az_h0);
+            ga = fma(a.az_ca, ea * ira, Pa);
+            gb = fma(a.az_ca, eb * irb, Pb);
+            const bool dampa = !(sra >= a.az_drm), dampb = !(srb >= a.az_drm);
+            if (__any_sync(kFullMask, dampa || dampb)) {
+                if (dampa) ga = aziz_damped(sra, ira, ea, a);
+                if (dampb) gb = aziz_damped(srb, irb, eb, a);
+            }
+        }
+    } else {
+        double v;
+        ga = pair_eval<POT, false>(ra, a, v);
+        gb = pair_eval<POT, false>(rb, a, v);
+    }
+    if (MASKED || CUT) {
+        if (!acta) ga = 0.0;
+        if (!actb) gb = 0.0;
+    }
+    // reaction forces: all six loads first, then the six stores -- written as load/FMA/store per component the compiler
+    // keeps that order (it cannot prove the slots distinct) and a step pays the shared-memory latency six times (ncu: the
+    // six FMAs behind the loads collected a quarter of the kernel's stall samples)
+    double oa[D], ob[D];
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        oa[c] = lds_f64(aa + OF + c * 256);
+        ob[c] = lds_f64(ab + OG + c * 256);
+    }
+#pragma unroll
+    for (int c = 0; c < D; ++c) fi[c] = fma(-gb, db[c], fma(-ga, da[c], fi[c]));
+#pragma unroll
+    for (int c = 0; c < D; ++c) {
+        sts_f64(aa + OF + c * 256, fma(ga, da[c], oa[c]));
+        sts_f64(ab + OG + c * 256, fma(gb, db[c], ob[c]));
+    }
+    __syncwarp();
+}
+
 template <int D, int POT, bool PBC, bool CUT, bool OBS>
 __global__ void __launch_bounds__(32 * kPairWarps, PIMDB_PAIR_MINBLOCKS) k_pair_tiles(PairArgs a) {
-    __shared__ double s_x[kPairWarps][D * 32], s_f[kPairWarps][D * 32];
+    constexpr bool ROT2 = PIMDB_PAIR_ROT2 && !OBS;
+    __shared__ __align__(16) double s_w[kPairWarps][3][D * 32];    // per warp: j tile | reaction forces | (ROT2) those of the odd rotations
     grid_launch_dependents();   // a launch chained behind this one (the next slice of the pair tiles) may be scheduled as soon as
                                 // every block of this grid has started
     tl_begin(a.tl);
@@ -170,16 +343,20 @@ __global__ void __launch_bounds__(32 * kPairWarps, PIMDB_PAIR_MINBLOCKS) k_pair_
     const long long gw = (long long)blockIdx.x * kPairWarps + warp;
     const long long item = gw / sp;
     const int part = (int)(gw - item * sp);
+    // Items run tile pair by tile pair (all beads of one pair are neighbours), the half-size diagonal tiles last: blocks
+    // are dispatched in index order, so the last wave consists of the shortest items and the SMs finish closer together.
     const bool live = item < (long long)a.nb * a.TP;      // no early exit: every warp reaches the block barrier
-    const int bl = live ? (int)(item / a.TP) : 0;
-    const ushort2 ij = a.tile_ij[live ? item % a.TP : 0];
+    const int bl = live ? (int)(item % a.nb) : 0;
+    const ushort2 ij = a.tile_ij[live ? item / a.nb : 0];
     const int I = ij.x, J = ij.y;
     const bool diag = (I == J);
     const double* xb = a.x + (size_t)bl * a.S;
     const int pi = I * kTile + lane, pj = J * kTile + lane;
     const bool vi = pi < a.N, vj = pj < a.N;
-    double* sx = s_x[warp];
-    double* sf = s_f[warp];
+    double* sx = s_w[warp][0];
+    double* sf = s_w[warp][1];
+    double* sg = s_w[warp][2];
+    const unsigned wsh = (unsigned)__cvta_generic_to_shared(sx);
 
     double xi[D], fi[D];
 #pragma unroll
@@ -187,6 +364,7 @@ __global__ void __launch_bounds__(32 * kPairWarps, PIMDB_PAIR_MINBLOCKS) k_pair_
         xi[c] = vi ? xb[(size_t)c * a.N + pi] : 0.0;
         sx[c * 32 + lane] = vj ? xb[(size_t)c * a.N + pj] : 0.0;
         sf[c * 32 + lane] = 0.0;
+        if (ROT2) sg[c * 32 + lane] = 0.0;
         fi[c] = 0.0;
     }
     __syncwarp();
@@ -194,18 +372,34 @@ __global__ void __launch_bounds__(32 * kPairWarps, PIMDB_PAIR_MINBLOCKS) k_pair_
     const int jbase = J * kTile;
 
     if (live) {
-        // my share of the rotations: t = 0..31 (off-diagonal) or 1..16 (diagonal), cut into `sp` equal runs
+        // my share of the rotations: t = 0..31 (off-diagonal) or 1..16 (diagonal), cut into `sp` equal runs (even lengths)
         const int nrot = (diag ? 16 : 32) / sp;
         const int tb = (diag ? 1 : 0) + part * nrot;
         if (!diag && (J + 1) * kTile <= a.N) {   // I < J, so tile I is full as well
+            if constexpr (ROT2) {
 #pragma unroll 1
-            for (int t = tb; t < tb + nrot; ++t)
-                pair_rotation<D, POT, PBC, CUT, OBS, false>(a, t, lane, false, true, jbase, xi, fi, vsum, virsum, sx, sf);
+                for (int t = tb; t < tb + nrot; t += 2)
+                    pair_rotation2<D, POT, PBC, CUT, false>(a, t, lane, false, true, jbase, xi, fi, wsh);
+            } else {
+#pragma unroll 1
+                for (int t = tb; t < tb + nrot; ++t)
+                    pair_rotation<D, POT, PBC, CUT, OBS, false>(a, t, lane, false, true, jbase, xi, fi, vsum, virsum, sx, sf);
+            }
         } else {
+            if constexpr (ROT2) {
 #pragma unroll 1
-            for (int t = tb; t < tb + nrot; ++t)
-                pair_rotation<D, POT, PBC, CUT, OBS, true>(a, t, lane, diag, vi, jbase, xi, fi, vsum, virsum, sx, sf);
+                for (int t = tb; t < tb + nrot; t += 2)
+                    pair_rotation2<D, POT, PBC, CUT, true>(a, t, lane, diag, vi, jbase, xi, fi, wsh);
+            } else {
+#pragma unroll 1
+                for (int t = tb; t < tb + nrot; ++t)
+                    pair_rotation<D, POT, PBC, CUT, OBS, true>(a, t, lane, diag, vi, jbase, xi, fi, vsum, virsum, sx, sf);
+            }
         }
+    }
+    if (ROT2) {     // (own slots only: the last step's __syncwarp has ordered every lane's updates)
+#pragma unroll
+        for (int c = 0; c < D; ++c) sf[c * 32 + lane] += sg[c * 32 + lane];
     }
 
     if (!OBS) {
@@ -223,8 +417,8 @@ __global__ void __launch_bounds__(32 * kPairWarps, PIMDB_PAIR_MINBLOCKS) k_pair_
             for (int q = 1; q < sp; ++q) {
 #pragma unroll
                 for (int c = 0; c < D; ++c) {
-                    fi[c] += s_x[warp + q][c * 32 + lane];
-                    fj[c] += s_f[warp + q][c * 32 + lane];
+                    fi[c] += s_w[warp + q][0][c * 32 + lane];
+                    fj[c] += s_w[warp + q][1][c * 32 + lane];
                 }
             }
             double* s = a.scratch + (size_t)bl * a.T * a.T * D * kTile;
@@ -246,90 +440,6 @@ __global__ void __launch_bounds__(32 * kPairWarps, PIMDB_PAIR_MINBLOCKS) k_pair_
             a.obs_part[2 * gw] = live ? vsum : 0.0;
             a.obs_part[2 * gw + 1] = live ? virsum : 0.0;
         }
-    }
-    tl_end(a.tl);
-}
-
-// ------------------------------------------------------------------------------------------------------
-// Two i-particles per lane. The single-row kernel above issues one instruction per warp every ~8 cycles: two thirds of
-// its stall cycles are fixed-latency dependencies of the FP64 chain of ONE pair (ncu: "wait" 3.5 of 8.1 cycles per
-// instruction), and the registers do not allow more warps. Here a warp owns the tile pairs (I, J) and (I+1, J) at once:
-// lane l keeps particle l of BOTH row tiles in registers and meets the same j particle in a rotation, so two independent
-// pair evaluations interleave in every lane, the j coordinates are loaded once for two pairs, and the two reaction forces
-// reach the j particle in one shared-memory read-modify-write. Only full, off-diagonal tiles (no masking); everything
-// else -- diagonal tiles, the tile next to the diagonal, ragged last tiles, cutoffs -- goes through the kernel above.
-// The reaction of both rows is accumulated together and written to the (J, I) slot of the scratch slab; the (J, I+1) slot
-// gets zeros, so the fixed-order sum of the assembly is unchanged.
-template <int D, int POT, bool PBC>
-__global__ void __launch_bounds__(32 * kPairWarps, 2) k_pair_tiles_dual(PairArgs a, int ndual) {
-    __shared__ double s_x[kPairWarps][D * 32], s_f[kPairWarps][D * 32];
-    grid_launch_dependents();
-    tl_begin(a.tl);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long gw = (long long)blockIdx.x * kPairWarps + warp;
-    if (gw >= (long long)a.nb * ndual) { tl_end(a.tl); return; }     // (no block-wide barrier in this kernel)
-    const int bl = (int)(gw / ndual);
-    const ushort4 it = a.dual_ijj[gw % ndual];
-    const int I1 = it.x, I2 = it.y, J = it.z;
-    const double* xb = a.x + (size_t)bl * a.S;
-    double* sx = s_x[warp];
-    double* sf = s_f[warp];
-    double x1[D], x2[D], f1[D], f2[D];
-#pragma unroll
-    for (int c = 0; c < D; ++c) {
-        x1[c] = xb[(size_t)c * a.N + I1 * kTile + lane];
-        x2[c] = xb[(size_t)c * a.N + I2 * kTile + lane];
-        sx[c * 32 + lane] = xb[(size_t)c * a.N + J * kTile + lane];
-        sf[c * 32 + lane] = 0.0;
-        f1[c] = 0.0; f2[c] = 0.0;
-    }
-    __syncwarp();
-#pragma unroll 1
-    for (int t = 0; t < 32; ++t) {
-        const int src = (lane + t) & 31;
-        double d1[D], d2[D];
-#pragma unroll
-        for (int c = 0; c < D; ++c) {
-            const double xo = sx[c * 32 + src];
-            d1[c] = x1[c] - xo;
-            d2[c] = x2[c] - xo;
-        }
-        if (PBC) {   // (I < J in both pairs: the separation is x_lower - x_higher as in the reference, no sign to fix at a tie)
-            min_image_vec<D>(d1, a.L, a.invL, a.tie_hi, false);
-            min_image_vec<D>(d2, a.L, a.invL, a.tie_hi, false);
-        }
-        double r1 = d1[0] * d1[0], r2 = d2[0] * d2[0];
-#pragma unroll
-        for (int c = 1; c < D; ++c) { r1 = fma(d1[c], d1[c], r1); r2 = fma(d2[c], d2[c], r2); }
-        double g1, g2, v;
-        if (POT == PIMDB_POT_AZIZ && __all_sync(kFullMask, r1 > a.az_far2 && r2 > a.az_far2)) {   // see pair_rotation
-            double y1, y2;
-            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y1) : "d"(r1));
-            asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y2) : "d"(r2));
-            y1 = fma(y1, fma(-r1, y1, 1.0), y1); y2 = fma(y2, fma(-r2, y2, 1.0), y2);
-            const double u1 = fma(y1, fma(-r1, y1, 1.0), y1), u2 = fma(y2, fma(-r2, y2, 1.0), y2);
-            const double q1 = u1 * u1, q2 = u2 * u2;
-            g1 = (q1 * q1) * fma(fma(a.az_h2, u1, a.az_h1), u1, a.az_h0);
-            g2 = (q2 * q2) * fma(fma(a.az_h2, u2, a.az_h1), u2, a.az_h0);
-        } else {
-            g1 = pair_eval<POT, false>(r1, a, v);
-            g2 = pair_eval<POT, false>(r2, a, v);
-        }
-#pragma unroll
-        for (int c = 0; c < D; ++c) {
-            f1[c] = fma(-g1, d1[c], f1[c]);
-            f2[c] = fma(-g2, d2[c], f2[c]);
-            sf[c * 32 + src] = fma(g2, d2[c], fma(g1, d1[c], sf[c * 32 + src]));
-        }
-        __syncwarp();
-    }
-    double* sc = a.scratch + (size_t)bl * a.T * a.T * D * kTile;
-#pragma unroll
-    for (int c = 0; c < D; ++c) {
-        sc[(((size_t)I1 * a.T + J) * D + c) * kTile + lane] = f1[c];
-        sc[(((size_t)I2 * a.T + J) * D + c) * kTile + lane] = f2[c];
-        sc[(((size_t)J * a.T + I1) * D + c) * kTile + lane] = sf[c * 32 + lane];
-        sc[(((size_t)J * a.T + I2) * D + c) * kTile + lane] = 0.0;
     }
     tl_end(a.tl);
 }
@@ -384,32 +494,6 @@ static void dispatch1(Sim* s, const PairArgs& a, int grid, bool early) {
 }
 
 // Enqueue the tile kernel for owned beads [bead_lo, bead_lo+nb) (nb <= bead_chunk).
-template <int D>
-static void dispatch_dual_d(Sim* s, const PairArgs& a, int grid, int ndual, bool early) {
-    auto go = [&](auto kernel) {
-        cudaLaunchConfig_t lc = {};
-        lc.gridDim = dim3(grid); lc.blockDim = dim3(32 * kPairWarps); lc.dynamicSmemBytes = 0; lc.stream = s->stream;
-        cudaLaunchAttribute at[1];
-        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[0].val.programmaticStreamSerializationAllowed = 1;
-        lc.attrs = at;
-        lc.numAttrs = early ? 1 : 0;
-        cudaLaunchKernelEx(&lc, kernel, a, ndual);
-    };
-    const bool pbc = s->cfg.pbc != 0;
-    switch (s->cfg.int_potential) {
-        case PIMDB_POT_AZIZ: pbc ? go(k_pair_tiles_dual<D, PIMDB_POT_AZIZ, true>) : go(k_pair_tiles_dual<D, PIMDB_POT_AZIZ, false>); break;
-        case PIMDB_POT_HARMONIC: pbc ? go(k_pair_tiles_dual<D, PIMDB_POT_HARMONIC, true>) : go(k_pair_tiles_dual<D, PIMDB_POT_HARMONIC, false>); break;
-        case PIMDB_POT_DIPOLE: pbc ? go(k_pair_tiles_dual<D, PIMDB_POT_DIPOLE, true>) : go(k_pair_tiles_dual<D, PIMDB_POT_DIPOLE, false>); break;
-        default: break;
-    }
-}
-static void dispatch_dual(Sim* s, const PairArgs& a, int grid, int ndual, bool early) {
-    if (s->D == 1) dispatch_dual_d<1>(s, a, grid, ndual, early);
-    else if (s->D == 2) dispatch_dual_d<2>(s, a, grid, ndual, early);
-    else dispatch_dual_d<3>(s, a, grid, ndual, early);
-}
-
 // `scratch_lo`: the slot of the scratch slab that bead `bead_lo` writes to (several launches can fill one slab)
 static int launch_chunk(Sim* s, int bead_lo, int nb, bool with_obs, bool early, int scratch_lo) {
     PairArgs a;
@@ -417,7 +501,6 @@ static int launch_chunk(Sim* s, int bead_lo, int nb, bool with_obs, bool early, 
     a.scratch = s->pair_scratch + (size_t)scratch_lo * s->T * s->T * s->D * kTile;
     a.obs_part = s->pair_scratch;  // the scratch slab doubles as the (V, virial) partial buffer
     a.tile_ij = s->tile_ij;
-    a.dual_ijj = s->dual_ijj;
     a.N = s->N; a.T = s->T; a.TP = s->TP; a.nb = nb; a.S = s->S;
     a.L = s->L; a.invL = 1.0 / s->L; a.rc = s->rc; a.par = s->pair_par;
     a.tie_hi = min_image_tie_threshold(s->L);
@@ -432,17 +515,6 @@ static int launch_chunk(Sim* s, int bead_lo, int nb, bool with_obs, bool early, 
         a.az_h1 = (double)(g0 * rm7 * rm2 * 8.0L * kAzC8);
         a.az_h2 = (double)(g0 * rm7 * rm2 * rm2 * 10.0L * kAzC10);
     }
-    // forces without a cutoff: the full off-diagonal tiles two rows at a time (k_pair_tiles_dual), the rest singly, as two
-    // launches chained by a programmatic launch (no wait: they are independent) so that the short single items fill the tail
-    // Measured on B200: the two-row kernel runs 8 independent pair chains per scheduler instead of 6 (98 registers, two
-    // blocks per SM) and is ~1.3x faster per SM, but its blocks live twice as long: at C3 (1.5 waves of them) the tail eats
-    // the gain (pair tiles 42 -> 46 us), at C4 (50 waves) it is worth 2 %. So: only for grids of at least four waves
-    // (PIMDB_PAIR_DUAL=0/1 forces it off / on).
-    static const char* dual_env = getenv("PIMDB_PAIR_DUAL");
-    const double dual_waves = (double)nb * s->n_dual / kPairWarps / (2.0 * s->sm_count);
-    const bool dual_wanted = dual_env ? atoi(dual_env) != 0 : dual_waves >= 4.0;
-    const bool dual = !with_obs && dual_wanted && s->n_dual > 0 && !(s->rc > 0.0);
-    if (dual) { a.tile_ij = s->rest_ij; a.TP = s->n_rest; }
     const long long items = (long long)nb * a.TP;
     // `split` > 1 cuts a tile pair's rotations over 2 or 4 warps. Measured on B200 at C3 (2.45 waves of tile pairs):
     // 52.0 / 52.2 / 58.3 us for split 1 / 2 / 4 -- the tail is not what limits the kernel, so the default stays 1.
@@ -463,16 +535,6 @@ static int launch_chunk(Sim* s, int bead_lo, int nb, bool with_obs, bool early, 
         k_pair_obs_reduce<<<1, 1024, 0, s->stream>>>(s->pair_scratch, (long long)grid * kPairWarps, &s->obs_d->pair_v, &s->obs_d->pair_vir);
         s->launches += 2;
     } else {
-        if (dual) {
-            PairArgs ad = a;
-            ad.tl = a.tl; a.tl = tl_slot(s);
-            const int gd = (int)(((long long)nb * s->n_dual + kPairWarps - 1) / kPairWarps);
-            dispatch_dual(s, ad, gd, s->n_dual, early);
-            s->launches += 1;
-            cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
-            cudaStreamIsCapturing(s->stream, &cap);
-            early = cap == cudaStreamCaptureStatusActive;     // the single items ride behind the dual ones
-        }
         if (s->D == 1) dispatch1<1, false>(s, a, grid, early);
         else if (s->D == 2) dispatch1<2, false>(s, a, grid, early);
         else dispatch1<3, false>(s, a, grid, early);
@@ -485,6 +547,9 @@ static int launch_chunk(Sim* s, int bead_lo, int nb, bool with_obs, bool early, 
     PIMDB_CUDA_TRY(s, cudaGetLastError());
     return PIMDB_OK;
 }
+
+// warps of pair tiles one SM holds at a time (api.cu sizes the slices of a large grid in waves of these)
+int pair_resident_warps_per_sm() { return kPairWarps * PIMDB_PAIR_MINBLOCKS; }
 
 int launch_pair_chunk(Sim* s, int bead_lo, int nb, bool with_obs, bool early, int scratch_lo) {
     return launch_chunk(s, bead_lo, nb, with_obs, early, scratch_lo);
