@@ -308,7 +308,12 @@ def rooflines(run: Runner, hbm_peak, peak_src, fp64_peak):
     nsteps = 40
     with torch.cuda.stream(run.stream):
         sim.timing_enable(True)
-        run.step(nsteps)
+        for _ in range(4):
+            # The eager, event-bracketed launches cost the host more than the kernels cost the device; with the device waiting
+            # for the host, an event pair also times the gap until the launch arrives. So the device is parked (~1.5 ms)
+            # while the host enqueues ten steps, and then runs them back to back.
+            torch.cuda._sleep(3_000_000)
+            run.step(nsteps // 4)
         run.barrier()
         pair_ms, npair = sim.timing_get(0)
         step_ms, _ = sim.timing_get(1)
@@ -355,8 +360,13 @@ def scrambled_pair_time(name, local_rank, torch):
     perm = np.random.default_rng(7).permutation(cfg.natoms)
     sim = DeviceSim(cfg, device=local_rank)
     sim.upload(np.ascontiguousarray(x[:, perm]), np.ascontiguousarray(p[:, perm]))
+    st = torch.cuda.Stream(device=local_rank)
+    sim.set_stream(st.cuda_stream)
     sim.timing_enable(True)
-    sim.step(20)
+    with torch.cuda.stream(st):
+        for _ in range(2):
+            torch.cuda._sleep(3_000_000)      # (see rooflines)
+            sim.step(10)
     ms, n = sim.timing_get(0)
     sim.timing_enable(False)
     sim.close()

@@ -150,6 +150,10 @@ static void free_all(Sim* s) {
     if (s->graph_dl_exec) cudaGraphExecDestroy(s->graph_dl_exec);
     if (s->graph_dl) cudaGraphDestroy(s->graph_dl);
     if (s->stream_c) cudaStreamDestroy(s->stream_c);
+    if (s->stream_n) cudaStreamDestroy(s->stream_n);
+    if (s->ev_nz_fork) cudaEventDestroy(s->ev_nz_fork);
+    if (s->ev_nz_join) cudaEventDestroy(s->ev_nz_join);
+    cudaFree(s->nz); cudaFree(s->nz_tag);
     if (s->ev_dl_fork) cudaEventDestroy(s->ev_dl_fork);
     if (s->ev_dl_join) cudaEventDestroy(s->ev_dl_join);
     for (auto* v : {&s->ev_pair, &s->ev_step, &s->ev_integ})
@@ -347,13 +351,26 @@ extern "C" int pimdb_create(const pimdb_config* cfg, pimdb_sim** out) {
         CREATE_TRY(cudaMalloc(&s->stamps, sizeof(unsigned long long) * 64));
         CREATE_TRY(cudaMemset(s->stamps, 0, sizeof(unsigned long long) * 64));
     }
-    CREATE_TRY(cudaMalloc(&s->com_part, sizeof(double) * 4 * kMaxPartials));
+    CREATE_TRY(cudaMalloc(&s->com_part, sizeof(double) * 2 * 4 * kMaxPartials));
+    CREATE_TRY(cudaMemset(s->com_part, 0, sizeof(double) * 2 * 4 * kMaxPartials));
     CREATE_TRY(cudaMalloc(&s->com, sizeof(double) * 4));
     CREATE_TRY(cudaMemset(s->com, 0, sizeof(double) * 4));
     CREATE_TRY(cudaMalloc(&s->tickets, sizeof(unsigned int) * 4));
     CREATE_TRY(cudaMemset(s->tickets, 0, sizeof(unsigned int) * 4));
     CREATE_TRY(cudaMalloc(&s->draw, sizeof(unsigned long long)));
     CREATE_TRY(cudaMemset(s->draw, 0, sizeof(unsigned long long)));
+    if (cfg->thermostat == PIMDB_THERMO_LANGEVIN && !cfg->nmthermostat && cfg->propagator == PIMDB_PROP_CARTESIAN &&
+        cfg->rng != PIMDB_RNG_RANMARS && !getenv("PIMDB_NO_NOISE_PREFETCH")) {
+        const size_t slot = (size_t)s->Ploc * s->D * s->N * sizeof(double);
+        CREATE_TRY(cudaMalloc(&s->nz, 2 * slot));
+        CREATE_TRY(cudaMalloc(&s->nz_tag, 2 * sizeof(unsigned long long)));
+        CREATE_TRY(cudaMemset(s->nz_tag, 0xff, 2 * sizeof(unsigned long long)));     // no draw has this index
+        CREATE_TRY(cudaStreamCreateWithPriority(&s->stream_n, cudaStreamNonBlocking, s->prio_lo));
+        CREATE_TRY(cudaEventCreateWithFlags(&s->ev_nz_fork, cudaEventDisableTiming));
+        CREATE_TRY(cudaEventCreateWithFlags(&s->ev_nz_join, cudaEventDisableTiming));
+        s->nz_on = true;
+    }
+    s->no_ticketless = getenv("PIMDB_NO_TICKETLESS") != nullptr;
     CREATE_TRY(cudaMalloc(&s->obs_d, sizeof(DevObs)));
     CREATE_TRY(cudaMemset(s->obs_d, 0, sizeof(DevObs)));
     CREATE_TRY(cudaHostAlloc(&s->obs_h, sizeof(DevObs), cudaHostAllocDefault));
@@ -554,7 +571,7 @@ extern "C" int pimdb_download_state(pimdb_sim* sim, double* x, double* p, double
 // and one launch fewer on the step's critical path.
 // `after_integrate`: the previous launch on the main stream was one of our integrator kernels (a captured step): the first
 // kernel of the exchange chain may be launched early behind it.
-static int enqueue_forces(Sim* s, bool assemble_later = false, bool after_integrate = false) {
+static int enqueue_forces_inner(Sim* s, bool assemble_later, bool after_integrate) {
     const bool ex = s->bosonic && (s->has_first || s->has_last);
     bool pair_early = false;
     if (ex) {
@@ -653,6 +670,22 @@ static int enqueue_forces(Sim* s, bool assemble_later = false, bool after_integr
     } else {
         if (!joined) API_TRY(join());
         if (!assemble_later) API_TRY(launch_assemble_chunk(s, 0, s->Ploc, false));
+    }
+    return PIMDB_OK;
+}
+
+// Inside an iteration with the counter-based Langevin thermostat, the noise of the next two thermostat half steps (the one
+// that closes this iteration and the one that opens the next) is drawn beside the force kernels, on its own low-priority
+// stream, launched last so that it takes whatever room the other grids leave (integrator.cu k_noise_prefetch).
+static int enqueue_forces(Sim* s, bool assemble_later = false, bool after_integrate = false) {
+    const bool prefetch = s->nz_on && s->nz_want;
+    if (prefetch) PIMDB_CUDA_TRY(s, cudaEventRecord(s->ev_nz_fork, s->stream));
+    API_TRY(enqueue_forces_inner(s, assemble_later, after_integrate));
+    if (prefetch) {
+        PIMDB_CUDA_TRY(s, cudaStreamWaitEvent(s->stream_n, s->ev_nz_fork, 0));
+        API_TRY(launch_noise_prefetch(s, s->stream_n, 2, s->nz_first_off));
+        PIMDB_CUDA_TRY(s, cudaEventRecord(s->ev_nz_join, s->stream_n));
+        PIMDB_CUDA_TRY(s, cudaStreamWaitEvent(s->stream, s->ev_nz_join, 0));
     }
     return PIMDB_OK;
 }
@@ -807,7 +840,20 @@ static bool early_halo_push(const Sim* s) {
     return !off && lazy_closing_com(s) && s->cfg.propagator == PIMDB_PROP_CARTESIAN;
 }
 
+// One handle owns every bead, velocity Verlet + Langevin on the counter-based stream + fixcom, forces assembled by the closing
+// kick: the iteration whose launches enqueue_step_inner writes out by hand (PIMDB_NO_TICKETLESS=1: the general path, A/B timing)
+static bool ticketless_langevin_step(const Sim* s) {
+    return !s->no_ticketless && s->all_local && !s->peer_on && s->cfg.fixcom && s->cfg.propagator == PIMDB_PROP_CARTESIAN &&
+           s->cfg.thermostat == PIMDB_THERMO_LANGEVIN && !s->cfg.nmthermostat && !s->rm_state && fuse_assembly(s);
+}
+static int enqueue_step_inner(Sim* s, bool defer_last_com);
 static int enqueue_step(Sim* s, bool defer_last_com) {
+    s->nz_want = true;
+    const int rc = enqueue_step_inner(s, defer_last_com);
+    s->nz_want = false;
+    return rc;
+}
+static int enqueue_step_inner(Sim* s, bool defer_last_com) {
     if (early_halo_push(s)) {
         //   [O | SUM -> peers | boundary slices -> neighbours]  [wait sums | SUBCM | B | A | fix received slices]  forces  [assemble | B | O]
         const unsigned o_pre = s->cfg.thermostat == PIMDB_THERMO_LANGEVIN ? OP_O_PRE : 0u;
@@ -823,6 +869,29 @@ static int enqueue_step(Sim* s, bool defer_last_com) {
         API_TRY(join_download_x(s));
         s->z_owed = true;
         return PIMDB_OK;
+    }
+    if (ticketless_langevin_step(s)) {
+        //   [SUBCM | O | SUM]  [SUBCM | B | A | halos]  forces  [assemble | B | O | SUM]
+        // The launches the general path below makes for this configuration, stage for stage; what differs is who advances the
+        // noise draw counter. There, the last block of every launch with an O stage (a ticket, a fence and an atomic round trip
+        // on the tail of two kernels per iteration); here the launch between them, which has no O stage and so no reader of the
+        // counter, adds 2 in its prologue: the opening O reads counter + 0 before it, the closing O counter - 1 after it.
+        s->li_no_ticket = true;
+        API_TRY(launch_integrate(s, (s->p_shift_pending ? OP_SUBCM : 0u) | OP_O_PRE | OP_SUM));
+        s->p_shift_pending = false;
+        allow_early_launch(s);
+        s->li_draw_bump = 2;
+        API_TRY(launch_integrate(s, OP_SUBCM | OP_B | OP_A | OP_HALO));
+        API_TRY(maybe_download_x(s));
+        s->nz_first_off = -1;
+        const int rcf = enqueue_forces(s, true, !s->dl_forked);
+        s->nz_first_off = 0;
+        API_TRY(rcf);
+        s->li_no_ticket = true; s->li_draw_off = -1;
+        API_TRY(launch_integrate(s, OP_ASSEMBLE | OP_B | OP_O_POST | OP_SUM));
+        if (defer_last_com) s->p_shift_pending = true;
+        else API_TRY(launch_integrate(s, OP_SUBCM));
+        return join_download_x(s);
     }
     Fuser fz(s);
     const bool lazy = lazy_closing_com(s);
@@ -851,8 +920,17 @@ static int make_entry_state_uniform(Sim* s) {
     if (lazy_closing_com(s)) return PIMDB_OK;   // an iteration starts the same way whether or not a Z is outstanding
     if (s->cfg.fixcom && !s->p_shift_pending) {
         if (s->peer_on) API_TRY(launch_integrate(s, OP_ZERO_SUM));   // every rank publishes zero sums
-        else PIMDB_CUDA_TRY(s, cudaMemsetAsync(s->com, 0, sizeof(double) * 4, s->stream));
+        else if (s->all_local) {      // block partials, summed by the consumer (integrator.cu): zero partials in array 0
+            PIMDB_CUDA_TRY(s, cudaMemsetAsync(s->com_part, 0, sizeof(double) * 4 * kMaxPartials, s->stream));
+            s->com_buf = 0;
+        } else PIMDB_CUDA_TRY(s, cudaMemsetAsync(s->com, 0, sizeof(double) * 4, s->stream));
         s->p_shift_pending = true;
+    }
+    if (s->cfg.fixcom && s->all_local && !s->peer_on && s->com_buf != 0) {
+        // the captured iteration names the partial arrays statically: the pending sums always enter it in array 0
+        PIMDB_CUDA_TRY(s, cudaMemcpyAsync(s->com_part, s->com_part + 4 * kMaxPartials, sizeof(double) * 4 * kMaxPartials,
+                                          cudaMemcpyDeviceToDevice, s->stream));
+        s->com_buf = 0;
     }
     return PIMDB_OK;
 }

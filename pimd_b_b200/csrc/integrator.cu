@@ -184,6 +184,12 @@ struct IntArgs {
     unsigned long long seed;
     unsigned ops;
     const double* noise;   // reference-compatible stream: [Ploc][N][D] gaussians of this half-step, or nullptr (Philox)
+    // com_mode 1 (the handle owns every bead, no peers): SUM leaves block partials in com_out, SUBCM adds up the com_nblk
+    // partials of com_in itself. use_ticket: the launch needs its last block (peer publication, totals for the host-driven
+    // shards, advancing the draw counter). draw_off / draw_bump: see Sim::li_draw_off.
+    int com_mode, com_nblk, use_ticket, draw_off, draw_bump;
+    const double* com_in; double* com_out;
+    const double* nz; const unsigned long long* nz_tag; size_t nz_slot;   // prefetched draws of the counter-based stream (k_noise_prefetch) or nullptr
     unsigned long long* tl;
     // ASSEMBLE
     const double* scratch; const double* exF;
@@ -220,6 +226,7 @@ __global__ void __launch_bounds__(256) k_integrate(IntArgs a) {
     __shared__ double sm[3 * 32];
     __shared__ double sh_cm[4];
     __shared__ unsigned long long sh_draw;
+    __shared__ int sh_nz;
     __shared__ unsigned sh_seq[3];
     __shared__ unsigned sh_words[kMaxPeers * kComWords];
     __shared__ bool is_last;
@@ -233,7 +240,9 @@ __global__ void __launch_bounds__(256) k_integrate(IntArgs a) {
     // update of them), centre-of-mass shift, hand-shake with the ring neighbours
     PIMDB_STAMP(0);
     if (tid == 0) {
-        sh_draw = do_o ? *a.draw : 0ull;
+        sh_draw = do_o ? *a.draw + (unsigned long long)(long long)a.draw_off : 0ull;
+        if (a.draw_bump && blockIdx.x == 0) *a.draw += (unsigned long long)a.draw_bump;   // (a launch without an O stage: nobody reads it here)
+        sh_nz = (do_o && a.nz && a.nz_tag[sh_draw & 1ull] == sh_draw) ? 1 : 0;   // this draw was made ahead: load it instead
         if (peer) { sh_seq[0] = a.peer.seq[0]; sh_seq[1] = a.peer.seq[1]; sh_seq[2] = a.peer.seq[2]; }
     }
     if (tid < 4) sh_cm[tid] = 0.0;
@@ -252,6 +261,21 @@ __global__ void __launch_bounds__(256) k_integrate(IntArgs a) {
                     t += __hiloint2double((int)sh_words[r * kComWords + 2 * tid + 1], (int)sh_words[r * kComWords + 2 * tid]);
                 sh_cm[tid] = t * a.inv_np;
             }
+        } else if (a.com_mode == 1) {
+            // the producer's blocks left one partial each: the order of the additions is the last-block pass's (a strided set per
+            // thread, then the block tree), so every block forms the same total, bit for bit
+            double tot[3] = {0.0, 0.0, 0.0};
+            for (int blk = tid; blk < a.com_nblk; blk += blockDim.x) {
+                for (int c = 0; c < 3; ++c) tot[c] += __ldcg(&a.com_in[blk * 4 + c]);
+            }
+            block_sum<3>(tot, sm);
+            if (tid == 0) {
+                for (int c = 0; c < 3; ++c) {
+                    sh_cm[c] = c < a.D ? tot[c] * a.inv_np : 0.0;
+                    if (blockIdx.x == 0) a.com[c] = tot[c];
+                }
+            }
+            __syncthreads();
         } else if (tid < 3) {
             sh_cm[tid] = tid < a.D ? a.com[tid] * a.inv_np : 0.0;
         }
@@ -269,6 +293,7 @@ __global__ void __launch_bounds__(256) k_integrate(IntArgs a) {
     __syncthreads();
     PIMDB_STAMP(3);
     const unsigned long long draw = sh_draw;
+    const double* nzp = sh_nz ? a.nz + (size_t)(draw & 1ull) * a.nz_slot : nullptr;
     const double cm[3] = {sh_cm[0], sh_cm[1], sh_cm[2]};
     double acc[3] = {0.0, 0.0, 0.0};
     bool stored_remote = false;
@@ -344,6 +369,9 @@ __global__ void __launch_bounds__(256) k_integrate(IntArgs a) {
             if (a.noise) {   // particle-major, axis-minor within a bead: the order langevin.cpp:18-26 consumes them
                 z0 = a.noise[((size_t)b * a.N + n0) * a.D + c];
                 z1 = two ? a.noise[((size_t)b * a.N + n0 + 1) * a.D + c] : 0.0;
+            } else if (nzp) {
+                const double2 zz = ld_pair<VEC>(nzp, o, two);
+                z0 = zz.x; z1 = zz.y;
             } else {
                 gaussian_pair((uint32_t)q, (uint32_t)((a.bead_begin + b) * a.D + c), draw, a.seed, z0, z1);
             }
@@ -427,11 +455,18 @@ __global__ void __launch_bounds__(256) k_integrate(IntArgs a) {
         }
     }
     PIMDB_STAMP(4);
-    if ((a.ops & (OP_SUM | OP_O_PRE | OP_O_POST | OP_ZERO_SUM)) || push_halo) {
+    if (!a.use_ticket) {
         if (a.ops & OP_SUM) {
             block_sum<3>(acc, sm);
             if (tid == 0) {
-                for (int c = 0; c < 3; ++c) a.com_part[blockIdx.x * 4 + c] = acc[c];
+                for (int c = 0; c < 3; ++c) a.com_out[blockIdx.x * 4 + c] = acc[c];
+            }
+        }
+    } else if ((a.ops & (OP_SUM | OP_O_PRE | OP_O_POST | OP_ZERO_SUM)) || push_halo) {
+        if (a.ops & OP_SUM) {
+            block_sum<3>(acc, sm);
+            if (tid == 0) {
+                for (int c = 0; c < 3; ++c) a.com_out[blockIdx.x * 4 + c] = acc[c];
             }
         }
         // (remote stores of this block's threads -> barrier -> ONE system-scope fence by thread 0 -> ticket: fences are
@@ -448,11 +483,11 @@ __global__ void __launch_bounds__(256) k_integrate(IntArgs a) {
         if (is_last) {
             PIMDB_STAMP(6);
             double tot[3] = {0.0, 0.0, 0.0};
-            if (a.ops & OP_SUM) {
+            if ((a.ops & OP_SUM) && a.com_mode == 0) {
                 __threadfence();
                 // fixed order: each thread takes a strided set of blocks, then a block reduction
                 for (int blk = tid; blk < (int)gridDim.x; blk += blockDim.x) {
-                    for (int c = 0; c < 3; ++c) tot[c] += __ldcg(&a.com_part[blk * 4 + c]);
+                    for (int c = 0; c < 3; ++c) tot[c] += __ldcg(&a.com_out[blk * 4 + c]);
                 }
                 block_sum<3>(tot, sm);
                 if (tid == 0) {
@@ -486,7 +521,7 @@ __global__ void __launch_bounds__(256) k_integrate(IntArgs a) {
             }
             if (tid == 0) {
                 *a.ticket = 0u;
-                if (do_o) *a.draw = draw + 1ull;
+                if (do_o) *a.draw = draw + 1ull;       // (draw_off is 0 whenever an O stage advances the counter itself)
             }
             PIMDB_STAMP(7);
         }
@@ -583,12 +618,73 @@ int launch_peer_push_halos(Sim* s) {
     return PIMDB_OK;
 }
 
+// The Gaussians of the next `ndraws` Langevin half steps of the counter-based stream, written in the layout k_integrate
+// reads the momenta in. They depend on (seed, draw index, global bead, axis, particle) only, so they can be drawn while the
+// forces are computed instead of on the step's serial path (Philox + Box-Muller is ~600 dependent instructions per thread:
+// the thermostat half step of C3 took 6 us for 0.8 MB of momenta). k_integrate uses a slot only when its tag names the draw
+// it is about to make, and otherwise draws in place: the numbers are the same either way.
+struct NoiseArgs {
+    double* nz; unsigned long long* tag; const unsigned long long* draw;
+    size_t slot;
+    int N, D, Ploc, bead_begin, ndraws, first_off;
+    unsigned long long seed;
+};
+template <bool VEC>
+__global__ void __launch_bounds__(256) k_noise_prefetch(NoiseArgs a) {
+    const unsigned long long d0 = *a.draw + (unsigned long long)(long long)a.first_off;
+    const int Q = (a.N + 1) >> 1;
+    const long long total = (long long)a.Ploc * a.D * Q;
+    for (int k = 0; k < a.ndraws; ++k) {
+        const unsigned long long draw = d0 + (unsigned long long)k;
+        double* dst = a.nz + (size_t)(draw & 1ull) * a.slot;
+        for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+            const long long row = idx / Q;
+            const int q = (int)(idx % Q);
+            const int b = (int)(row / a.D), c = (int)(row % a.D);
+            const int n0 = 2 * q;
+            const bool two = VEC || (n0 + 1) < a.N;
+            double2 z;
+            gaussian_pair((uint32_t)q, (uint32_t)((a.bead_begin + b) * a.D + c), draw, a.seed, z.x, z.y);
+            st_pair<VEC>(dst, (size_t)row * a.N + n0, z, two);
+        }
+        // (stream order puts every consumer behind this whole grid, so the tag may be written at any point of it)
+        if (blockIdx.x == 0 && threadIdx.x == 0) a.tag[draw & 1ull] = draw;
+    }
+}
+
+int launch_noise_prefetch(Sim* s, cudaStream_t st, int ndraws, int first_off) {
+    NoiseArgs a;
+    a.nz = s->nz; a.tag = s->nz_tag; a.draw = s->draw;
+    a.slot = (size_t)s->Ploc * s->D * s->N;
+    a.N = s->N; a.D = s->D; a.Ploc = s->Ploc; a.bead_begin = s->b0; a.ndraws = ndraws; a.first_off = first_off;
+    a.seed = s->cfg.seed;
+    const long long total = (long long)s->Ploc * s->D * ((s->N + 1) / 2);
+    const int grid = (int)std::max<long long>(1, std::min<long long>((total + 255) / 256, 4LL * s->sm_count));
+    if ((s->N & 1) == 0) k_noise_prefetch<true><<<grid, 256, 0, st>>>(a);
+    else k_noise_prefetch<false><<<grid, 256, 0, st>>>(a);
+    s->launches += 1;
+    PIMDB_CUDA_TRY(s, cudaGetLastError());
+    return PIMDB_OK;
+}
+
 int launch_integrate(Sim* s, unsigned ops) {
     IntArgs a;
     a.x = s->x; a.p = s->p;
     a.f = (ops & OP_B_PHYS) ? s->fp : s->f;
     a.fw = s->f;
     a.com_part = s->com_part; a.com = s->com; a.ticket = s->tickets; a.draw = s->draw;
+    {
+        const bool do_o = (ops & (OP_O_PRE | OP_O_POST)) != 0;
+        const bool consumer = s->all_local && !s->peer_on;
+        a.com_mode = consumer ? 1 : 0;
+        a.com_in = s->com_part + (size_t)(consumer ? s->com_buf : 0) * 4 * kMaxPartials;
+        a.com_out = s->com_part + (size_t)(consumer ? (s->com_buf ^ 1) : 0) * 4 * kMaxPartials;
+        if (consumer && (ops & OP_SUM)) s->com_buf ^= 1;
+        a.draw_off = do_o ? s->li_draw_off : 0;
+        a.draw_bump = do_o ? 0 : s->li_draw_bump;
+        a.use_ticket = (!consumer || (do_o && !s->li_no_ticket)) ? 1 : 0;
+        s->li_draw_off = 0; s->li_draw_bump = 0; s->li_no_ticket = false;
+    }
     a.N = s->N; a.D = s->D; a.Ploc = s->Ploc; a.bead_begin = s->b0; a.S = s->S;
     a.c1 = s->c1; a.c2 = s->c2;
     a.hdt = 0.5 * s->cfg.dt; a.dt_over_m = s->cfg.dt / s->cfg.mass;
@@ -596,6 +692,7 @@ int launch_integrate(Sim* s, unsigned ops) {
     a.seed = s->cfg.seed;
     a.ops = ops;
     a.noise = nullptr;
+    a.nz = s->nz_on ? s->nz : nullptr; a.nz_tag = s->nz_tag; a.nz_slot = (size_t)s->Ploc * s->D * s->N;
     if (s->rm_state && (ops & (OP_O_PRE | OP_O_POST))) {
         int rc = launch_ranmars_fill(s);
         if (rc != PIMDB_OK) return rc;
@@ -617,6 +714,7 @@ int launch_integrate(Sim* s, unsigned ops) {
     if (ops & OP_ASSEMBLE) s->split_stale = true;
     const size_t items = (size_t)s->Ploc * s->D * ((s->N + 1) / 2);
     const int grid = grid_for(items, 256, kMaxPartials);
+    a.com_nblk = grid;      // (every k_integrate launch of a handle has this grid)
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     if (s->timing) {
         cudaEventCreate(&e0); cudaEventCreate(&e1);

@@ -129,7 +129,7 @@ struct Sim {
     long long* dbg_buf = nullptr;                                          // profiling aid (PIMDB_EXCH_DEBUG)
     double *exTab = nullptr; size_t exTabCap = 0;                          // on-demand E / prob tables
     // reductions
-    double* com_part = nullptr;        // [kMaxPartials][4]
+    double* com_part = nullptr;        // [2][kMaxPartials][4]
     double* com = nullptr;             // [4] finalized sum of momenta over owned beads (allreduce target)
     unsigned int* tickets = nullptr;   // last-block-done counters
     unsigned long long* draw = nullptr;  // device counter of thermostat half-steps (noise draw index)
@@ -153,6 +153,12 @@ struct Sim {
     double* dl_x_host = nullptr;       // page-locked destination baked into graph_dl
     double* dl_hook = nullptr;         // set while an iteration is being enqueued with that hook
     cudaStream_t stream_c = nullptr; cudaEvent_t ev_dl_fork = nullptr, ev_dl_join = nullptr; bool dl_forked = false;
+    // Langevin noise of the counter-based stream, drawn ahead of its half step while the forces are computed (integrator.cu
+    // k_noise_prefetch): two slots [own beads][D][N], nz_tag[slot] = index of the draw the slot holds
+    double* nz = nullptr; unsigned long long* nz_tag = nullptr;
+    cudaStream_t stream_n = nullptr; cudaEvent_t ev_nz_fork = nullptr, ev_nz_join = nullptr;
+    bool nz_on = false, nz_want = false;
+    bool no_ticketless = false;        // PIMDB_NO_TICKETLESS=1 when the handle was created (api.cu ticketless_langevin_step)
     bool p_shift_pending = false;      // fixcom: COM shift computed but not yet subtracted from p
     // peer-memory bead sharding (pimdb_peer_attach)
     bool peer_on = false;
@@ -163,6 +169,14 @@ struct Sim {
     bool z_owed = false;               // peer mode, Langevin / no thermostat: the closing zeroMomentum of the last iteration
                                        // has not been carried out (it is subsumed by the first one of the next iteration)
     bool pdl_recur = false;            // the next recurrence launch may use programmatic stream serialisation
+    // momentum sums on a handle that owns every bead (no peers): a SUM stage leaves one partial per block, the SUBCM stage of a
+    // later launch adds them up in the fixed order itself -- no last-block pass on the producer's critical path. Two partial
+    // arrays, because one launch may consume the old sums and produce new ones: com_buf = the array holding the latest.
+    int com_buf = 0;
+    // one-shot modifiers of the next launch_integrate (a captured step places them statically): offset added to the draw
+    // counter an O stage reads; amount a launch WITHOUT an O stage adds to the counter; O stage leaves the counter alone
+    int li_draw_off = 0, li_draw_bump = 0; bool li_no_ticket = false;
+    int nz_first_off = 0;              // k_noise_prefetch draws counter + nz_first_off, + 1 (see enqueue_step)
     bool pdl_next = false;             // the next k_integrate / factor-tile launch follows a kernel of ours on the same stream in
                                        // a captured step: launch it with programmatic stream serialisation (it waits for that
                                        // grid first thing; what is hidden is its launch latency)
@@ -215,6 +229,7 @@ enum : unsigned { OP_SUBCM = 1, OP_O_PRE = 2, OP_B = 4, OP_O_POST = 8, OP_A = 16
                   OP_HALO_EARLY = 2048, OP_HALO_FIX = 4096
 };
 int launch_integrate(Sim* s, unsigned ops);
+int launch_noise_prefetch(Sim* s, cudaStream_t st, int ndraws, int first_off);
 int launch_peer_push_halos(Sim* s);
 int launch_peer_allgather(Sim* s, bool with_x, bool kick);   // owned beads of (x and) p -> every rank's gather buffer
 int launch_nm_propagate(Sim* s);

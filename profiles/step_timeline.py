@@ -23,3 +23,9 @@ for rep in range(3):
     print(f"step {rep}: kernels in launch order [start us, end us, duration us]")
     for i, (a, b) in enumerate(t):
         print(f"   #{i}: {(a - t0) / 1e3:8.2f} {(b - t0) / 1e3:8.2f} {(b - a) / 1e3:8.2f}")
+    fs = sim.lib.pimdb_debug_integrate_stamps; fs.restype = C.c_int; fs.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong)]
+    sb = (C.c_ulonglong * 64)()
+    k = fs(sim.h, sb)
+    st = np.array(sb[:], dtype=np.uint64).reshape(8, 8).astype(np.int64)
+    for i in range(min(k, 8)):   # block 0: start, counters read, sums in, waits done, main loop done, ticket taken; last block: 6, 7 = end
+        print(f"   k_integrate launch {i}: phase stamps", " ".join(f"{(v - t0) / 1e3:7.2f}" if v else "      -" for v in st[i]))

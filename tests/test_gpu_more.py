@@ -487,3 +487,36 @@ def test_step_download_equals_step_then_download(gpu_required):
     a.step(1)
     assert np.array_equal(hx, a.get("x")) and np.array_equal(b.get("p"), a.get("p"))
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("natoms", [64, 33])
+def test_prefetched_langevin_noise_is_the_in_place_noise(gpu_required, natoms, monkeypatch):
+    """The Gaussians of the counter-based Langevin stream are drawn ahead, beside the force kernels (k_noise_prefetch), and the
+    thermostat half steps load them; a handle created with PIMDB_NO_NOISE_PREFETCH=1 draws them in place. Same numbers, bit
+    for bit, through pimdb_step (captured and repeated), through the call-by-call entry points in between, and after the
+    momenta were replaced from the host (even and odd particle counts: vector and scalar kernels)."""
+    cfg = SimConfig(nbeads=8, natoms=natoms, ndim=3, bosonic=True, fixcom=True, pbc=True, temperature=2 * wl.KELVIN,
+                    mass=4.0026 * wl.DALTON, size=wl.helium_box(64), interaction="aziz", cutoff=-1.0 * wl.ANGSTROM,
+                    external="free", thermostat="langevin", seed=777, dt=wl.FEMTOSECOND)
+    import dataclasses
+    x, p = wl.initial_state(dataclasses.replace(cfg, natoms=64), "c3", seed=3)
+    x, p = np.ascontiguousarray(x[:, :natoms]), np.ascontiguousarray(p[:, :natoms])
+    a = DeviceSim(cfg)
+    monkeypatch.setenv("PIMDB_NO_NOISE_PREFETCH", "1")
+    b = DeviceSim(cfg)
+    monkeypatch.delenv("PIMDB_NO_NOISE_PREFETCH")
+    # (the third handle also takes the general launch sequence, where the last block of every thermostat launch advances the
+    # draw counter; a and b let the kick-and-drift launch between the two thermostat launches advance it)
+    monkeypatch.setenv("PIMDB_NO_TICKETLESS", "1")
+    c = DeviceSim(cfg)
+    for s in (a, b, c):
+        s.upload(x, p)
+        s.step(3)
+        s.thermostat_step(); s.zero_momentum()      # a half step outside pimdb_step consumes the slot drawn for "the next opening"
+        s.step(2)
+        s.set("p", p)
+        s.step(1); s.step(4)
+    for k in ("x", "p", "f"):
+        assert np.array_equal(a.get(k), b.get(k)), k
+        assert np.array_equal(a.get(k), c.get(k)), k
+    a.close(); b.close(); c.close()
