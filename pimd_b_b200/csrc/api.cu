@@ -360,7 +360,11 @@ extern "C" int pimdb_create(const pimdb_config* cfg, pimdb_sim** out) {
     CREATE_TRY(cudaMalloc(&s->draw, sizeof(unsigned long long)));
     CREATE_TRY(cudaMemset(s->draw, 0, sizeof(unsigned long long)));
     if (cfg->thermostat == PIMDB_THERMO_LANGEVIN && !cfg->nmthermostat && cfg->propagator == PIMDB_PROP_CARTESIAN &&
-        cfg->rng != PIMDB_RNG_RANMARS && !getenv("PIMDB_NO_NOISE_PREFETCH")) {
+        cfg->rng != PIMDB_RNG_RANMARS && !getenv("PIMDB_NO_NOISE_PREFETCH") &&
+        (size_t)s->Ploc * s->D * s->N <= (size_t)(getenv("PIMDB_NOISE_PREFETCH_MAX") ? atol(getenv("PIMDB_NOISE_PREFETCH_MAX")) : 262144)) {
+        // (small systems only, where the thermostat launches are latency-bound: measured on B200, C3 -- 98 k momenta -- gains
+        // 1.5-2 us of a 64 us iteration; at C4 -- 786 k -- it is neutral and at C5 -- 6.3 M -- the extra 200 MB of traffic per
+        // iteration beside the HBM-bound exchange kernels costs 2.5 %)
         const size_t slot = (size_t)s->Ploc * s->D * s->N * sizeof(double);
         CREATE_TRY(cudaMalloc(&s->nz, 2 * slot));
         CREATE_TRY(cudaMalloc(&s->nz_tag, 2 * sizeof(unsigned long long)));
