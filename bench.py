@@ -166,7 +166,7 @@ class Runner:
         import torch
         from pimd_b_b200.engine import DeviceSim
         self.torch = torch
-        self.name, self.world, self.rank = name, world, rank
+        self.name, self.world, self.rank, self.local_rank = name, world, rank, local_rank
         self.cfg = workloads.config(name)
         self.x, self.p = workloads.initial_state(self.cfg, name)
         self.dev = torch.device("cuda", local_rank)
@@ -323,7 +323,20 @@ def rooflines(run: Runner, hbm_peak, peak_src, fp64_peak):
     nloc = run.hi - run.lo
     roofline = None
     if cfg.interaction != "free" and npair:
-        flops = workloads.pair_flops_per_step(cfg) * nloc / cfg.nbeads / max(1, npair // nsteps)
+        per_step = max(1, npair // nsteps)
+        flops = workloads.pair_flops_per_step(cfg) * nloc / cfg.nbeads / per_step
+        # the kernel with the GPU to itself: 20 x (the pair-tile launches of one step) back to back between two CUDA events
+        import ctypes as C
+        fn = sim.lib.pimdb_debug_pair_tiles_only
+        fn.restype = C.c_int; fn.argtypes = [C.c_void_p, C.c_int]
+        with torch.cuda.stream(run.stream):
+            fn(sim.h, 3)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(run.stream); fn(sim.h, 20); e1.record(run.stream)
+            e1.synchronize()
+        alone_ms = e0.elapsed_time(e1) / 20 / per_step
+        in_step_ms = pair_ms
+        pair_ms = alone_ms
         ach = flops / (pair_ms * 1e-3) * 1e-12
         traffic, fp64_pipe = None, {}
         try:
@@ -337,9 +350,18 @@ def rooflines(run: Runner, hbm_peak, peak_src, fp64_peak):
                     "frac": ach / fp64_peak if fp64_peak else None, "traffic": traffic,
                     "traffic_source": "profiles/r02_ncu_summary.json (ncu --set full, bytes per launch, N=1 C3 capture)",
                     "peak_source": "DFMA micro-benchmark in this run (MEASURED_PEAKS.json has no FP64 figure)",
-                    "flops_per_launch": flops, "ms_per_launch": pair_ms, "launches_timed": npair,
-                    "share_of_step": pair_ms * (npair / nsteps) / step_ms if step_ms else None,
-                    "eager_step_ms": step_ms, "fp64_pipe_pct_ncu": fp64_pipe}
+                    "flops_per_launch": flops, "ms_per_launch": pair_ms,
+                    "timing": "CUDA events around 20 x the step's pair-tile launches, back to back, nothing beside them "
+                              "(the kernel timed alone: a step overlaps it with the exchange chain, which an event pair in an "
+                              "eager step charges to it -- in_eager_step)",
+                    "in_eager_step": {"ms_per_launch": in_step_ms, "frac": flops / (in_step_ms * 1e-3) * 1e-12 / fp64_peak if fp64_peak else None,
+                                      "launches_timed": npair, "eager_step_ms": step_ms,
+                                      "share_of_step": in_step_ms * (npair / nsteps) / step_ms if step_ms else None},
+                    "fp64_pipe_pct_ncu": fp64_pipe}
+        if run.world == 1:
+            tl = captured_step_timeline(run.name, run.local_rank, torch)
+            if tl:
+                roofline["in_captured_step"] = {**tl, "frac": flops * per_step / (tl["pair_tiles_ms"] * 1e-3) * 1e-12 / fp64_peak if fp64_peak else None}
     ach_gbs = integ_bytes / (integ_ms * 1e-3) * 1e-9 if integ_ms else None
     integ = {"kernel": "k_integrate", "bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s",
              "frac": ach_gbs / hbm_peak if ach_gbs else None, "peak_source": peak_src,
@@ -349,6 +371,46 @@ def rooflines(run: Runner, hbm_peak, peak_src, fp64_peak):
                      "launch latency (~2 us), not by HBM",
              "bytes_per_step_survey": workloads.integrator_bytes_per_step(cfg) * nloc / cfg.nbeads}
     return roofline, integ
+
+
+def captured_step_timeline(name, local_rank, torch):
+    """How long the kernels of the captured (graph-replayed) step take where they run, overlapped: a second handle created with
+    PIMDB_TIMELINE=1 has every block stamp %globaltimer; [first block start, last block end] per kernel, median of 20 steps."""
+    import ctypes as C
+    from pimd_b_b200.engine import DeviceSim
+    cfg = workloads.config(name)
+    x, p = workloads.initial_state(cfg, name)
+    os.environ["PIMDB_TIMELINE"] = "1"
+    try:
+        sim = DeviceSim(cfg, device=local_rank)
+    finally:
+        del os.environ["PIMDB_TIMELINE"]
+    try:
+        sim.upload(x, p)
+        sim.step(30); sim.synchronize()
+        fn = sim.lib.pimdb_debug_timeline; fn.restype = C.c_int; fn.argtypes = [C.c_void_p, C.POINTER(C.c_ulonglong)]
+        fk = sim.lib.pimdb_debug_timeline_kinds; fk.restype = C.c_int; fk.argtypes = [C.c_void_p, C.POINTER(C.c_ubyte)]
+        buf, kinds = (C.c_ulonglong * 64)(), (C.c_ubyte * 32)()
+        fn(sim.h, buf)
+        rows = []
+        for _ in range(20):
+            sim.step(1); sim.synchronize()
+            n = min(fn(sim.h, buf), 32)
+            fk(sim.h, kinds)
+            t = np.array(buf[:], dtype=np.uint64).reshape(32, 2)[:n].astype(np.int64)
+            k = np.array(kinds[:n])
+            def span(kind):
+                sel = t[k == kind]
+                return float(sel[:, 1].max() - sel[:, 0].min()) * 1e-6 if len(sel) else None
+            rows.append((span(5), span(2), span(3), span(4), float(t[:, 1].max() - t[:, 0].min()) * 1e-6))
+        med = lambda i: float(np.median([r[i] for r in rows])) if rows and rows[0][i] is not None else None
+        return {"pair_tiles_ms": med(0), "exchange_factor_tiles_ms": med(1), "exchange_recurrences_ms": med(2),
+                "exchange_exterior_forces_ms": med(3), "step_span_ms": med(4),
+                "method": "%globaltimer stamps by every block, first start -> last end per kernel kind, captured step, warm"}
+    except Exception:
+        return None
+    finally:
+        sim.close()
 
 
 def scrambled_pair_time(name, local_rank, torch):
@@ -362,13 +424,16 @@ def scrambled_pair_time(name, local_rank, torch):
     sim.upload(np.ascontiguousarray(x[:, perm]), np.ascontiguousarray(p[:, perm]))
     st = torch.cuda.Stream(device=local_rank)
     sim.set_stream(st.cuda_stream)
-    sim.timing_enable(True)
+    import ctypes as C
+    fn = sim.lib.pimdb_debug_pair_tiles_only
+    fn.restype = C.c_int; fn.argtypes = [C.c_void_p, C.c_int]
     with torch.cuda.stream(st):
-        for _ in range(2):
-            torch.cuda._sleep(3_000_000)      # (see rooflines)
-            sim.step(10)
-    ms, n = sim.timing_get(0)
-    sim.timing_enable(False)
+        sim.step(5)                       # (a few steps so that the beads are no longer on top of each other)
+        fn(sim.h, 3)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(st); fn(sim.h, 20); e1.record(st)
+        e1.synchronize()
+    ms = e0.elapsed_time(e1) / 20
     sim.close()
     return ms
 

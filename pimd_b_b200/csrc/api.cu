@@ -1513,6 +1513,14 @@ extern "C" int pimdb_debug_timeline(pimdb_sim* sim, unsigned long long* out) {
     return s->tl_next;
 }
 
+// ... and which kernel each of those slots belongs to (see tl_slot): out[32]
+extern "C" int pimdb_debug_timeline_kinds(pimdb_sim* sim, unsigned char* out) {
+    Sim* s = reinterpret_cast<Sim*>(sim);
+    if (!s || !out || !s->tl) return 0;
+    memcpy(out, s->tl_kind, 32);
+    return s->tl_next;
+}
+
 // Profiling aid (PIMDB_TIMELINE=1): the %globaltimer stamps of the phases of the k_integrate launches of the captured step
 // (block 0: 0 start, 1 counters read, 2 sums in, 3 halo / credit waits done, 4 main loop done, 5 ticket taken; last block: 6, 7 end).
 extern "C" int pimdb_debug_integrate_stamps(pimdb_sim* sim, unsigned long long* out) {
@@ -1543,6 +1551,23 @@ extern "C" int pimdb_debug_exchange_blocks(pimdb_sim* sim, int* out) {
 }
 
 // ----------------------------------------------------------------------------------------------------
+// Profiling aid (not part of the reference surface, not declared in pimdb200.h): the pair-tile kernel of every owned bead,
+// `reps` launches back to back on the handle's stream with nothing beside them. The caller brackets the call with CUDA
+// events: (elapsed / reps) is the kernel's duration when it has the GPU to itself (bench.py, roofline.alone).
+extern "C" int pimdb_debug_pair_tiles_only(pimdb_sim* sim, int reps) {
+    Sim* s = reinterpret_cast<Sim*>(sim);
+    if (!s || !s->pair_on || reps < 1) return PIMDB_ERR_INVALID_ARGUMENT;
+    PIMDB_CUDA_TRY(s, cudaSetDevice(s->device));
+    const bool timing = s->timing;
+    s->timing = false;
+    int rc = PIMDB_OK;
+    for (int r = 0; r < reps && rc == PIMDB_OK; ++r)
+        for (int lo = 0; lo < s->Ploc && rc == PIMDB_OK; lo += s->bead_chunk)
+            rc = launch_pair_chunk(s, lo, std::min(s->bead_chunk, s->Ploc - lo), false);
+    s->timing = timing;
+    return rc;
+}
+
 // Profiling aid (not part of the reference surface, not declared in pimdb200.h): average warm duration in
 // microseconds of the two halves of the exchange chain, measured with CUDA events on the handle's stream.
 //   out[0] = prefix sums + Boltzmann factors, out[1] = recurrences + exterior forces

@@ -1771,9 +1771,9 @@ static int run_recursion(Sim* s, const ExArgs& a, cudaStream_t st) {
 template <int D>
 static int exchange_impl(Sim* s, cudaStream_t st, int part) {
     ExArgs a = make_args(s);
-    if (part == 0) a.tl0 = tl_slot(s);
-    if (part == 1 || part == 2) a.tl1 = tl_slot(s);
-    if (part == 1 || part == 3) a.tl2 = tl_slot(s);
+    if (part == 0) a.tl0 = tl_slot(s, 2);
+    if (part == 1 || part == 2) a.tl1 = tl_slot(s, 3);
+    if (part == 1 || part == 3) a.tl2 = tl_slot(s, 4);
     if (part == 0) {
         if (a.Kf) {      // N <= 8192: factor tiles + diagonal-block inverses; up to N = 512 the tiles recompute the prefix sums
             const int nb = (s->N + 31) / 32;

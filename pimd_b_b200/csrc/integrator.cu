@@ -134,7 +134,7 @@ int launch_assemble_chunk(Sim* s, int bead_lo, int nb, bool with_pair) {
     a.k = s->kspring; a.kext = s->kext; a.L = s->L; a.invL = 1.0 / s->L;
     a.pbc = s->cfg.pbc; a.ext_pot = s->cfg.ext_potential; a.write_split = 1;
     a.mass = s->cfg.mass;
-    a.tl = tl_slot(s);
+    a.tl = tl_slot(s, 1);
     a.halo_flag = s->peer_on ? s->peer.mine->halo_flag : nullptr;   // (address arithmetic only: the mailbox is device memory)
     a.halo_seq = s->peer_on ? s->peer.seq + 1 : nullptr;
     a.timeout_ns = s->peer.timeout_ns; a.err = s->err_d;
@@ -698,7 +698,7 @@ int launch_integrate(Sim* s, unsigned ops) {
         if (rc != PIMDB_OK) return rc;
         a.noise = s->rm_noise;
     }
-    a.tl = tl_slot(s);
+    a.tl = tl_slot(s, 1);
     a.scratch = s->pair_on ? s->pair_scratch : nullptr; a.exF = s->exF;
     a.T = s->T;
     a.first_local = (s->bosonic && s->has_first) ? 0 : -1;

@@ -143,6 +143,7 @@ struct Sim {
     double *nh_state = nullptr; size_t nh_len = 0;
     RanMarsState* rm_state = nullptr; double* rm_noise = nullptr;   // reference-compatible noise mode (ranmars.cu): [Ploc], [Ploc][N][D]
     unsigned long long* stamps = nullptr; int stamp_next = 0;   // phase stamps of the k_integrate launches [8][8] (PIMDB_TIMELINE=1)
+    unsigned char tl_kind[32] = {};
     unsigned long long* tl = nullptr; int tl_next = 0;   // in-kernel timeline slots [32][2] (PIMDB_TIMELINE=1), next slot
     // graph
     cudaGraph_t graph = nullptr; cudaGraphExec_t graph_exec = nullptr;
@@ -189,7 +190,14 @@ struct Sim {
     std::string err;
 };
 
-inline unsigned long long* tl_slot(Sim* s) { return s->tl ? s->tl + 2 * (s->tl_next++ % 32) : nullptr; }
+// kind of kernel a timeline slot belongs to: 1 k_integrate / k_assemble, 2 exchange factor tiles (+ prefix), 3 recurrences,
+// 4 exterior forces, 5 pair tiles
+inline unsigned long long* tl_slot(Sim* s, int kind) {
+    if (!s->tl) return nullptr;
+    const int i = s->tl_next++ % 32;
+    s->tl_kind[i] = (unsigned char)kind;
+    return s->tl + 2 * i;
+}
 
 // launch helpers --------------------------------------------------------------------------------------
 inline int grid_for(size_t items, int block, int max_blocks = 8 * kNumSM) {

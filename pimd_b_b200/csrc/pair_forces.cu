@@ -519,7 +519,7 @@ static int launch_chunk(Sim* s, int bead_lo, int nb, bool with_obs, bool early, 
     // `split` > 1 cuts a tile pair's rotations over 2 or 4 warps. Measured on B200 at C3 (2.45 waves of tile pairs):
     // 52.0 / 52.2 / 58.3 us for split 1 / 2 / 4 -- the tail is not what limits the kernel, so the default stays 1.
     a.split = 1;
-    a.tl = with_obs ? nullptr : tl_slot(s);
+    a.tl = with_obs ? nullptr : tl_slot(s, 5);
     if (const char* e = getenv("PIMDB_PAIR_SPLIT")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) a.split = v; }
     const long long gwarps = items * a.split;
     const int grid = (int)((gwarps + kPairWarps - 1) / kPairWarps);
