@@ -1365,7 +1365,10 @@ __global__ void __launch_bounds__(256, 1) k_exch_recur_cluster_multi(ExArgs a) {
 // its Boltzmann factor -- the other recurrence's weights and one bead slice -- is staged in shared memory once per
 // block (even blocks serve the first bead, odd blocks the last), and a task issues all of its factor loads (16 B each,
 // L2) before it uses the first one, so a task costs one L2 round trip instead of one per term.
-constexpr int kFW = 4;                       // warps per block (127 registers x 128 threads: fits where ONE pair-tile block retired)
+#ifndef PIMDB_EXCH_FW
+#define PIMDB_EXCH_FW 4
+#endif
+constexpr int kFW = PIMDB_EXCH_FW;           // warps per block (127 registers x 128 threads: fits where ONE pair-tile block retired)
 constexpr int kFU = 16;                      // terms per lane held in flight (covers N <= 512)
 // STAGE: 1 = weights, exponents and the bead slice in shared memory (N <= ~5000), 2 = weights and exponents only (the
 // slice is read from global memory; N <= 8192), 0 = nothing staged and no chunk skipping (larger N)
@@ -1747,9 +1750,13 @@ static int run_recursion(Sim* s, const ExArgs& a, cudaStream_t st) {
         const int nb = nblk, nb2 = (nb + 3) & ~1, wpc = (nb + kClusterSize - 1) / kClusterSize;
         const size_t smem_cl = sizeof(double) * ((size_t)wpc * 3 * 512 + 32 * nb + 32 * wpc + nb2) + 8 * ((size_t)nb2 + wpc * 3 + (wpc & 1))
                                + sizeof(int) * ((size_t)32 * nb + nb2) + 16;
-        if (smem_cl > 48 * 1024)
-            cudaFuncSetAttribute(k_exch_recur_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_cl);
-        launch_chain(s, k_exch_recur_cluster, a, 2 * kClusterSize, 32 * wpc, smem_cl, st, kClusterSize, pdl);
+        // PIMDB_RECUR_SMEM_KB (experiment): pad the dynamic shared memory of a recurrence block so that fewer (or no) pair-tile
+        // blocks fit beside it on its SM -- the recurrence is a latency chain and shares its SM's issue slots with them
+        size_t smem_req = smem_cl;
+        if (const char* e = getenv("PIMDB_RECUR_SMEM_KB")) smem_req = std::max(smem_cl, (size_t)atoi(e) * 1024);
+        if (smem_req > 48 * 1024)
+            cudaFuncSetAttribute(k_exch_recur_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_req);
+        launch_chain(s, k_exch_recur_cluster, a, 2 * kClusterSize, 32 * wpc, smem_req, st, kClusterSize, pdl);
         return PIMDB_OK;
     }
     // scalar recurrence, one unknown per step: the cross-check path (PIMDB_EXCH_NOBLOCKED=1) and N > 8192
