@@ -863,12 +863,19 @@ static int enqueue_step_inner(Sim* s, bool defer_last_com) {
         const unsigned o_pre = s->cfg.thermostat == PIMDB_THERMO_LANGEVIN ? OP_O_PRE : 0u;
         const unsigned o_post = s->cfg.thermostat == PIMDB_THERMO_LANGEVIN ? OP_O_POST : 0u;
         s->p_shift_pending = false; s->z_owed = false;
+        // (the noise draw counter is advanced by the launch in the middle, which has no O stage, as in the one-handle iteration
+        // below: the closing launch then needs no last block at all -- its early credit belongs to the flag protocol of the
+        // late halo push, which this path does not use)
+        const bool bump = o_pre != 0 && !s->rm_state && !s->no_ticketless;
+        s->li_no_ticket = bump;
         API_TRY(launch_integrate(s, o_pre | OP_SUM | OP_HALO_EARLY));
         allow_early_launch(s);
+        s->li_draw_bump = bump ? 2 : 0;
         API_TRY(launch_integrate(s, OP_SUBCM | OP_B | OP_A | OP_HALO_FIX));
         API_TRY(maybe_download_x(s));
         const bool fuse = fuse_assembly(s);
         API_TRY(enqueue_forces(s, fuse, !s->dl_forked));
+        s->li_no_ticket = bump; s->li_draw_off = bump ? -1 : 0;
         API_TRY(launch_integrate(s, (fuse ? OP_ASSEMBLE : 0u) | OP_B | o_post));
         API_TRY(join_download_x(s));
         s->z_owed = true;

@@ -187,7 +187,7 @@ struct IntArgs {
     // com_mode 1 (the handle owns every bead, no peers): SUM leaves block partials in com_out, SUBCM adds up the com_nblk
     // partials of com_in itself. use_ticket: the launch needs its last block (peer publication, totals for the host-driven
     // shards, advancing the draw counter). draw_off / draw_bump: see Sim::li_draw_off.
-    int com_mode, com_nblk, use_ticket, draw_off, draw_bump;
+    int com_mode, com_nblk, use_ticket, draw_off, draw_bump, draw_inc;
     const double* com_in; double* com_out;
     const double* nz; const unsigned long long* nz_tag; size_t nz_slot;   // prefetched draws of the counter-based stream (k_noise_prefetch) or nullptr
     unsigned long long* tl;
@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(256) k_integrate(IntArgs a) {
                 for (int c = 0; c < 3; ++c) a.com_out[blockIdx.x * 4 + c] = acc[c];
             }
         }
-    } else if ((a.ops & (OP_SUM | OP_O_PRE | OP_O_POST | OP_ZERO_SUM)) || push_halo) {
+    } else {
         if (a.ops & OP_SUM) {
             block_sum<3>(acc, sm);
             if (tid == 0) {
@@ -521,7 +521,7 @@ __global__ void __launch_bounds__(256) k_integrate(IntArgs a) {
             }
             if (tid == 0) {
                 *a.ticket = 0u;
-                if (do_o) *a.draw = draw + 1ull;       // (draw_off is 0 whenever an O stage advances the counter itself)
+                if (a.draw_inc) *a.draw = draw + 1ull;       // (draw_off is 0 whenever an O stage advances the counter itself)
             }
             PIMDB_STAMP(7);
         }
@@ -682,7 +682,13 @@ int launch_integrate(Sim* s, unsigned ops) {
         if (consumer && (ops & OP_SUM)) s->com_buf ^= 1;
         a.draw_off = do_o ? s->li_draw_off : 0;
         a.draw_bump = do_o ? 0 : s->li_draw_bump;
-        a.use_ticket = (!consumer || (do_o && !s->li_no_ticket)) ? 1 : 0;
+        a.draw_inc = (do_o && !s->li_no_ticket) ? 1 : 0;
+        // who needs the last block: an O stage that advances the counter itself (on bead shards it also publishes the early
+        // credit of the flag protocol then); on bead shards the momentum sums (published to the peers / left as totals for the
+        // host-driven shards) and the flag of a halo push
+        bool ticket = a.draw_inc != 0;
+        if (!consumer) ticket = ticket || (ops & (OP_SUM | OP_ZERO_SUM)) != 0 || (s->peer_on && (ops & OP_HALO) != 0);
+        a.use_ticket = ticket ? 1 : 0;
         s->li_draw_off = 0; s->li_draw_bump = 0; s->li_no_ticket = false;
     }
     a.N = s->N; a.D = s->D; a.Ploc = s->Ploc; a.bead_begin = s->b0; a.S = s->S;
