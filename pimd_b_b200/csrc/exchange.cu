@@ -1750,10 +1750,15 @@ static int run_recursion(Sim* s, const ExArgs& a, cudaStream_t st) {
         const int nb = nblk, nb2 = (nb + 3) & ~1, wpc = (nb + kClusterSize - 1) / kClusterSize;
         const size_t smem_cl = sizeof(double) * ((size_t)wpc * 3 * 512 + 32 * nb + 32 * wpc + nb2) + 8 * ((size_t)nb2 + wpc * 3 + (wpc & 1))
                                + sizeof(int) * ((size_t)32 * nb + nb2) + 16;
-        // PIMDB_RECUR_SMEM_KB (experiment): pad the dynamic shared memory of a recurrence block so that fewer (or no) pair-tile
-        // blocks fit beside it on its SM -- the recurrence is a latency chain and shares its SM's issue slots with them
+        // On a bead shard the recurrence blocks ask for (nearly) all the shared memory of their SMs, so that no pair-tile block
+        // fits beside them: the recurrence is a latency chain, and sharing its SM's issue slots with 20 pair-tile warps stretches
+        // it from 17 to 26 us at N = 512. A shard has fewer pair tiles than the exchange chain is long, so the 16 SMs are not
+        // missed (measured on 2 GPUs at C3: 70.8 -> 68.2 us per step); a handle that owns every bead is balanced between the two
+        // arms and loses what the recurrence gains (62.1 -> 63.9 us), so it does not. PIMDB_RECUR_SMEM_KB overrides (0 = off).
         size_t smem_req = smem_cl;
-        if (const char* e = getenv("PIMDB_RECUR_SMEM_KB")) smem_req = std::max(smem_cl, (size_t)atoi(e) * 1024);
+        size_t pad_kb = s->peer_on ? 218 : 0;
+        if (const char* e = getenv("PIMDB_RECUR_SMEM_KB")) pad_kb = (size_t)std::max(0, atoi(e));
+        smem_req = std::max(smem_cl, std::min<size_t>(pad_kb, 227) * 1024);
         if (smem_req > 48 * 1024)
             cudaFuncSetAttribute(k_exch_recur_cluster, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_req);
         launch_chain(s, k_exch_recur_cluster, a, 2 * kClusterSize, 32 * wpc, smem_req, st, kClusterSize, pdl);
