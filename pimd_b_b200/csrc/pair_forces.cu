@@ -136,8 +136,8 @@ __device__ __forceinline__ void pair_rotation(const PairArgs& a, int t, int lane
     if (POT == PIMDB_POT_AZIZ && !OBS && __all_sync(kFullMask, r2 > a.az_far2)) {
         double y;
         asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(r2));
-        y = fma(y, fma(-r2, y, 1.0), y);
-        const double u = fma(y, fma(-r2, y, 1.0), y);
+        const double e = fma(-r2, y, 1.0);                 // one third-order step: y (1 + e + e^2), remainder e^3 <= 2^-60
+        const double u = fma(y, fma(e, e, e), y);
         const double u2 = u * u;
         g = (u2 * u2) * fma(fma(a.az_h2, u, a.az_h1), u, a.az_h0);
     } else {
@@ -274,8 +274,9 @@ __device__ __forceinline__ void pair_rotation2(const PairArgs& a, int t, int lan
             double ya, yb;
             asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(ya) : "d"(ra));
             asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(yb) : "d"(rb));
-            ya = fma(ya, fma(-ra, ya, 1.0), ya); yb = fma(yb, fma(-rb, yb, 1.0), yb);
-            const double ua = fma(ya, fma(-ra, ya, 1.0), ya), ub = fma(yb, fma(-rb, yb, 1.0), yb);
+            // one third-order step each: y (1 + e + e^2), e = 1 - r y; the seed is good to 2^-20, the remainder e^3 to 2^-60
+            const double ea = fma(-ra, ya, 1.0), eb = fma(-rb, yb, 1.0);
+            const double ua = fma(ya, fma(ea, ea, ea), ya), ub = fma(yb, fma(eb, eb, eb), yb);
             const double qa = ua * ua, qb = ub * ub;
             ga = (qa * qa) * fma(fma(a.az_h2, ua, a.az_h1), ua, a.az_h0);
             gb = (qb * qb) * fma(fma(a.az_h2, ub, a.az_h1), ub, a.az_h0);
