@@ -1167,6 +1167,7 @@ struct PeerBlob {
     long long pid;
     unsigned long long boot_tag;       // distinguishes handles of different processes with recycled pids (create-time stamp)
     int device, natoms, nbeads, ndim, bead_begin, bead_end;
+    char uuid[16];                     // of the exporting handle's GPU: two shards on ONE GPU compete for its SMs
     void* x;                           // device pointers, meaningful inside the exporting process only
     void* mailbox;
     cudaIpcMemHandle_t x_ipc, mailbox_ipc;
@@ -1184,6 +1185,11 @@ extern "C" int pimdb_peer_export(pimdb_sim* sim, void* blob_out) {
     memset(&b, 0, sizeof b);
     b.magic = kBlobMagic; b.version = PIMDB_ABI_VERSION;
     b.pid = (long long)getpid();
+    {
+        cudaDeviceProp prop;
+        PIMDB_CUDA_TRY(s, cudaGetDeviceProperties(&prop, s->device));
+        memcpy(b.uuid, prop.uuid.bytes, 16);
+    }
     b.device = s->device; b.natoms = s->N; b.nbeads = s->P; b.ndim = s->D; b.bead_begin = s->b0; b.bead_end = s->b1;
     b.x = s->x; b.mailbox = s->mailbox;
     PIMDB_CUDA_TRY(s, cudaIpcGetMemHandle(&b.x_ipc, s->x));
@@ -1234,6 +1240,9 @@ extern "C" int pimdb_peer_attach(pimdb_sim* sim, int world, int rank, const void
         if (b.bead_begin != expect || b.bead_end <= b.bead_begin) return fail(s, PIMDB_ERR_INVALID_ARGUMENT, "bead ranges must tile [0, nbeads) in rank order");
         expect = b.bead_end;
     }
+    s->peer_shares_gpu = false;
+    for (int r = 0; r < world; ++r)
+        if (r != rank && memcmp(tab[r].uuid, tab[rank].uuid, 16) == 0) s->peer_shares_gpu = true;
     if (expect != s->P || tab[rank].bead_begin != s->b0 || tab[rank].bead_end != s->b1)
         return fail(s, PIMDB_ERR_INVALID_ARGUMENT, "bead ranges must tile [0, nbeads) in rank order (and blobs[rank] must be this handle's)");
     PeerDev pd{};

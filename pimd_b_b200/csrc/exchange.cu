@@ -1756,7 +1756,7 @@ static int run_recursion(Sim* s, const ExArgs& a, cudaStream_t st) {
         // missed (measured on 2 GPUs at C3: 70.8 -> 68.2 us per step); a handle that owns every bead is balanced between the two
         // arms and loses what the recurrence gains (62.1 -> 63.9 us), so it does not. PIMDB_RECUR_SMEM_KB overrides (0 = off).
         size_t smem_req = smem_cl;
-        size_t pad_kb = s->peer_on ? 218 : 0;
+        size_t pad_kb = (s->peer_on && !s->peer_shares_gpu) ? 218 : 0;    // (shards sharing one GPU would starve each other's clusters)
         if (const char* e = getenv("PIMDB_RECUR_SMEM_KB")) pad_kb = (size_t)std::max(0, atoi(e));
         smem_req = std::max(smem_cl, std::min<size_t>(pad_kb, 227) * 1024);
         if (smem_req > 48 * 1024)

@@ -159,6 +159,7 @@ struct Sim {
     double* nz = nullptr; unsigned long long* nz_tag = nullptr;
     cudaStream_t stream_n = nullptr; cudaEvent_t ev_nz_fork = nullptr, ev_nz_join = nullptr;
     bool nz_on = false, nz_want = false;
+    bool peer_shares_gpu = false;      // another shard of the ring lives on this handle's GPU (tests, PIMDB_SHARD_SAME_DEVICE)
     bool no_ticketless = false;        // PIMDB_NO_TICKETLESS=1 when the handle was created (api.cu ticketless_langevin_step)
     bool p_shift_pending = false;      // fixcom: COM shift computed but not yet subtracted from p
     // peer-memory bead sharding (pimdb_peer_attach)
