@@ -5,18 +5,19 @@
 // AzizPotential / DipolePotential / HarmonicPotential ::gradV, ::V (src/potentials/*.cpp), and the second
 // pair loop of EnergyObservable::calculatePotential (src/observables/energy.cpp:76-94).
 //
-// Decomposition: the N particles of a bead are cut into T = ceil(N/32) tiles. One WARP owns one unordered
-// tile pair (I<=J) of one bead -- or, when the launch would otherwise fill the GPU fewer than ~6 times over, one
-// half / quarter of its 32 rotations (`split`; C3 has 8704 tile pairs for 3552 resident warps: 2.45 waves, so a
-// third of the machine idles through the tail unless the items are finer). Lane l holds particle 32I+l ("i") in
-// registers; the j tile and its reaction-force accumulators live in shared memory, and the 32 rotations
+// Decomposition: the N particles of a bead are cut into T = ceil(N/32) tiles. One WARP owns one unordered tile pair
+// (I<=J) of one bead (or one half / quarter of its rotations, `split`, an experiment switch). Lane l holds particle
+// 32I+l ("i") in registers; the j tile and its reaction-force accumulators live in shared memory, and the 32 rotations
 // (l, (l+t)%32) enumerate the 32x32 tile: in a rotation every lane touches a different j, so the shared-memory
 // reads and read-modify-writes are conflict-free and need no atomics. Every unordered pair is evaluated exactly once
-// (Newton's third law). Diagonal tiles run the rotations t=1..16 only (t=16 on half the lanes). The warps that
-// share a tile pair combine their partial sums through shared memory in a fixed order, then ONE of them writes the
-// two 32-particle partial force vectors to a scratch slab S[bead][tile K][other tile M][axis][lane]; the assemble
-// kernel sums the T partials of every particle in fixed order M=0..T-1 (deterministic, bit-reproducible) and adds
-// the external and spring forces.
+// (Newton's third law). Diagonal tiles run the rotations t=1..16 only (t=16 on half the lanes). Force-only launches
+// take TWO rotations per loop step (pair_rotation2: two independent pair chains per lane, two reaction accumulators).
+// The warps that share a tile pair combine their partial sums through shared memory in a fixed order, then ONE of them
+// writes the two 32-particle partial force vectors to a scratch slab S[bead][tile K][other tile M][axis][lane]; the
+// assembly (k_assemble, or the closing k_integrate) sums the T partials of every particle in fixed order M=0..T-1
+// (deterministic, bit-reproducible) and adds the external and spring forces.
+// Work items are ordered tile pair by tile pair (all beads of one pair are neighbours), diagonal tiles last; blocks of
+// 4 warps, 5 per SM.
 #include "internal.cuh"
 #include "device_utils.cuh"
 
