@@ -12,6 +12,11 @@
   momentum sums are stored into the peers' memory over NVLink by the step's own kernels, one CUDA-graph replay per rank
   and step, no host collective inside the timed region; time = max over ranks; the system is the same at every N, so
   scaling is "strong". PIMDB_SHARD_MODE=nccl selects the host-driven NCCL choreography of round 1 for comparison.
+* `roofline` (pair-tile kernel, FP64 pipe): the kernel timed alone -- CUDA events around 20 x the step's pair-tile launches,
+  back to back -- against the DFMA peak measured in this run; `roofline.in_eager_step` = the duration between an event
+  pair in an eager step (it also times the exchange kernels that run beside it), `roofline.in_captured_step` = the
+  durations of the force-phase kernels inside the graph-replayed step from %globaltimer stamps (N=1 only; a second handle
+  created with PIMDB_TIMELINE=1). `roofline_integrator`: achieved GB/s of the fused integrator launches (eager pass).
 * The line also carries `c4`: the same measurement on He-4 N=2048 P=128 (BASELINE configs[3], the configuration that
   names bead sharding), at every N.
 * --impl reference: the reference's own CPU implementation (oracle/_ref/pimdb_ndim3, unmodified sources, one
