@@ -498,10 +498,14 @@ static int upload_arrays(Sim* s, int n, const int* which, const double* const* h
     // The caller may reuse its buffers as soon as the call returns (pageable and page-locked alike): wait for the copies,
     // not for the transpose.
     PIMDB_CUDA_TRY(s, cudaEventRecord(s->ev_copy, s->stream));
-    API_TRY(launch_aos_to_soa(s, n, dst, halo));
-    bool x_changed = false;
-    for (int i = 0; i < n; ++i) x_changed = x_changed || which[i] == PIMDB_X;
-    if (x_changed && s->all_local) API_TRY(launch_fill_halos(s));
+    bool x_changed = false, p_changed = false;
+    for (int i = 0; i < n; ++i) { x_changed = x_changed || which[i] == PIMDB_X; p_changed = p_changed || which[i] == PIMDB_P; }
+    // (a full ring: the transpose fills its halo slabs too; new momenta on a handle that owns every bead: it also leaves zero
+    // momentum sums pending -- p - 0.0 == p bit for bit -- which is the state a captured iteration starts from, see
+    // make_entry_state_uniform: no separate memset in front of the next pimdb_step)
+    const bool zero_com = p_changed && s->cfg.fixcom && s->all_local && !s->peer_on;
+    API_TRY(launch_aos_to_soa(s, n, dst, halo, x_changed && s->all_local, zero_com));
+    if (zero_com) { s->p_shift_pending = true; s->com_buf = 0; }
     if (x_changed && s->peer_on) API_TRY(launch_peer_push_halos(s));
     if (wait_for_copy || !all_pinned) PIMDB_CUDA_TRY(s, cudaEventSynchronize(s->ev_copy));
     return PIMDB_OK;

@@ -782,9 +782,13 @@ struct TransposeArgs {
     double* aos;           // staging buffer
     int n, N, D;
     long long total;       // elements per array
+    int ring_arr, Ploc;    // k_aos_to_soa: array `ring_arr` (-1: none) owns the whole ring -- its first / last bead also go to
+                           // the trailing / leading halo slab (what k_fill_halos does, without the extra launch)
+    double* zero; int nzero;   // k_aos_to_soa: doubles to clear on the way (the pending momentum sums when p is replaced)
 };
 __global__ void k_aos_to_soa(TransposeArgs a) {
     const long long ND = (long long)a.N * a.D;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.nzero; i += gridDim.x * blockDim.x) a.zero[i] = 0.0;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.total * a.n; i += (long long)gridDim.x * blockDim.x) {
         const int arr = (int)(i / a.total);
         const long long j = i - arr * a.total;
@@ -792,7 +796,12 @@ __global__ void k_aos_to_soa(TransposeArgs a) {
         const int r = (int)(j % ND);
         const int c = r / a.N, n = r % a.N;       // j indexes the SoA side (coalesced writes)
         double* dst = arr == 0 ? a.soa[0] : (arr == 1 ? a.soa[1] : a.soa[2]);
-        dst[j] = a.aos[arr * a.total + (b * a.N + n) * a.D + c];
+        const double v = a.aos[arr * a.total + (b * a.N + n) * a.D + c];
+        dst[j] = v;
+        if (arr == a.ring_arr) {
+            if (b == 0) dst[(long long)a.Ploc * ND + r] = v;             // trailing halo = bead 0
+            if (b == a.Ploc - 1) dst[r - ND] = v;                         // leading halo = last bead
+        }
     }
 }
 __global__ void k_soa_to_aos(TransposeArgs a) {
@@ -808,9 +817,14 @@ __global__ void k_soa_to_aos(TransposeArgs a) {
     }
 }
 
-int launch_aos_to_soa(Sim* s, int n, double* const* dst_soa, const bool* has_halo) {
+int launch_aos_to_soa(Sim* s, int n, double* const* dst_soa, const bool* has_halo, bool fill_ring, bool zero_com) {
     TransposeArgs a{};
-    for (int i = 0; i < n; ++i) a.soa[i] = dst_soa[i] + (has_halo[i] ? s->S : 0);
+    a.ring_arr = -1; a.Ploc = s->Ploc;
+    if (zero_com) { a.zero = s->com_part; a.nzero = 4 * kMaxPartials; }
+    for (int i = 0; i < n; ++i) {
+        a.soa[i] = dst_soa[i] + (has_halo[i] ? s->S : 0);
+        if (fill_ring && has_halo[i]) a.ring_arr = i;        // (x is the only array with halo slabs)
+    }
     a.aos = s->stage_d; a.n = n; a.N = s->N; a.D = s->D; a.total = (long long)s->Ploc * s->S;
     k_aos_to_soa<<<grid_for(a.total * n, 256), 256, 0, s->stream>>>(a);
     s->launches += 1;

@@ -249,7 +249,7 @@ int ranmars_create(Sim* s);
 int launch_ranmars_fill(Sim* s);   // the next thermostat half-step's gaussians, all owned beads
 int launch_nose_hoover(Sim* s);
 int launch_nose_hoover_energy(Sim* s, double* out_dev);
-int launch_aos_to_soa(Sim* s, int n, double* const* dst_soa, const bool* has_halo);          // up to 3 arrays per launch
+int launch_aos_to_soa(Sim* s, int n, double* const* dst_soa, const bool* has_halo, bool fill_ring = false, bool zero_com = false);          // up to 3 arrays per launch
 int launch_soa_to_aos(Sim* s, int n, const double* const* src_soa, const bool* has_halo, cudaStream_t st = nullptr);
 int launch_peer_wait_halos(Sim* s);
 
