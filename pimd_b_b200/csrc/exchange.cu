@@ -1368,13 +1368,14 @@ __global__ void __launch_bounds__(256, 1) k_exch_recur_cluster_multi(ExArgs a) {
 #ifndef PIMDB_EXCH_FW
 #define PIMDB_EXCH_FW 4
 #endif
-constexpr int kFW = PIMDB_EXCH_FW;           // warps per block (127 registers x 128 threads: fits where ONE pair-tile block retired)
+constexpr int kFW = PIMDB_EXCH_FW;           // warps per block
 constexpr int kFU = 16;                      // terms per lane held in flight (covers N <= 512)
 // STAGE: 1 = weights, exponents and the bead slice in shared memory (N <= ~5000), 2 = weights and exponents only (the
 // slice is read from global memory; N <= 8192), 0 = nothing staged and no chunk skipping (larger N)
-// (At most 160 registers: 160 x 128 = 20480 is exactly what ONE retiring pair-tile block (80 registers x 256 threads) frees,
-// so a block of this kernel can take the first SM slot that opens up while the pair tiles are still being dispatched; at 165
-// it had to wait for two neighbouring slots, i.e. for the tail of the pair-tile grid.)
+// (At most 160 registers: 160 x 128 = 20480 was exactly what ONE retiring pair-tile block of round 1 (80 registers x 256
+// threads) freed; at 165 the kernel had to wait for two neighbouring slots. The round-2 pair-tile blocks are smaller (94
+// registers x 128 threads), and smaller blocks of this kernel were measured -- 2 and 1 warps, 10.3 and 13.1 us against 7.4 --
+// so the shape stays: what delays its start now is the pair-tile grid still dispatching, not the size of a freed slot.)
 // KSRC: the factors come from the block-scaled tiles (N > 512) instead of the 16-byte tables
 template <int D, int STAGE, bool KSRC, bool EXACT>
 __device__ __forceinline__ void exch_forces_body(const ExArgs& a, double* fsm) {

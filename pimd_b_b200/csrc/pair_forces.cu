@@ -518,8 +518,8 @@ static int launch_chunk(Sim* s, int bead_lo, int nb, bool with_obs, bool early, 
         a.az_h2 = (double)(g0 * rm7 * rm2 * rm2 * 10.0L * kAzC10);
     }
     const long long items = (long long)nb * a.TP;
-    // `split` > 1 cuts a tile pair's rotations over 2 or 4 warps. Measured on B200 at C3 (2.45 waves of tile pairs):
-    // 52.0 / 52.2 / 58.3 us for split 1 / 2 / 4 -- the tail is not what limits the kernel, so the default stays 1.
+    // `split` > 1 cuts a tile pair's rotations over 2 or 4 warps (PIMDB_PAIR_SPLIT, an experiment switch). Measured on B200 at
+    // C3: 43.1 / 45.2 us (pair tiles + assembly) for split 1 / 2 -- finer items do not pay for the extra combination step.
     a.split = 1;
     a.tl = with_obs ? nullptr : tl_slot(s, 5);
     if (const char* e = getenv("PIMDB_PAIR_SPLIT")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4) a.split = v; }
