@@ -878,7 +878,10 @@ static int enqueue_step_inner(Sim* s, bool defer_last_com) {
         API_TRY(launch_integrate(s, OP_SUBCM | OP_B | OP_A | OP_HALO_FIX));
         API_TRY(maybe_download_x(s));
         const bool fuse = fuse_assembly(s);
-        API_TRY(enqueue_forces(s, fuse, !s->dl_forked));
+        s->nz_first_off = bump ? -1 : 0;      // (the counter already stands at "next opening": the closing draw is the one before)
+        const int rcf = enqueue_forces(s, fuse, !s->dl_forked);
+        s->nz_first_off = 0;
+        API_TRY(rcf);
         s->li_no_ticket = bump; s->li_draw_off = bump ? -1 : 0;
         API_TRY(launch_integrate(s, (fuse ? OP_ASSEMBLE : 0u) | OP_B | o_post));
         API_TRY(join_download_x(s));
